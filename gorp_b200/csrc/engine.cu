@@ -1,0 +1,655 @@
+// Engine + C ABI of libgorpcuda (include/gorp_cuda.h). Host orchestration only; the kernels are in kernels/.
+//
+// Device pipeline per batch (one stream, no host round trip except reading the line count of the text form):
+//   text form : K1 count -> scan -> K1 scatter -> K1 finish            => line_off[n+1], n_lines
+//   both forms: K2 dfa_scan => ext_id, span_cnt -> scan => span_off -> K4 tdfa_capture => spans -> K3 histogram
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gorp_cuda.h"
+#include "host/model.hpp"
+#include "kernels/kernels.cuh"
+
+using namespace gorp;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CK(expr)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t _e = (expr);                                                                                   \
+        if (_e != cudaSuccess)                                                                                     \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorName(_e) + " (" + cudaGetErrorString(_e) + ")"); \
+    } while (0)
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        return f();
+    } catch (const DefinitionParseError& e) {
+        return fail(GORP_E_DEFINITION, e.what());
+    } catch (const UnsupportedError& e) {
+        return fail(GORP_E_UNSUPPORTED, e.what());
+    } catch (const BlobError& e) {
+        return fail(GORP_E_BLOB, e.what());
+    } catch (const CudaError& e) {
+        return fail(GORP_E_CUDA, e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(GORP_E_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(GORP_E_INTERNAL, e.what());
+    }
+}
+
+// ------------------------------------------------------------------ device buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            CK(cudaMalloc(&p, want));
+        }
+        cap = want;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+template <class T>
+T* upload(const std::vector<T>& v, std::vector<void*>& owned) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, std::max<size_t>(v.size() * sizeof(T), 16)));
+    owned.push_back(p);
+    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return static_cast<T*>(p);
+}
+
+constexpr int kMaxTimed = 12;
+
+struct DeviceCtx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> owned;  // immutable tables
+    DfaDev dfa{};
+    CapDev cap{};
+    uint32_t* d_slots = nullptr;
+    uint32_t n_ext = 0;
+    uint32_t max_slots = 0;
+    // per-call scratch, serialised by `mu`
+    std::mutex mu;
+    DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, span_cnt, span_off, spans, hist, scalars;
+    cudaEvent_t ev[kMaxTimed + 1]{};
+    const char* ev_name[kMaxTimed]{};
+    int n_ev = 0;
+    float last_ms[kMaxTimed]{};
+    int last_n = 0;
+
+    ~DeviceCtx() {
+        cudaSetDevice(device);
+        for (void* p : owned) cudaFree(p);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct HostResult {  // pinned host arrays behind a gorp_result
+    void* p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[5] = {0, 0, 0, 0, 0};
+    void reserve(int i, size_t bytes) {
+        if (bytes <= cap[i]) return;
+        if (p[i]) cudaFreeHost(p[i]);
+        p[i] = nullptr;
+        cap[i] = 0;
+        size_t want = bytes + bytes / 8 + 64;
+        CK(cudaMallocHost(&p[i], want));
+        cap[i] = want;
+    }
+    ~HostResult() {
+        for (auto q : p)
+            if (q) cudaFreeHost(q);
+    }
+};
+
+}  // namespace
+
+struct gorp_engine {
+    CompiledDefinition def;
+    bool match_only = false;
+    std::vector<std::unique_ptr<DeviceCtx>> devs;
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<HostResult>> pool;
+};
+
+namespace {
+
+void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
+    CK(cudaSetDevice(c.device));
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    c.sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (auto& e : c.ev) CK(cudaEventCreate(&e));
+    // combined DFA
+    const size_t S = m.dfa.n_states, C = m.dfa.n_classes;
+    c.dfa.n_states = static_cast<uint32_t>(S);
+    c.dfa.n_classes = static_cast<uint32_t>(C);
+    c.dfa.cls = upload(m.dfa.classmap, c.owned);
+    c.dfa.accept_first = upload(m.dfa.accept_first, c.owned);
+    if (S * C < 0xFFFF) {
+        std::vector<uint16_t> t(S * C);
+        for (size_t i = 0; i < S * C; ++i) t[i] = m.dfa.trans[i] < 0 ? 0xFFFF : static_cast<uint16_t>(m.dfa.trans[i] * C);
+        c.dfa.trans16 = upload(t, c.owned);
+    } else {
+        if (S * C > 0x7FFFFFFFull) throw UnsupportedError("combined DFA table too large");
+        std::vector<int32_t> t(S * C);
+        for (size_t i = 0; i < S * C; ++i) t[i] = m.dfa.trans[i] < 0 ? -1 : static_cast<int32_t>(m.dfa.trans[i] * C);
+        c.dfa.trans32 = upload(t, c.owned);
+    }
+    // capture automata
+    const size_t E = m.n_groups.size();
+    c.n_ext = static_cast<uint32_t>(E);
+    std::vector<uint32_t> slots(E);
+    for (size_t e = 0; e < E; ++e) slots[e] = 2 * m.n_groups[e];
+    c.d_slots = upload(slots, c.owned);
+    for (uint32_t v : slots) c.max_slots = std::max(c.max_slots, v);
+    c.cap.n_ext = static_cast<uint32_t>(E);
+    c.cap.match_only = match_only ? 1u : 0u;
+    if (!match_only) {
+        std::vector<ExtDev> ext(E);
+        std::vector<uint32_t> trans, opoff;
+        std::vector<uint16_t> ops;
+        std::vector<uint8_t> fin, acc;
+        for (size_t e = 0; e < E; ++e) {
+            const Tdfa& t = m.tdfas[e];
+            if (t.n_regs > static_cast<uint32_t>(kMaxTdfaRegs))
+                throw UnsupportedError(strfmt("extraction #%zu needs %u tag registers (limit %d)", e, t.n_regs, kMaxTdfaRegs));
+            ext[e] = {static_cast<uint32_t>(trans.size()), static_cast<uint32_t>(opoff.size()), static_cast<uint32_t>(ops.size()),
+                      static_cast<uint32_t>(fin.size()), static_cast<uint32_t>(acc.size()), t.n_slots};
+            trans.insert(trans.end(), t.trans.begin(), t.trans.end());
+            opoff.insert(opoff.end(), t.op_off.begin(), t.op_off.end());
+            ops.insert(ops.end(), t.ops.begin(), t.ops.end());
+            fin.insert(fin.end(), t.fin.begin(), t.fin.end());
+            acc.insert(acc.end(), t.accepting.begin(), t.accepting.end());
+        }
+        c.cap.cls = upload(m.symbols.classmap, c.owned);
+        c.cap.n_classes = m.symbols.n_classes;
+        c.cap.pair_hi_class = m.symbols.pair_hi_class;
+        c.cap.ext = upload(ext, c.owned);
+        c.cap.tdfa_trans = upload(trans, c.owned);
+        c.cap.tdfa_op_off = upload(opoff, c.owned);
+        c.cap.tdfa_ops = upload(ops, c.owned);
+        c.cap.tdfa_fin = upload(fin, c.owned);
+        c.cap.tdfa_accepting = upload(acc, c.owned);
+    }
+}
+
+struct Timer {
+    DeviceCtx& c;
+    cudaStream_t s;
+    bool on;
+    Timer(DeviceCtx& c_, cudaStream_t s_, bool on_) : c(c_), s(s_), on(on_) {
+        c.n_ev = 0;
+        if (on) cudaEventRecord(c.ev[0], s);
+    }
+    void mark(const char* name) {
+        if (!on || c.n_ev >= kMaxTimed) return;
+        c.ev_name[c.n_ev] = name;
+        ++c.n_ev;
+        cudaEventRecord(c.ev[c.n_ev], s);
+    }
+    void collect() {
+        c.last_n = 0;
+        if (!on) return;
+        for (int i = 0; i < c.n_ev; ++i) cudaEventElapsedTime(&c.last_ms[i], c.ev[i], c.ev[i + 1]);
+        c.last_n = c.n_ev;
+    }
+};
+
+// Runs the device pipeline. Text form when d_off == nullptr. Caller holds c.mu and has set the device.
+// Returns n_lines (synchronises once for the text form to size the per-line arrays).
+int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, const int64_t* d_off, int64_t n_lines,
+                     cudaStream_t stream, bool timed, gorp_device_result* out) {
+    Launch L{stream, c.sm_count};
+    Timer tm(c, stream, timed);
+    c.scalars.reserve(64);
+    int64_t* d_n_lines = c.scalars.as<int64_t>();
+    const int64_t* d_line_off;
+    int sep;
+    if (!d_off) {
+        sep = 1;
+        const int64_t n_tiles = (n_units + kNlTile - 1) / kNlTile;
+        c.tile_counts.reserve(static_cast<size_t>(n_tiles + 1) * 4);
+        c.tile_base.reserve(static_cast<size_t>(n_tiles + 2) * 8);
+        c.scan_scratch.reserve(static_cast<size_t>(n_tiles / 4096 + 8) * 8);
+        k1_count_newlines(L, d_text, n_units, c.tile_counts.as<uint32_t>());
+        tm.mark("k1_count_newlines");
+        scan_u32_to_i64(L, c.tile_counts.as<uint32_t>(), n_tiles, c.tile_base.as<int64_t>(), c.scan_scratch.as<int64_t>());
+        tm.mark("scan_tiles");
+        // the one host round trip of the text form: the newline total (and the last unit) size the per-line arrays
+        int64_t total_nl = 0;
+        uint16_t last_unit = 0x0A;
+        CK(cudaMemcpyAsync(&total_nl, c.tile_base.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
+        if (n_units > 0) CK(cudaMemcpyAsync(&last_unit, d_text + n_units - 1, 2, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        n_lines = total_nl + (last_unit != 0x0A ? 1 : 0);
+        c.line_off.reserve(static_cast<size_t>(total_nl + 3) * 8);
+        k1_scatter_newlines(L, d_text, n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
+        k1_finish(L, d_text, n_units, c.tile_base.as<int64_t>() + n_tiles, c.line_off.as<int64_t>(), d_n_lines);
+        tm.mark("k1_scatter_newlines");
+        d_line_off = c.line_off.as<int64_t>();
+    } else {
+        sep = 0;
+        d_line_off = d_off;
+        CK(cudaMemcpyAsync(d_n_lines, &n_lines, 8, cudaMemcpyHostToDevice, stream));
+    }
+    const size_t nl = static_cast<size_t>(n_lines);
+    c.ext_id.reserve((nl + 1) * 4);
+    c.span_cnt.reserve((nl + 1) * 4);
+    c.span_off.reserve((nl + 2) * 8);
+    c.scan_scratch.reserve((nl / 4096 + 8) * 8);
+    c.hist.reserve((c.n_ext + 2) * 8);
+    k2_dfa_scan(L, c.dfa, d_text, d_line_off, sep, n_lines, c.d_slots, c.ext_id.as<int32_t>(), c.span_cnt.as<uint32_t>());
+    tm.mark("k2_dfa_scan");
+    scan_u32_to_i64(L, c.span_cnt.as<uint32_t>(), n_lines, c.span_off.as<int64_t>(), c.scan_scratch.as<int64_t>());
+    tm.mark("k5_span_offsets");
+    // span entries are bounded by n_lines * (widest extraction): no round trip needed to size the buffer
+    const size_t span_bound = nl * c.max_slots;
+    c.spans.reserve((span_bound + 4) * 4);
+    if (!c.cap.match_only)
+        k4_tdfa_capture(L, c.cap, d_text, d_line_off, sep, n_lines, c.span_off.as<int64_t>(), c.ext_id.as<int32_t>(),
+                        c.spans.as<int32_t>());
+    tm.mark("k4_tdfa_capture");
+    CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
+    k3_histogram(L, c.ext_id.as<int32_t>(), n_lines, c.n_ext, c.hist.as<unsigned long long>());
+    tm.mark("k3_histogram");
+    CK(cudaGetLastError());
+    if (out) {
+        out->n_lines = n_lines;
+        out->d_ext_id = c.ext_id.as<int32_t>();
+        out->d_line_off = d_line_off;
+        out->d_span_off = c.span_off.as<int64_t>();
+        out->d_spans = c.spans.as<int32_t>();
+        out->d_histogram = c.hist.as<int64_t>();
+        out->d_n_lines = d_n_lines;
+    }
+    if (timed) {
+        CK(cudaStreamSynchronize(stream));
+        tm.collect();
+    }
+    return n_lines;
+}
+
+int extract_host(gorp_engine* e, const uint16_t* text, int64_t n_units, const int64_t* off, int64_t n_lines, gorp_result* out) {
+    if (!e || !out || (!text && n_units > 0) || n_units < 0 || n_lines < 0) return fail(GORP_E_ARG, "bad argument");
+    if (e->devs.empty()) return fail(GORP_E_CUDA, "engine has no CUDA device");
+    return guarded([&]() -> int {
+        DeviceCtx& c = *e->devs[0];
+        std::lock_guard<std::mutex> lock(c.mu);
+        CK(cudaSetDevice(c.device));
+        c.text.reserve(static_cast<size_t>(n_units) * 2 + 32);
+        if (n_units) CK(cudaMemcpyAsync(c.text.p, text, static_cast<size_t>(n_units) * 2, cudaMemcpyHostToDevice, c.stream));
+        const int64_t* d_off = nullptr;
+        if (off) {
+            c.off_in.reserve(static_cast<size_t>(n_lines + 1) * 8);
+            CK(cudaMemcpyAsync(c.off_in.p, off, static_cast<size_t>(n_lines + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+            d_off = c.off_in.as<int64_t>();
+        }
+        gorp_device_result dr{};
+        const int64_t nl = run_pipeline(c, c.text.as<uint16_t>(), n_units, d_off, n_lines, c.stream, false, &dr);
+        std::unique_ptr<HostResult> hr;
+        {
+            std::lock_guard<std::mutex> pl(e->pool_mu);
+            if (!e->pool.empty()) {
+                hr = std::move(e->pool.back());
+                e->pool.pop_back();
+            }
+        }
+        if (!hr) hr = std::make_unique<HostResult>();
+        int64_t n_spans = 0;
+        CK(cudaMemcpyAsync(&n_spans, dr.d_span_off + nl, 8, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        const size_t E2 = e->def.extractions.size() + 2;
+        hr->reserve(0, static_cast<size_t>(nl + 1) * 4);
+        hr->reserve(1, static_cast<size_t>(nl + 1) * 8);
+        hr->reserve(2, static_cast<size_t>(nl + 1) * 8);
+        hr->reserve(3, static_cast<size_t>(n_spans + 1) * 4);
+        hr->reserve(4, E2 * 8);
+        if (nl) CK(cudaMemcpyAsync(hr->p[0], dr.d_ext_id, static_cast<size_t>(nl) * 4, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(hr->p[1], dr.d_line_off, static_cast<size_t>(nl + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(hr->p[2], dr.d_span_off, static_cast<size_t>(nl + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+        if (n_spans) CK(cudaMemcpyAsync(hr->p[3], dr.d_spans, static_cast<size_t>(n_spans) * 4, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(hr->p[4], dr.d_histogram, E2 * 8, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        out->n_lines = nl;
+        out->n_extractions = static_cast<int32_t>(e->def.extractions.size());
+        out->reserved = 0;
+        out->ext_id = static_cast<const int32_t*>(hr->p[0]);
+        out->line_off = static_cast<const int64_t*>(hr->p[1]);
+        out->span_off = static_cast<const int64_t*>(hr->p[2]);
+        out->spans = static_cast<const int32_t*>(hr->p[3]);
+        out->histogram = static_cast<const int64_t*>(hr->p[4]);
+        out->owner = hr.release();
+        return GORP_OK;
+    });
+}
+
+// ---- blob walking without copies (for the introspection entry points)
+struct BlobView {
+    const uint8_t* base;
+    size_t len;
+    uint32_t S, C, E;
+    size_t classmap, trans, acc_first, acc_off, acc_list, ext0;
+};
+
+bool view_blob(const void* blob, size_t len, BlobView& v) {
+    // parse_blob validates everything (magic, checksum, ranges); the view only records offsets
+    CompiledDefinition d = parse_blob(blob, len);
+    v.base = static_cast<const uint8_t*>(blob);
+    v.len = len;
+    v.S = d.dfa.n_states;
+    v.C = d.dfa.n_classes;
+    v.E = static_cast<uint32_t>(d.extractions.size());
+    v.classmap = 40;
+    v.trans = v.classmap + 65536 * 2;
+    v.acc_first = v.trans + static_cast<size_t>(v.S) * v.C * 4;
+    v.acc_off = v.acc_first + static_cast<size_t>(v.S) * 4;
+    v.acc_list = v.acc_off + static_cast<size_t>(v.S + 1) * 4;
+    v.ext0 = v.acc_list + d.dfa.accept_list.size() * 4;
+    return true;
+}
+
+struct StrRef {
+    const uint16_t* p;
+    uint32_t n;
+};
+
+size_t read_str(const BlobView& v, size_t at, StrRef& s) {
+    uint32_t n;
+    std::memcpy(&n, v.base + at, 4);
+    s.p = reinterpret_cast<const uint16_t*>(v.base + at + 4);
+    s.n = n;
+    size_t next = at + 4 + static_cast<size_t>(n) * 2;
+    return (next + 3) & ~size_t(3);
+}
+
+// walks to extraction `index`; fills info and (optionally) the k-th extractor name
+void locate_extraction(const BlobView& v, uint32_t index, gorp_extraction_info* info, uint32_t k, StrRef* name_k) {
+    size_t at = v.ext0;
+    for (uint32_t e = 0;; ++e) {
+        uint32_t groups;
+        std::memcpy(&groups, v.base + at, 4);
+        at += 4;
+        StrRef name, autom, jdk;
+        at = read_str(v, at, name);
+        at = read_str(v, at, autom);
+        at = read_str(v, at, jdk);
+        uint32_t nn;
+        std::memcpy(&nn, v.base + at, 4);
+        at += 4;
+        for (uint32_t j = 0; j < nn; ++j) {
+            StrRef s;
+            at = read_str(v, at, s);
+            if (e == index && name_k && j == k) *name_k = s;
+        }
+        uint32_t jl;
+        std::memcpy(&jl, v.base + at, 4);
+        at += 4;
+        const char* json = reinterpret_cast<const char*>(v.base + at);
+        at = (at + jl + 3) & ~size_t(3);
+        if (e == index) {
+            if (info) {
+                info->n_groups = groups;
+                info->n_extractor_names = nn;
+                info->name = name.p;
+                info->name_len = name.n;
+                info->automaton_regex = autom.p;
+                info->automaton_regex_len = autom.n;
+                info->jdk_regex = jdk.p;
+                info->jdk_regex_len = jdk.n;
+                info->append_json = json;
+                info->append_json_len = jl;
+            }
+            return;
+        }
+    }
+}
+
+int export_blob(const CompiledDefinition& d, bool match_only, void** blob, size_t* blob_len) {
+    std::vector<uint8_t> b = serialize_blob(d);
+    if (match_only) {
+        uint32_t flags = 1;
+        std::memcpy(b.data() + 8 + 16, &flags, 4);  // header.flags; not covered by the body checksum
+    }
+    void* p = std::malloc(b.size());
+    if (!p) return fail(GORP_E_OOM, "out of host memory");
+    std::memcpy(p, b.data(), b.size());
+    *blob = p;
+    *blob_len = b.size();
+    return GORP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gorp_abi_version(void) { return GORP_ABI_VERSION; }
+
+const char* gorp_last_error(void) { return g_error.c_str(); }
+
+int gorp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gorp_compile_definition(const char* grp_utf8, size_t len, void** blob, size_t* blob_len) {
+    if (!grp_utf8 || !blob || !blob_len) return fail(GORP_E_ARG, "null argument");
+    return guarded([&]() -> int { return export_blob(compile_definition(utf8_to_utf16(grp_utf8, len)), false, blob, blob_len); });
+}
+
+int gorp_compile_patterns(const uint16_t* const* patterns, const uint32_t* lens, uint32_t n, void** blob, size_t* blob_len) {
+    if (!patterns || !lens || !blob || !blob_len || n == 0) return fail(GORP_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        CompiledDefinition d;
+        std::vector<ustring> pats;
+        for (uint32_t i = 0; i < n; ++i) pats.emplace_back(reinterpret_cast<const char16_t*>(patterns[i]), lens[i]);
+        d.dfa = compile_patterns(pats);
+        for (uint32_t i = 0; i < n; ++i) {
+            CompiledExtraction x;
+            x.strings.name = utf8_to_utf16(strfmt("#%u", i).c_str(), strfmt("#%u", i).size());
+            x.strings.automaton_regex = pats[i];
+            d.extractions.push_back(std::move(x));
+        }
+        return export_blob(d, true, blob, blob_len);
+    });
+}
+
+void gorp_blob_free(void* blob) { std::free(blob); }
+
+int gorp_blob_get_info(const void* blob, size_t len, gorp_blob_info* out) {
+    if (!blob || !out) return fail(GORP_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        BlobView v;
+        view_blob(blob, len, v);
+        out->n_states = v.S;
+        out->n_classes = v.C;
+        out->n_extractions = v.E;
+        out->reserved = 0;
+        return GORP_OK;
+    });
+}
+
+int gorp_blob_get_extraction(const void* blob, size_t len, uint32_t index, gorp_extraction_info* out) {
+    if (!blob || !out) return fail(GORP_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        BlobView v;
+        view_blob(blob, len, v);
+        if (index >= v.E) return fail(GORP_E_ARG, "extraction index out of range");
+        locate_extraction(v, index, out, 0, nullptr);
+        return GORP_OK;
+    });
+}
+
+int gorp_blob_get_extractor_name(const void* blob, size_t len, uint32_t extraction, uint32_t k, const uint16_t** name,
+                                 uint32_t* name_len) {
+    if (!blob || !name || !name_len) return fail(GORP_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        BlobView v;
+        view_blob(blob, len, v);
+        if (extraction >= v.E) return fail(GORP_E_ARG, "extraction index out of range");
+        gorp_extraction_info info{};
+        StrRef s{nullptr, 0};
+        locate_extraction(v, extraction, &info, k, &s);
+        if (k >= info.n_extractor_names) return fail(GORP_E_ARG, "extractor index out of range");
+        *name = s.p;
+        *name_len = s.n;
+        return GORP_OK;
+    });
+}
+
+int gorp_blob_get_tables(const void* blob, size_t len, const uint16_t** classmap, const int32_t** transitions,
+                         const int32_t** accept_first, const uint32_t** accept_off, const int32_t** accept_list) {
+    if (!blob) return fail(GORP_E_ARG, "null argument");
+    return guarded([&]() -> int {
+        BlobView v;
+        view_blob(blob, len, v);
+        if (classmap) *classmap = reinterpret_cast<const uint16_t*>(v.base + v.classmap);
+        if (transitions) *transitions = reinterpret_cast<const int32_t*>(v.base + v.trans);
+        if (accept_first) *accept_first = reinterpret_cast<const int32_t*>(v.base + v.acc_first);
+        if (accept_off) *accept_off = reinterpret_cast<const uint32_t*>(v.base + v.acc_off);
+        if (accept_list) *accept_list = reinterpret_cast<const int32_t*>(v.base + v.acc_list);
+        return GORP_OK;
+    });
+}
+
+int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_devices, gorp_engine** out) {
+    if (!blob || !out) return fail(GORP_E_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&]() -> int {
+        auto eng = std::make_unique<gorp_engine>();
+        eng->def = parse_blob(blob, len);
+        uint32_t flags;
+        std::memcpy(&flags, static_cast<const uint8_t*>(blob) + 8 + 16, 4);
+        eng->match_only = (flags & 1u) != 0;
+        DeviceModel model;
+        if (eng->match_only) {
+            model.dfa = compact_tables(eng->def.dfa);
+            model.n_groups.assign(eng->def.extractions.size(), 0);
+        } else {
+            model = build_device_model(eng->def);
+        }
+        int avail = 0;
+        if (cudaGetDeviceCount(&avail) != cudaSuccess || avail == 0) {
+            cudaGetLastError();
+            return fail(GORP_E_CUDA, "no CUDA device available (libgorpcuda has no CPU fallback)");
+        }
+        std::vector<int> devs;
+        if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+        else devs.push_back(0);
+        for (int d : devs) {
+            if (d < 0 || d >= avail) return fail(GORP_E_ARG, strfmt("device %d out of range (have %d)", d, avail));
+            auto ctx = std::make_unique<DeviceCtx>();
+            ctx->device = d;
+            build_device(*ctx, model, eng->match_only);
+            eng->devs.push_back(std::move(ctx));
+        }
+        *out = eng.release();
+        return GORP_OK;
+    });
+}
+
+void gorp_engine_destroy(gorp_engine* e) { delete e; }
+
+int gorp_extract_lines(gorp_engine* e, const uint16_t* text, const int64_t* off, int64_t n_lines, gorp_result* out) {
+    if (!off) return fail(GORP_E_ARG, "null offsets");
+    return extract_host(e, text, n_lines > 0 ? off[n_lines] : 0, off, n_lines, out);
+}
+
+int gorp_extract_text(gorp_engine* e, const uint16_t* text, int64_t n_units, gorp_result* out) {
+    return extract_host(e, text, n_units, nullptr, 0, out);
+}
+
+void gorp_result_release(gorp_engine* e, gorp_result* r) {
+    if (!r || !r->owner) return;
+    std::unique_ptr<HostResult> hr(static_cast<HostResult*>(r->owner));
+    r->owner = nullptr;
+    if (e) {
+        std::lock_guard<std::mutex> pl(e->pool_mu);
+        if (e->pool.size() < 4) e->pool.push_back(std::move(hr));
+    }
+}
+
+int gorp_extract_text_device(gorp_engine* e, int dev_index, const uint16_t* d_text, int64_t n_units, void* stream, int sync,
+                             gorp_device_result* out) {
+    if (!e || dev_index < 0 || dev_index >= static_cast<int>(e->devs.size()) || n_units < 0 || (reinterpret_cast<uintptr_t>(d_text) & 15))
+        return fail(GORP_E_ARG, "bad argument (d_text must be 16-byte aligned)");
+    return guarded([&]() -> int {
+        DeviceCtx& c = *e->devs[dev_index];
+        std::lock_guard<std::mutex> lock(c.mu);
+        CK(cudaSetDevice(c.device));
+        run_pipeline(c, d_text, n_units, nullptr, 0, stream ? static_cast<cudaStream_t>(stream) : c.stream, sync != 0, out);
+        return GORP_OK;
+    });
+}
+
+int gorp_extract_lines_device(gorp_engine* e, int dev_index, const uint16_t* d_text, const int64_t* d_off, int64_t n_lines,
+                              void* stream, int sync, gorp_device_result* out) {
+    if (!e || dev_index < 0 || dev_index >= static_cast<int>(e->devs.size()) || !d_off || n_lines < 0 ||
+        (reinterpret_cast<uintptr_t>(d_text) & 15))
+        return fail(GORP_E_ARG, "bad argument (d_text must be 16-byte aligned)");
+    return guarded([&]() -> int {
+        DeviceCtx& c = *e->devs[dev_index];
+        std::lock_guard<std::mutex> lock(c.mu);
+        CK(cudaSetDevice(c.device));
+        run_pipeline(c, d_text, 0, d_off, n_lines, stream ? static_cast<cudaStream_t>(stream) : c.stream, sync != 0, out);
+        return GORP_OK;
+    });
+}
+
+int gorp_last_kernel_times(gorp_engine* e, int dev_index, const char** names, float* ms, int cap, int* n) {
+    if (!e || dev_index < 0 || dev_index >= static_cast<int>(e->devs.size()) || !n) return fail(GORP_E_ARG, "bad argument");
+    DeviceCtx& c = *e->devs[dev_index];
+    std::lock_guard<std::mutex> lock(c.mu);
+    int k = std::min(cap, c.last_n);
+    for (int i = 0; i < k; ++i) {
+        if (names) names[i] = c.ev_name[i];
+        if (ms) ms[i] = c.last_ms[i];
+    }
+    *n = k;
+    return GORP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// sm_100a kernels of the gorp batch extraction path. See kernels.cuh for the reference functions they replace.
+#include "kernels.cuh"
+
+namespace gorp {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    // streaming 128-bit load: the text is read once per pass, keep it out of L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t nl_pairs(uint32_t w) {  // 0xFFFF per UTF-16 unit equal to '\n'
+    return __vcmpeq2(w, 0x000A000Au);
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ K1: newline index
+__global__ void __launch_bounds__(kThreads) nl_count_kernel(const uint16_t* __restrict__ text, int64_t n_units,
+                                                            uint32_t* __restrict__ tile_counts) {
+    const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * kNlTile;
+    uint32_t cnt = 0;
+    if (tile0 + kNlTile <= n_units) {
+        const uint4* src = reinterpret_cast<const uint4*>(text + tile0);
+#pragma unroll
+        for (int j = 0; j < kNlTile / 8 / kThreads; ++j) {
+            uint4 v = ld_stream(src + j * kThreads + threadIdx.x);
+            cnt += __popc(nl_pairs(v.x)) + __popc(nl_pairs(v.y)) + __popc(nl_pairs(v.z)) + __popc(nl_pairs(v.w));
+        }
+        cnt >>= 4;
+    } else {
+        for (int64_t p = tile0 + threadIdx.x; p < n_units; p += kThreads) cnt += text[p] == 0x0A;
+    }
+    __shared__ uint32_t warp_tot[kThreads / 32];
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += warp_tot[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) nl_scatter_kernel(const uint16_t* __restrict__ text, int64_t n_units,
+                                                              const int64_t* __restrict__ tile_base,
+                                                              int64_t* __restrict__ line_off) {
+    constexpr int kPer = kNlTile / kThreads;  // 32 consecutive units per thread
+    const int64_t tile0 = static_cast<int64_t>(blockIdx.x) * kNlTile;
+    const int64_t mine = tile0 + static_cast<int64_t>(threadIdx.x) * kPer;
+    uint32_t mask = 0;  // bit k: unit mine+k is '\n'
+    if (mine + kPer <= n_units) {
+        const uint4* src = reinterpret_cast<const uint4*>(text + mine);
+#pragma unroll
+        for (int j = 0; j < kPer / 8; ++j) {
+            uint4 v = __ldg(src + j);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t m = nl_pairs(w[k]);
+                mask |= ((m & 1u) | ((m >> 15) & 2u)) << (j * 8 + k * 2);
+            }
+        }
+    } else {
+        for (int k = 0; k < kPer; ++k)
+            if (mine + k < n_units && text[mine + k] == 0x0A) mask |= 1u << k;
+    }
+    // block exclusive scan of per-thread counts
+    uint32_t cnt = __popc(mask), incl = cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __shared__ uint32_t warp_tot[kThreads / 32];
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w)
+        if (w < warp) base += warp_tot[w];
+    int64_t slot = 1 + tile_base[blockIdx.x] + base + (incl - cnt);  // line_off[j] = start of line j (j >= 1)
+    while (mask) {
+        int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        line_off[slot++] = mine + k + 1;
+    }
+}
+
+__global__ void nl_finish_kernel(const uint16_t* __restrict__ text, int64_t n_units, const int64_t* __restrict__ total_nl,
+                                 int64_t* __restrict__ line_off, int64_t* __restrict__ n_lines_out) {
+    const int64_t nl = *total_nl;
+    line_off[0] = 0;
+    int64_t n_lines = nl;
+    if (n_units > 0 && text[n_units - 1] != 0x0A) {  // a final line without '\n' counts
+        n_lines = nl + 1;
+        line_off[n_lines] = n_units + 1;
+    }
+    *n_lines_out = n_lines;
+}
+
+// ------------------------------------------------------------------ exclusive scan (u32 -> i64)
+constexpr int kScanTile = 4096;  // 256 threads x 16
+
+__global__ void __launch_bounds__(kThreads) scan_sums_kernel(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ sums) {
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanTile;
+    uint32_t s = 0;
+    for (int k = threadIdx.x; k < kScanTile; k += kThreads)
+        if (base + k < n) s += in[base + k];
+    __shared__ uint32_t warp_tot[kThreads / 32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kThreads / 32; ++w) t += warp_tot[w];
+        sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) scan_top_kernel(int64_t* __restrict__ sums, int64_t nb) {
+    // single block: exclusive scan of sums[0..nb) in place, sums[nb] = total
+    __shared__ int64_t part[1024];
+    const int64_t per = (nb + 1023) / 1024;
+    const int64_t lo = threadIdx.x * per, hi = min(lo + per, nb);
+    int64_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += sums[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            int64_t t = part[i];
+            part[i] = run;
+            run += t;
+        }
+        sums[nb] = run;
+    }
+    __syncthreads();
+    int64_t run = part[threadIdx.x];
+    for (int64_t i = lo; i < hi; ++i) {
+        int64_t t = sums[i];
+        sums[i] = run;
+        run += t;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) scan_apply_kernel(const uint32_t* __restrict__ in, int64_t n,
+                                                              const int64_t* __restrict__ sums, int64_t nb,
+                                                              int64_t* __restrict__ out) {
+    constexpr int kPer = kScanTile / kThreads;
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanTile + static_cast<int64_t>(threadIdx.x) * kPer;
+    uint32_t v[kPer];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t incl = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __shared__ uint32_t warp_tot[kThreads / 32];
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w)
+        if (w < warp) wbase += warp_tot[w];
+    int64_t run = sums[blockIdx.x] + wbase + (incl - s);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[nb];
+}
+
+// ------------------------------------------------------------------ line reader shared by K2 / K4
+// Calls f(unit, pos) for every UTF-16 unit of [a, b) until f returns false. 128-bit loads once 16-byte aligned
+// (the text base is 16-byte aligned, so alignment is a property of the position alone).
+template <class F>
+__device__ __forceinline__ void for_units(const uint16_t* __restrict__ text, int64_t a, int64_t b, F&& f) {
+    int64_t p = a;
+    while (p < b && (p & 7)) {
+        if (!f(static_cast<uint32_t>(__ldg(text + p)), p)) return;
+        ++p;
+    }
+    while (p + 8 <= b) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + p));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!f(w[k] & 0xFFFFu, p + 2 * k)) return;
+            if (!f(w[k] >> 16, p + 2 * k + 1)) return;
+        }
+        p += 8;
+    }
+    while (p < b) {
+        if (!f(static_cast<uint32_t>(__ldg(text + p)), p)) return;
+        ++p;
+    }
+}
+
+// ------------------------------------------------------------------ K2: combined DFA, one line per thread
+template <bool kSmemTable>
+__global__ void __launch_bounds__(kThreads) dfa_scan_kernel(DfaDev d, const uint16_t* __restrict__ text,
+                                                            const int64_t* __restrict__ line_off, int sep, int64_t n_lines,
+                                                            const uint32_t* __restrict__ slots_per_ext,
+                                                            int32_t* __restrict__ ext_id, uint32_t* __restrict__ span_cnt) {
+    extern __shared__ uint16_t smem[];
+    uint16_t* s_cls = smem;          // [128] ASCII slice of the class map
+    uint16_t* s_trans = smem + 128;  // [S*C] when kSmemTable
+    for (int i = threadIdx.x; i < 128; i += kThreads) s_cls[i] = d.cls[i];
+    if (kSmemTable)
+        for (uint32_t i = threadIdx.x; i < d.n_states * d.n_classes; i += kThreads) s_trans[i] = d.trans16[i];
+    __syncthreads();
+    const bool wide = d.trans16 == nullptr;
+    for (int64_t line = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; line < n_lines;
+         line += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const int64_t a = line_off[line], b = line_off[line + 1] - sep;
+        uint32_t st = 0;  // premultiplied state (state * n_classes)
+        bool dead = false;
+        if (!wide) {
+            const uint16_t* __restrict__ tr = kSmemTable ? s_trans : d.trans16;
+            for_units(text, a, b, [&](uint32_t u, int64_t) {
+                const uint32_t c = u < 128 ? s_cls[u] : __ldg(d.cls + u);
+                st = kSmemTable ? tr[st + c] : __ldg(tr + st + c);
+                dead = st == kDead16;
+                return !dead;
+            });
+        } else {
+            for_units(text, a, b, [&](uint32_t u, int64_t) {
+                const uint32_t c = u < 128 ? s_cls[u] : __ldg(d.cls + u);
+                const int32_t nx = __ldg(d.trans32 + st + c);
+                dead = nx < 0;
+                st = static_cast<uint32_t>(nx);
+                return !dead;
+            });
+        }
+        int32_t e = -1;
+        if (!dead) e = __ldg(d.accept_first + st / d.n_classes);
+        ext_id[line] = e;
+        span_cnt[line] = e >= 0 ? __ldg(slots_per_ext + e) : 0u;
+    }
+}
+
+// ------------------------------------------------------------------ K4: capture automaton (TDFA), one line per thread
+__global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const uint16_t* __restrict__ text,
+                                                                const int64_t* __restrict__ line_off, int sep,
+                                                                int64_t n_lines, const int64_t* __restrict__ span_off,
+                                                                int32_t* __restrict__ ext_id, int32_t* __restrict__ spans) {
+    __shared__ uint16_t s_cls[128];
+    for (int i = threadIdx.x; i < 128; i += kThreads) s_cls[i] = c.cls[i];
+    __syncthreads();
+    for (int64_t line = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; line < n_lines;
+         line += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const int32_t e = ext_id[line];
+        if (e < 0) continue;
+        const ExtDev x = c.ext[e];
+        if (x.n_slots == 0 && c.match_only) continue;
+        const int64_t a = line_off[line], b = line_off[line + 1] - sep;
+        const uint32_t* __restrict__ tr = c.tdfa_trans + x.trans_off;
+        const uint32_t* __restrict__ opo = c.tdfa_op_off + x.opoff_off;
+        const uint16_t* __restrict__ ops = c.tdfa_ops + x.ops_off;
+        int32_t regs[kMaxTdfaRegs];
+        uint32_t st = 0;
+        bool ok = true;
+        for_units(text, a, b, [&](uint32_t u, int64_t p) {
+            uint32_t k;
+            if (u < 128) {
+                k = s_cls[u];
+            } else {
+                k = __ldg(c.cls + u);
+                // a high surrogate followed by a low surrogate is ONE java.util.regex character
+                if ((u & 0xFC00u) == 0xD800u && p + 1 < b && (__ldg(text + p + 1) & 0xFC00u) == 0xDC00u) k = c.pair_hi_class;
+            }
+            const uint32_t ent = __ldg(tr + st * c.n_classes + k);
+            const uint32_t nx = ent & 0xFFFFu;
+            if (nx == kDead16) { ok = false; return false; }
+            const uint32_t ol = ent >> 16;
+            if (ol) {
+                const uint32_t o0 = __ldg(opo + ol), o1 = __ldg(opo + ol + 1);
+                const int32_t pos = static_cast<int32_t>(p - a);
+                for (uint32_t q = o0; q < o1; ++q) {
+                    const uint32_t op = __ldg(ops + q);
+                    const uint32_t src = op & 0xFFu;
+                    regs[op >> 8] = src == 0xFFu ? pos : regs[src];
+                }
+            }
+            st = nx;
+            return true;
+        });
+        if (ok) ok = __ldg(c.tdfa_accepting + x.acc_off + st) != 0;
+        int32_t* out = spans + span_off[line];
+        if (!ok) {
+            ext_id[line] = -2 - e;
+            for (uint32_t s = 0; s < x.n_slots; ++s) out[s] = -1;
+            continue;
+        }
+        const uint8_t* __restrict__ fin = c.tdfa_fin + x.fin_off + st * x.n_slots;
+        const int32_t len = static_cast<int32_t>(b - a);
+        for (uint32_t s = 0; s < x.n_slots; ++s) {
+            const uint32_t f = __ldg(fin + s);
+            out[s] = f == 0xFFu ? -1 : (f == 0xFEu ? len : regs[f]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K3: histogram by extraction id
+constexpr int kHistSmemBins = 2048;
+
+__global__ void __launch_bounds__(kThreads) histogram_kernel(const int32_t* __restrict__ ext_id, int64_t n_lines, uint32_t n_ext,
+                                                             unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t bins[kHistSmemBins];
+    const uint32_t nb = n_ext + 2;
+    const bool local = nb <= kHistSmemBins;
+    if (local) {
+        for (uint32_t i = threadIdx.x; i < nb; i += kThreads) bins[i] = 0;
+        __syncthreads();
+    }
+    for (int64_t line = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; line < n_lines;
+         line += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const int32_t e = ext_id[line];
+        const uint32_t bin = e >= 0 ? static_cast<uint32_t>(e) : (e == -1 ? n_ext : n_ext + 1);
+        if (local) atomicAdd(&bins[bin], 1u);
+        else atomicAdd(&hist[bin], 1ull);
+    }
+    if (local) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nb; i += kThreads)
+            if (bins[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(bins[i]));
+    }
+}
+
+int blocks_for(int64_t n, int per_block) { return static_cast<int>((n + per_block - 1) / per_block); }
+
+}  // namespace
+
+void k1_count_newlines(const Launch& L, const uint16_t* text, int64_t n_units, uint32_t* tile_counts) {
+    if (n_units <= 0) return;
+    nl_count_kernel<<<blocks_for(n_units, kNlTile), kThreads, 0, L.stream>>>(text, n_units, tile_counts);
+}
+
+void k1_scatter_newlines(const Launch& L, const uint16_t* text, int64_t n_units, const int64_t* tile_base, int64_t* line_off) {
+    if (n_units <= 0) return;
+    nl_scatter_kernel<<<blocks_for(n_units, kNlTile), kThreads, 0, L.stream>>>(text, n_units, tile_base, line_off);
+}
+
+void k1_finish(const Launch& L, const uint16_t* text, int64_t n_units, const int64_t* total_newlines, int64_t* line_off,
+               int64_t* n_lines_out) {
+    nl_finish_kernel<<<1, 1, 0, L.stream>>>(text, n_units, total_newlines, line_off, n_lines_out);
+}
+
+void scan_u32_to_i64(const Launch& L, const uint32_t* in, int64_t n, int64_t* out, int64_t* scratch) {
+    const int64_t nb = n > 0 ? (n + kScanTile - 1) / kScanTile : 0;
+    if (nb > 0) scan_sums_kernel<<<static_cast<int>(nb), kThreads, 0, L.stream>>>(in, n, scratch);
+    scan_top_kernel<<<1, 1024, 0, L.stream>>>(scratch, nb);
+    scan_apply_kernel<<<static_cast<int>(nb > 0 ? nb : 1), kThreads, 0, L.stream>>>(in, n, scratch, nb, out);
+}
+
+static int persistent_grid(const Launch& L, const void* fn, size_t smem, int64_t n_lines) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    int64_t want = (n_lines + kThreads - 1) / kThreads;
+    int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;  // one resident wave, grid-stride over the rest
+    return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+void k2_dfa_scan(const Launch& L, const DfaDev& d, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
+                 const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt) {
+    if (n_lines <= 0) return;
+    const size_t table_bytes = static_cast<size_t>(d.n_states) * d.n_classes * 2;
+    const bool in_smem = d.trans16 != nullptr && table_bytes <= 96 * 1024;
+    const size_t smem = 256 + (in_smem ? table_bytes : 0);
+    if (in_smem) {
+        cudaFuncSetAttribute(dfa_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        int g = persistent_grid(L, reinterpret_cast<const void*>(dfa_scan_kernel<true>), smem, n_lines);
+        dfa_scan_kernel<true><<<g, kThreads, smem, L.stream>>>(d, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+    } else {
+        int g = persistent_grid(L, reinterpret_cast<const void*>(dfa_scan_kernel<false>), smem, n_lines);
+        dfa_scan_kernel<false><<<g, kThreads, smem, L.stream>>>(d, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+    }
+}
+
+void k4_tdfa_capture(const Launch& L, const CapDev& c, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
+                     const int64_t* span_off, int32_t* ext_id, int32_t* spans) {
+    if (n_lines <= 0) return;
+    int g = persistent_grid(L, reinterpret_cast<const void*>(tdfa_capture_kernel), 0, n_lines);
+    tdfa_capture_kernel<<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_off, ext_id, spans);
+}
+
+void k3_histogram(const Launch& L, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist) {
+    if (n_lines <= 0) return;
+    int g = persistent_grid(L, reinterpret_cast<const void*>(histogram_kernel), 0, n_lines);
+    histogram_kernel<<<g, kThreads, 0, L.stream>>>(ext_id, n_lines, n_ext, hist);
+}
+
+}  // namespace gorp

@@ -1,0 +1,44 @@
+"""Builds and loads tests/host/hosttest.cpp (test-only CPU interpreter of the product's compiled tables)."""
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    out = os.path.join(HERE, "_build", "libgorp_hosttest.so")
+    srcs = [os.path.join(HERE, "host", "hosttest.cpp")] + sorted(glob.glob(os.path.join(ROOT, "gorp_b200/csrc/host/*.cpp")))
+    deps = srcs + glob.glob(os.path.join(ROOT, "gorp_b200/csrc/host/*.hpp"))
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", out] + srcs)
+    _lib = C.CDLL(out)
+    return _lib
+
+
+def run(blob_bytes: bytes, text: np.ndarray, starts: np.ndarray, ends: np.ndarray, stride: int):
+    lib = load()
+    text = np.ascontiguousarray(text, dtype=np.uint16)
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    ends = np.ascontiguousarray(ends, dtype=np.int64)
+    n = len(starts)
+    ext = np.empty(n, dtype=np.int32)
+    spans = np.full((n, max(stride, 1)), -1, dtype=np.int32)
+    stats = np.zeros(8, dtype=np.uint32)
+    err = C.create_string_buffer(1024)
+    P = C.c_void_p
+    rc = lib.ht_run(blob_bytes, C.c_size_t(len(blob_bytes)), P(text.ctypes.data), P(starts.ctypes.data), P(ends.ctypes.data),
+                    C.c_int64(n), P(ext.ctypes.data), P(spans.ctypes.data), C.c_int(max(stride, 1)), P(stats.ctypes.data), err,
+                    C.c_int(1024))
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return ext, spans[:, :stride], stats

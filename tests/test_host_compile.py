@@ -1,0 +1,148 @@
+"""Host-side compile logic of the product (definition front-end, brics DFA product, JDK -> Pike program -> TDFA)
+checked on the CPU: the tables libgorpcuda derives are interpreted by the test-only library tests/host/hosttest.cpp
+and compared with the oracle. No compute call of the product runs here (there is no GPU)."""
+import numpy as np
+import pytest
+
+from gorp_b200 import DefinitionParseException, DefinitionReader, UnsupportedDefinition
+from oracle import frontend, gorp_oracle, jdkre
+from tests import hostlib
+from tests import reference_vectors as V
+
+TRICKY_LINES = [
+    "", "x", "[1]: GET 2ms /a", "[1]: GET 2ms /a\x0b", "[1]: GET 2ms /a\x08b", "[1]:\x0bGET 2ms /a",
+    "[12]: PUT 5ms /\U0001F600/x", "[12]: POST 5ms /\ud83d", "[12]: HEAD 77ms /p\u0085q", "[12]: HEAD 77ms /p\u2028",
+    "[12]: GET 5ms /\ud83d\ude00\ud83d", "[12]: GET 5ms /\ude00\ud83d\ude00", "[3]: PUT 1ms /x\r",
+    "<1>ts (Accepted) ", "<1>t\x0bs (Accepted) ", "<1>\U00010000 (Accepted) \t ", "value=foobar",
+    "[1]:  \t GET   2ms \t /a", "[1]: GETX 2ms /a", "[1]: get_1 2ms /a b", "[1]: GET 2ms ",
+]
+
+ALL_DEFS = [V.FULL_SIMPLE, V.FULL_INTERMEDIATE, V.FULL_FULL, V.PARAM_EXTRACTOR, V.PARAM_TEMPLATE, V.POLY_SIMPLE,
+            V.POLY_INTERMEDIATE, V.POLY_QUOTED, V.POLY_COMPLEX, (V.README_DEF, []), (V.SIMPLE_GRP, [])]
+
+
+def pack(lines):
+    units = [np.asarray(jdkre.to_units(s), dtype=np.uint16) for s in lines]
+    text = np.concatenate([np.concatenate((u, [10])) for u in units]).astype(np.uint16)
+    starts, ends = gorp_oracle.split_lines(text)
+    assert len(starts) == len(lines)
+    return text, starts, ends
+
+
+def compare_host_tables(definition, lines):
+    g = DefinitionReader.reader(definition).read()
+    o = gorp_oracle.Gorp(definition)
+    text, starts, ends = pack(lines)
+    G = max(len(x.extractor_names) for x in o.extractions)
+    ext, spans, stats = hostlib.run(g.blob().bytes(), text, starts, ends, 2 * G)
+    oe, osp = o.extract_batch(text, (starts, ends), threads=1)
+    bad = [i for i in range(len(lines)) if ext[i] != oe[i] or (spans[i] != osp[i]).any()]
+    assert not bad, [(lines[i], int(ext[i]), int(oe[i]), spans[i].tolist(), osp[i].tolist()) for i in bad[:5]]
+    return stats
+
+
+@pytest.mark.parametrize("case", ALL_DEFS)
+def test_tables_reproduce_oracle(case):
+    compare_host_tables(case[0], [c[0] for c in case[1]] + TRICKY_LINES)
+
+
+@pytest.mark.parametrize("case", ALL_DEFS)
+def test_exported_tables_are_the_reference_tables(case):
+    """The blob holds Automata._alphabet/_transitions/_accept exactly as the oracle's restatement builds them."""
+    g = DefinitionReader.reader(case[0]).read()
+    a = gorp_oracle.Gorp(case[0]).matcher.automata
+    cm, tr, af, al = g.blob().tables()
+    assert g.blob().info()[:2] == (a.n_states, a.stride)
+    assert (cm == a.alphabet).all() and (tr.reshape(-1) == a.transitions).all() and (af == a.accept_first).all()
+    assert al == a.accept
+
+
+@pytest.mark.parametrize("case", V.DERIVED_STRINGS)
+def test_generated_strings(case):
+    g = DefinitionReader.reader(case[0]).read()
+    xs = g.getExtractions()
+    assert len(xs) == len(case[1])
+    for x, (name, autom, jdk, names) in zip(xs, case[1]):
+        assert (x.getName(), x._automaton_source, x.getRegexpSource(), x.getExtractorNames()) == (name, autom, jdk, names)
+
+
+@pytest.mark.parametrize("case", V.ERROR_KATS)
+def test_definition_errors(case):
+    with pytest.raises(DefinitionParseException) as ei:
+        DefinitionReader.reader(case[0]).read()
+    msg = str(ei.value).lower()
+    for sub in case[1]:
+        assert sub.lower() in msg, (sub, msg)
+
+
+def test_append_and_names():
+    g = DefinitionReader.reader("pattern %a a\ntemplate @base (%a:foo)\nextract rule1 {  \n"
+                                "  template @base value=$MyValue(%a:%{\\w+})\n  append { \"enabled\" : true, \"x\" : 3 }\n}").read()
+    x = g.getExtractions()[0]
+    assert x.getExtra() == {"enabled": True, "x": 3}
+    assert x.getRegexpSource() == "\\(a:foo\\)[ \t]+value=(a:\\w+)"
+    assert x.getExtractorNames() == ["MyValue"]
+
+
+UNSUPPORTED = [
+    "pattern %p a\\b\nextract x {\n template %p\n}\n",          # \b: backspace vs word boundary
+    "pattern %p ^a\nextract x {\n template %p\n}\n",            # anchors (D5)
+    "pattern %p a*+\nextract x {\n template %p\n}\n",           # possessive (D8)
+    "pattern %p [a[b]]\nextract x {\n template %p\n}\n",        # nested class (D9)
+    "pattern %p (a*)*\nextract x {\n template %p\n}\n",         # nullable loop body
+]
+
+
+@pytest.mark.parametrize("definition", UNSUPPORTED)
+def test_unsupported_definitions_are_refused(definition):
+    with pytest.raises(UnsupportedDefinition):
+        DefinitionReader.reader(definition).read()
+    with pytest.raises(jdkre.Unsupported):
+        gorp_oracle.Gorp(definition)
+
+
+FUZZ_PATTERNS = [
+    # (definition body pattern pieces exercising ambiguity / priorities / counted repeats / lazy / alternation)
+    "extract a {\n template $x(%{.*}) $y(%{.*})\n}\n",
+    "extract a {\n template $x(%{.*}):$y(%{.*}):$z(%{.*})\n}\n",
+    "extract a {\n template $x(%{[a-c]*})$y(%{[b-d]*})$z(%{[a-d]*})\n}\n",
+    "extract a {\n template $x(%{(a|ab)})$y(%{(c|bcd)})$z(%{d*})\n}\n",
+    "extract a {\n template $x(%{a{2,4}})$y(%{a{0,3}})$z(%{a*})\n}\n",
+    "extract a {\n template $x(%{a*?})$y(%{a+?})$z(%{a*})\n}\n",
+    "extract a {\n template $x(%{(ab|a)(bc|c)?})$y(%{[abc]*})\n}\n",
+    "extract a {\n template $x(%{\\S+}) $y(%{\\S+( \\S+)*})\n}\n",
+    "extract a {\n template $x(%{[^:]*}):$y(%{.{1,3}})$z(%{.*})\n}\n",
+    "extract first {\n template $x(%{a+})b\n}\nextract second {\n template $x(%{[ab]+})\n}\nextract third {\n template $y(%{.*})\n}\n",
+    "extract a {\n template $x(%{(a|b)*})$y(%{(ab)*})$z(%{b?a?})\n}\n",
+    "extract a {\n template $o($i(%{a*})$j(%{b*}))$k(%{[ab]*})\n}\n",
+]
+
+
+@pytest.mark.parametrize("definition", FUZZ_PATTERNS)
+def test_fuzz_small_alphabet(definition):
+    """Every string over a tiny alphabet up to length 7 (plus random longer ones): TDFA == backtracking oracle."""
+    import itertools
+    rng = np.random.default_rng(7)
+    alpha = "abcd: "
+    lines = ["".join(t) for n in range(0, 6) for t in itertools.product("abc:", repeat=n)]
+    lines += ["".join(rng.choice(list(alpha), size=rng.integers(6, 24))) for _ in range(3000)]
+    stats = compare_host_tables(definition, lines)
+    assert stats[3] < 5000
+
+
+def test_product_dfa_language_vs_component_dfas():
+    """build_product == running every component DFA on its own (PolyMatcher.match semantics, all accept lists)."""
+    from oracle import brics
+    pats = V.MULTI_PATTERNS
+    from gorp_b200 import Blob
+    b = Blob.from_patterns(pats)
+    cm, tr, af, al = b.tables()
+    m = brics.PolyMatcher(pats)
+    for s, want in V.MULTI_CASES:
+        p = 0
+        for c in jdkre.to_units(s):
+            p = tr[p, cm[c]]
+            if p < 0:
+                break
+        got = [] if p < 0 else al[p]
+        assert got == want == m.match(jdkre.to_units(s)), s
