@@ -48,7 +48,7 @@ SYMBOLS = [
     "gorp_abi_version", "gorp_last_error", "gorp_device_count", "gorp_compile_definition", "gorp_compile_patterns",
     "gorp_blob_free", "gorp_blob_get_info", "gorp_blob_get_extraction", "gorp_blob_get_extractor_name",
     "gorp_blob_get_tables", "gorp_engine_create", "gorp_engine_destroy", "gorp_extract_lines", "gorp_extract_text",
-    "gorp_result_release", "gorp_extract_text_device", "gorp_extract_lines_device", "gorp_last_kernel_times",
+    "gorp_result_release", "gorp_extract_text_device", "gorp_extract_lines_device", "gorp_kernel_times",
 ]
 
 lib.gorp_abi_version.restype = C.c_int
@@ -77,8 +77,9 @@ lib.gorp_extract_text_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_in
                                          C.POINTER(DeviceResult)]
 lib.gorp_extract_lines_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
                                           C.POINTER(DeviceResult)]
-lib.gorp_last_kernel_times.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int,
-                                       C.POINTER(C.c_int)]
+lib.gorp_kernel_times.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.c_int,
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
+FLAG_SYNC, FLAG_TIME_KERNELS = 1, 2
 
 
 def last_error() -> str:

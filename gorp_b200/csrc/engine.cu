@@ -107,11 +107,14 @@ struct DeviceCtx {
     // per-call scratch, serialised by `mu`
     std::mutex mu;
     DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, span_cnt, span_off, spans, hist, scalars;
+    // per-kernel device time: CUDA events on the launching stream, accumulated over timed calls
     cudaEvent_t ev[kMaxTimed + 1]{};
     const char* ev_name[kMaxTimed]{};
-    int n_ev = 0;
-    float last_ms[kMaxTimed]{};
-    int last_n = 0;
+    int n_ev = 0;             // events pending collection (recorded by the last timed call)
+    double acc_ms[kMaxTimed]{};
+    int64_t acc_calls = 0;
+    int acc_n = 0;
+    int64_t launches = 0;     // kernels launched by this context (all calls)
 
     ~DeviceCtx() {
         cudaSetDevice(device);
@@ -213,25 +216,35 @@ void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
     }
 }
 
+void collect_times(DeviceCtx& c) {
+    if (c.n_ev == 0) return;
+    cudaEventSynchronize(c.ev[c.n_ev]);
+    for (int i = 0; i < c.n_ev; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c.ev[i], c.ev[i + 1]);
+        c.acc_ms[i] += ms;
+    }
+    c.acc_n = c.n_ev;
+    c.acc_calls += 1;
+    c.n_ev = 0;
+}
+
 struct Timer {
     DeviceCtx& c;
     cudaStream_t s;
     bool on;
     Timer(DeviceCtx& c_, cudaStream_t s_, bool on_) : c(c_), s(s_), on(on_) {
-        c.n_ev = 0;
-        if (on) cudaEventRecord(c.ev[0], s);
+        if (on) {
+            collect_times(c);  // the previous timed call, if any
+            cudaEventRecord(c.ev[0], s);
+        }
     }
-    void mark(const char* name) {
+    void mark(const char* name, int launches) {
+        c.launches += launches;
         if (!on || c.n_ev >= kMaxTimed) return;
         c.ev_name[c.n_ev] = name;
         ++c.n_ev;
         cudaEventRecord(c.ev[c.n_ev], s);
-    }
-    void collect() {
-        c.last_n = 0;
-        if (!on) return;
-        for (int i = 0; i < c.n_ev; ++i) cudaEventElapsedTime(&c.last_ms[i], c.ev[i], c.ev[i + 1]);
-        c.last_n = c.n_ev;
     }
 };
 
@@ -252,9 +265,9 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         c.tile_base.reserve(static_cast<size_t>(n_tiles + 2) * 8);
         c.scan_scratch.reserve(static_cast<size_t>(n_tiles / 4096 + 8) * 8);
         k1_count_newlines(L, d_text, n_units, c.tile_counts.as<uint32_t>());
-        tm.mark("k1_count_newlines");
+        tm.mark("k1_count_newlines", 1);
         scan_u32_to_i64(L, c.tile_counts.as<uint32_t>(), n_tiles, c.tile_base.as<int64_t>(), c.scan_scratch.as<int64_t>());
-        tm.mark("scan_tiles");
+        tm.mark("scan_tiles", 3);
         // the one host round trip of the text form: the newline total (and the last unit) size the per-line arrays
         int64_t total_nl = 0;
         uint16_t last_unit = 0x0A;
@@ -265,7 +278,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         c.line_off.reserve(static_cast<size_t>(total_nl + 3) * 8);
         k1_scatter_newlines(L, d_text, n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
         k1_finish(L, d_text, n_units, c.tile_base.as<int64_t>() + n_tiles, c.line_off.as<int64_t>(), d_n_lines);
-        tm.mark("k1_scatter_newlines");
+        tm.mark("k1_scatter_newlines", 2);
         d_line_off = c.line_off.as<int64_t>();
     } else {
         sep = 0;
@@ -279,19 +292,19 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     c.scan_scratch.reserve((nl / 4096 + 8) * 8);
     c.hist.reserve((c.n_ext + 2) * 8);
     k2_dfa_scan(L, c.dfa, d_text, d_line_off, sep, n_lines, c.d_slots, c.ext_id.as<int32_t>(), c.span_cnt.as<uint32_t>());
-    tm.mark("k2_dfa_scan");
+    tm.mark("k2_dfa_scan", 1);
     scan_u32_to_i64(L, c.span_cnt.as<uint32_t>(), n_lines, c.span_off.as<int64_t>(), c.scan_scratch.as<int64_t>());
-    tm.mark("k5_span_offsets");
+    tm.mark("k5_span_offsets", 3);
     // span entries are bounded by n_lines * (widest extraction): no round trip needed to size the buffer
     const size_t span_bound = nl * c.max_slots;
     c.spans.reserve((span_bound + 4) * 4);
     if (!c.cap.match_only)
         k4_tdfa_capture(L, c.cap, d_text, d_line_off, sep, n_lines, c.span_off.as<int64_t>(), c.ext_id.as<int32_t>(),
                         c.spans.as<int32_t>());
-    tm.mark("k4_tdfa_capture");
+    tm.mark("k4_tdfa_capture", c.cap.match_only ? 0 : 1);
     CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
     k3_histogram(L, c.ext_id.as<int32_t>(), n_lines, c.n_ext, c.hist.as<unsigned long long>());
-    tm.mark("k3_histogram");
+    tm.mark("k3_histogram", 1);
     CK(cudaGetLastError());
     if (out) {
         out->n_lines = n_lines;
@@ -301,10 +314,6 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         out->d_spans = c.spans.as<int32_t>();
         out->d_histogram = c.hist.as<int64_t>();
         out->d_n_lines = d_n_lines;
-    }
-    if (timed) {
-        CK(cudaStreamSynchronize(stream));
-        tm.collect();
     }
     return n_lines;
 }
@@ -612,7 +621,7 @@ void gorp_result_release(gorp_engine* e, gorp_result* r) {
     }
 }
 
-int gorp_extract_text_device(gorp_engine* e, int dev_index, const uint16_t* d_text, int64_t n_units, void* stream, int sync,
+int gorp_extract_text_device(gorp_engine* e, int dev_index, const uint16_t* d_text, int64_t n_units, void* stream, int flags,
                              gorp_device_result* out) {
     if (!e || dev_index < 0 || dev_index >= static_cast<int>(e->devs.size()) || n_units < 0 || (reinterpret_cast<uintptr_t>(d_text) & 15))
         return fail(GORP_E_ARG, "bad argument (d_text must be 16-byte aligned)");
@@ -620,13 +629,15 @@ int gorp_extract_text_device(gorp_engine* e, int dev_index, const uint16_t* d_te
         DeviceCtx& c = *e->devs[dev_index];
         std::lock_guard<std::mutex> lock(c.mu);
         CK(cudaSetDevice(c.device));
-        run_pipeline(c, d_text, n_units, nullptr, 0, stream ? static_cast<cudaStream_t>(stream) : c.stream, sync != 0, out);
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c.stream;
+        run_pipeline(c, d_text, n_units, nullptr, 0, st, (flags & GORP_FLAG_TIME_KERNELS) != 0, out);
+        if (flags & GORP_FLAG_SYNC) CK(cudaStreamSynchronize(st));
         return GORP_OK;
     });
 }
 
 int gorp_extract_lines_device(gorp_engine* e, int dev_index, const uint16_t* d_text, const int64_t* d_off, int64_t n_lines,
-                              void* stream, int sync, gorp_device_result* out) {
+                              void* stream, int flags, gorp_device_result* out) {
     if (!e || dev_index < 0 || dev_index >= static_cast<int>(e->devs.size()) || !d_off || n_lines < 0 ||
         (reinterpret_cast<uintptr_t>(d_text) & 15))
         return fail(GORP_E_ARG, "bad argument (d_text must be 16-byte aligned)");
@@ -634,21 +645,34 @@ int gorp_extract_lines_device(gorp_engine* e, int dev_index, const uint16_t* d_t
         DeviceCtx& c = *e->devs[dev_index];
         std::lock_guard<std::mutex> lock(c.mu);
         CK(cudaSetDevice(c.device));
-        run_pipeline(c, d_text, 0, d_off, n_lines, stream ? static_cast<cudaStream_t>(stream) : c.stream, sync != 0, out);
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c.stream;
+        run_pipeline(c, d_text, 0, d_off, n_lines, st, (flags & GORP_FLAG_TIME_KERNELS) != 0, out);
+        if (flags & GORP_FLAG_SYNC) CK(cudaStreamSynchronize(st));
         return GORP_OK;
     });
 }
 
-int gorp_last_kernel_times(gorp_engine* e, int dev_index, const char** names, float* ms, int cap, int* n) {
+int gorp_kernel_times(gorp_engine* e, int dev_index, const char** names, double* total_ms, int cap, int* n, int64_t* calls,
+                       int64_t* launches, int reset) {
     if (!e || dev_index < 0 || dev_index >= static_cast<int>(e->devs.size()) || !n) return fail(GORP_E_ARG, "bad argument");
     DeviceCtx& c = *e->devs[dev_index];
     std::lock_guard<std::mutex> lock(c.mu);
-    int k = std::min(cap, c.last_n);
+    cudaSetDevice(c.device);
+    collect_times(c);
+    int k = std::min(cap, c.acc_n);
     for (int i = 0; i < k; ++i) {
         if (names) names[i] = c.ev_name[i];
-        if (ms) ms[i] = c.last_ms[i];
+        if (total_ms) total_ms[i] = c.acc_ms[i];
     }
     *n = k;
+    if (calls) *calls = c.acc_calls;
+    if (launches) *launches = c.launches;
+    if (reset) {
+        for (auto& v : c.acc_ms) v = 0;
+        c.acc_calls = 0;
+        c.acc_n = 0;
+        c.launches = 0;
+    }
     return GORP_OK;
 }
 

@@ -112,11 +112,15 @@ int gorp_extract_text(gorp_engine* e, const uint16_t* text, int64_t n_units, gor
 void gorp_result_release(gorp_engine* e, gorp_result* r);
 
 /* --- device-resident variants: `d_text` (and `d_off`) already live in the HBM of the engine's device `dev_index`
- * (index into the `devices` array given at creation); results stay in device memory owned by the engine until the
- * next call on the same (engine, dev_index). `stream` is a cudaStream_t (NULL = the engine's own stream); the call
- * only enqueues work unless `sync` is non-zero. Used by bench.py for the HBM-resident `value`. */
+ * (index into the `devices` array given at creation) and must be 16-byte aligned; results stay in device memory
+ * owned by the engine until the next call on the same (engine, dev_index). `stream` is a cudaStream_t (NULL = the
+ * engine's own stream). The call enqueues the kernels on that stream; the text form waits once for the newline
+ * count (it sizes the per-line arrays). Used by bench.py for the HBM-resident `value`. */
+#define GORP_FLAG_SYNC 1          /* cudaStreamSynchronize before returning */
+#define GORP_FLAG_TIME_KERNELS 2  /* bracket every kernel with CUDA events on `stream` (see gorp_kernel_times) */
+
 typedef struct gorp_device_result {
-    int64_t n_lines;          /* valid after synchronisation when the text form is used with sync == 0: -1 until then */
+    int64_t n_lines;
     const int32_t* d_ext_id;
     const int64_t* d_line_off;
     const int64_t* d_span_off;
@@ -126,13 +130,15 @@ typedef struct gorp_device_result {
 } gorp_device_result;
 
 int gorp_extract_text_device(gorp_engine* e, int dev_index, const uint16_t* d_text, int64_t n_units, void* stream,
-                             int sync, gorp_device_result* out);
+                             int flags, gorp_device_result* out);
 int gorp_extract_lines_device(gorp_engine* e, int dev_index, const uint16_t* d_text, const int64_t* d_off,
-                              int64_t n_lines, void* stream, int sync, gorp_device_result* out);
+                              int64_t n_lines, void* stream, int flags, gorp_device_result* out);
 
-/* Per-kernel device time (CUDA events on the launching stream) of the most recent device-resident call on
- * (e, dev_index) made with sync != 0: names[i] / ms[i], i < *n (at most `cap`). */
-int gorp_last_kernel_times(gorp_engine* e, int dev_index, const char** names, float* ms, int cap, int* n);
+/* Device time per pipeline stage, summed over the calls made with GORP_FLAG_TIME_KERNELS on (e, dev_index) since the
+ * last reset: names[i] / total_ms[i] for i < *n (at most `cap`), `calls` = timed calls, `launches` = kernels launched
+ * by this context (all calls). Waits for the last timed call to finish. */
+int gorp_kernel_times(gorp_engine* e, int dev_index, const char** names, double* total_ms, int cap, int* n,
+                      int64_t* calls, int64_t* launches, int reset);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (gorp_b200.api -> libgorpcuda.so), against the
+oracle on the same inputs. Bit-exact: same extraction index / MISS / capture failure per line, identical spans."""
+import itertools
+
+import numpy as np
+import pytest
+
+from gorp_b200 import DefinitionReader, ExtractionException, corpus
+from oracle import gorp_oracle, jdkre
+from tests import reference_vectors as V
+from tests.test_host_compile import ALL_DEFS, FUZZ_PATTERNS, TRICKY_LINES
+
+pytestmark = pytest.mark.gpu
+
+
+def dense_spans(batch, width):
+    """CSR spans of an ExtractionBatch -> [n, width] matrix padded with -1 (oracle layout)."""
+    n = batch.n_lines
+    out = np.full((n, max(width, 1)), -1, dtype=np.int32)
+    cnt = (batch.span_off[1:] - batch.span_off[:-1]).astype(np.int64)
+    if n and cnt.sum():
+        rows = np.repeat(np.arange(n), cnt)
+        cols = np.arange(int(cnt.sum())) - np.repeat(batch.span_off[:-1], cnt)
+        out[rows, cols] = batch.spans
+    return out[:, :width]
+
+
+def check_against_oracle(definition, text=None, lines=None, gorp=None):
+    g = gorp or DefinitionReader.reader(definition).read()
+    o = gorp_oracle.Gorp(definition)
+    G = max(len(x.extractor_names) for x in o.extractions)
+    if lines is not None:
+        b = g.extract_batch_lines(lines)
+        units = [np.asarray(jdkre.to_units(s), dtype=np.uint16) for s in lines]
+        off = np.zeros(len(lines) + 1, dtype=np.int64)
+        np.cumsum([len(u) for u in units], out=off[1:])
+        flat = np.concatenate(units) if units else np.zeros(0, np.uint16)
+        oe, osp = o.extract_batch(flat, off, threads=0)
+        assert (b.line_off == off).all()
+    else:
+        b = g.extract_batch_text(text)
+        starts, ends = gorp_oracle.split_lines(text)
+        oe, osp = o.extract_batch(text, (starts, ends), threads=0)
+        assert b.n_lines == len(starts)
+        assert (b.line_off[:-1] == starts).all() and (b.line_off[1:] - 1 == ends).all()
+    assert (b.ext_id == oe).all(), np.flatnonzero(b.ext_id != oe)[:10]
+    # span counts: 2*groups for matched AND capture-failed lines (the latter all -1), 0 for misses
+    ng = np.asarray([len(x.extractor_names) for x in o.extractions], dtype=np.int64)
+    e_of = np.where(oe >= 0, oe, np.where(oe <= -2, -2 - oe, 0))
+    want_cnt = np.where(oe == -1, 0, 2 * ng[e_of])
+    assert ((b.span_off[1:] - b.span_off[:-1]) == want_cnt).all()
+    assert (dense_spans(b, 2 * G) == osp).all()
+    E = len(o.extractions)
+    hist = np.zeros(E + 2, dtype=np.int64)
+    np.add.at(hist, np.where(oe >= 0, oe, np.where(oe == -1, E, E + 1)), 1)
+    assert (b.histogram == hist).all()
+    return g, b, oe
+
+
+# ---------------------------------------------------------------- the reference's own vectors through the GPU
+@pytest.mark.parametrize("case", V.FULL_EXACT)
+def test_reference_extract_vectors_exact(case):
+    g = DefinitionReader.reader(case[0]).read()
+    for s, want in case[1]:
+        r = g.extract(s)
+        assert r is not None and r.asMap("id") == want and r.getInput() == s
+
+
+@pytest.mark.parametrize("case", V.FULL_SUBSET)
+def test_reference_extract_vectors_subset(case):
+    g = DefinitionReader.reader(case[0]).read()
+    for s, want in case[1]:
+        m = g.extract(s).asMap("id")
+        for k, v in want.items():
+            assert m[k] == v
+
+
+@pytest.mark.parametrize("case", V.POLY_DSL)
+def test_reference_polymatch_vectors(case):
+    g = DefinitionReader.reader(case[0]).read()
+    b = g.extract_batch_lines([s for s, _ in case[1]])
+    for i, (_, want) in enumerate(case[1]):
+        e = int(b.ext_id[i])
+        assert (e if e >= -1 else -2 - e) == want[0]
+
+
+def test_multipattern_first_accept():
+    from gorp_b200 import Blob, Gorp
+    g = Gorp(Blob.from_patterns(V.MULTI_PATTERNS))
+    b = g.extract_batch_lines([s for s, _ in V.MULTI_CASES])
+    assert b.ext_id.tolist() == [w[0] if w else -1 for _, w in V.MULTI_CASES]
+
+
+def test_readme_sample_line_is_a_miss_and_exception_text():
+    g = DefinitionReader.reader(V.README_DEF).read()
+    assert g.extract("102456879: GET 123ms 200 /rest-service/v1/endpoint?foo=bar") is None
+    # U+000B inside \S+ : DFA accepts, java.util.regex rejects -> ExtractionException
+    with pytest.raises(ExtractionException) as ei:
+        g.extract("[1]: GET 2ms /a\x0bb")
+    assert "Internal error: high-level match for extraction #1 (GetRequest) failed to match generated regexp: " in str(ei.value)
+    assert g.extractSafe("[1]: GET 2ms /a\x0bb") is None
+    rs = g.extractAll(["[1]: PUT 2ms /a", "nope", "[1]: HEAD 2ms /b"])
+    assert [r.getId() if r else None for r in rs] == ["PutRequest", None, "OtherRequest"]
+
+
+# ---------------------------------------------------------------- oracle parity on seeded inputs
+@pytest.mark.parametrize("case", ALL_DEFS)
+def test_tricky_lines_text_and_lines_form(case):
+    lines = [c[0] for c in case[1]] + TRICKY_LINES
+    g, _, _ = check_against_oracle(case[0], lines=lines)
+    units = [np.asarray(jdkre.to_units(s), dtype=np.uint16) for s in lines]
+    text = np.concatenate([np.concatenate((u, [10])) for u in units]).astype(np.uint16)
+    check_against_oracle(case[0], text=text, gorp=g)
+
+
+@pytest.mark.parametrize("definition", FUZZ_PATTERNS)
+def test_fuzz_small_alphabet(definition):
+    rng = np.random.default_rng(11)
+    lines = ["".join(t) for n in range(0, 6) for t in itertools.product("abc:", repeat=n)]
+    lines += ["".join(rng.choice(list("abcd: "), size=rng.integers(6, 40))) for _ in range(5000)]
+    check_against_oracle(definition, lines=lines)
+
+
+@pytest.mark.parametrize("name,n", [("simple", 300000), ("readme", 300000)])
+def test_config_corpora(name, n):
+    d, gen = corpus.CONFIGS[name]
+    text = gen(n)
+    _, b, oe = check_against_oracle(d, text=text)
+    assert b.n_lines == n and (oe >= 0).sum() > n // 3
+
+
+def test_edge_cases():
+    g = DefinitionReader.reader(V.README_DEF).read()
+    z = np.zeros(0, dtype=np.uint16)
+    assert g.extract_batch_text(z).n_lines == 0
+    assert g.extract_batch_lines([]).n_lines == 0
+    for s in ["\n", "\n\n", "[1]: GET 2ms /a", "[1]: GET 2ms /a\n", "\n[1]: GET 2ms /a", "a\n\nb", "[1]: GET 2ms /a\r\n[1]: GET 2ms /a"]:
+        check_against_oracle(V.README_DEF, text=np.asarray(jdkre.to_units(s), dtype=np.uint16), gorp=g)
+    # List<String> form: strings may be empty or contain '\n' themselves (it is data there)
+    check_against_oracle(V.README_DEF, lines=["", "[1]: GET 2ms /a\nb", "", "[1]: GET 2ms /a", ""], gorp=g)
+    # a definition that accepts the empty line
+    d = "extract e {\n template $x(%{a*})\n}\n"
+    check_against_oracle(d, text=np.asarray(jdkre.to_units("\n\naa\n"), dtype=np.uint16))
+
+
+def test_long_and_ragged_lines():
+    rng = np.random.default_rng(5)
+    lines = []
+    for k in range(400):
+        n = int(rng.choice([0, 1, 7, 8, 9, 63, 64, 65, 1000, 5000, 10000]))
+        path = "/" + "".join(rng.choice(list("abcdefghij0123456789/"), size=n))
+        lines.append("[%d]: %s %dms %s" % (rng.integers(1, 10**9), rng.choice(["GET", "PUT", "POST", "x y"]), rng.integers(1, 999), path))
+    lines.append("[1]: GET 2ms /" + "\U0001F600" * 3000)
+    lines.append("[1]: GET 2ms /" + "a" * 9000 + " tail")
+    check_against_oracle(V.README_DEF, lines=lines)
+    check_against_oracle(V.README_DEF, text=np.concatenate(
+        [np.concatenate((np.asarray(jdkre.to_units(s), dtype=np.uint16), [10])) for s in lines]).astype(np.uint16))
+
+
+def test_non_ascii_divergence_corpus():
+    """Config-5 style inputs: non-ASCII fields, surrogate pairs, lone surrogates, the DFA-vs-JDK divergence characters."""
+    rng = np.random.default_rng(9)
+    specials = ["\x0b", "\x08", "\u0085", "\u2028", "\u2029", "\r", "\ud83d", "\ude00", "\U0001F600", "\u00e9", "\u0416",
+                "\u4e2d", "\U00010400", "\t", "\x0c"]
+    lines = []
+    for k in range(20000):
+        path = list("/" + "".join(rng.choice(list("abcxyz012/"), size=rng.integers(3, 30))))
+        for _ in range(rng.integers(0, 3)):
+            path.insert(rng.integers(0, len(path) + 1), specials[rng.integers(0, len(specials))])
+        lines.append("[%d]: %s %dms %s" % (rng.integers(1, 10**9), rng.choice(["GET", "PUT", "HEAD", "\u0416"]), rng.integers(1, 999), "".join(path)))
+    _, b, oe = check_against_oracle(V.README_DEF, lines=lines)
+    assert (oe <= -2).sum() > 100 and (oe == -1).sum() > 100 and (oe >= 0).sum() > 1000
+
+
+def test_full_size_properties():
+    """Config #2 at scale (tiling a seeded block): the results of a tiled corpus are the tiled results of the block."""
+    d, gen = corpus.CONFIGS["readme"]
+    block = gen(250000, seed=123)
+    reps = 16
+    g, b1, _ = check_against_oracle(d, text=block)
+    big = np.tile(block, reps)
+    b = g.extract_batch_text(big)
+    assert b.n_lines == reps * b1.n_lines
+    assert (b.histogram == reps * b1.histogram).all()
+    assert (b.ext_id.reshape(reps, -1) == b1.ext_id[None, :]).all()
+    assert (b.spans.reshape(reps, -1) == b1.spans[None, :]).all()
+    assert (np.diff(b.line_off) > 0).all() and (np.diff(b.span_off) >= 0).all()
