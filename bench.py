@@ -140,6 +140,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--ref-lines", type=int, default=16_000_000)
     ap.add_argument("--cpu-lines", type=int, default=16_000_000)
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -216,6 +218,8 @@ def main():
     # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H inside the timed region)
     e2e = None
     try:
+        if args.skip_e2e:
+            raise RuntimeError("skipped (--skip-e2e)")
         avail_gb = 0.0
         for ln in open("/proc/meminfo"):
             if ln.startswith("MemAvailable"):
@@ -266,6 +270,8 @@ def main():
         # CPU baseline on rank 0: bounded sample of the same workload
         from oracle import gorp_oracle
         cores = os.cpu_count() or 1
+        if args.skip_cpu:
+            args.cpu_lines = BLOCK_LINES
         creps = max(1, args.cpu_lines // BLOCK_LINES)
         ctext = np.tile(block, creps)
         cst = gorp_oracle.split_lines(ctext)

@@ -167,16 +167,32 @@ void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
     c.dfa.n_states = static_cast<uint32_t>(S);
     c.dfa.n_classes = static_cast<uint32_t>(C);
     c.dfa.cls = upload(m.dfa.classmap, c.owned);
-    c.dfa.accept_first = upload(m.dfa.accept_first, c.owned);
-    if (S * C < 0xFFFF) {
-        std::vector<uint16_t> t(S * C);
-        for (size_t i = 0; i < S * C; ++i) t[i] = m.dfa.trans[i] < 0 ? 0xFFFF : static_cast<uint16_t>(m.dfa.trans[i] * C);
-        c.dfa.trans16 = upload(t, c.owned);
-    } else {
-        if (S * C > 0x7FFFFFFFull) throw UnsupportedError("combined DFA table too large");
-        std::vector<int32_t> t(S * C);
-        for (size_t i = 0; i < S * C; ++i) t[i] = m.dfa.trans[i] < 0 ? -1 : static_cast<int32_t>(m.dfa.trans[i] * C);
-        c.dfa.trans32 = upload(t, c.owned);
+    {
+        // device layout: one extra absorbing "dead" row and one extra "identity" column (see kernels.cu)
+        const size_t R = S + 1, K = C + 1;
+        std::vector<int32_t> af(m.dfa.accept_first);
+        af.push_back(-1);
+        c.dfa.accept_first = upload(af, c.owned);
+        if (R * K > 0x7FFFFFFFull) throw UnsupportedError("combined DFA table too large");
+        auto next = [&](size_t s, size_t k) -> uint32_t {
+            if (s == S) return static_cast<uint32_t>(S * K);
+            if (k == C) return static_cast<uint32_t>(s * K);
+            int32_t t = m.dfa.trans[s * C + k];
+            return static_cast<uint32_t>((t < 0 ? S : static_cast<size_t>(t)) * K);
+        };
+        if (R * K <= 0xFFFF) {
+            std::vector<uint16_t> t(R * K);
+            for (size_t s = 0; s < R; ++s)
+                for (size_t k = 0; k < K; ++k) t[s * K + k] = static_cast<uint16_t>(next(s, k));
+            c.dfa.trans = upload(t, c.owned);
+            c.dfa.wide = 0;
+        } else {
+            std::vector<uint32_t> t(R * K);
+            for (size_t s = 0; s < R; ++s)
+                for (size_t k = 0; k < K; ++k) t[s * K + k] = next(s, k);
+            c.dfa.trans = upload(t, c.owned);
+            c.dfa.wide = 1;
+        }
     }
     // capture automata
     const size_t E = m.n_groups.size();
@@ -196,13 +212,25 @@ void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
             const Tdfa& t = m.tdfas[e];
             if (t.n_regs > static_cast<uint32_t>(kMaxTdfaRegs))
                 throw UnsupportedError(strfmt("extraction #%zu needs %u tag registers (limit %d)", e, t.n_regs, kMaxTdfaRegs));
-            ext[e] = {static_cast<uint32_t>(trans.size()), static_cast<uint32_t>(opoff.size()), static_cast<uint32_t>(ops.size()),
-                      static_cast<uint32_t>(fin.size()), static_cast<uint32_t>(acc.size()), t.n_slots};
-            trans.insert(trans.end(), t.trans.begin(), t.trans.end());
+            ext[e] = {t.n_states, static_cast<uint32_t>(trans.size()), static_cast<uint32_t>(opoff.size()),
+                      static_cast<uint32_t>(ops.size()), static_cast<uint32_t>(fin.size()), static_cast<uint32_t>(acc.size()),
+                      t.n_slots};
+            // rows + dead row, columns + identity column
+            const uint32_t Sd = t.n_states, Cn = t.n_classes;
+            for (uint32_t s = 0; s <= Sd; ++s) {
+                for (uint32_t k = 0; k < Cn; ++k) {
+                    uint32_t ent = s == Sd ? 0xFFFFu : t.trans[static_cast<size_t>(s) * Cn + k];
+                    if ((ent & 0xFFFFu) == 0xFFFFu) ent = Sd;  // dead: no register ops
+                    trans.push_back(ent);
+                }
+                trans.push_back(s);  // identity: stay, no ops
+            }
             opoff.insert(opoff.end(), t.op_off.begin(), t.op_off.end());
             ops.insert(ops.end(), t.ops.begin(), t.ops.end());
             fin.insert(fin.end(), t.fin.begin(), t.fin.end());
+            fin.insert(fin.end(), t.n_slots, 0xFF);
             acc.insert(acc.end(), t.accepting.begin(), t.accepting.end());
+            acc.push_back(0);
         }
         c.cap.cls = upload(m.symbols.classmap, c.owned);
         c.cap.n_classes = m.symbols.n_classes;
@@ -629,7 +657,7 @@ int gorp_extract_text_device(gorp_engine* e, int dev_index, const uint16_t* d_te
         DeviceCtx& c = *e->devs[dev_index];
         std::lock_guard<std::mutex> lock(c.mu);
         CK(cudaSetDevice(c.device));
-        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c.stream;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
         run_pipeline(c, d_text, n_units, nullptr, 0, st, (flags & GORP_FLAG_TIME_KERNELS) != 0, out);
         if (flags & GORP_FLAG_SYNC) CK(cudaStreamSynchronize(st));
         return GORP_OK;
@@ -645,7 +673,7 @@ int gorp_extract_lines_device(gorp_engine* e, int dev_index, const uint16_t* d_t
         DeviceCtx& c = *e->devs[dev_index];
         std::lock_guard<std::mutex> lock(c.mu);
         CK(cudaSetDevice(c.device));
-        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c.stream;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
         run_pipeline(c, d_text, 0, d_off, n_lines, st, (flags & GORP_FLAG_TIME_KERNELS) != 0, out);
         if (flags & GORP_FLAG_SYNC) CK(cudaStreamSynchronize(st));
         return GORP_OK;

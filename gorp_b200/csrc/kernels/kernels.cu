@@ -190,76 +190,62 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(const uint32_t* __
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[nb];
 }
 
-// ------------------------------------------------------------------ line reader shared by K2 / K4
-// Calls f(unit, pos) for every UTF-16 unit of [a, b) until f returns false. 128-bit loads once 16-byte aligned
-// (the text base is 16-byte aligned, so alignment is a property of the position alone).
-template <class F>
-__device__ __forceinline__ void for_units(const uint16_t* __restrict__ text, int64_t a, int64_t b, F&& f) {
-    int64_t p = a;
-    while (p < b && (p & 7)) {
-        if (!f(static_cast<uint32_t>(__ldg(text + p)), p)) return;
-        ++p;
-    }
-    while (p + 8 <= b) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + p));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!f(w[k] & 0xFFFFu, p + 2 * k)) return;
-            if (!f(w[k] >> 16, p + 2 * k + 1)) return;
-        }
-        p += 8;
-    }
-    while (p < b) {
-        if (!f(static_cast<uint32_t>(__ldg(text + p)), p)) return;
-        ++p;
-    }
+// ------------------------------------------------------------------ line walking shared by K2 / K4
+// A line [a, b) is walked in 16-byte aligned chunks of 8 UTF-16 units with ONE loop shape for every thread, so a
+// warp never splits into per-thread head/tail code: units of the chunk that lie outside the line are fed to the
+// automaton as the extra "identity" symbol (a column whose every entry is a self-loop), and a dead automaton is
+// an explicit absorbing state that is only tested once per chunk. The aligned chunk that holds a valid unit can
+// never cross a page, so the over-read of up to 7 units on either side is always mapped memory.
+__device__ __forceinline__ uint32_t unit_of(const uint4& v, int k) {
+    const uint32_t w = (k >> 1) == 0 ? v.x : (k >> 1) == 1 ? v.y : (k >> 1) == 2 ? v.z : v.w;
+    return (k & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
 // ------------------------------------------------------------------ K2: combined DFA, one line per thread
-template <bool kSmemTable>
+// Table layout: rows = states + 1 (last row = dead, absorbing), columns = classes + 1 (last column = identity),
+// entries premultiplied (next_row * n_cols).
+template <bool kSmemTable, typename Entry>
 __global__ void __launch_bounds__(kThreads) dfa_scan_kernel(DfaDev d, const uint16_t* __restrict__ text,
                                                             const int64_t* __restrict__ line_off, int sep, int64_t n_lines,
                                                             const uint32_t* __restrict__ slots_per_ext,
                                                             int32_t* __restrict__ ext_id, uint32_t* __restrict__ span_cnt) {
-    extern __shared__ uint16_t smem[];
-    uint16_t* s_cls = smem;          // [128] ASCII slice of the class map
-    uint16_t* s_trans = smem + 128;  // [S*C] when kSmemTable
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t* s_cls = reinterpret_cast<uint16_t*>(smem_raw);  // [128] ASCII slice of the class map
+    Entry* s_trans = reinterpret_cast<Entry*>(smem_raw + 256);  // [(S+1)*(C+1)] when kSmemTable
+    const Entry* __restrict__ g_trans = reinterpret_cast<const Entry*>(d.trans);
     for (int i = threadIdx.x; i < 128; i += kThreads) s_cls[i] = d.cls[i];
+    const uint32_t n_cols = d.n_classes + 1, ident = d.n_classes;
     if (kSmemTable)
-        for (uint32_t i = threadIdx.x; i < d.n_states * d.n_classes; i += kThreads) s_trans[i] = d.trans16[i];
+        for (uint32_t i = threadIdx.x; i < (d.n_states + 1) * n_cols; i += kThreads) s_trans[i] = g_trans[i];
     __syncthreads();
-    const bool wide = d.trans16 == nullptr;
+    const uint32_t dead = d.n_states * n_cols;
     for (int64_t line = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; line < n_lines;
          line += static_cast<int64_t>(gridDim.x) * kThreads) {
         const int64_t a = line_off[line], b = line_off[line + 1] - sep;
-        uint32_t st = 0;  // premultiplied state (state * n_classes)
-        bool dead = false;
-        if (!wide) {
-            const uint16_t* __restrict__ tr = kSmemTable ? s_trans : d.trans16;
-            for_units(text, a, b, [&](uint32_t u, int64_t) {
-                const uint32_t c = u < 128 ? s_cls[u] : __ldg(d.cls + u);
-                st = kSmemTable ? tr[st + c] : __ldg(tr + st + c);
-                dead = st == kDead16;
-                return !dead;
-            });
-        } else {
-            for_units(text, a, b, [&](uint32_t u, int64_t) {
-                const uint32_t c = u < 128 ? s_cls[u] : __ldg(d.cls + u);
-                const int32_t nx = __ldg(d.trans32 + st + c);
-                dead = nx < 0;
-                st = static_cast<uint32_t>(nx);
-                return !dead;
-            });
+        uint32_t st = 0;
+        int64_t q = a & ~int64_t(7);
+        uint32_t lo = static_cast<uint32_t>(a - q);
+        for (; q < b; q += 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + q));
+            const uint32_t n = b - q < 8 ? static_cast<uint32_t>(b - q) : 8u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t u = unit_of(v, k);
+                uint32_t c = u < 128 ? s_cls[u] : __ldg(d.cls + u);
+                c = (static_cast<uint32_t>(k) - lo < n - lo) ? c : ident;
+                st = kSmemTable ? static_cast<uint32_t>(s_trans[st + c]) : static_cast<uint32_t>(__ldg(g_trans + st + c));
+            }
+            lo = 0;
+            if (st == dead) break;
         }
-        int32_t e = -1;
-        if (!dead) e = __ldg(d.accept_first + st / d.n_classes);
+        const int32_t e = __ldg(d.accept_first + st / n_cols);  // the dead row carries -1
         ext_id[line] = e;
         span_cnt[line] = e >= 0 ? __ldg(slots_per_ext + e) : 0u;
     }
 }
 
 // ------------------------------------------------------------------ K4: capture automaton (TDFA), one line per thread
+// Per extraction: rows = states + 1 (last = dead), columns = symbol classes + 1 (last = identity: same state, no ops).
 __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const uint16_t* __restrict__ text,
                                                                 const int64_t* __restrict__ line_off, int sep,
                                                                 int64_t n_lines, const int64_t* __restrict__ span_off,
@@ -267,45 +253,53 @@ __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const 
     __shared__ uint16_t s_cls[128];
     for (int i = threadIdx.x; i < 128; i += kThreads) s_cls[i] = c.cls[i];
     __syncthreads();
+    const uint32_t n_cols = c.n_classes + 1, ident = c.n_classes;
     for (int64_t line = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; line < n_lines;
          line += static_cast<int64_t>(gridDim.x) * kThreads) {
         const int32_t e = ext_id[line];
         if (e < 0) continue;
         const ExtDev x = c.ext[e];
-        if (x.n_slots == 0 && c.match_only) continue;
         const int64_t a = line_off[line], b = line_off[line + 1] - sep;
         const uint32_t* __restrict__ tr = c.tdfa_trans + x.trans_off;
         const uint32_t* __restrict__ opo = c.tdfa_op_off + x.opoff_off;
         const uint16_t* __restrict__ ops = c.tdfa_ops + x.ops_off;
         int32_t regs[kMaxTdfaRegs];
         uint32_t st = 0;
-        bool ok = true;
-        for_units(text, a, b, [&](uint32_t u, int64_t p) {
-            uint32_t k;
-            if (u < 128) {
-                k = s_cls[u];
-            } else {
-                k = __ldg(c.cls + u);
-                // a high surrogate followed by a low surrogate is ONE java.util.regex character
-                if ((u & 0xFC00u) == 0xD800u && p + 1 < b && (__ldg(text + p + 1) & 0xFC00u) == 0xDC00u) k = c.pair_hi_class;
-            }
-            const uint32_t ent = __ldg(tr + st * c.n_classes + k);
-            const uint32_t nx = ent & 0xFFFFu;
-            if (nx == kDead16) { ok = false; return false; }
-            const uint32_t ol = ent >> 16;
-            if (ol) {
-                const uint32_t o0 = __ldg(opo + ol), o1 = __ldg(opo + ol + 1);
-                const int32_t pos = static_cast<int32_t>(p - a);
-                for (uint32_t q = o0; q < o1; ++q) {
-                    const uint32_t op = __ldg(ops + q);
-                    const uint32_t src = op & 0xFFu;
-                    regs[op >> 8] = src == 0xFFu ? pos : regs[src];
+        int64_t q = a & ~int64_t(7);
+        uint32_t lo = static_cast<uint32_t>(a - q);
+        for (; q < b; q += 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + q));
+            const uint32_t n = b - q < 8 ? static_cast<uint32_t>(b - q) : 8u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t u = unit_of(v, k);
+                uint32_t sym;
+                if (u < 128) {
+                    sym = s_cls[u];
+                } else {
+                    sym = __ldg(c.cls + u);
+                    // a high surrogate followed by a low surrogate is ONE java.util.regex character
+                    if ((u & 0xFC00u) == 0xD800u && q + k + 1 < b && (__ldg(text + q + k + 1) & 0xFC00u) == 0xDC00u)
+                        sym = c.pair_hi_class;
                 }
+                sym = (static_cast<uint32_t>(k) - lo < n - lo) ? sym : ident;
+                const uint32_t ent = __ldg(tr + st * n_cols + sym);
+                const uint32_t ol = ent >> 16;
+                if (ol) {
+                    const uint32_t o0 = __ldg(opo + ol), o1 = __ldg(opo + ol + 1);
+                    const int32_t pos = static_cast<int32_t>(q + k - a);
+                    for (uint32_t i = o0; i < o1; ++i) {
+                        const uint32_t op = __ldg(ops + i);
+                        const uint32_t src = op & 0xFFu;
+                        regs[op >> 8] = src == 0xFFu ? pos : regs[src];
+                    }
+                }
+                st = ent & 0xFFFFu;
             }
-            st = nx;
-            return true;
-        });
-        if (ok) ok = __ldg(c.tdfa_accepting + x.acc_off + st) != 0;
+            lo = 0;
+            if (st == x.n_states) break;  // dead
+        }
+        const bool ok = __ldg(c.tdfa_accepting + x.acc_off + st) != 0;  // the dead row is not accepting
         int32_t* out = spans + span_off[line];
         if (!ok) {
             ext_id[line] = -2 - e;
@@ -382,19 +376,28 @@ static int persistent_grid(const Launch& L, const void* fn, size_t smem, int64_t
     return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+template <bool kSmem, typename Entry>
+static void launch_dfa(const Launch& L, const DfaDev& d, size_t smem, const uint16_t* text, const int64_t* line_off, int sep,
+                       int64_t n_lines, const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt) {
+    auto fn = dfa_scan_kernel<kSmem, Entry>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    int g = persistent_grid(L, reinterpret_cast<const void*>(fn), smem, n_lines);
+    fn<<<g, kThreads, smem, L.stream>>>(d, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+}
+
 void k2_dfa_scan(const Launch& L, const DfaDev& d, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
                  const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt) {
     if (n_lines <= 0) return;
-    const size_t table_bytes = static_cast<size_t>(d.n_states) * d.n_classes * 2;
-    const bool in_smem = d.trans16 != nullptr && table_bytes <= 96 * 1024;
+    const size_t esz = d.wide ? 4 : 2;
+    const size_t table_bytes = static_cast<size_t>(d.n_states + 1) * (d.n_classes + 1) * esz;
+    const bool in_smem = table_bytes <= 96 * 1024;
     const size_t smem = 256 + (in_smem ? table_bytes : 0);
-    if (in_smem) {
-        cudaFuncSetAttribute(dfa_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        int g = persistent_grid(L, reinterpret_cast<const void*>(dfa_scan_kernel<true>), smem, n_lines);
-        dfa_scan_kernel<true><<<g, kThreads, smem, L.stream>>>(d, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+    if (!d.wide) {
+        if (in_smem) launch_dfa<true, uint16_t>(L, d, smem, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+        else launch_dfa<false, uint16_t>(L, d, smem, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
     } else {
-        int g = persistent_grid(L, reinterpret_cast<const void*>(dfa_scan_kernel<false>), smem, n_lines);
-        dfa_scan_kernel<false><<<g, kThreads, smem, L.stream>>>(d, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+        if (in_smem) launch_dfa<true, uint32_t>(L, d, smem, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+        else launch_dfa<false, uint32_t>(L, d, smem, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
     }
 }
 

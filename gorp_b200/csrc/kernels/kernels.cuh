@@ -13,18 +13,19 @@
 namespace gorp {
 
 constexpr int kMaxTdfaRegs = 32;   // run-time register file per line (tag registers of the capture automaton)
-constexpr uint32_t kDead16 = 0xFFFFu;
 
 struct DfaDev {                    // combined multi-regex DFA, compacted (host/automata.hpp: CompactDfa)
     const uint16_t* cls;           // [65536] unit -> class
-    const uint16_t* trans16;       // [S*C] premultiplied next-state offset (next*C), 0xFFFF = dead; null if too big
-    const int32_t* trans32;        // [S*C] premultiplied, -1 = dead (used when S*C > 65535)
-    const int32_t* accept_first;   // [S]
-    uint32_t n_states, n_classes;
+    const void* trans;             // [(S+1)*(C+1)] premultiplied next-row offset (next*(C+1)); u16 entries, or u32
+                                   // when `wide`. Row S = dead (absorbing); column C = identity (self-loop).
+    const int32_t* accept_first;   // [S+1], entry S = -1
+    uint32_t n_states, n_classes;  // S, C (without the dead row / identity column)
+    uint32_t wide;
 };
 
 struct ExtDev {                    // per-extraction capture automaton (host/capture.hpp: Tdfa)
-    uint32_t trans_off;            // into tdfa_trans
+    uint32_t n_states;             // S; row S of the table = dead (absorbing, not accepting)
+    uint32_t trans_off;            // into tdfa_trans: [(S+1) * (n_classes+1)], last column = identity
     uint32_t opoff_off;            // into tdfa_op_off
     uint32_t ops_off;              // into tdfa_ops
     uint32_t fin_off;              // into tdfa_fin

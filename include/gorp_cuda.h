@@ -114,7 +114,7 @@ void gorp_result_release(gorp_engine* e, gorp_result* r);
 /* --- device-resident variants: `d_text` (and `d_off`) already live in the HBM of the engine's device `dev_index`
  * (index into the `devices` array given at creation) and must be 16-byte aligned; results stay in device memory
  * owned by the engine until the next call on the same (engine, dev_index). `stream` is a cudaStream_t (NULL = the
- * engine's own stream). The call enqueues the kernels on that stream; the text form waits once for the newline
+ * CUDA default stream, as everywhere in CUDA). The call enqueues the kernels on that stream; the text form waits once for the newline
  * count (it sizes the per-line arrays). Used by bench.py for the HBM-resident `value`. */
 #define GORP_FLAG_SYNC 1          /* cudaStreamSynchronize before returning */
 #define GORP_FLAG_TIME_KERNELS 2  /* bracket every kernel with CUDA events on `stream` (see gorp_kernel_times) */
