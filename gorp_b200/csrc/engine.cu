@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -100,10 +101,16 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     std::vector<void*> owned;  // immutable tables
     DfaDev dfa{};
+    DfaDirectDev dfa_direct{};
+    TdfaFastDev cap_fast{};
     CapDev cap{};
     uint32_t* d_slots = nullptr;
     uint32_t n_ext = 0;
     uint32_t max_slots = 0;
+    bool force_general = false;  // GORP_FORCE_GENERAL=1: always use the general (masked) kernels
+    bool force_unfused = false;  // GORP_FORCE_UNFUSED=1: never use the fused kernel (K1..K5 pipeline instead)
+    double lines_per_unit = 1.0 / 24.0;  // running estimate that sizes the fused kernel's output arrays
+    DevBuf tile_state;
     // per-call scratch, serialised by `mu`
     std::mutex mu;
     DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, span_cnt, span_off, spans, hist, scalars;
@@ -161,6 +168,8 @@ void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
     CK(cudaGetDeviceProperties(&prop, c.device));
     c.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (const char* f = std::getenv("GORP_FORCE_GENERAL")) c.force_general = f[0] == '1';
+    if (const char* f = std::getenv("GORP_FORCE_UNFUSED")) c.force_unfused = f[0] == '1';
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
     // combined DFA
     const size_t S = m.dfa.n_states, C = m.dfa.n_classes;
@@ -192,6 +201,41 @@ void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
                 for (size_t k = 0; k < K; ++k) t[s * K + k] = next(s, k);
             c.dfa.trans = upload(t, c.owned);
             c.dfa.wide = 1;
+        }
+    }
+    // fast tier: directly ASCII-indexed rows (see kernels.cuh: DfaDirectDev)
+    {
+        const size_t E = m.n_groups.size();
+        const size_t skip_base = S, fin_base = S + 7, R = fin_base + 1 + E;
+        if (R * 512 <= 96 * 1024) {
+            std::vector<uint32_t> rows(R * 128);
+            for (size_t r = 0; r < R; ++r)
+                for (size_t u = 0; u < 128; ++u) {
+                    uint32_t nx;
+                    if (r < S) {
+                        if (u == 0x0A) {
+                            nx = static_cast<uint32_t>(fin_base + 1 + m.dfa.accept_first[r]);
+                        } else {
+                            int32_t t = m.dfa.trans[r * C + m.dfa.classmap[u]];
+                            nx = t < 0 ? static_cast<uint32_t>(fin_base) : static_cast<uint32_t>(t);
+                        }
+                    } else if (r < fin_base) {
+                        nx = r == skip_base ? 0u : static_cast<uint32_t>(r - 1);
+                    } else {
+                        nx = static_cast<uint32_t>(r);
+                    }
+                    rows[r * 128 + u] = nx;
+                }
+            c.dfa_direct.rows = upload(rows, c.owned);
+            c.dfa_direct.n_rows = static_cast<uint32_t>(R);
+            c.dfa_direct.n_states = static_cast<uint32_t>(S);
+            c.dfa_direct.skip_base = static_cast<uint32_t>(skip_base);
+            c.dfa_direct.fin_base = static_cast<uint32_t>(fin_base);
+            c.dfa_direct.cls = c.dfa.cls;
+            c.dfa_direct.trans_plain = upload(m.dfa.trans, c.owned);
+            c.dfa_direct.accept_first = c.dfa.accept_first;
+            c.dfa_direct.n_classes = static_cast<uint32_t>(C);
+            c.dfa_direct.enabled = 1;
         }
     }
     // capture automata
@@ -231,6 +275,62 @@ void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
             fin.insert(fin.end(), t.n_slots, 0xFF);
             acc.insert(acc.end(), t.accepting.begin(), t.accepting.end());
             acc.push_back(0);
+        }
+        // fast tier image: cls128 (class*4, '\n' -> dedicated column) + per-extraction tables (kernels.cuh: TdfaFastDev)
+        {
+            const uint32_t Cn = m.symbols.n_classes, K = Cn + 1, NL = Cn, row_bytes = K * 4;
+            std::vector<uint32_t> image(128);
+            for (uint32_t u = 0; u < 128; ++u) image[u] = (u == 0x0A ? NL : m.symbols.classmap[u]) * 4;
+            std::vector<FastExtDev> fext(E);
+            uint32_t max_regs = 0;
+            bool ok = true;
+            for (size_t e = 0; e < E && ok; ++e) {
+                const Tdfa& t = m.tdfas[e];
+                const uint32_t Sx = t.n_states, rows = 2 * Sx + 9;
+                if (static_cast<uint64_t>(rows) * row_bytes > 0xFFFC) { ok = false; break; }
+                max_regs = std::max(max_regs, t.n_regs);
+                fext[e] = {static_cast<uint32_t>(image.size() * 4), row_bytes, Sx, (Sx + 7) * row_bytes, (Sx + 8) * row_bytes,
+                           (Sx + 9) * row_bytes};
+                const size_t base = image.size();
+                image.resize(base + static_cast<size_t>(rows) * K);
+                auto put = [&](uint32_t r, uint32_t k, uint32_t next_row, uint32_t dst) {
+                    image[base + static_cast<size_t>(r) * K + k] = (next_row * row_bytes) | (dst << 16);
+                };
+                for (uint32_t r = 0; r < rows; ++r)
+                    for (uint32_t k = 0; k < K; ++k) {
+                        if (r < Sx) {
+                            if (k == NL) { put(r, k, Sx + 9 + r, 0xFFFE); continue; }  // LEN := position of the '\n'
+                            const uint32_t ent = t.trans[static_cast<size_t>(r) * Cn + k];
+                            const uint32_t nx = ent & 0xFFFFu, ol = ent >> 16;
+                            if (nx == 0xFFFFu) { put(r, k, Sx + 7, 0xFFFF); continue; }
+                            const uint32_t o0 = t.op_off[ol], o1 = t.op_off[ol + 1];
+                            if (o1 == o0) put(r, k, nx, 0xFFFF);
+                            else if (o1 - o0 == 1 && (t.ops[o0] & 0xFF) == 0xFF) put(r, k, nx, t.ops[o0] >> 8);
+                            else put(r, k, Sx + 8, 0xFFFF);  // SLOW: replayed through the general tables
+                        } else if (r < Sx + 7) {
+                            put(r, k, r == Sx ? 0u : r - 1, 0xFFFF);  // SKIP chain
+                        } else {
+                            put(r, k, r, 0xFFFF);  // DEAD / SLOW / FRZ: absorbing
+                        }
+                    }
+            }
+            while (image.size() % 4) image.push_back(0);  // keep what follows the image 16-byte aligned in shared memory
+            const uint32_t reg_stride = kFusedThreads * 4;
+            const size_t reg_bytes = static_cast<size_t>(max_regs + 2) * reg_stride;
+            if (ok && image.size() * 4 + reg_bytes <= 160 * 1024 && (max_regs + 2) * reg_stride <= 0x10000) {
+                // resolve the register byte offsets now that the register count is known:
+                // r -> r*stride, dummy -> max_regs*stride, LEN -> (max_regs+1)*stride
+                for (size_t i = 128; i < image.size(); ++i) {
+                    uint32_t dst = image[i] >> 16;
+                    dst = dst == 0xFFFF ? max_regs : (dst == 0xFFFE ? max_regs + 1 : dst);
+                    image[i] = (image[i] & 0xFFFFu) | ((dst * reg_stride) << 16);
+                }
+                c.cap_fast.image = upload(image, c.owned);
+                c.cap_fast.image_words = static_cast<uint32_t>(image.size());
+                c.cap_fast.n_regs = max_regs;
+                c.cap_fast.ext = upload(fext, c.owned);
+                c.cap_fast.enabled = 1;
+            }
         }
         c.cap.cls = upload(m.symbols.classmap, c.owned);
         c.cap.n_classes = m.symbols.n_classes;
@@ -276,6 +376,72 @@ struct Timer {
     }
 };
 
+// Text form through the fused kernel. Returns false when the batch has to go through the unfused pipeline.
+bool run_fused(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
+               int64_t& n_lines, gorp_device_result* out) {
+    if (n_units <= 0 || c.force_general || c.force_unfused) return false;
+    FusedParams P{};
+    P.text = d_text;
+    P.n_units = n_units;
+    P.n_tiles = (n_units + kFusedTile - 1) / kFusedTile;
+    P.dfa = c.dfa_direct;
+    P.cap_fast = c.cap_fast;
+    P.cap = c.cap;
+    P.slots_per_ext = c.d_slots;
+    P.n_ext = c.n_ext;
+    if (!k0_fused_supported(P)) return false;
+    Launch L{stream, c.sm_count};
+    c.hist.reserve((c.n_ext + 2) * 8);
+    // look-back state: [tile_lines n_tiles][tile_spans n_tiles][ticket (8 B)][totals 3 x int64]
+    const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 16 + 8 + 24;
+    c.tile_state.reserve(state_bytes);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
+        if (attempt == 1) cap_lines = n_lines + 16;
+        const int64_t cap_spans = cap_lines * std::max<uint32_t>(c.max_slots, 1);
+        c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
+        c.line_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
+        c.span_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
+        c.spans.reserve(static_cast<size_t>(cap_spans + 4) * 4);
+        P.ext_id = c.ext_id.as<int32_t>();
+        P.line_off = c.line_off.as<int64_t>();
+        P.span_off = c.span_off.as<int64_t>();
+        P.spans = c.spans.as<int32_t>();
+        P.hist = c.hist.as<unsigned long long>();
+        P.cap_lines = cap_lines;
+        P.cap_spans = cap_spans;
+        unsigned char* st = c.tile_state.as<unsigned char>();
+        P.tile_lines = reinterpret_cast<unsigned long long*>(st);
+        P.tile_spans = P.tile_lines + P.n_tiles;
+        P.ticket = reinterpret_cast<unsigned int*>(P.tile_spans + P.n_tiles);
+        P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 16 + 8);
+        CK(cudaMemsetAsync(st, 0, state_bytes, stream));
+        CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
+        k0_fused_extract(L, P);
+        tm.mark("k0_fused_extract", 1);
+        CK(cudaGetLastError());
+        int64_t totals[3] = {0, 0, 0};
+        CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (totals[2] & 2) return false;  // a tile with more line starts than the kernel stages: unfused pipeline
+        n_lines = totals[0];
+        c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
+        if (totals[2] & 1) continue;  // capacity overflow: rerun once with the exact size
+        CK(cudaMemcpyAsync(d_scalars, P.totals, 8, cudaMemcpyDeviceToDevice, stream));
+        if (out) {
+            out->n_lines = n_lines;
+            out->d_ext_id = P.ext_id;
+            out->d_line_off = P.line_off;
+            out->d_span_off = P.span_off;
+            out->d_spans = P.spans;
+            out->d_histogram = c.hist.as<int64_t>();
+            out->d_n_lines = d_scalars;
+        }
+        return true;
+    }
+    return false;
+}
+
 // Runs the device pipeline. Text form when d_off == nullptr. Caller holds c.mu and has set the device.
 // Returns n_lines (synchronises once for the text form to size the per-line arrays).
 int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, const int64_t* d_off, int64_t n_lines,
@@ -286,6 +452,8 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     int64_t* d_n_lines = c.scalars.as<int64_t>();
     const int64_t* d_line_off;
     int sep;
+    bool ends_with_nl = true;
+    if (!d_off && run_fused(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off) {
         sep = 1;
         const int64_t n_tiles = (n_units + kNlTile - 1) / kNlTile;
@@ -303,6 +471,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         if (n_units > 0) CK(cudaMemcpyAsync(&last_unit, d_text + n_units - 1, 2, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         n_lines = total_nl + (last_unit != 0x0A ? 1 : 0);
+        ends_with_nl = last_unit == 0x0A;
         c.line_off.reserve(static_cast<size_t>(total_nl + 3) * 8);
         k1_scatter_newlines(L, d_text, n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
         k1_finish(L, d_text, n_units, c.tile_base.as<int64_t>() + n_tiles, c.line_off.as<int64_t>(), d_n_lines);
@@ -319,17 +488,41 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     c.span_off.reserve((nl + 2) * 8);
     c.scan_scratch.reserve((nl / 4096 + 8) * 8);
     c.hist.reserve((c.n_ext + 2) * 8);
-    k2_dfa_scan(L, c.dfa, d_text, d_line_off, sep, n_lines, c.d_slots, c.ext_id.as<int32_t>(), c.span_cnt.as<uint32_t>());
-    tm.mark("k2_dfa_scan", 1);
+    if (sep == 1 && c.dfa_direct.enabled && !c.force_general) {
+        // every line but (possibly) the last is terminated by '\n': fast tier; an unterminated last line goes through
+        // the general kernel
+        const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
+        k2_dfa_direct(L, c.dfa_direct, d_text, d_line_off, n_fast, c.d_slots, c.ext_id.as<int32_t>(), c.span_cnt.as<uint32_t>());
+        if (n_fast < n_lines)
+            k2_dfa_scan(L, c.dfa, d_text, d_line_off + n_fast, sep, 1, c.d_slots, c.ext_id.as<int32_t>() + n_fast,
+                        c.span_cnt.as<uint32_t>() + n_fast);
+        tm.mark("k2_dfa_scan", n_fast < n_lines ? 2 : 1);
+    } else {
+        k2_dfa_scan(L, c.dfa, d_text, d_line_off, sep, n_lines, c.d_slots, c.ext_id.as<int32_t>(), c.span_cnt.as<uint32_t>());
+        tm.mark("k2_dfa_scan", 1);
+    }
     scan_u32_to_i64(L, c.span_cnt.as<uint32_t>(), n_lines, c.span_off.as<int64_t>(), c.scan_scratch.as<int64_t>());
     tm.mark("k5_span_offsets", 3);
     // span entries are bounded by n_lines * (widest extraction): no round trip needed to size the buffer
     const size_t span_bound = nl * c.max_slots;
     c.spans.reserve((span_bound + 4) * 4);
-    if (!c.cap.match_only)
-        k4_tdfa_capture(L, c.cap, d_text, d_line_off, sep, n_lines, c.span_off.as<int64_t>(), c.ext_id.as<int32_t>(),
-                        c.spans.as<int32_t>());
-    tm.mark("k4_tdfa_capture", c.cap.match_only ? 0 : 1);
+    if (!c.cap.match_only) {
+        if (sep == 1 && c.cap_fast.enabled && !c.force_general) {
+            const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
+            k4_tdfa_fast(L, c.cap_fast, c.cap, d_text, n_units, d_line_off, n_fast, c.span_off.as<int64_t>(), c.ext_id.as<int32_t>(),
+                         c.spans.as<int32_t>());
+            if (n_fast < n_lines)
+                k4_tdfa_capture(L, c.cap, d_text, d_line_off + n_fast, sep, 1, c.span_off.as<int64_t>() + n_fast,
+                                c.ext_id.as<int32_t>() + n_fast, c.spans.as<int32_t>());
+            tm.mark("k4_tdfa_capture", n_fast < n_lines ? 2 : 1);
+        } else {
+            k4_tdfa_capture(L, c.cap, d_text, d_line_off, sep, n_lines, c.span_off.as<int64_t>(), c.ext_id.as<int32_t>(),
+                            c.spans.as<int32_t>());
+            tm.mark("k4_tdfa_capture", 1);
+        }
+    } else {
+        tm.mark("k4_tdfa_capture", 0);
+    }
     CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
     k3_histogram(L, c.ext_id.as<int32_t>(), n_lines, c.n_ext, c.hist.as<unsigned long long>());
     tm.mark("k3_histogram", 1);

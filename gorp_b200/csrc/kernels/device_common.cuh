@@ -1,0 +1,119 @@
+// Device helpers shared by the fast tiers (fast.cu) and the fused kernel (fused.cu). Header-only (no -rdc).
+#pragma once
+#include "kernels.cuh"
+
+namespace gorp {
+namespace dev {
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t unit_at(const uint4& v, int k) {
+    const uint32_t w = (k >> 1) == 0 ? v.x : (k >> 1) == 1 ? v.y : (k >> 1) == 2 ? v.z : v.w;
+    return (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+// one combined-DFA step on an ASCII unit held in byte kByte (0 or 2) of w: state = LDS[state + 4*unit]
+template <int kByte>
+__device__ __forceinline__ uint32_t dfa_step(uint32_t st, uint32_t w) {
+    uint32_t b, addr;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(b), "r"(st));
+    return lds32(addr);
+}
+
+// one capture-automaton step: class lookup, row lookup, unconditional "register := position" store
+// (transitions without a command store into the per-thread dummy register)
+template <int kByte>
+__device__ __forceinline__ void cap_step(uint32_t& st, uint32_t w, uint32_t cls_abs, uint32_t tab_abs, uint32_t reg_abs,
+                                         uint32_t pos) {
+    uint32_t b, addr;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(b), "r"(cls_abs));
+    const uint32_t c4 = lds32(addr);
+    const uint32_t ent = lds32(tab_abs + st + c4);
+    st = ent & 0xFFFCu;
+    sts32(reg_abs + (ent >> 16), pos);
+}
+
+// DFA, one chunk unit by unit (chunks that hold a unit >= 0x80): class map and plain table in global memory.
+// `st` is an absolute shared-memory row address on entry and exit.
+static __device__ __noinline__ uint32_t dfa_slow_chunk(const DfaDirectDev& d, uint32_t tbase, uint32_t st, uint4 v) {
+    uint32_t row = (st - tbase) >> 9;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        if (row >= d.fin_base) break;
+        const uint32_t u = unit_at(v, k);
+        if (row >= d.skip_base) {
+            row = row == d.skip_base ? 0u : row - 1;
+        } else if (u == 0x0Au) {
+            row = d.fin_base + 1 + __ldg(d.accept_first + row);
+        } else {
+            const int32_t t = __ldg(d.trans_plain + row * d.n_classes + __ldg(d.cls + u));
+            row = t < 0 ? d.fin_base : static_cast<uint32_t>(t);
+        }
+    }
+    return tbase + (row << 9);
+}
+
+// Capture automaton, one chunk unit by unit through the general tables (units >= 0x80, surrogate pairs, transitions
+// with several register commands). `q` = text position of the chunk, `a` = text position of the line start; units at
+// or beyond n_units read as '\n'. `st` is a fast-tier row offset on entry and exit; the line length is stored to the
+// LEN register at the terminating '\n'.
+static __device__ __noinline__ uint32_t tdfa_slow_chunk(const CapDev& c, const ExtDev& x, const FastExtDev& fx, uint32_t st,
+                                                        const uint16_t* __restrict__ text, int64_t q, int64_t a, int64_t n_units,
+                                                        uint32_t reg_abs, uint32_t reg_stride, uint32_t len_off) {
+    const uint32_t S = fx.n_states;
+    uint32_t row = st / fx.row_bytes;
+    const uint32_t n_cols = c.n_classes + 1;
+    const uint32_t* __restrict__ tr = c.tdfa_trans + x.trans_off;
+    const uint32_t* __restrict__ opo = c.tdfa_op_off + x.opoff_off;
+    const uint16_t* __restrict__ ops = c.tdfa_ops + x.ops_off;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        if (row >= S + 7) break;  // DEAD / FRZ
+        const int64_t p = q + k;
+        const uint32_t u = p < n_units ? __ldg(text + p) : 0x0Au;
+        if (row >= S) {  // SKIP_j
+            row = row == S ? 0u : row - 1;
+            continue;
+        }
+        const uint32_t pos = static_cast<uint32_t>(p - a);
+        if (u == 0x0Au) {
+            sts32(reg_abs + len_off, pos);
+            row = S + 9 + row;
+            break;
+        }
+        uint32_t sym = __ldg(c.cls + u);
+        // a high surrogate followed by a low surrogate is ONE java.util.regex character
+        if ((u & 0xFC00u) == 0xD800u && p + 1 < n_units && (__ldg(text + p + 1) & 0xFC00u) == 0xDC00u) sym = c.pair_hi_class;
+        const uint32_t ent = __ldg(tr + row * n_cols + sym);
+        const uint32_t ol = ent >> 16;
+        if (ol) {
+            const uint32_t o0 = __ldg(opo + ol), o1 = __ldg(opo + ol + 1);
+            for (uint32_t i = o0; i < o1; ++i) {
+                const uint32_t op = __ldg(ops + i);
+                const uint32_t src = op & 0xFFu;
+                const uint32_t val = src == 0xFFu ? pos : lds32(reg_abs + src * reg_stride);
+                sts32(reg_abs + (op >> 8) * reg_stride, val);
+            }
+        }
+        row = ent & 0xFFFFu;
+        if (row == S) row = S + 7;  // the general table's dead row index is S
+    }
+    return row * fx.row_bytes;
+}
+
+}  // namespace dev
+}  // namespace gorp

@@ -13,6 +13,11 @@
 namespace gorp {
 
 constexpr int kMaxTdfaRegs = 32;   // run-time register file per line (tag registers of the capture automaton)
+constexpr int kFusedThreads = 512;  // CTA size of the fused kernel AND of the fast capture tier (register offsets in the
+                                    // capture image are pre-multiplied by kFusedThreads * 4)
+constexpr int kFusedTile = 16384;   // UTF-16 units per tile
+constexpr int kFusedMaxLines = 1024;
+constexpr int kFusedHistBins = 1024;
 
 struct DfaDev {                    // combined multi-regex DFA, compacted (host/automata.hpp: CompactDfa)
     const uint16_t* cls;           // [65536] unit -> class
@@ -46,6 +51,47 @@ struct CapDev {
     uint32_t match_only;
 };
 
+// K2 fast tier ("T0"): combined DFA as directly ASCII-indexed rows in shared memory, text form only.
+// Row r = 128 u32 entries (512 B) holding the NEXT ROW; the kernel rewrites them into absolute shared-memory
+// addresses, so one step is  addr = state + unit*4 ; state = LDS[addr].  Rows:
+//   [0, S)               DFA states (0 = start); column '\n' leads to FIN(accept_first(state))
+//   [skip_base, +7)      SKIP_1..SKIP_7: swallow the units that precede the line inside its first 16-byte chunk
+//   [fin_base, +1+E)     FIN(-1) (= dead, no match), FIN(0..E-1): absorbing; reached at the line's '\n'
+// A chunk that holds any unit >= 0x80 takes the slow per-unit path through the class map (global memory).
+struct DfaDirectDev {
+    const uint32_t* rows;          // [n_rows * 128] next row index
+    uint32_t n_rows, n_states, skip_base, fin_base;
+    const uint16_t* cls;           // [65536] slow path: unit -> class
+    const int32_t* trans_plain;    // [S*C]   slow path: next state or -1
+    const int32_t* accept_first;   // [S]
+    uint32_t n_classes;
+    uint32_t enabled;
+};
+
+// K4 fast tier: per-extraction capture automaton as class-indexed rows in shared memory, text form only.
+// Row layout per extraction (row = n_cols u32 entries): [0,S) states, [S,S+7) SKIP_1..7, S+7 DEAD, S+8 SLOW (trap),
+// S+9+s FRZ(s) (reached at the line's '\n' from state s; absorbing). Entry: bits 2..15 next row byte offset (relative
+// to the extraction's table), bits 16..31 byte offset of the tag register to set to the current position (or of the
+// per-thread dummy register). Transitions that need more than "one register := position" lead to SLOW and the chunk
+// is replayed through the general tables. Tag registers live in shared memory: reg r of thread t at r*blockDim*4 + t*4.
+struct FastExtDev {
+    uint32_t tab_off;      // byte offset of this extraction's table inside the shared-memory image
+    uint32_t row_bytes;    // n_cols * 4
+    uint32_t n_states;
+    uint32_t dead_off;     // (S+7) * row_bytes ; everything >= dead_off stops the walk
+    uint32_t slow_off;     // (S+8) * row_bytes
+    uint32_t frz_off;      // (S+9) * row_bytes
+};
+
+struct TdfaFastDev {
+    const uint32_t* image;       // [image_words] = cls128 (pre-scaled class*4) followed by all tables
+    uint32_t image_words;
+    uint32_t n_regs;             // tag registers incl. scratch; register n_regs = dummy, n_regs + 1 = LEN (the line
+                                 // length, stored by the '\n' transition); n_regs + 2 registers per thread
+    const FastExtDev* ext;       // [E]
+    uint32_t enabled;
+};
+
 struct Launch {
     cudaStream_t stream;
     int sm_count;
@@ -66,9 +112,42 @@ void scan_u32_to_i64(const Launch&, const uint32_t* in, int64_t n, int64_t* out,
 void k2_dfa_scan(const Launch&, const DfaDev&, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
                  const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt);
 
+// K2 fast tier: lines [0, n_lines) must each be terminated by '\n' in the text (the caller excludes a final
+// unterminated line and runs it through k2_dfa_scan).
+void k2_dfa_direct(const Launch&, const DfaDirectDev&, const uint16_t* text, const int64_t* line_off, int64_t n_lines,
+                   const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt);
+
 // K4: capture automaton over the matched lines. Writes spans at span_off[i]; capture failure => ext_id = -2-e, spans -1.
 void k4_tdfa_capture(const Launch&, const CapDev&, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
                      const int64_t* span_off, int32_t* ext_id, int32_t* spans);
+
+// K4 fast tier: lines [0, n_lines) are '\n'-terminated in the text.
+void k4_tdfa_fast(const Launch&, const TdfaFastDev&, const CapDev&, const uint16_t* text, int64_t n_units,
+                  const int64_t* line_off, int64_t n_lines, const int64_t* span_off, int32_t* ext_id, int32_t* spans);
+
+// K0: fused persistent kernel (text form): newline discovery + DFA + look-back offsets + capture in one HBM pass.
+struct FusedParams {
+    const uint16_t* text;
+    int64_t n_units;
+    int64_t n_tiles;
+    DfaDirectDev dfa;
+    TdfaFastDev cap_fast;
+    CapDev cap;
+    const uint32_t* slots_per_ext;
+    uint32_t n_ext;
+    int32_t* ext_id;
+    int64_t* line_off;
+    int64_t* span_off;
+    int32_t* spans;
+    unsigned long long* hist;
+    int64_t cap_lines, cap_spans;        // capacity of the per-line arrays (entries, excluding the +1) / of spans
+    unsigned long long* tile_lines;      // [n_tiles] look-back state, zeroed by the caller: flag(2) | value(62)
+    unsigned long long* tile_spans;      // [n_tiles]
+    unsigned int* ticket;                // zeroed by the caller
+    int64_t* totals;                     // [0] n_lines, [1] n_spans, [2] flags: 1 = capacity overflow, 2 = fallback needed
+};
+bool k0_fused_supported(const FusedParams&);
+void k0_fused_extract(const Launch&, const FusedParams&);
 
 // K3: per-extraction histogram (E entries, then MISS, then capture failures).
 void k3_histogram(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist);
