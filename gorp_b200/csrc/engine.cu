@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../include/gorp_cuda.h"
-#include "host/model.hpp"
+#include "host/fused.hpp"
 #include "kernels/kernels.cuh"
 
 using namespace gorp;
@@ -104,11 +104,14 @@ struct DeviceCtx {
     DfaDirectDev dfa_direct{};
     TdfaFastDev cap_fast{};
     CapDev cap{};
+    OnePassDev onepass{};
+    uint32_t onepass_shrink = 0;  // too-dense retries remembered across calls
     uint32_t* d_slots = nullptr;
     uint32_t n_ext = 0;
     uint32_t max_slots = 0;
     bool force_general = false;  // GORP_FORCE_GENERAL=1: always use the general (masked) kernels
     bool force_unfused = false;  // GORP_FORCE_UNFUSED=1: never use the fused kernel (K1..K5 pipeline instead)
+    bool force_twopass = false;  // GORP_FORCE_TWOPASS=1: never use the one-pass automaton kernel
     double lines_per_unit = 1.0 / 24.0;  // running estimate that sizes the fused kernel's output arrays
     DevBuf tile_state;
     // per-call scratch, serialised by `mu`
@@ -162,7 +165,7 @@ struct gorp_engine {
 
 namespace {
 
-void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
+void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fused, bool match_only) {
     CK(cudaSetDevice(c.device));
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, c.device));
@@ -170,6 +173,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     if (const char* f = std::getenv("GORP_FORCE_GENERAL")) c.force_general = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_UNFUSED")) c.force_unfused = f[0] == '1';
+    if (const char* f = std::getenv("GORP_FORCE_TWOPASS")) c.force_twopass = f[0] == '1';
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
     // combined DFA
     const size_t S = m.dfa.n_states, C = m.dfa.n_classes;
@@ -332,6 +336,95 @@ void build_device(DeviceCtx& c, const DeviceModel& m, bool match_only) {
                 c.cap_fast.enabled = 1;
             }
         }
+        // one-pass tier: DFA x capture automata folded into one automaton (host/fused.hpp, kernels/onepass.cu)
+        {
+            const FusedAutomaton& A = fused;
+            if (A.available) {
+                const uint32_t Sx = A.n_states, J = A.n_jcls, n_out = static_cast<uint32_t>(A.outcomes.size());
+                // columns: [0,128) = ASCII units, then one column per joint class that a unit >= 0x80 (or a pair) can take
+                std::vector<int32_t> col_of_j(J, -1);
+                std::vector<uint32_t> j_of_col;
+                auto col = [&](uint32_t j) {
+                    if (col_of_j[j] < 0) {
+                        col_of_j[j] = static_cast<int32_t>(128 + j_of_col.size());
+                        j_of_col.push_back(j);
+                    }
+                    return static_cast<uint16_t>(col_of_j[j]);
+                };
+                std::vector<uint16_t> xcol(65536);
+                for (uint32_t u = 0; u < 128; ++u) xcol[u] = static_cast<uint16_t>(u);
+                for (uint32_t u = 128; u < 65536; ++u) xcol[u] = col(A.jcls[u]);
+                for (uint32_t u = 0xD800; u < 0xDC00; ++u) col(A.pair_of[A.jcls[u]]);
+                const uint32_t width = static_cast<uint32_t>((128 + j_of_col.size() + 3) & ~size_t(3));
+                std::vector<uint16_t> pair_col(width, 0);
+                for (uint32_t k = 0; k < width; ++k) pair_col[k] = static_cast<uint16_t>(k);
+                for (size_t k = 0; k < j_of_col.size(); ++k) pair_col[128 + k] = col(A.pair_of[j_of_col[k]]);
+                const uint32_t skip_base = Sx, fin_base = Sx + 7, n_rows = fin_base + n_out;
+                const uint32_t len_slot = A.n_op_slots + 1, n_slots = A.n_op_slots + 2;
+                const bool fits = static_cast<uint64_t>(n_rows) * width / 4 < (1u << 14) && n_slots < 250;
+                if (fits) {
+                    std::vector<uint32_t> rows(static_cast<size_t>(n_rows) * width, 0);
+                    for (uint32_t r = 0; r < n_rows; ++r)
+                        for (uint32_t k = 0; k < width; ++k) {
+                            uint32_t next = r, slot = 0;
+                            if (r < Sx) {
+                                if (k == 0x0A) {
+                                    next = fin_base + A.outcome_of[r];
+                                    slot = len_slot;
+                                } else if (k < 128 || k - 128 < j_of_col.size()) {
+                                    const uint32_t j = k < 128 ? A.jcls[k] : j_of_col[k - 128];
+                                    const uint32_t ent = A.trans[static_cast<size_t>(r) * J + j];
+                                    if ((ent & 0xFFFFu) == 0xFFFFu) next = fin_base;  // dead: MISS
+                                    else next = ent & 0xFFFFu, slot = ent >> 16;
+                                } else {
+                                    next = fin_base;  // padding column, never addressed
+                                }
+                            } else if (r < fin_base) {
+                                next = r == skip_base ? 0u : r - 1;  // SKIP chain
+                            }
+                            rows[static_cast<size_t>(r) * width + k] = (next << 16) | slot;
+                        }
+                    uint32_t max_slots = 0;
+                    for (uint32_t g : m.n_groups) max_slots = std::max(max_slots, 2 * g);
+                    max_slots = std::max(max_slots, 1u);
+                    std::vector<int32_t> out_ext(n_out);
+                    std::vector<uint32_t> out_res(static_cast<size_t>(n_out) * max_slots, 0), init;
+                    for (uint32_t o = 0; o < n_out; ++o) {
+                        out_ext[o] = A.outcomes[o].ext_code;
+                        if (out_ext[o] < 0) continue;
+                        for (uint32_t k = 0; k < 2 * m.n_groups[out_ext[o]]; ++k) {
+                            uint32_t packed = A.res[A.outcomes[o].res_off + k], fixed = 0, n = 0;
+                            for (uint32_t sh = 0; sh < 32 && (packed >> sh) & 0xFFu; sh += 8, ++n) {
+                                const uint32_t id = (packed >> sh) & 0xFFu;
+                                fixed |= (id == FusedAutomaton::kLenSlot ? len_slot : id) << sh;
+                            }
+                            if (n > 1)
+                                for (uint32_t sh = 0; sh < 8 * n; sh += 8) {
+                                    const uint32_t id = (fixed >> sh) & 0xFFu;
+                                    if (std::find(init.begin(), init.end(), id) == init.end()) init.push_back(id);
+                                }
+                            out_res[static_cast<size_t>(o) * max_slots + k] = fixed;
+                        }
+                    }
+                    c.onepass.rows = upload(rows, c.owned);
+                    c.onepass.n_rows = n_rows;
+                    c.onepass.width = width;
+                    c.onepass.n_states = Sx;
+                    c.onepass.skip_base = skip_base;
+                    c.onepass.fin_base = fin_base;
+                    c.onepass.n_outcomes = n_out;
+                    c.onepass.n_slots = n_slots;
+                    c.onepass.out_ext = upload(out_ext, c.owned);
+                    c.onepass.out_res = upload(out_res, c.owned);
+                    c.onepass.max_slots = max_slots;
+                    c.onepass.xcol = upload(xcol, c.owned);
+                    c.onepass.pair_col = upload(pair_col, c.owned);
+                    c.onepass.init_slots = upload(init, c.owned);
+                    c.onepass.n_init = static_cast<uint32_t>(init.size());
+                    c.onepass.enabled = 1;
+                }
+            }
+        }
         c.cap.cls = upload(m.symbols.classmap, c.owned);
         c.cap.n_classes = m.symbols.n_classes;
         c.cap.pair_hi_class = m.symbols.pair_hi_class;
@@ -375,6 +468,81 @@ struct Timer {
         cudaEventRecord(c.ev[c.n_ev], s);
     }
 };
+
+// Text form through the one-pass kernel. Returns false when the batch has to take another path.
+bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
+                 int64_t& n_lines, gorp_device_result* out) {
+    if (n_units <= 0 || c.force_general || c.force_unfused || c.force_twopass || !c.onepass.enabled) return false;
+    Launch L{stream, c.sm_count};
+    c.hist.reserve((c.n_ext + 2) * 8);
+    bool exact = false;
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        uint32_t threads = 0, tile = 0;
+        if (!k0_onepass_plan(c.onepass, c.lines_per_unit, c.onepass_shrink, &threads, &tile)) return false;
+        OnePassParams P{};
+        P.text = d_text;
+        P.n_units = n_units;
+        P.tile_units = tile;
+        P.per = tile / threads;
+        P.n_tiles = (n_units + tile - 1) / tile;
+        P.a = c.onepass;
+        P.slots_per_ext = c.d_slots;
+        P.n_ext = c.n_ext;
+        // look-back state: [status n_tiles][prefix 2*n_tiles][ticket (8 B)][totals 3 x int64]
+        const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 24 + 8 + 24;
+        c.tile_state.reserve(state_bytes);
+        int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
+        if (exact) cap_lines = n_lines + 16;
+        const int64_t cap_spans = cap_lines * std::max<uint32_t>(c.max_slots, 1);
+        c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
+        c.line_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
+        c.span_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
+        c.spans.reserve(static_cast<size_t>(cap_spans + 4) * 4);
+        P.ext_id = c.ext_id.as<int32_t>();
+        P.line_off = c.line_off.as<int64_t>();
+        P.span_off = c.span_off.as<int64_t>();
+        P.spans = c.spans.as<int32_t>();
+        P.hist = c.hist.as<unsigned long long>();
+        P.cap_lines = cap_lines;
+        P.cap_spans = cap_spans;
+        unsigned char* st = c.tile_state.as<unsigned char>();
+        P.tile_status = reinterpret_cast<unsigned long long*>(st);
+        P.tile_prefix = reinterpret_cast<long long*>(st + static_cast<size_t>(P.n_tiles) * 8);
+        P.ticket = reinterpret_cast<unsigned int*>(st + static_cast<size_t>(P.n_tiles) * 24);
+        P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 24 + 8);
+        CK(cudaMemsetAsync(st, 0, static_cast<size_t>(P.n_tiles) * 8, stream));
+        CK(cudaMemsetAsync(P.ticket, 0, 32, stream));
+        CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
+        k0_onepass_extract(L, P, threads);
+        tm.mark("k0_onepass_extract", 1);
+        CK(cudaGetLastError());
+        int64_t totals[3] = {0, 0, 0};
+        CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (totals[2] & 2) {  // a tile held more line starts than the CTA has threads: smaller tiles
+            ++c.onepass_shrink;
+            continue;
+        }
+        n_lines = totals[0];
+        c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
+        if (totals[2] & 1) {  // capacity overflow: rerun with the exact size
+            exact = true;
+            continue;
+        }
+        CK(cudaMemcpyAsync(d_scalars, P.totals, 8, cudaMemcpyDeviceToDevice, stream));
+        if (out) {
+            out->n_lines = n_lines;
+            out->d_ext_id = P.ext_id;
+            out->d_line_off = P.line_off;
+            out->d_span_off = P.span_off;
+            out->d_spans = P.spans;
+            out->d_histogram = c.hist.as<int64_t>();
+            out->d_n_lines = d_scalars;
+        }
+        return true;
+    }
+    return false;
+}
 
 // Text form through the fused kernel. Returns false when the batch has to go through the unfused pipeline.
 bool run_fused(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
@@ -453,6 +621,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     const int64_t* d_line_off;
     int sep;
     bool ends_with_nl = true;
+    if (!d_off && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off && run_fused(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off) {
         sep = 1;
@@ -795,11 +964,13 @@ int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_d
         std::memcpy(&flags, static_cast<const uint8_t*>(blob) + 8 + 16, 4);
         eng->match_only = (flags & 1u) != 0;
         DeviceModel model;
+        FusedAutomaton fused;
         if (eng->match_only) {
             model.dfa = compact_tables(eng->def.dfa);
             model.n_groups.assign(eng->def.extractions.size(), 0);
         } else {
             model = build_device_model(eng->def);
+            fused = build_fused(model);
         }
         int avail = 0;
         if (cudaGetDeviceCount(&avail) != cudaSuccess || avail == 0) {
@@ -813,7 +984,7 @@ int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_d
             if (d < 0 || d >= avail) return fail(GORP_E_ARG, strfmt("device %d out of range (have %d)", d, avail));
             auto ctx = std::make_unique<DeviceCtx>();
             ctx->device = d;
-            build_device(*ctx, model, eng->match_only);
+            build_device(*ctx, model, fused, eng->match_only);
             eng->devs.push_back(std::move(ctx));
         }
         *out = eng.release();

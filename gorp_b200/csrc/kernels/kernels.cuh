@@ -149,6 +149,49 @@ struct FusedParams {
 bool k0_fused_supported(const FusedParams&);
 void k0_fused_extract(const Launch&, const FusedParams&);
 
+// K0': one-pass persistent kernel (text form) over the folded automaton of host/fused.hpp — see kernels/onepass.cu.
+constexpr uint32_t kOnePassOverhang = 1024;  // units staged beyond the tile (lines that cross the tile end)
+constexpr int kOnePassHistBins = 256;
+struct OnePassDev {
+    const uint32_t* rows;        // [n_rows * width] raw entries: (next row << 16) | slot id
+                                 //   rows [0, n_states) automaton states, [skip_base, +7) SKIP_1..7 (units that precede
+                                 //   the line in its first 16-byte chunk), [fin_base, +n_outcomes) absorbing outcome rows
+                                 //   columns [0,128) ASCII units directly, [128, width) classes of the other units
+    uint32_t n_rows, width;      // width is a multiple of 4
+    uint32_t n_states, skip_base, fin_base, n_outcomes;
+    uint32_t n_slots;            // slot 0 = dummy (transitions without commands), 1..n_op op slots, n_op+1 = LEN
+    const int32_t* out_ext;      // [n_outcomes] -1 MISS | e | -2-e
+    const uint32_t* out_res;     // [n_outcomes * max_slots] per group boundary: up to 4 slot ids, one per byte, 0 ends
+    uint32_t max_slots;          // 2 * groups of the widest extraction
+    const uint16_t* xcol;        // [65536] unit -> column
+    const uint16_t* pair_col;    // [width] column of a high surrogate that is followed by a low surrogate
+    const uint32_t* init_slots;  // [n_init] slots reset to -1 per line (those read through a multi-writer maximum)
+    uint32_t n_init;
+    uint32_t enabled;
+};
+struct OnePassParams {
+    const uint16_t* text;
+    int64_t n_units, n_tiles;
+    uint32_t tile_units, per;            // tile_units = blockDim * per
+    OnePassDev a;
+    const uint32_t* slots_per_ext;
+    uint32_t n_ext;
+    int32_t* ext_id;
+    int64_t* line_off;
+    int64_t* span_off;
+    int32_t* spans;
+    unsigned long long* hist;
+    int64_t cap_lines, cap_spans;
+    unsigned long long* tile_status;     // [n_tiles] zeroed by the caller: flag(2) | spans(32) << 20 | lines(20)
+    long long* tile_prefix;              // [2 * n_tiles] inclusive (lines, spans) prefix, valid once the flag says so
+    unsigned int* ticket;                // zeroed by the caller
+    int64_t* totals;                     // [0] n_lines, [1] n_spans, [2] flags: 1 = capacity overflow, 2 = tile too dense
+};
+size_t onepass_smem_bytes(const OnePassDev&, uint32_t threads, uint32_t tile_units);
+// picks CTA size and tile size for the expected line density; `shrink` = number of too-dense retries so far
+bool k0_onepass_plan(const OnePassDev&, double lines_per_unit, uint32_t shrink, uint32_t* threads, uint32_t* tile_units);
+void k0_onepass_extract(const Launch&, const OnePassParams&, uint32_t threads);
+
 // K3: per-extraction histogram (E entries, then MISS, then capture failures).
 void k3_histogram(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist);
 

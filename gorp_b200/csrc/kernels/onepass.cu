@@ -1,0 +1,447 @@
+// K0' — one-pass persistent extraction kernel (sm_100a): every UTF-16 unit is looked at ONCE.
+//
+// The combined DFA (PolyMatcher.match) and the capture automaton of the winning extraction (Matcher.matches() +
+// group(i)) are folded on the host into one automaton (host/fused.hpp); this kernel runs it:
+//
+//   per unit :  ent = LDS[row(ent) + 4*unit]              one shared-memory lookup, the only dependent chain
+//               STS slot(ent)[thread] = position          "last position at which command list `slot` fired"
+//   per line :  the '\n' column leads to the absorbing row of the line's OUTCOME (MISS | MATCH e | CAPTURE_FAIL e);
+//               a group boundary = max over the (<= 4) op slots that write its register.
+//
+// Work decomposition: persistent CTAs take tiles of `tile_units` units by in-order ticket. A tile is pulled into
+// shared memory by ONE TMA bulk copy (cp.async.bulk + mbarrier complete_tx), double-buffered: the copy of the next
+// tile runs while the current one is processed. A CTA owns the lines that START in its tile (after a '\n' of the
+// tile; tile 0 also owns offset 0): phase A finds them (128-bit LDS, __vcmpeq2, block scan), phase B walks one line
+// per thread, phase C scans the span counts, phase D publishes/looks back the (lines, spans) prefix across tiles
+// (decoupled look-back, one warp, 32 predecessors per probe), phase E writes the result rows. The host sizes the
+// tile so that it holds slightly fewer lines than the CTA has threads; a tile with more line starts than threads
+// raises FLAG_FALLBACK and the host reruns the batch with a smaller tile.
+#include "device_common.cuh"
+
+namespace gorp {
+
+namespace {
+
+using namespace dev;
+
+constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62;
+constexpr uint32_t kOver = kOnePassOverhang;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// 8 units at text position `pos` straight from global memory; units at or beyond n_units read as '\n'
+__device__ __noinline__ uint4 load_chunk_global(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units) {
+    if (pos + 8 <= n_units) return __ldg(reinterpret_cast<const uint4*>(text + pos));
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t p0 = pos + 2 * j, p1 = p0 + 1;
+        const uint32_t lo = p0 < n_units ? __ldg(text + p0) : 0x0Au;
+        const uint32_t hi = p1 < n_units ? __ldg(text + p1) : 0x0Au;
+        w[j] = lo | (hi << 16);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Entry layout in shared memory (rewritten from the raw table when the CTA starts):
+//   bits 31..18  next row, in units of 16 bytes from the start of the row area
+//   bits 17..14  zero
+//   bits 13..0   op slot, in units of 4 bytes from the start of the slot area (slot id * blockDim)
+// so that  next lookup address = (ent >> 14) + (rows_abs + 4*unit)   is a single LEA.HI on the dependent chain.
+template <int kByte>
+__device__ __forceinline__ void one_step(uint32_t& ent, uint32_t w, uint32_t rows_abs, uint32_t slot_abs, uint32_t pos) {
+    uint32_t b, a;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(b), "r"(rows_abs));
+    ent = lds32((ent >> 14) + a);
+    uint32_t m, sa;
+    asm("and.b32 %0, %1, 0x3FFF;" : "=r"(m) : "r"(ent));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(sa) : "r"(m), "r"(slot_abs));
+    sts32(sa, pos);
+}
+
+// A chunk that holds a unit >= 0x80: unit by unit through the column map (global, L1/L2 resident). A high surrogate
+// followed by a low surrogate takes the PAIR column (java.util.regex consumes the pair as one character).
+__device__ __noinline__ uint32_t slow_chunk(const OnePassDev& a, uint32_t ent, uint4 v, const uint16_t* __restrict__ text,
+                                            int64_t q, int64_t n_units, uint32_t rows_abs, uint32_t slot_abs, uint32_t pos,
+                                            uint32_t fin_ent) {
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        if (ent >= fin_ent) break;
+        const uint32_t u = unit_at(v, k);
+        uint32_t col = u;
+        if (u >= 0x80u) {
+            col = __ldg(a.xcol + u);
+            if ((u & 0xFC00u) == 0xD800u) {
+                const int64_t p1 = q + k + 1;
+                const uint32_t nx = k < 7 ? unit_at(v, k + 1) : (p1 < n_units ? __ldg(text + p1) : 0x0Au);
+                if ((nx & 0xFC00u) == 0xDC00u) col = __ldg(a.pair_col + col);
+            }
+        }
+        ent = lds32((ent >> 14) + rows_abs + col * 4);
+        sts32(slot_abs + ((ent & 0x3FFFu) << 2), pos + k);
+    }
+    return ent;
+}
+
+__device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // s_warp reuse
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+        const uint32_t x = s_warp[w];
+        if (w < warp) base += x;
+        tot += x;
+    }
+    *total = tot;
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t kT = blockDim.x;
+    const OnePassDev& A = P.a;
+    const uint32_t T = P.tile_units, kBuf = T + kOver;
+    // ---- carve shared memory (every area 16-byte aligned)
+    uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* s_res = s_rows + A.n_rows * A.width;
+    int32_t* s_oext = reinterpret_cast<int32_t*>(s_res + ((A.n_outcomes * A.max_slots + 3) & ~3u));
+    uint32_t* s_slots = reinterpret_cast<uint32_t*>(s_oext + ((A.n_outcomes + 3) & ~3u));
+    uint16_t* s_text0 = reinterpret_cast<uint16_t*>(s_slots + A.n_slots * kT);
+    uint16_t* s_text1 = s_text0 + kBuf + 8;
+    uint16_t* s_start = s_text1 + kBuf + 8;
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ uint32_t s_warp[16];
+    __shared__ uint32_t s_hist[kOnePassHistBins];
+    __shared__ long long s_next_tile, s_line_base, s_span_base;
+    __shared__ int s_skip_writes;
+
+    const uint32_t rows_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_rows));
+    uint32_t slot_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_slots)) + threadIdx.x * 4;
+    asm volatile("mov.u32 %0, %0;" : "+r"(slot_abs));  // one opaque register: keeps the per-step store address at LOP3 + LEA
+    const uint32_t text_abs0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_text0));
+    const uint32_t text_abs1 = static_cast<uint32_t>(__cvta_generic_to_shared(s_text1));
+    const uint32_t bar0 = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar[0]));
+    const uint32_t slot_stride = kT * 4;
+
+    const uint32_t row_q = A.width / 4;  // row size in 16-byte units
+    for (uint32_t i = threadIdx.x; i < A.n_rows * A.width; i += kT) {
+        const uint32_t raw = __ldg(A.rows + i);
+        s_rows[i] = (((raw >> 16) * row_q) << 18) | ((raw & 0xFFFFu) * kT);
+    }
+    for (uint32_t i = threadIdx.x; i < A.n_outcomes * A.max_slots; i += kT) s_res[i] = __ldg(A.out_res + i);
+    for (uint32_t i = threadIdx.x; i < A.n_outcomes; i += kT) s_oext[i] = __ldg(A.out_ext + i);
+    const uint32_t fin_ent = (A.fin_base * row_q) << 18;
+    const uint32_t inv_row_q = 65536u / row_q + 1u;
+    const uint32_t n_bins = P.n_ext + 2;
+    const bool smem_hist = n_bins <= kOnePassHistBins;
+
+    auto issue_load = [&](int64_t tile, uint32_t b) {  // thread 0 only
+        const int64_t t0 = tile * T;
+        const int64_t avail = P.n_units - t0 < kBuf ? P.n_units - t0 : kBuf;
+        const uint32_t bulk_units = static_cast<uint32_t>(avail) & ~7u;
+        if (bulk_units) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar0 + 8 * b, bulk_units * 2);
+            tma_bulk_g2s(b ? text_abs1 : text_abs0, P.text + t0, bulk_units * 2, bar0 + 8 * b);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const long long first = atomicAdd(P.ticket, 1u);
+        s_next_tile = first;
+        if (first < P.n_tiles) issue_load(first, 0);
+    }
+    __syncthreads();
+    int64_t tile = s_next_tile;
+    uint32_t buf = 0, phase = 0;  // phase bit b = parity to wait for on barrier b
+
+    while (tile < P.n_tiles) {
+        __syncthreads();  // everyone has read s_next_tile; the other buffer is no longer being read
+        if (threadIdx.x == 0) {
+            const long long nx = atomicAdd(P.ticket, 1u);
+            s_next_tile = nx;
+            if (nx < P.n_tiles) issue_load(nx, buf ^ 1);
+        }
+        const int64_t t0 = tile * T;
+        const uint32_t text_abs = buf ? text_abs1 : text_abs0;
+        uint16_t* s_text = buf ? s_text1 : s_text0;
+        const int64_t avail = P.n_units - t0 < kBuf ? P.n_units - t0 : kBuf;  // > 0
+        const uint32_t bulk_units = static_cast<uint32_t>(avail) & ~7u;
+        for (uint32_t i = bulk_units + threadIdx.x; i < kBuf + 8; i += kT)
+            s_text[i] = i < avail ? __ldg(P.text + t0 + i) : static_cast<uint16_t>(0x0A);
+        if (smem_hist)
+            for (uint32_t i = threadIdx.x; i < n_bins; i += kT) s_hist[i] = 0;
+        if (bulk_units) {
+            mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+        }
+        __syncthreads();
+
+        // ---- A: line starts owned by this tile = (position of a '\n' in [t0, t0+T)) + 1, if < n_units
+        const uint32_t per = P.per;  // units per thread, multiple of 8, <= 64
+        unsigned long long nl_mask = 0;
+        {
+            const uint32_t u0 = threadIdx.x * per;
+            for (uint32_t j = 0; j < per / 8; ++j) {
+                const uint4 v = lds128(text_abs + (u0 + j * 8) * 2);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                uint32_t m8 = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t m = __vcmpeq2(w[k], 0x000A000Au);
+                    m8 |= ((m & 1u) | ((m >> 15) & 2u)) << (k * 2);
+                }
+                nl_mask |= static_cast<unsigned long long>(m8) << (j * 8);
+            }
+            // a '\n' at position p starts a line only if p + 1 < n_units (the padding beyond the text is '\n' too)
+            const int64_t room = P.n_units - 1 - (t0 + u0);
+            if (room < static_cast<int64_t>(per)) nl_mask = room <= 0 ? 0ull : (nl_mask & ((1ull << room) - 1ull));
+        }
+        const uint32_t extra = tile == 0 ? 1u : 0u;  // the line at offset 0
+        uint32_t n_t;
+        uint32_t my = block_scan(static_cast<uint32_t>(__popcll(nl_mask)), s_warp, &n_t) + extra;
+        n_t += extra;
+        const bool too_dense = n_t > kT;
+        if (!too_dense) {
+            if (extra && threadIdx.x == 0) s_start[0] = 0;
+            const uint32_t u0 = threadIdx.x * per;
+            while (nl_mask) {
+                const int k = __ffsll(static_cast<long long>(nl_mask)) - 1;
+                nl_mask &= nl_mask - 1;
+                s_start[my++] = static_cast<uint16_t>(u0 + k + 1);  // 1 .. T
+            }
+        }
+        __syncthreads();
+
+        // ---- B: one line per thread through the one-pass automaton
+        const bool have_line = !too_dense && threadIdx.x < n_t;
+        uint32_t outcome = 0;
+        if (have_line) {
+            for (uint32_t k = 0; k < A.n_init; ++k) sts32(slot_abs + __ldg(A.init_slots + k) * slot_stride, 0xFFFFFFFFu);
+            const uint32_t rel = s_start[threadIdx.x];
+            uint32_t q = rel & ~7u;
+            const uint32_t lo = rel & 7u;
+            uint32_t ent = lo ? ((A.skip_base + lo - 1) * row_q) << 18 : 0u;
+            uint32_t pos = q - rel;  // wraps while skipping: only ever stored to the dummy slot
+            do {
+                const uint4 v = q < kBuf ? lds128(text_abs + q * 2) : load_chunk_global(P.text, t0 + q, P.n_units);
+                if (((v.x | v.y | v.z | v.w) & 0xFF80FF80u) == 0u) {
+                    one_step<0>(ent, v.x, rows_abs, slot_abs, pos);
+                    one_step<2>(ent, v.x, rows_abs, slot_abs, pos + 1);
+                    one_step<0>(ent, v.y, rows_abs, slot_abs, pos + 2);
+                    one_step<2>(ent, v.y, rows_abs, slot_abs, pos + 3);
+                    one_step<0>(ent, v.z, rows_abs, slot_abs, pos + 4);
+                    one_step<2>(ent, v.z, rows_abs, slot_abs, pos + 5);
+                    one_step<0>(ent, v.w, rows_abs, slot_abs, pos + 6);
+                    one_step<2>(ent, v.w, rows_abs, slot_abs, pos + 7);
+                } else {
+                    ent = slow_chunk(A, ent, v, P.text, t0 + q, P.n_units, rows_abs, slot_abs, pos, fin_ent);
+                }
+                q += 8;
+                pos += 8;
+            } while (ent < fin_ent);
+            outcome = (((ent >> 18) - A.fin_base * row_q) * inv_row_q) >> 16;  // exact: a multiple of row_q below 2^14
+        }
+
+        // ---- C: span counts (2*groups for MATCH and CAPTURE_FAIL lines) and their exclusive scan within the tile
+        int32_t ext = -1;
+        uint32_t cnt = 0;
+        if (have_line) {
+            ext = s_oext[outcome];
+            if (ext != -1) cnt = __ldg(P.slots_per_ext + (ext >= 0 ? ext : -2 - ext));
+        }
+        uint32_t span_t;
+        const uint32_t spoff = block_scan(cnt, s_warp, &span_t);
+
+        // ---- D: decoupled look-back over tiles for (lines, spans): warp 0, 32 predecessors per probe
+        if (threadIdx.x < 32) {
+            const uint32_t lane = threadIdx.x;
+            const unsigned long long my_lines = too_dense ? 0ull : n_t, my_spans = span_t;
+            unsigned long long pre_l = 0, pre_s = 0;
+            if (tile > 0) {
+                if (lane == 0) st_release(P.tile_status + tile, kStAgg | my_lines | (my_spans << 20));
+                for (int64_t j = tile - 1;; j -= 32) {
+                    const int64_t idx = j - lane;
+                    unsigned long long v = kStPre;  // before tile 0: an empty inclusive prefix
+                    if (idx >= 0) {
+                        v = ld_acquire(P.tile_status + idx);
+                        while ((v >> 62) == 0) v = ld_acquire(P.tile_status + idx);
+                    }
+                    const uint32_t pmask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                    const uint32_t first = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1u : 32u;
+                    unsigned long long l = 0, s = 0;
+                    if (lane < first) {
+                        l = v & 0xFFFFFull;
+                        s = (v >> 20) & 0xFFFFFFFFull;
+                    } else if (lane == first && idx >= 0) {
+                        l = static_cast<unsigned long long>(P.tile_prefix[2 * idx]);
+                        s = static_cast<unsigned long long>(P.tile_prefix[2 * idx + 1]);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        l += __shfl_xor_sync(0xffffffffu, l, o);
+                        s += __shfl_xor_sync(0xffffffffu, s, o);
+                    }
+                    pre_l += l;
+                    pre_s += s;
+                    if (pmask) break;
+                }
+            }
+            if (lane == 0) {
+                P.tile_prefix[2 * tile] = static_cast<long long>(pre_l + my_lines);
+                P.tile_prefix[2 * tile + 1] = static_cast<long long>(pre_s + my_spans);
+                st_release(P.tile_status + tile, kStPre);
+                s_line_base = static_cast<long long>(pre_l);
+                s_span_base = static_cast<long long>(pre_s);
+                int skip = too_dense ? 1 : 0;
+                if (too_dense) atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 2ull);
+                if (static_cast<long long>(pre_l + my_lines) > P.cap_lines || static_cast<long long>(pre_s + my_spans) > P.cap_spans) {
+                    atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 1ull);
+                    skip = 1;
+                }
+                s_skip_writes = skip;
+                if (tile == P.n_tiles - 1) {
+                    P.totals[0] = static_cast<int64_t>(pre_l + my_lines);
+                    P.totals[1] = static_cast<int64_t>(pre_s + my_spans);
+                }
+            }
+        }
+        __syncthreads();
+        const int64_t line_base = s_line_base, span_base = s_span_base;
+        const bool skip_writes = s_skip_writes != 0;
+
+        // ---- E: result rows, group boundaries, histogram
+        if (!skip_writes) {
+            if (have_line) {
+                const int64_t row = line_base + threadIdx.x;
+                P.ext_id[row] = ext;
+                P.line_off[row] = t0 + s_start[threadIdx.x];
+                P.span_off[row] = span_base + spoff;
+                if (cnt) {
+                    int32_t* out = P.spans + span_base + spoff;
+                    if (ext >= 0) {
+                        const uint32_t* res = s_res + outcome * A.max_slots;
+                        for (uint32_t k = 0; k < cnt; ++k) {
+                            int32_t val = -1;
+                            for (uint32_t packed = res[k]; packed; packed >>= 8)
+                                val = max(val, static_cast<int32_t>(lds32(slot_abs + (packed & 0xFFu) * slot_stride)));
+                            out[k] = val;
+                        }
+                    } else {
+                        for (uint32_t k = 0; k < cnt; ++k) out[k] = -1;
+                    }
+                }
+                const uint32_t bin = ext >= 0 ? static_cast<uint32_t>(ext) : (ext == -1 ? P.n_ext : P.n_ext + 1);
+                if (smem_hist) atomicAdd(&s_hist[bin], 1u);
+                else atomicAdd(P.hist + bin, 1ull);
+            }
+            if (tile == P.n_tiles - 1 && threadIdx.x == 0) {
+                const int64_t nl = line_base + n_t;
+                // line i spans [line_off[i], line_off[i+1] - 1): a text that does not end in '\n' gets n_units + 1
+                P.line_off[nl] = P.n_units + (P.text[P.n_units - 1] == 0x0A ? 0 : 1);
+                P.span_off[nl] = span_base + span_t;
+            }
+            if (smem_hist) {
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < n_bins; i += kT)
+                    if (s_hist[i]) atomicAdd(P.hist + i, static_cast<unsigned long long>(s_hist[i]));
+            }
+        }
+        tile = s_next_tile;
+        buf ^= 1;
+    }
+}
+
+}  // namespace
+
+size_t onepass_smem_bytes(const OnePassDev& a, uint32_t threads, uint32_t tile_units) {
+    size_t b = static_cast<size_t>(a.n_rows) * a.width * 4;
+    b += static_cast<size_t>((a.n_outcomes * a.max_slots + 3) & ~3u) * 4;
+    b += static_cast<size_t>((a.n_outcomes + 3) & ~3u) * 4;
+    b += static_cast<size_t>(a.n_slots) * threads * 4;
+    b += 2 * static_cast<size_t>(tile_units + kOnePassOverhang + 8) * 2;
+    b += static_cast<size_t>(threads) * (2 + 2 + 4);
+    return b + 128;
+}
+
+bool k0_onepass_plan(const OnePassDev& a, double lines_per_unit, uint32_t shrink, uint32_t* threads, uint32_t* tile_units) {
+    if (!a.enabled) return false;
+    // the tile should hold ~0.85 * threads line starts; per = tile/threads is 8 * odd (conflict-free 128-bit phase-A
+    // loads) and <= 64 (one 64-bit newline mask per thread)
+    const uint32_t kT = 256;
+    if (static_cast<uint64_t>(a.n_slots) * kT > 0x3FFFu) return false;
+    double want = 0.85 * kT / (lines_per_unit > 1e-9 ? lines_per_unit : 1e-9) / kT;  // units per thread
+    uint32_t per = 56;
+    for (uint32_t cand : {56u, 40u, 24u, 8u})
+        if (want < cand + 8) per = cand;
+    if (want >= 56) per = 56;
+    for (uint32_t s = 0; s < shrink; ++s) per = per > 40 ? 40 : per > 24 ? 24 : 8;
+    for (;;) {
+        if (onepass_smem_bytes(a, kT, kT * per) <= 113 * 1024) break;  // two CTAs per SM
+        if (per == 8) {
+            if (onepass_smem_bytes(a, kT, kT * per) <= 226 * 1024) break;
+            return false;
+        }
+        per = per > 40 ? 40 : per > 24 ? 24 : 8;
+    }
+    *threads = kT;
+    *tile_units = kT * per;
+    return true;
+}
+
+void k0_onepass_extract(const Launch& L, const OnePassParams& P, uint32_t threads) {
+    const size_t smem = onepass_smem_bytes(P.a, threads, P.tile_units);
+    cudaFuncSetAttribute(onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onepass_kernel, static_cast<int>(threads), smem);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
+    int g = static_cast<int>(P.n_tiles < cap ? P.n_tiles : cap);
+    if (g < 1) g = 1;
+    onepass_kernel<<<g, threads, smem, L.stream>>>(P);
+}
+
+}  // namespace gorp

@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "../../gorp_b200/csrc/host/model.hpp"
+#include "../../gorp_b200/csrc/host/fused.hpp"
 
 using namespace gorp;
 
@@ -64,6 +64,67 @@ extern "C" int ht_run(const void* blob, size_t len, const uint16_t* text, const 
             for (uint32_t k = 0; k < t.n_slots && static_cast<int>(k) < stride; ++k) {
                 uint8_t f = t.fin[static_cast<size_t>(s) * t.n_slots + k];
                 spans[l * stride + k] = f == 0xFF ? -1 : (f == 0xFE ? static_cast<int32_t>(L) : regs[f]);
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
+
+// The one-pass automaton (host/fused.hpp) interpreted the way kernels/onepass.cu runs it: one table lookup per unit,
+// "last position" per op slot, group boundaries resolved from the outcome at end of line.
+// stats: [0] available, [1] states, [2] joint classes, [3] op slots, [4] outcomes. Returns 1 when not available.
+extern "C" int ht_run_fused(const void* blob, size_t len, const uint16_t* text, const int64_t* starts, const int64_t* ends,
+                            int64_t n, int32_t* ext, int32_t* spans, int stride, uint32_t* stats, char* err, int errlen) {
+    try {
+        CompiledDefinition def = parse_blob(blob, len);
+        DeviceModel m = build_device_model(def);
+        FusedAutomaton A = build_fused(m);
+        if (stats) {
+            stats[0] = A.available;
+            stats[1] = A.n_states;
+            stats[2] = A.n_jcls;
+            stats[3] = A.n_op_slots;
+            stats[4] = static_cast<uint32_t>(A.outcomes.size());
+        }
+        if (!A.available) {
+            std::snprintf(err, errlen, "%s", A.why_not.c_str());
+            return 1;
+        }
+        const uint32_t J = A.n_jcls;
+        std::vector<int32_t> last(A.n_op_slots + 1);
+        for (int64_t l = 0; l < n; ++l) {
+            const uint16_t* u = text + starts[l];
+            const int64_t L = ends[l] - starts[l];
+            for (int k = 0; k < stride; ++k) spans[l * stride + k] = -1;
+            std::fill(last.begin(), last.end(), -1);
+            uint32_t st = 0;
+            bool dead = false;
+            for (int64_t i = 0; i < L; ++i) {
+                uint32_t j = A.jcls[u[i]];
+                if ((u[i] & 0xFC00) == 0xD800 && i + 1 < L && (u[i + 1] & 0xFC00) == 0xDC00) j = A.pair_of[j];
+                const uint32_t ent = A.trans[static_cast<size_t>(st) * J + j];
+                if ((ent & 0xFFFF) == 0xFFFF) {
+                    dead = true;
+                    break;
+                }
+                if (ent >> 16) last[ent >> 16] = static_cast<int32_t>(i);
+                st = ent & 0xFFFF;
+            }
+            const FusedAutomaton::Outcome& o = A.outcomes[dead ? 0 : A.outcome_of[st]];
+            ext[l] = o.ext_code;
+            if (o.ext_code < 0) continue;
+            const uint32_t ns = 2 * m.n_groups[o.ext_code];
+            for (uint32_t k = 0; k < ns && static_cast<int>(k) < stride; ++k) {
+                uint32_t packed = A.res[o.res_off + k];
+                int32_t v = -1;
+                for (; packed; packed >>= 8) {
+                    const uint32_t id = packed & 0xFF;
+                    v = std::max(v, id == FusedAutomaton::kLenSlot ? static_cast<int32_t>(L) : last[id]);
+                }
+                spans[l * stride + k] = v;
             }
         }
         return 0;

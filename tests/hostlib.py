@@ -25,7 +25,8 @@ def load():
     return _lib
 
 
-def run(blob_bytes: bytes, text: np.ndarray, starts: np.ndarray, ends: np.ndarray, stride: int):
+def run(blob_bytes: bytes, text: np.ndarray, starts: np.ndarray, ends: np.ndarray, stride: int, fused: bool = False):
+    """fused=True interprets the one-pass automaton (host/fused.hpp); returns None for ext when it is not available."""
     lib = load()
     text = np.ascontiguousarray(text, dtype=np.uint16)
     starts = np.ascontiguousarray(starts, dtype=np.int64)
@@ -36,9 +37,12 @@ def run(blob_bytes: bytes, text: np.ndarray, starts: np.ndarray, ends: np.ndarra
     stats = np.zeros(8, dtype=np.uint32)
     err = C.create_string_buffer(1024)
     P = C.c_void_p
-    rc = lib.ht_run(blob_bytes, C.c_size_t(len(blob_bytes)), P(text.ctypes.data), P(starts.ctypes.data), P(ends.ctypes.data),
+    fn = lib.ht_run_fused if fused else lib.ht_run
+    rc = fn(blob_bytes, C.c_size_t(len(blob_bytes)), P(text.ctypes.data), P(starts.ctypes.data), P(ends.ctypes.data),
                     C.c_int64(n), P(ext.ctypes.data), P(spans.ctypes.data), C.c_int(max(stride, 1)), P(stats.ctypes.data), err,
                     C.c_int(1024))
+    if rc == 1 and fused:
+        return None, err.value.decode(), stats
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return ext, spans[:, :stride], stats

@@ -185,3 +185,39 @@ def test_full_size_properties():
     assert (b.ext_id.reshape(reps, -1) == b1.ext_id[None, :]).all()
     assert (b.spans.reshape(reps, -1) == b1.spans[None, :]).all()
     assert (np.diff(b.line_off) > 0).all() and (np.diff(b.span_off) >= 0).all()
+
+
+TIERS = {"onepass": {}, "twopass_fused": {"GORP_FORCE_TWOPASS": "1"}, "unfused_fast": {"GORP_FORCE_UNFUSED": "1"},
+         "general": {"GORP_FORCE_GENERAL": "1"}}
+
+
+@pytest.mark.parametrize("tier", list(TIERS))
+def test_every_kernel_tier_text_form(tier, monkeypatch):
+    """The text form takes the fastest tier the definition allows; force each tier in turn (the engine reads the
+    GORP_FORCE_* switches when it is created) and hold all of them to the same oracle."""
+    for k in ("GORP_FORCE_TWOPASS", "GORP_FORCE_UNFUSED", "GORP_FORCE_GENERAL"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in TIERS[tier].items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(21)
+    for name, n in (("simple", 60000), ("readme", 120000)):
+        d, gen = corpus.CONFIGS[name]
+        check_against_oracle(d, text=gen(n, seed=77))
+    # dense, ragged and non-ASCII text: many short/empty lines (tiles with more line starts than threads), long lines
+    specials = ["\\x0b", "\\x08", "", " ", "\\r", "\\ud83d", "\\ude00", "\\U0001F600", "\\u00e9", "\\u4e2d", "\\t"]
+    specials = [s.encode("ascii").decode("unicode_escape") for s in specials]
+    lines = []
+    for k in range(30000):
+        r = rng.random()
+        if r < 0.3:
+            lines.append("")
+        elif r < 0.4:
+            lines.append("x" * int(rng.integers(1, 4)))
+        else:
+            path = list("/" + "".join(rng.choice(list("abcxyz012/"), size=int(rng.choice([3, 10, 30, 200, 3000], p=[.3, .3, .3, .09, .01])))))
+            for _ in range(rng.integers(0, 2)):
+                path.insert(rng.integers(0, len(path) + 1), specials[rng.integers(0, len(specials))])
+            lines.append("[%d]: %s %dms %s" % (rng.integers(1, 10**9), rng.choice(["GET", "PUT", "HEAD"]), rng.integers(1, 999), "".join(path)))
+    text = np.concatenate([np.concatenate((np.asarray(jdkre.to_units(s), dtype=np.uint16), [10])) for s in lines]).astype(np.uint16)
+    check_against_oracle(V.README_DEF, text=text)
+    check_against_oracle(V.README_DEF, text=text[:-1])  # last line not terminated

@@ -29,12 +29,15 @@ def pack(lines):
     return text, starts, ends
 
 
-def compare_host_tables(definition, lines):
+def compare_host_tables(definition, lines, fused=False, need_fused=True):
     g = DefinitionReader.reader(definition).read()
     o = gorp_oracle.Gorp(definition)
     text, starts, ends = pack(lines)
     G = max(len(x.extractor_names) for x in o.extractions)
-    ext, spans, stats = hostlib.run(g.blob().bytes(), text, starts, ends, 2 * G)
+    ext, spans, stats = hostlib.run(g.blob().bytes(), text, starts, ends, 2 * G, fused=fused)
+    if ext is None:  # the one-pass automaton was refused for this definition (the two-pass tables still serve it)
+        assert not need_fused, spans
+        return stats
     oe, osp = o.extract_batch(text, (starts, ends), threads=1)
     bad = [i for i in range(len(lines)) if ext[i] != oe[i] or (spans[i] != osp[i]).any()]
     assert not bad, [(lines[i], int(ext[i]), int(oe[i]), spans[i].tolist(), osp[i].tolist()) for i in bad[:5]]
@@ -44,6 +47,13 @@ def compare_host_tables(definition, lines):
 @pytest.mark.parametrize("case", ALL_DEFS)
 def test_tables_reproduce_oracle(case):
     compare_host_tables(case[0], [c[0] for c in case[1]] + TRICKY_LINES)
+
+
+@pytest.mark.parametrize("case", ALL_DEFS)
+def test_one_pass_automaton_reproduces_oracle(case):
+    """host/fused.hpp: DFA x capture automata folded into one automaton, interpreted as kernels/onepass.cu runs it."""
+    stats = compare_host_tables(case[0], [c[0] for c in case[1]] + TRICKY_LINES, fused=True)
+    assert stats[0] == 1
 
 
 @pytest.mark.parametrize("case", ALL_DEFS)
@@ -128,6 +138,7 @@ def test_fuzz_small_alphabet(definition):
     lines += ["".join(rng.choice(list(alpha), size=rng.integers(6, 24))) for _ in range(3000)]
     stats = compare_host_tables(definition, lines)
     assert stats[3] < 5000
+    compare_host_tables(definition, lines, fused=True, need_fused=False)
 
 
 def test_product_dfa_language_vs_component_dfas():
