@@ -115,17 +115,28 @@ __device__ __noinline__ uint32_t slow_chunk(const OnePassDev& a, uint32_t ent, u
     return ent;
 }
 
-__device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// ---- named barriers: the CTA is kT worker threads (8 warps) + one IO warp
+constexpr uint32_t kIoThreads = 32;
+constexpr uint32_t kBarWorkers = 1;  // workers only
+constexpr uint32_t kBarFull = 2;     // workers arrive, IO warp waits: the result stage holds a finished tile
+constexpr uint32_t kBarFree = 3;     // IO warp arrives, workers wait: the result stage may be overwritten
+constexpr uint32_t kSortBins = 64;
+
+__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// exclusive scan over the kT worker threads (worker barrier inside)
+__device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* s_warp, uint32_t* total, uint32_t kT) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kT >> 5;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    __syncthreads();  // s_warp reuse
+    bar_sync(kBarWorkers, kT);  // s_warp reuse
     if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
+    bar_sync(kBarWorkers, kT);
     uint32_t base = 0, tot = 0;
     for (int w = 0; w < nw; ++w) {
         const uint32_t x = s_warp[w];
@@ -136,9 +147,15 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* s_warp, uin
     return base + incl - v;
 }
 
+struct StageHdr {  // 32 bytes
+    long long tile;  // -1: no more tiles
+    uint32_t n_lines, n_spans, too_dense, pad[3];
+};
+
 __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t kT = blockDim.x;
+    const uint32_t kT = blockDim.x - kIoThreads;  // worker threads
+    const uint32_t kAll = blockDim.x;
     const OnePassDev& A = P.a;
     const uint32_t T = P.tile_units, kBuf = T + kOver;
     // ---- carve shared memory (every area 16-byte aligned)
@@ -148,34 +165,36 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
     uint32_t* s_slots = reinterpret_cast<uint32_t*>(s_oext + ((A.n_outcomes + 3) & ~3u));
     uint16_t* s_text0 = reinterpret_cast<uint16_t*>(s_slots + A.n_slots * kT);
     uint16_t* s_text1 = s_text0 + kBuf + 8;
-    uint16_t* s_start = s_text1 + kBuf + 8;
+    uint16_t* s_start = s_text1 + kBuf + 8;                     // [kT] line starts of the tile, in text order
+    uint16_t* s_perm = s_start + kT;                            // [kT] worker thread -> line of the tile (sorted by length)
+    StageHdr* st_hdr = reinterpret_cast<StageHdr*>(s_perm + kT);  // result stage, handed to the IO warp
+    int32_t* st_ext = reinterpret_cast<int32_t*>(st_hdr + 1);   // [kT]
+    uint32_t* st_spoff = reinterpret_cast<uint32_t*>(st_ext + kT);  // [kT] span offset inside the tile
+    int32_t* st_spans = reinterpret_cast<int32_t*>(st_spoff + kT);  // [kT * max_slots], packed in line order
+    uint16_t* st_start = reinterpret_cast<uint16_t*>(st_spans + kT * A.max_slots);  // [kT]
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ uint32_t s_warp[16];
+    __shared__ uint32_t s_bins[kSortBins];
     __shared__ uint32_t s_hist[kOnePassHistBins];
-    __shared__ long long s_next_tile, s_line_base, s_span_base;
-    __shared__ int s_skip_writes;
+    __shared__ long long s_next_tile;
 
     const uint32_t rows_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_rows));
-    uint32_t slot_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_slots)) + threadIdx.x * 4;
-    asm volatile("mov.u32 %0, %0;" : "+r"(slot_abs));  // one opaque register: keeps the per-step store address at LOP3 + LEA
     const uint32_t text_abs0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_text0));
     const uint32_t text_abs1 = static_cast<uint32_t>(__cvta_generic_to_shared(s_text1));
     const uint32_t bar0 = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar[0]));
-    const uint32_t slot_stride = kT * 4;
 
     const uint32_t row_q = A.width / 4;  // row size in 16-byte units
-    for (uint32_t i = threadIdx.x; i < A.n_rows * A.width; i += kT) {
+    for (uint32_t i = threadIdx.x; i < A.n_rows * A.width; i += kAll) {
         const uint32_t raw = __ldg(A.rows + i);
         s_rows[i] = (((raw >> 16) * row_q) << 18) | ((raw & 0xFFFFu) * kT);
     }
-    for (uint32_t i = threadIdx.x; i < A.n_outcomes * A.max_slots; i += kT) s_res[i] = __ldg(A.out_res + i);
-    for (uint32_t i = threadIdx.x; i < A.n_outcomes; i += kT) s_oext[i] = __ldg(A.out_ext + i);
-    const uint32_t fin_ent = (A.fin_base * row_q) << 18;
-    const uint32_t inv_row_q = 65536u / row_q + 1u;
+    for (uint32_t i = threadIdx.x; i < A.n_outcomes * A.max_slots; i += kAll) s_res[i] = __ldg(A.out_res + i);
+    for (uint32_t i = threadIdx.x; i < A.n_outcomes; i += kAll) s_oext[i] = __ldg(A.out_ext + i);
     const uint32_t n_bins = P.n_ext + 2;
     const bool smem_hist = n_bins <= kOnePassHistBins;
+    for (uint32_t i = threadIdx.x; i < kOnePassHistBins; i += kAll) s_hist[i] = 0;
 
-    auto issue_load = [&](int64_t tile, uint32_t b) {  // thread 0 only
+    auto issue_load = [&](int64_t tile, uint32_t b) {  // worker thread 0 only
         const int64_t t0 = tile * T;
         const int64_t avail = P.n_units - t0 < kBuf ? P.n_units - t0 : kBuf;
         const uint32_t bulk_units = static_cast<uint32_t>(avail) & ~7u;
@@ -195,11 +214,117 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
         if (first < P.n_tiles) issue_load(first, 0);
     }
     __syncthreads();
+
+    if (threadIdx.x >= kT) {
+        // =============================================================== IO warp
+        // Per finished tile: publish its (lines, spans) aggregate, look back over the predecessors (decoupled
+        // look-back, 32 tiles per probe), publish the inclusive prefix, then copy the staged result rows out with
+        // coalesced stores. The workers are already on the next tile meanwhile.
+        const uint32_t lane = threadIdx.x - kT;
+        for (;;) {
+            bar_sync(kBarFull, kAll);
+            const long long tile = st_hdr->tile;
+            if (tile < 0) break;
+            const uint32_t n_t = st_hdr->n_lines, span_t = st_hdr->n_spans;
+            const bool too_dense = st_hdr->too_dense != 0;
+            const unsigned long long my_lines = n_t, my_spans = span_t;
+            unsigned long long pre_l = 0, pre_s = 0;
+            if (tile > 0) {
+                if (lane == 0) st_release(P.tile_status + tile, kStAgg | my_lines | (my_spans << 20));
+                for (int64_t j = tile - 1;; j -= 32) {
+                    const int64_t idx = j - lane;
+                    unsigned long long v = kStPre;  // before tile 0: an empty inclusive prefix
+                    if (idx >= 0) {
+                        v = ld_acquire(P.tile_status + idx);
+                        while ((v >> 62) == 0) {
+                            __nanosleep(64);
+                            v = ld_acquire(P.tile_status + idx);
+                        }
+                    }
+                    const uint32_t pmask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                    const uint32_t first = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1u : 32u;
+                    unsigned long long l = 0, s = 0;
+                    if (lane < first) {
+                        l = v & 0xFFFFFull;
+                        s = (v >> 20) & 0xFFFFFFFFull;
+                    } else if (lane == first && idx >= 0) {
+                        l = static_cast<unsigned long long>(P.tile_prefix[2 * idx]);
+                        s = static_cast<unsigned long long>(P.tile_prefix[2 * idx + 1]);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        l += __shfl_xor_sync(0xffffffffu, l, o);
+                        s += __shfl_xor_sync(0xffffffffu, s, o);
+                    }
+                    pre_l += l;
+                    pre_s += s;
+                    if (pmask) break;
+                }
+            }
+            const long long line_base = static_cast<long long>(pre_l), span_base = static_cast<long long>(pre_s);
+            const long long line_end = line_base + static_cast<long long>(my_lines), span_end = span_base + static_cast<long long>(my_spans);
+            const bool over = line_end > P.cap_lines || span_end > P.cap_spans;
+            if (lane == 0) {
+                P.tile_prefix[2 * tile] = line_end;
+                P.tile_prefix[2 * tile + 1] = span_end;
+                st_release(P.tile_status + tile, kStPre);
+                if (too_dense) atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 2ull);
+                if (over) atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 1ull);
+                if (tile == P.n_tiles - 1) {
+                    P.totals[0] = line_end;
+                    P.totals[1] = span_end;
+                }
+            }
+            if (!over && !too_dense) {
+                const int64_t t0 = tile * T;
+                for (uint32_t j = lane; j < n_t; j += 32) {
+                    const long long row = line_base + j;
+                    const int32_t e = st_ext[j];
+                    P.ext_id[row] = e;
+                    P.line_off[row] = t0 + st_start[j];
+                    P.span_off[row] = span_base + st_spoff[j];
+                    const uint32_t bin = e >= 0 ? static_cast<uint32_t>(e) : (e == -1 ? P.n_ext : P.n_ext + 1);
+                    if (smem_hist) atomicAdd(&s_hist[bin], 1u);
+                    else atomicAdd(P.hist + bin, 1ull);
+                }
+                int32_t* dst = P.spans + span_base;
+                if ((span_base & 3) == 0) {
+                    const uint32_t n4 = span_t >> 2;
+                    for (uint32_t i = lane; i < n4; i += 32) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(st_spans)[i];
+                    for (uint32_t i = (n4 << 2) + lane; i < span_t; i += 32) dst[i] = st_spans[i];
+                } else {  // span counts are even (2 per group): always 8-byte aligned
+                    const uint32_t n2 = span_t >> 1;
+                    for (uint32_t i = lane; i < n2; i += 32) reinterpret_cast<int2*>(dst)[i] = reinterpret_cast<const int2*>(st_spans)[i];
+                }
+                if (tile == P.n_tiles - 1 && lane == 0) {
+                    // line i spans [line_off[i], line_off[i+1] - 1): a text that does not end in '\n' gets n_units + 1
+                    P.line_off[line_end] = P.n_units + (P.text[P.n_units - 1] == 0x0A ? 0 : 1);
+                    P.span_off[line_end] = span_end;
+                }
+            }
+            __syncwarp();
+            bar_arrive(kBarFree, kAll);
+        }
+        if (smem_hist) {
+            __syncwarp();
+            for (uint32_t i = lane; i < n_bins; i += 32)
+                if (s_hist[i]) atomicAdd(P.hist + i, static_cast<unsigned long long>(s_hist[i]));
+        }
+        return;
+    }
+
+    // =================================================================== workers
+    uint32_t slot_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_slots)) + threadIdx.x * 4;
+    asm volatile("mov.u32 %0, %0;" : "+r"(slot_abs));  // one opaque register: keeps the per-step store address at LOP3 + LEA
+    const uint32_t slot_stride = kT * 4;
+    const uint32_t fin_ent = (A.fin_base * row_q) << 18;
+    const uint32_t inv_row_q = 65536u / row_q + 1u;
     int64_t tile = s_next_tile;
     uint32_t buf = 0, phase = 0;  // phase bit b = parity to wait for on barrier b
+    uint32_t iter = 0;
 
     while (tile < P.n_tiles) {
-        __syncthreads();  // everyone has read s_next_tile; the other buffer is no longer being read
+        bar_sync(kBarWorkers, kT);  // everyone has read s_next_tile; the other text buffer is no longer being read
         if (threadIdx.x == 0) {
             const long long nx = atomicAdd(P.ticket, 1u);
             s_next_tile = nx;
@@ -212,13 +337,12 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
         const uint32_t bulk_units = static_cast<uint32_t>(avail) & ~7u;
         for (uint32_t i = bulk_units + threadIdx.x; i < kBuf + 8; i += kT)
             s_text[i] = i < avail ? __ldg(P.text + t0 + i) : static_cast<uint16_t>(0x0A);
-        if (smem_hist)
-            for (uint32_t i = threadIdx.x; i < n_bins; i += kT) s_hist[i] = 0;
+        if (threadIdx.x < kSortBins) s_bins[threadIdx.x] = 0;
         if (bulk_units) {
             mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
             phase ^= 1u << buf;
         }
-        __syncthreads();
+        bar_sync(kBarWorkers, kT);
 
         // ---- A: line starts owned by this tile = (position of a '\n' in [t0, t0+T)) + 1, if < n_units
         const uint32_t per = P.per;  // units per thread, multiple of 8, <= 64
@@ -242,7 +366,7 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
         }
         const uint32_t extra = tile == 0 ? 1u : 0u;  // the line at offset 0
         uint32_t n_t;
-        uint32_t my = block_scan(static_cast<uint32_t>(__popcll(nl_mask)), s_warp, &n_t) + extra;
+        uint32_t my = block_scan(static_cast<uint32_t>(__popcll(nl_mask)), s_warp, &n_t, kT) + extra;
         n_t += extra;
         const bool too_dense = n_t > kT;
         if (!too_dense) {
@@ -254,14 +378,35 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
                 s_start[my++] = static_cast<uint16_t>(u0 + k + 1);  // 1 .. T
             }
         }
-        __syncthreads();
+        bar_sync(kBarWorkers, kT);
+
+        // ---- A': counting sort of the tile's lines by the number of 16-byte chunks they span, so that the 32 lines
+        // of a warp take (almost) the same number of loop iterations. The tile's last line ends beyond the tile:
+        // top bin.
+        const bool have_line = !too_dense && threadIdx.x < n_t;
+        uint32_t key = 0, rank = 0;
+        if (have_line) {
+            const uint32_t a = s_start[threadIdx.x];
+            key = kSortBins - 1;
+            if (threadIdx.x + 1 < n_t) {
+                const uint32_t chunks = ((a & 7u) + (s_start[threadIdx.x + 1] - a) + 7u) >> 3;
+                key = chunks < kSortBins - 1 ? chunks : kSortBins - 1;
+            }
+            rank = atomicAdd(&s_bins[key], 1u);
+        }
+        bar_sync(kBarWorkers, kT);
+        if (have_line) {
+            for (uint32_t b = 0; b < key; ++b) rank += s_bins[b];
+            s_perm[rank] = static_cast<uint16_t>(threadIdx.x);
+        }
+        bar_sync(kBarWorkers, kT);
 
         // ---- B: one line per thread through the one-pass automaton
-        const bool have_line = !too_dense && threadIdx.x < n_t;
-        uint32_t outcome = 0;
+        uint32_t outcome = 0, line = 0;
         if (have_line) {
+            line = s_perm[threadIdx.x];
             for (uint32_t k = 0; k < A.n_init; ++k) sts32(slot_abs + __ldg(A.init_slots + k) * slot_stride, 0xFFFFFFFFu);
-            const uint32_t rel = s_start[threadIdx.x];
+            const uint32_t rel = s_start[line];
             uint32_t q = rel & ~7u;
             const uint32_t lo = rel & 7u;
             uint32_t ent = lo ? ((A.skip_base + lo - 1) * row_q) << 18 : 0u;
@@ -286,113 +431,60 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
             outcome = (((ent >> 18) - A.fin_base * row_q) * inv_row_q) >> 16;  // exact: a multiple of row_q below 2^14
         }
 
-        // ---- C: span counts (2*groups for MATCH and CAPTURE_FAIL lines) and their exclusive scan within the tile
+        // ---- C: stage the tile's result rows for the IO warp (span counts: 2*groups for MATCH and CAPTURE_FAIL)
         int32_t ext = -1;
         uint32_t cnt = 0;
         if (have_line) {
             ext = s_oext[outcome];
             if (ext != -1) cnt = __ldg(P.slots_per_ext + (ext >= 0 ? ext : -2 - ext));
         }
+        if (iter > 0) bar_sync(kBarFree, kAll);  // the IO warp has copied the previous tile out
+        if (have_line) {
+            st_ext[line] = ext;
+            st_spoff[line] = cnt;
+        }
+        bar_sync(kBarWorkers, kT);
         uint32_t span_t;
-        const uint32_t spoff = block_scan(cnt, s_warp, &span_t);
-
-        // ---- D: decoupled look-back over tiles for (lines, spans): warp 0, 32 predecessors per probe
-        if (threadIdx.x < 32) {
-            const uint32_t lane = threadIdx.x;
-            const unsigned long long my_lines = too_dense ? 0ull : n_t, my_spans = span_t;
-            unsigned long long pre_l = 0, pre_s = 0;
-            if (tile > 0) {
-                if (lane == 0) st_release(P.tile_status + tile, kStAgg | my_lines | (my_spans << 20));
-                for (int64_t j = tile - 1;; j -= 32) {
-                    const int64_t idx = j - lane;
-                    unsigned long long v = kStPre;  // before tile 0: an empty inclusive prefix
-                    if (idx >= 0) {
-                        v = ld_acquire(P.tile_status + idx);
-                        while ((v >> 62) == 0) v = ld_acquire(P.tile_status + idx);
-                    }
-                    const uint32_t pmask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-                    const uint32_t first = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1u : 32u;
-                    unsigned long long l = 0, s = 0;
-                    if (lane < first) {
-                        l = v & 0xFFFFFull;
-                        s = (v >> 20) & 0xFFFFFFFFull;
-                    } else if (lane == first && idx >= 0) {
-                        l = static_cast<unsigned long long>(P.tile_prefix[2 * idx]);
-                        s = static_cast<unsigned long long>(P.tile_prefix[2 * idx + 1]);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        l += __shfl_xor_sync(0xffffffffu, l, o);
-                        s += __shfl_xor_sync(0xffffffffu, s, o);
-                    }
-                    pre_l += l;
-                    pre_s += s;
-                    if (pmask) break;
-                }
-            }
-            if (lane == 0) {
-                P.tile_prefix[2 * tile] = static_cast<long long>(pre_l + my_lines);
-                P.tile_prefix[2 * tile + 1] = static_cast<long long>(pre_s + my_spans);
-                st_release(P.tile_status + tile, kStPre);
-                s_line_base = static_cast<long long>(pre_l);
-                s_span_base = static_cast<long long>(pre_s);
-                int skip = too_dense ? 1 : 0;
-                if (too_dense) atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 2ull);
-                if (static_cast<long long>(pre_l + my_lines) > P.cap_lines || static_cast<long long>(pre_s + my_spans) > P.cap_spans) {
-                    atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 1ull);
-                    skip = 1;
-                }
-                s_skip_writes = skip;
-                if (tile == P.n_tiles - 1) {
-                    P.totals[0] = static_cast<int64_t>(pre_l + my_lines);
-                    P.totals[1] = static_cast<int64_t>(pre_s + my_spans);
-                }
+        {
+            const bool row = !too_dense && threadIdx.x < n_t;
+            const uint32_t c = row ? st_spoff[threadIdx.x] : 0u;
+            const uint32_t excl = block_scan(c, s_warp, &span_t, kT);
+            if (row) {
+                st_spoff[threadIdx.x] = excl;
+                st_start[threadIdx.x] = s_start[threadIdx.x];
             }
         }
-        __syncthreads();
-        const int64_t line_base = s_line_base, span_base = s_span_base;
-        const bool skip_writes = s_skip_writes != 0;
-
-        // ---- E: result rows, group boundaries, histogram
-        if (!skip_writes) {
-            if (have_line) {
-                const int64_t row = line_base + threadIdx.x;
-                P.ext_id[row] = ext;
-                P.line_off[row] = t0 + s_start[threadIdx.x];
-                P.span_off[row] = span_base + spoff;
-                if (cnt) {
-                    int32_t* out = P.spans + span_base + spoff;
-                    if (ext >= 0) {
-                        const uint32_t* res = s_res + outcome * A.max_slots;
-                        for (uint32_t k = 0; k < cnt; ++k) {
-                            int32_t val = -1;
-                            for (uint32_t packed = res[k]; packed; packed >>= 8)
-                                val = max(val, static_cast<int32_t>(lds32(slot_abs + (packed & 0xFFu) * slot_stride)));
-                            out[k] = val;
-                        }
-                    } else {
-                        for (uint32_t k = 0; k < cnt; ++k) out[k] = -1;
-                    }
+        bar_sync(kBarWorkers, kT);
+        if (cnt) {
+            int32_t* out = st_spans + st_spoff[line];
+            if (ext >= 0) {
+                const uint32_t* res = s_res + outcome * A.max_slots;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    int32_t val = -1;
+                    for (uint32_t packed = res[k]; packed; packed >>= 8)
+                        val = max(val, static_cast<int32_t>(lds32(slot_abs + (packed & 0xFFu) * slot_stride)));
+                    out[k] = val;
                 }
-                const uint32_t bin = ext >= 0 ? static_cast<uint32_t>(ext) : (ext == -1 ? P.n_ext : P.n_ext + 1);
-                if (smem_hist) atomicAdd(&s_hist[bin], 1u);
-                else atomicAdd(P.hist + bin, 1ull);
-            }
-            if (tile == P.n_tiles - 1 && threadIdx.x == 0) {
-                const int64_t nl = line_base + n_t;
-                // line i spans [line_off[i], line_off[i+1] - 1): a text that does not end in '\n' gets n_units + 1
-                P.line_off[nl] = P.n_units + (P.text[P.n_units - 1] == 0x0A ? 0 : 1);
-                P.span_off[nl] = span_base + span_t;
-            }
-            if (smem_hist) {
-                __syncthreads();
-                for (uint32_t i = threadIdx.x; i < n_bins; i += kT)
-                    if (s_hist[i]) atomicAdd(P.hist + i, static_cast<unsigned long long>(s_hist[i]));
+            } else {
+                for (uint32_t k = 0; k < cnt; ++k) out[k] = -1;
             }
         }
+        if (threadIdx.x == 0) {
+            st_hdr->tile = tile;
+            st_hdr->n_lines = too_dense ? 0u : n_t;
+            st_hdr->n_spans = span_t;
+            st_hdr->too_dense = too_dense ? 1u : 0u;
+        }
+        __threadfence_block();
+        bar_arrive(kBarFull, kAll);
         tile = s_next_tile;
         buf ^= 1;
+        ++iter;
     }
+    if (iter > 0) bar_sync(kBarFree, kAll);
+    if (threadIdx.x == 0) st_hdr->tile = -1;
+    __threadfence_block();
+    bar_arrive(kBarFull, kAll);
 }
 
 }  // namespace
@@ -403,29 +495,32 @@ size_t onepass_smem_bytes(const OnePassDev& a, uint32_t threads, uint32_t tile_u
     b += static_cast<size_t>((a.n_outcomes + 3) & ~3u) * 4;
     b += static_cast<size_t>(a.n_slots) * threads * 4;
     b += 2 * static_cast<size_t>(tile_units + kOnePassOverhang + 8) * 2;
-    b += static_cast<size_t>(threads) * (2 + 2 + 4);
+    b += static_cast<size_t>(threads) * (2 + 2);                           // s_start, s_perm
+    b += 32 + static_cast<size_t>(threads) * (4 + 4 + 2 + 4 * a.max_slots);  // result stage
     return b + 128;
 }
 
 bool k0_onepass_plan(const OnePassDev& a, double lines_per_unit, uint32_t shrink, uint32_t* threads, uint32_t* tile_units) {
     if (!a.enabled) return false;
-    // the tile should hold ~0.85 * threads line starts; per = tile/threads is 8 * odd (conflict-free 128-bit phase-A
-    // loads) and <= 64 (one 64-bit newline mask per thread)
+    // `threads` worker threads walk one line each; the tile (threads * per units) should hold at most ~0.9 * threads
+    // line starts. per is a multiple of 8 and <= 64 (one 64-bit newline mask per thread).
     const uint32_t kT = 256;
     if (static_cast<uint64_t>(a.n_slots) * kT > 0x3FFFu) return false;
-    double want = 0.85 * kT / (lines_per_unit > 1e-9 ? lines_per_unit : 1e-9) / kT;  // units per thread
-    uint32_t per = 56;
-    for (uint32_t cand : {56u, 40u, 24u, 8u})
-        if (want < cand + 8) per = cand;
-    if (want >= 56) per = 56;
-    for (uint32_t s = 0; s < shrink; ++s) per = per > 40 ? 40 : per > 24 ? 24 : 8;
+    const double lpu = lines_per_unit > 1e-9 ? lines_per_unit : 1e-9;
+    uint32_t per = 8;
+    for (uint32_t cand = 64; cand >= 8; cand -= 8)
+        if (cand * lpu <= 0.90) {
+            per = cand;
+            break;
+        }
+    for (uint32_t s = 0; s < shrink && per > 8; ++s) per = per > 16 ? (per * 3 / 4) & ~7u : 8;
     for (;;) {
         if (onepass_smem_bytes(a, kT, kT * per) <= 113 * 1024) break;  // two CTAs per SM
         if (per == 8) {
             if (onepass_smem_bytes(a, kT, kT * per) <= 226 * 1024) break;
             return false;
         }
-        per = per > 40 ? 40 : per > 24 ? 24 : 8;
+        per -= 8;
     }
     *threads = kT;
     *tile_units = kT * per;
@@ -434,14 +529,15 @@ bool k0_onepass_plan(const OnePassDev& a, double lines_per_unit, uint32_t shrink
 
 void k0_onepass_extract(const Launch& L, const OnePassParams& P, uint32_t threads) {
     const size_t smem = onepass_smem_bytes(P.a, threads, P.tile_units);
+    const int block = static_cast<int>(threads + 32);  // + the IO warp
     cudaFuncSetAttribute(onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onepass_kernel, static_cast<int>(threads), smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onepass_kernel, block, smem);
     if (per_sm < 1) per_sm = 1;
     const int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
     int g = static_cast<int>(P.n_tiles < cap ? P.n_tiles : cap);
     if (g < 1) g = 1;
-    onepass_kernel<<<g, threads, smem, L.stream>>>(P);
+    onepass_kernel<<<g, block, smem, L.stream>>>(P);
 }
 
 }  // namespace gorp
