@@ -235,7 +235,7 @@ def main():
 
         def e2e_step():
             _check(lib.gorp_extract_text(eng, h_np.ctypes.data, h_np.size, C.byref(res)))
-            nl, ns = res.n_lines, res.span_off[res.n_lines]
+            nl, ns = res.n_lines, res.n_lines * res.span_stride
             lib.gorp_result_release(eng, C.byref(res))
             return nl, ns
         e2e_step()
@@ -248,7 +248,7 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        d2h = nl * 4 + (nl + 1) * 16 + ns * 4 + 5 * 8
+        d2h = nl * 4 + (nl + 1) * 8 + ns * 4 + 5 * 8
         e2e = {"value": e2e_lines * world / float(tt.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h_np.size * 2),
                "d2h_bytes_per_step": int(d2h), "lines_per_step_per_gpu": int(e2e_lines), "ms_per_step": float(tt.item()) * 1e3,
                "timing": "host wall clock around gorp_extract_text (it returns after the last D2H), max over ranks"}

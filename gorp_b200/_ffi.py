@@ -18,9 +18,9 @@ GORP_OK, GORP_E_ARG, GORP_E_DEFINITION, GORP_E_UNSUPPORTED, GORP_E_BLOB, GORP_E_
 
 
 class Result(C.Structure):
-    _fields_ = [("n_lines", C.c_int64), ("n_extractions", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("n_lines", C.c_int64), ("n_extractions", C.c_int32), ("span_stride", C.c_int32),
                 ("ext_id", C.POINTER(C.c_int32)), ("line_off", C.POINTER(C.c_int64)),
-                ("span_off", C.POINTER(C.c_int64)), ("spans", C.POINTER(C.c_int32)),
+                ("spans", C.POINTER(C.c_int32)),
                 ("histogram", C.POINTER(C.c_int64)), ("owner", C.c_void_p)]
 
 
@@ -38,8 +38,9 @@ class ExtractionInfo(C.Structure):
 
 
 class DeviceResult(C.Structure):
-    _fields_ = [("n_lines", C.c_int64), ("d_ext_id", C.c_void_p), ("d_line_off", C.c_void_p),
-                ("d_span_off", C.c_void_p), ("d_spans", C.c_void_p), ("d_histogram", C.c_void_p),
+    _fields_ = [("n_lines", C.c_int64), ("span_stride", C.c_int32), ("reserved", C.c_int32),
+                ("d_ext_id", C.c_void_p), ("d_line_off", C.c_void_p),
+                ("d_spans", C.c_void_p), ("d_histogram", C.c_void_p),
                 ("d_n_lines", C.c_void_p)]
 
 

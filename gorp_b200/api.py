@@ -201,9 +201,9 @@ class ExtractionBatch:
         self.gorp, self.units, self.sep, self.n_lines = gorp, units, sep, n
         self.ext_id = np.ctypeslib.as_array(res.ext_id, (max(n, 1),))[:n].copy()
         self.line_off = np.ctypeslib.as_array(res.line_off, (n + 1,)).copy()
-        self.span_off = np.ctypeslib.as_array(res.span_off, (n + 1,)).copy()
-        ns = int(self.span_off[n]) if n else 0
-        self.spans = np.ctypeslib.as_array(res.spans, (max(ns, 1),))[:ns].copy()
+        self.span_stride = w = int(res.span_stride)
+        # one fixed-size row of (start, end) pairs per line; entries beyond 2 * groups(ext_id) are -1
+        self.spans = np.ctypeslib.as_array(res.spans, (max(n * w, 1),))[:n * w].copy().reshape(n, w)
         self.histogram = np.ctypeslib.as_array(res.histogram, (res.n_extractions + 2,)).copy()
 
     def __len__(self):
@@ -214,8 +214,10 @@ class ExtractionBatch:
         return self.units[a:b].tobytes().decode("utf-16-le", "surrogatepass")
 
     def spans_of(self, i):
-        a, b = int(self.span_off[i]), int(self.span_off[i + 1])
-        s = self.spans[a:b]
+        e = int(self.ext_id[i])
+        if e < 0:
+            return []
+        s = self.spans[i, :2 * len(self.gorp._extractions[e].getExtractorNames())]
         return list(zip(s[0::2].tolist(), s[1::2].tolist()))
 
     def result(self, i, safe=False):

@@ -1,8 +1,9 @@
 // Engine + C ABI of libgorpcuda (include/gorp_cuda.h). Host orchestration only; the kernels are in kernels/.
 //
 // Device pipeline per batch (one stream, no host round trip except reading the line count of the text form):
-//   text form : K1 count -> scan -> K1 scatter -> K1 finish            => line_off[n+1], n_lines
-//   both forms: K2 dfa_scan => ext_id, span_cnt -> scan => span_off -> K4 tdfa_capture => spans -> K3 histogram
+//   text form, small definitions: K0' one-pass kernel (kernels/onepass.cu)     => everything in one HBM pass
+//   otherwise  text form : K1 count -> scan -> K1 scatter -> K1 finish          => line_off[n+1], n_lines
+//              both forms: K2 dfa_scan => ext_id -> K4 tdfa_capture => result rows of spans -> K3 histogram
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -110,13 +111,12 @@ struct DeviceCtx {
     uint32_t n_ext = 0;
     uint32_t max_slots = 0;
     bool force_general = false;  // GORP_FORCE_GENERAL=1: always use the general (masked) kernels
-    bool force_unfused = false;  // GORP_FORCE_UNFUSED=1: never use the fused kernel (K1..K5 pipeline instead)
-    bool force_twopass = false;  // GORP_FORCE_TWOPASS=1: never use the one-pass automaton kernel
-    double lines_per_unit = 1.0 / 24.0;  // running estimate that sizes the fused kernel's output arrays
+    bool force_twopass = false;  // GORP_FORCE_TWOPASS=1: never use the one-pass automaton kernel (K1 -> K2 -> K4 instead)
+    double lines_per_unit = 1.0 / 24.0;  // running estimate that sizes the one-pass kernel's tiles and output arrays
     DevBuf tile_state;
     // per-call scratch, serialised by `mu`
     std::mutex mu;
-    DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, span_cnt, span_off, spans, hist, scalars;
+    DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, spans, hist, scalars;
     // per-kernel device time: CUDA events on the launching stream, accumulated over timed calls
     cudaEvent_t ev[kMaxTimed + 1]{};
     const char* ev_name[kMaxTimed]{};
@@ -136,8 +136,8 @@ struct DeviceCtx {
 };
 
 struct HostResult {  // pinned host arrays behind a gorp_result
-    void* p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[5] = {0, 0, 0, 0, 0};
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t cap[4] = {0, 0, 0, 0};
     void reserve(int i, size_t bytes) {
         if (bytes <= cap[i]) return;
         if (p[i]) cudaFreeHost(p[i]);
@@ -172,7 +172,6 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     c.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     if (const char* f = std::getenv("GORP_FORCE_GENERAL")) c.force_general = f[0] == '1';
-    if (const char* f = std::getenv("GORP_FORCE_UNFUSED")) c.force_unfused = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TWOPASS")) c.force_twopass = f[0] == '1';
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
     // combined DFA
@@ -319,7 +318,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     }
             }
             while (image.size() % 4) image.push_back(0);  // keep what follows the image 16-byte aligned in shared memory
-            const uint32_t reg_stride = kFusedThreads * 4;
+            const uint32_t reg_stride = kCapFastThreads * 4;
             const size_t reg_bytes = static_cast<size_t>(max_regs + 2) * reg_stride;
             if (ok && image.size() * 4 + reg_bytes <= 160 * 1024 && (max_regs + 2) * reg_stride <= 0x10000) {
                 // resolve the register byte offsets now that the register count is known:
@@ -472,7 +471,7 @@ struct Timer {
 // Text form through the one-pass kernel. Returns false when the batch has to take another path.
 bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
                  int64_t& n_lines, gorp_device_result* out) {
-    if (n_units <= 0 || c.force_general || c.force_unfused || c.force_twopass || !c.onepass.enabled) return false;
+    if (n_units <= 0 || c.force_general || c.force_twopass || !c.onepass.enabled) return false;
     Launch L{stream, c.sm_count};
     c.hist.reserve((c.n_ext + 2) * 8);
     bool exact = false;
@@ -488,30 +487,25 @@ bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
         P.a = c.onepass;
         P.slots_per_ext = c.d_slots;
         P.n_ext = c.n_ext;
-        // look-back state: [status n_tiles][prefix 2*n_tiles][ticket (8 B)][totals 3 x int64]
-        const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 24 + 8 + 24;
+        P.span_stride = c.max_slots;
+        // look-back state: [status n_tiles][ticket (8 B)][totals 3 x int64]
+        const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 8 + 8 + 24;
         c.tile_state.reserve(state_bytes);
         int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
         if (exact) cap_lines = n_lines + 16;
-        const int64_t cap_spans = cap_lines * std::max<uint32_t>(c.max_slots, 1);
         c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
         c.line_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
-        c.span_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
-        c.spans.reserve(static_cast<size_t>(cap_spans + 4) * 4);
+        c.spans.reserve((static_cast<size_t>(cap_lines) * c.max_slots + 4) * 4);
         P.ext_id = c.ext_id.as<int32_t>();
         P.line_off = c.line_off.as<int64_t>();
-        P.span_off = c.span_off.as<int64_t>();
         P.spans = c.spans.as<int32_t>();
         P.hist = c.hist.as<unsigned long long>();
         P.cap_lines = cap_lines;
-        P.cap_spans = cap_spans;
         unsigned char* st = c.tile_state.as<unsigned char>();
         P.tile_status = reinterpret_cast<unsigned long long*>(st);
-        P.tile_prefix = reinterpret_cast<long long*>(st + static_cast<size_t>(P.n_tiles) * 8);
-        P.ticket = reinterpret_cast<unsigned int*>(st + static_cast<size_t>(P.n_tiles) * 24);
-        P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 24 + 8);
-        CK(cudaMemsetAsync(st, 0, static_cast<size_t>(P.n_tiles) * 8, stream));
-        CK(cudaMemsetAsync(P.ticket, 0, 32, stream));
+        P.ticket = reinterpret_cast<unsigned int*>(st + static_cast<size_t>(P.n_tiles) * 8);
+        P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 8 + 8);
+        CK(cudaMemsetAsync(st, 0, state_bytes, stream));
         CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
         k0_onepass_extract(L, P, threads);
         tm.mark("k0_onepass_extract", 1);
@@ -519,7 +513,7 @@ bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
         int64_t totals[3] = {0, 0, 0};
         CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        if (totals[2] & 2) {  // a tile held more line starts than the CTA has threads: smaller tiles
+        if (totals[2] & 2) {  // a tile held more line starts than the CTA has worker threads: smaller tiles
             ++c.onepass_shrink;
             continue;
         }
@@ -532,75 +526,9 @@ bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
         CK(cudaMemcpyAsync(d_scalars, P.totals, 8, cudaMemcpyDeviceToDevice, stream));
         if (out) {
             out->n_lines = n_lines;
+            out->span_stride = static_cast<int32_t>(c.max_slots);
             out->d_ext_id = P.ext_id;
             out->d_line_off = P.line_off;
-            out->d_span_off = P.span_off;
-            out->d_spans = P.spans;
-            out->d_histogram = c.hist.as<int64_t>();
-            out->d_n_lines = d_scalars;
-        }
-        return true;
-    }
-    return false;
-}
-
-// Text form through the fused kernel. Returns false when the batch has to go through the unfused pipeline.
-bool run_fused(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
-               int64_t& n_lines, gorp_device_result* out) {
-    if (n_units <= 0 || c.force_general || c.force_unfused) return false;
-    FusedParams P{};
-    P.text = d_text;
-    P.n_units = n_units;
-    P.n_tiles = (n_units + kFusedTile - 1) / kFusedTile;
-    P.dfa = c.dfa_direct;
-    P.cap_fast = c.cap_fast;
-    P.cap = c.cap;
-    P.slots_per_ext = c.d_slots;
-    P.n_ext = c.n_ext;
-    if (!k0_fused_supported(P)) return false;
-    Launch L{stream, c.sm_count};
-    c.hist.reserve((c.n_ext + 2) * 8);
-    // look-back state: [tile_lines n_tiles][tile_spans n_tiles][ticket (8 B)][totals 3 x int64]
-    const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 16 + 8 + 24;
-    c.tile_state.reserve(state_bytes);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
-        if (attempt == 1) cap_lines = n_lines + 16;
-        const int64_t cap_spans = cap_lines * std::max<uint32_t>(c.max_slots, 1);
-        c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
-        c.line_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
-        c.span_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
-        c.spans.reserve(static_cast<size_t>(cap_spans + 4) * 4);
-        P.ext_id = c.ext_id.as<int32_t>();
-        P.line_off = c.line_off.as<int64_t>();
-        P.span_off = c.span_off.as<int64_t>();
-        P.spans = c.spans.as<int32_t>();
-        P.hist = c.hist.as<unsigned long long>();
-        P.cap_lines = cap_lines;
-        P.cap_spans = cap_spans;
-        unsigned char* st = c.tile_state.as<unsigned char>();
-        P.tile_lines = reinterpret_cast<unsigned long long*>(st);
-        P.tile_spans = P.tile_lines + P.n_tiles;
-        P.ticket = reinterpret_cast<unsigned int*>(P.tile_spans + P.n_tiles);
-        P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 16 + 8);
-        CK(cudaMemsetAsync(st, 0, state_bytes, stream));
-        CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
-        k0_fused_extract(L, P);
-        tm.mark("k0_fused_extract", 1);
-        CK(cudaGetLastError());
-        int64_t totals[3] = {0, 0, 0};
-        CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        if (totals[2] & 2) return false;  // a tile with more line starts than the kernel stages: unfused pipeline
-        n_lines = totals[0];
-        c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
-        if (totals[2] & 1) continue;  // capacity overflow: rerun once with the exact size
-        CK(cudaMemcpyAsync(d_scalars, P.totals, 8, cudaMemcpyDeviceToDevice, stream));
-        if (out) {
-            out->n_lines = n_lines;
-            out->d_ext_id = P.ext_id;
-            out->d_line_off = P.line_off;
-            out->d_span_off = P.span_off;
             out->d_spans = P.spans;
             out->d_histogram = c.hist.as<int64_t>();
             out->d_n_lines = d_scalars;
@@ -622,7 +550,6 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     int sep;
     bool ends_with_nl = true;
     if (!d_off && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
-    if (!d_off && run_fused(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off) {
         sep = 1;
         const int64_t n_tiles = (n_units + kNlTile - 1) / kNlTile;
@@ -653,40 +580,30 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     }
     const size_t nl = static_cast<size_t>(n_lines);
     c.ext_id.reserve((nl + 1) * 4);
-    c.span_cnt.reserve((nl + 1) * 4);
-    c.span_off.reserve((nl + 2) * 8);
-    c.scan_scratch.reserve((nl / 4096 + 8) * 8);
     c.hist.reserve((c.n_ext + 2) * 8);
+    // every line but (possibly) the last is terminated by '\n' in the text form: fast tiers; an unterminated last line
+    // goes through the general kernels
+    const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
     if (sep == 1 && c.dfa_direct.enabled && !c.force_general) {
-        // every line but (possibly) the last is terminated by '\n': fast tier; an unterminated last line goes through
-        // the general kernel
-        const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
-        k2_dfa_direct(L, c.dfa_direct, d_text, d_line_off, n_fast, c.d_slots, c.ext_id.as<int32_t>(), c.span_cnt.as<uint32_t>());
-        if (n_fast < n_lines)
-            k2_dfa_scan(L, c.dfa, d_text, d_line_off + n_fast, sep, 1, c.d_slots, c.ext_id.as<int32_t>() + n_fast,
-                        c.span_cnt.as<uint32_t>() + n_fast);
+        k2_dfa_direct(L, c.dfa_direct, d_text, d_line_off, n_fast, c.ext_id.as<int32_t>());
+        if (n_fast < n_lines) k2_dfa_scan(L, c.dfa, d_text, d_line_off + n_fast, sep, 1, c.ext_id.as<int32_t>() + n_fast);
         tm.mark("k2_dfa_scan", n_fast < n_lines ? 2 : 1);
     } else {
-        k2_dfa_scan(L, c.dfa, d_text, d_line_off, sep, n_lines, c.d_slots, c.ext_id.as<int32_t>(), c.span_cnt.as<uint32_t>());
+        k2_dfa_scan(L, c.dfa, d_text, d_line_off, sep, n_lines, c.ext_id.as<int32_t>());
         tm.mark("k2_dfa_scan", 1);
     }
-    scan_u32_to_i64(L, c.span_cnt.as<uint32_t>(), n_lines, c.span_off.as<int64_t>(), c.scan_scratch.as<int64_t>());
-    tm.mark("k5_span_offsets", 3);
-    // span entries are bounded by n_lines * (widest extraction): no round trip needed to size the buffer
-    const size_t span_bound = nl * c.max_slots;
-    c.spans.reserve((span_bound + 4) * 4);
-    if (!c.cap.match_only) {
+    // result rows of `spans`: max_slots entries per line, no offsets needed
+    const uint32_t stride = c.max_slots;
+    c.spans.reserve((nl * stride + 4) * 4);
+    if (!c.cap.match_only && stride > 0) {
         if (sep == 1 && c.cap_fast.enabled && !c.force_general) {
-            const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
-            k4_tdfa_fast(L, c.cap_fast, c.cap, d_text, n_units, d_line_off, n_fast, c.span_off.as<int64_t>(), c.ext_id.as<int32_t>(),
-                         c.spans.as<int32_t>());
+            k4_tdfa_fast(L, c.cap_fast, c.cap, d_text, n_units, d_line_off, n_fast, stride, c.ext_id.as<int32_t>(), c.spans.as<int32_t>());
             if (n_fast < n_lines)
-                k4_tdfa_capture(L, c.cap, d_text, d_line_off + n_fast, sep, 1, c.span_off.as<int64_t>() + n_fast,
-                                c.ext_id.as<int32_t>() + n_fast, c.spans.as<int32_t>());
+                k4_tdfa_capture(L, c.cap, d_text, d_line_off + n_fast, sep, 1, stride, c.ext_id.as<int32_t>() + n_fast,
+                                c.spans.as<int32_t>() + static_cast<size_t>(n_fast) * stride);
             tm.mark("k4_tdfa_capture", n_fast < n_lines ? 2 : 1);
         } else {
-            k4_tdfa_capture(L, c.cap, d_text, d_line_off, sep, n_lines, c.span_off.as<int64_t>(), c.ext_id.as<int32_t>(),
-                            c.spans.as<int32_t>());
+            k4_tdfa_capture(L, c.cap, d_text, d_line_off, sep, n_lines, stride, c.ext_id.as<int32_t>(), c.spans.as<int32_t>());
             tm.mark("k4_tdfa_capture", 1);
         }
     } else {
@@ -698,9 +615,9 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     CK(cudaGetLastError());
     if (out) {
         out->n_lines = n_lines;
+        out->span_stride = static_cast<int32_t>(stride);
         out->d_ext_id = c.ext_id.as<int32_t>();
         out->d_line_off = d_line_off;
-        out->d_span_off = c.span_off.as<int64_t>();
         out->d_spans = c.spans.as<int32_t>();
         out->d_histogram = c.hist.as<int64_t>();
         out->d_n_lines = d_n_lines;
@@ -734,29 +651,24 @@ int extract_host(gorp_engine* e, const uint16_t* text, int64_t n_units, const in
             }
         }
         if (!hr) hr = std::make_unique<HostResult>();
-        int64_t n_spans = 0;
-        CK(cudaMemcpyAsync(&n_spans, dr.d_span_off + nl, 8, cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaStreamSynchronize(c.stream));
+        const size_t n_spans = static_cast<size_t>(nl) * static_cast<size_t>(dr.span_stride);
         const size_t E2 = e->def.extractions.size() + 2;
         hr->reserve(0, static_cast<size_t>(nl + 1) * 4);
         hr->reserve(1, static_cast<size_t>(nl + 1) * 8);
-        hr->reserve(2, static_cast<size_t>(nl + 1) * 8);
-        hr->reserve(3, static_cast<size_t>(n_spans + 1) * 4);
-        hr->reserve(4, E2 * 8);
+        hr->reserve(2, (n_spans + 1) * 4);
+        hr->reserve(3, E2 * 8);
         if (nl) CK(cudaMemcpyAsync(hr->p[0], dr.d_ext_id, static_cast<size_t>(nl) * 4, cudaMemcpyDeviceToHost, c.stream));
         CK(cudaMemcpyAsync(hr->p[1], dr.d_line_off, static_cast<size_t>(nl + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaMemcpyAsync(hr->p[2], dr.d_span_off, static_cast<size_t>(nl + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
-        if (n_spans) CK(cudaMemcpyAsync(hr->p[3], dr.d_spans, static_cast<size_t>(n_spans) * 4, cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaMemcpyAsync(hr->p[4], dr.d_histogram, E2 * 8, cudaMemcpyDeviceToHost, c.stream));
+        if (n_spans) CK(cudaMemcpyAsync(hr->p[2], dr.d_spans, n_spans * 4, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(hr->p[3], dr.d_histogram, E2 * 8, cudaMemcpyDeviceToHost, c.stream));
         CK(cudaStreamSynchronize(c.stream));
         out->n_lines = nl;
         out->n_extractions = static_cast<int32_t>(e->def.extractions.size());
-        out->reserved = 0;
+        out->span_stride = dr.span_stride;
         out->ext_id = static_cast<const int32_t*>(hr->p[0]);
         out->line_off = static_cast<const int64_t*>(hr->p[1]);
-        out->span_off = static_cast<const int64_t*>(hr->p[2]);
-        out->spans = static_cast<const int32_t*>(hr->p[3]);
-        out->histogram = static_cast<const int64_t*>(hr->p[4]);
+        out->spans = static_cast<const int32_t*>(hr->p[2]);
+        out->histogram = static_cast<const int64_t*>(hr->p[3]);
         out->owner = hr.release();
         return GORP_OK;
     });

@@ -10,8 +10,7 @@ using namespace dev;
 
 __global__ void __launch_bounds__(kFastThreads) dfa_direct_kernel(DfaDirectDev d, const uint16_t* __restrict__ text,
                                                                   const int64_t* __restrict__ line_off, int64_t n_lines,
-                                                                  const uint32_t* __restrict__ slots_per_ext,
-                                                                  int32_t* __restrict__ ext_id, uint32_t* __restrict__ span_cnt) {
+                                                                  int32_t* __restrict__ ext_id) {
     extern __shared__ __align__(16) uint32_t s_rows[];
     const uint32_t tbase = static_cast<uint32_t>(__cvta_generic_to_shared(s_rows));
     for (uint32_t i = threadIdx.x; i < d.n_rows * 128u; i += kFastThreads) s_rows[i] = tbase + (__ldg(d.rows + i) << 9);
@@ -42,17 +41,16 @@ __global__ void __launch_bounds__(kFastThreads) dfa_direct_kernel(DfaDirectDev d
         } while (st < fin_abs);
         const int32_t e = static_cast<int32_t>((st - fin_abs) >> 9) - 1;
         ext_id[line] = e;
-        span_cnt[line] = e >= 0 ? __ldg(slots_per_ext + e) : 0u;
     }
 }
 
 // ------------------------------------------------------------------ K4 fast tier
-constexpr int kCapThreads = kFusedThreads;
+constexpr int kCapThreads = kCapFastThreads;
 
 __global__ void __launch_bounds__(kCapThreads, 2) tdfa_fast_kernel(TdfaFastDev f, CapDev c, const uint16_t* __restrict__ text,
                                                                    int64_t n_units,
                                                                    const int64_t* __restrict__ line_off, int64_t n_lines,
-                                                                const int64_t* __restrict__ span_off,
+                                                                uint32_t span_stride,
                                                                 int32_t* __restrict__ ext_id, int32_t* __restrict__ spans) {
     extern __shared__ __align__(16) uint32_t s_img[];
     for (uint32_t i = threadIdx.x; i < f.image_words; i += kCapThreads) s_img[i] = __ldg(f.image + i);
@@ -64,7 +62,11 @@ __global__ void __launch_bounds__(kCapThreads, 2) tdfa_fast_kernel(TdfaFastDev f
     for (int64_t line = static_cast<int64_t>(blockIdx.x) * kCapThreads + threadIdx.x; line < n_lines;
          line += static_cast<int64_t>(gridDim.x) * kCapThreads) {
         const int32_t e = ext_id[line];
-        if (e < 0) continue;
+        int32_t* out = spans + line * span_stride;
+        if (e < 0) {
+            for (uint32_t k = 0; k < span_stride; ++k) out[k] = -1;
+            continue;
+        }
         const FastExtDev fx = f.ext[e];
         const ExtDev x = c.ext[e];
         const uint32_t tab_abs = cls_abs + fx.tab_off;
@@ -93,7 +95,6 @@ __global__ void __launch_bounds__(kCapThreads, 2) tdfa_fast_kernel(TdfaFastDev f
             q += 8;
             pos += 8;
         }
-        int32_t* out = spans + span_off[line];
         bool ok = st >= fx.frz_off;
         uint32_t s = 0;
         if (ok) {
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kCapThreads, 2) tdfa_fast_kernel(TdfaFastDev f
         }
         if (!ok) {
             ext_id[line] = -2 - e;
-            for (uint32_t k = 0; k < x.n_slots; ++k) out[k] = -1;
+            for (uint32_t k = 0; k < span_stride; ++k) out[k] = -1;
             continue;
         }
         const uint8_t* __restrict__ fin = c.tdfa_fin + x.fin_off + s * x.n_slots;
@@ -111,13 +112,14 @@ __global__ void __launch_bounds__(kCapThreads, 2) tdfa_fast_kernel(TdfaFastDev f
             const uint32_t r = __ldg(fin + k);
             out[k] = r == 0xFFu ? -1 : (r == 0xFEu ? len : static_cast<int32_t>(lds32(reg_abs + r * reg_stride)));
         }
+        for (uint32_t k = x.n_slots; k < span_stride; ++k) out[k] = -1;
     }
 }
 
 }  // namespace
 
 void k2_dfa_direct(const Launch& L, const DfaDirectDev& d, const uint16_t* text, const int64_t* line_off, int64_t n_lines,
-                   const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt) {
+                   int32_t* ext_id) {
     if (n_lines <= 0) return;
     const size_t smem = static_cast<size_t>(d.n_rows) * 512;
     if (smem > 48 * 1024)
@@ -128,14 +130,14 @@ void k2_dfa_direct(const Launch& L, const DfaDirectDev& d, const uint16_t* text,
     int64_t want = (n_lines + kFastThreads - 1) / kFastThreads;
     int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
     int g = static_cast<int>(want < cap ? want : cap);
-    dfa_direct_kernel<<<g, kFastThreads, smem, L.stream>>>(d, text, line_off, n_lines, slots_per_ext, ext_id, span_cnt);
+    dfa_direct_kernel<<<g, kFastThreads, smem, L.stream>>>(d, text, line_off, n_lines, ext_id);
 }
 
 }  // namespace gorp
 
 namespace gorp {
 void k4_tdfa_fast(const Launch& L, const TdfaFastDev& f, const CapDev& c, const uint16_t* text, int64_t n_units,
-                  const int64_t* line_off, int64_t n_lines, const int64_t* span_off, int32_t* ext_id, int32_t* spans) {
+                  const int64_t* line_off, int64_t n_lines, uint32_t span_stride, int32_t* ext_id, int32_t* spans) {
     if (n_lines <= 0) return;
     const size_t smem = static_cast<size_t>(f.image_words) * 4 + static_cast<size_t>(f.n_regs + 2) * kCapThreads * 4;
     if (smem > 48 * 1024)
@@ -146,6 +148,6 @@ void k4_tdfa_fast(const Launch& L, const TdfaFastDev& f, const CapDev& c, const 
     int64_t want = (n_lines + kCapThreads - 1) / kCapThreads;
     int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
     int g = static_cast<int>(want < cap ? want : cap);
-    tdfa_fast_kernel<<<g, kCapThreads, smem, L.stream>>>(f, c, text, n_units, line_off, n_lines, span_off, ext_id, spans);
+    tdfa_fast_kernel<<<g, kCapThreads, smem, L.stream>>>(f, c, text, n_units, line_off, n_lines, span_stride, ext_id, spans);
 }
 }  // namespace gorp

@@ -207,8 +207,7 @@ __device__ __forceinline__ uint32_t unit_of(const uint4& v, int k) {
 template <bool kSmemTable, typename Entry>
 __global__ void __launch_bounds__(kThreads) dfa_scan_kernel(DfaDev d, const uint16_t* __restrict__ text,
                                                             const int64_t* __restrict__ line_off, int sep, int64_t n_lines,
-                                                            const uint32_t* __restrict__ slots_per_ext,
-                                                            int32_t* __restrict__ ext_id, uint32_t* __restrict__ span_cnt) {
+                                                            int32_t* __restrict__ ext_id) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t* s_cls = reinterpret_cast<uint16_t*>(smem_raw);  // [128] ASCII slice of the class map
     Entry* s_trans = reinterpret_cast<Entry*>(smem_raw + 256);  // [(S+1)*(C+1)] when kSmemTable
@@ -240,7 +239,6 @@ __global__ void __launch_bounds__(kThreads) dfa_scan_kernel(DfaDev d, const uint
         }
         const int32_t e = __ldg(d.accept_first + st / n_cols);  // the dead row carries -1
         ext_id[line] = e;
-        span_cnt[line] = e >= 0 ? __ldg(slots_per_ext + e) : 0u;
     }
 }
 
@@ -248,7 +246,7 @@ __global__ void __launch_bounds__(kThreads) dfa_scan_kernel(DfaDev d, const uint
 // Per extraction: rows = states + 1 (last = dead), columns = symbol classes + 1 (last = identity: same state, no ops).
 __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const uint16_t* __restrict__ text,
                                                                 const int64_t* __restrict__ line_off, int sep,
-                                                                int64_t n_lines, const int64_t* __restrict__ span_off,
+                                                                int64_t n_lines, uint32_t span_stride,
                                                                 int32_t* __restrict__ ext_id, int32_t* __restrict__ spans) {
     __shared__ uint16_t s_cls[128];
     for (int i = threadIdx.x; i < 128; i += kThreads) s_cls[i] = c.cls[i];
@@ -257,7 +255,11 @@ __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const 
     for (int64_t line = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; line < n_lines;
          line += static_cast<int64_t>(gridDim.x) * kThreads) {
         const int32_t e = ext_id[line];
-        if (e < 0) continue;
+        int32_t* out = spans + line * span_stride;
+        if (e < 0) {
+            for (uint32_t s = 0; s < span_stride; ++s) out[s] = -1;
+            continue;
+        }
         const ExtDev x = c.ext[e];
         const int64_t a = line_off[line], b = line_off[line + 1] - sep;
         const uint32_t* __restrict__ tr = c.tdfa_trans + x.trans_off;
@@ -300,10 +302,9 @@ __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const 
             if (st == x.n_states) break;  // dead
         }
         const bool ok = __ldg(c.tdfa_accepting + x.acc_off + st) != 0;  // the dead row is not accepting
-        int32_t* out = spans + span_off[line];
         if (!ok) {
             ext_id[line] = -2 - e;
-            for (uint32_t s = 0; s < x.n_slots; ++s) out[s] = -1;
+            for (uint32_t s = 0; s < span_stride; ++s) out[s] = -1;
             continue;
         }
         const uint8_t* __restrict__ fin = c.tdfa_fin + x.fin_off + st * x.n_slots;
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const 
             const uint32_t f = __ldg(fin + s);
             out[s] = f == 0xFFu ? -1 : (f == 0xFEu ? len : regs[f]);
         }
+        for (uint32_t s = x.n_slots; s < span_stride; ++s) out[s] = -1;
     }
 }
 
@@ -378,34 +380,34 @@ static int persistent_grid(const Launch& L, const void* fn, size_t smem, int64_t
 
 template <bool kSmem, typename Entry>
 static void launch_dfa(const Launch& L, const DfaDev& d, size_t smem, const uint16_t* text, const int64_t* line_off, int sep,
-                       int64_t n_lines, const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt) {
+                       int64_t n_lines, int32_t* ext_id) {
     auto fn = dfa_scan_kernel<kSmem, Entry>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     int g = persistent_grid(L, reinterpret_cast<const void*>(fn), smem, n_lines);
-    fn<<<g, kThreads, smem, L.stream>>>(d, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+    fn<<<g, kThreads, smem, L.stream>>>(d, text, line_off, sep, n_lines, ext_id);
 }
 
 void k2_dfa_scan(const Launch& L, const DfaDev& d, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
-                 const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt) {
+                 int32_t* ext_id) {
     if (n_lines <= 0) return;
     const size_t esz = d.wide ? 4 : 2;
     const size_t table_bytes = static_cast<size_t>(d.n_states + 1) * (d.n_classes + 1) * esz;
     const bool in_smem = table_bytes <= 96 * 1024;
     const size_t smem = 256 + (in_smem ? table_bytes : 0);
     if (!d.wide) {
-        if (in_smem) launch_dfa<true, uint16_t>(L, d, smem, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
-        else launch_dfa<false, uint16_t>(L, d, smem, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+        if (in_smem) launch_dfa<true, uint16_t>(L, d, smem, text, line_off, sep, n_lines, ext_id);
+        else launch_dfa<false, uint16_t>(L, d, smem, text, line_off, sep, n_lines, ext_id);
     } else {
-        if (in_smem) launch_dfa<true, uint32_t>(L, d, smem, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
-        else launch_dfa<false, uint32_t>(L, d, smem, text, line_off, sep, n_lines, slots_per_ext, ext_id, span_cnt);
+        if (in_smem) launch_dfa<true, uint32_t>(L, d, smem, text, line_off, sep, n_lines, ext_id);
+        else launch_dfa<false, uint32_t>(L, d, smem, text, line_off, sep, n_lines, ext_id);
     }
 }
 
 void k4_tdfa_capture(const Launch& L, const CapDev& c, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
-                     const int64_t* span_off, int32_t* ext_id, int32_t* spans) {
+                     uint32_t span_stride, int32_t* ext_id, int32_t* spans) {
     if (n_lines <= 0) return;
     int g = persistent_grid(L, reinterpret_cast<const void*>(tdfa_capture_kernel), 0, n_lines);
-    tdfa_capture_kernel<<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_off, ext_id, spans);
+    tdfa_capture_kernel<<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_stride, ext_id, spans);
 }
 
 void k3_histogram(const Launch& L, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist) {

@@ -5,7 +5,7 @@
 //   K2 dfa_scan         — PolyMatcher.match + Automata.step/accept (autom/PolyMatcher.java:123-133,
 //                         autom/Automata.java:133-139) and the first-index dispatch of Gorp.java:166-167
 //   K4 tdfa_capture     — JDKRegexpCookedExtraction.match/_constructMatch (jdkre/JDKRegexpCookedExtraction.java:36-59)
-//   K3 histogram, K5 span offsets (exclusive scan) — result assembly of model/CookedExtraction.java:54-57
+//   K3 histogram, fixed-stride result rows — result assembly of model/CookedExtraction.java:54-57
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,11 +13,8 @@
 namespace gorp {
 
 constexpr int kMaxTdfaRegs = 32;   // run-time register file per line (tag registers of the capture automaton)
-constexpr int kFusedThreads = 512;  // CTA size of the fused kernel AND of the fast capture tier (register offsets in the
-                                    // capture image are pre-multiplied by kFusedThreads * 4)
-constexpr int kFusedTile = 16384;   // UTF-16 units per tile
-constexpr int kFusedMaxLines = 1024;
-constexpr int kFusedHistBins = 1024;
+constexpr int kCapFastThreads = 512;  // CTA size of the fast capture tier (register offsets in the capture image are
+                                      // pre-multiplied by kCapFastThreads * 4)
 
 struct DfaDev {                    // combined multi-regex DFA, compacted (host/automata.hpp: CompactDfa)
     const uint16_t* cls;           // [65536] unit -> class
@@ -108,46 +105,23 @@ void k1_finish(const Launch&, const uint16_t* text, int64_t n_units, const int64
 // exclusive scan: out[i] = sum_{j<i} in[j], out[n] = total (int64). scratch >= ceil(n/4096)+1 int64.
 void scan_u32_to_i64(const Launch&, const uint32_t* in, int64_t n, int64_t* out, int64_t* scratch);
 
-// K2: combined DFA, one line per thread. Writes ext_id (>=0 | -1) and span_cnt = 2*groups(ext) (0 on miss).
+// K2: combined DFA, one line per thread. Writes ext_id (>=0 | -1).
 void k2_dfa_scan(const Launch&, const DfaDev&, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
-                 const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt);
+                 int32_t* ext_id);
 
 // K2 fast tier: lines [0, n_lines) must each be terminated by '\n' in the text (the caller excludes a final
 // unterminated line and runs it through k2_dfa_scan).
 void k2_dfa_direct(const Launch&, const DfaDirectDev&, const uint16_t* text, const int64_t* line_off, int64_t n_lines,
-                   const uint32_t* slots_per_ext, int32_t* ext_id, uint32_t* span_cnt);
+                   int32_t* ext_id);
 
-// K4: capture automaton over the matched lines. Writes spans at span_off[i]; capture failure => ext_id = -2-e, spans -1.
+// K4: capture automaton over the matched lines. Writes the result row spans[i*span_stride ..]: 2*groups entries, the
+// rest of the row (and the whole row of a MISS / capture-failed line) is -1; capture failure => ext_id = -2-e.
 void k4_tdfa_capture(const Launch&, const CapDev&, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
-                     const int64_t* span_off, int32_t* ext_id, int32_t* spans);
+                     uint32_t span_stride, int32_t* ext_id, int32_t* spans);
 
 // K4 fast tier: lines [0, n_lines) are '\n'-terminated in the text.
 void k4_tdfa_fast(const Launch&, const TdfaFastDev&, const CapDev&, const uint16_t* text, int64_t n_units,
-                  const int64_t* line_off, int64_t n_lines, const int64_t* span_off, int32_t* ext_id, int32_t* spans);
-
-// K0: fused persistent kernel (text form): newline discovery + DFA + look-back offsets + capture in one HBM pass.
-struct FusedParams {
-    const uint16_t* text;
-    int64_t n_units;
-    int64_t n_tiles;
-    DfaDirectDev dfa;
-    TdfaFastDev cap_fast;
-    CapDev cap;
-    const uint32_t* slots_per_ext;
-    uint32_t n_ext;
-    int32_t* ext_id;
-    int64_t* line_off;
-    int64_t* span_off;
-    int32_t* spans;
-    unsigned long long* hist;
-    int64_t cap_lines, cap_spans;        // capacity of the per-line arrays (entries, excluding the +1) / of spans
-    unsigned long long* tile_lines;      // [n_tiles] look-back state, zeroed by the caller: flag(2) | value(62)
-    unsigned long long* tile_spans;      // [n_tiles]
-    unsigned int* ticket;                // zeroed by the caller
-    int64_t* totals;                     // [0] n_lines, [1] n_spans, [2] flags: 1 = capacity overflow, 2 = fallback needed
-};
-bool k0_fused_supported(const FusedParams&);
-void k0_fused_extract(const Launch&, const FusedParams&);
+                  const int64_t* line_off, int64_t n_lines, uint32_t span_stride, int32_t* ext_id, int32_t* spans);
 
 // K0': one-pass persistent kernel (text form) over the folded automaton of host/fused.hpp — see kernels/onepass.cu.
 constexpr uint32_t kOnePassOverhang = 1024;  // units staged beyond the tile (lines that cross the tile end)
@@ -176,16 +150,16 @@ struct OnePassParams {
     OnePassDev a;
     const uint32_t* slots_per_ext;
     uint32_t n_ext;
+    uint32_t span_stride;                // int32 entries per result row of `spans` (2 * groups of the widest extraction)
     int32_t* ext_id;
     int64_t* line_off;
-    int64_t* span_off;
-    int32_t* spans;
+    int32_t* spans;                      // [cap_lines * span_stride]
     unsigned long long* hist;
-    int64_t cap_lines, cap_spans;
-    unsigned long long* tile_status;     // [n_tiles] zeroed by the caller: flag(2) | spans(32) << 20 | lines(20)
-    long long* tile_prefix;              // [2 * n_tiles] inclusive (lines, spans) prefix, valid once the flag says so
+    int64_t cap_lines;
+    unsigned long long* tile_status;     // [n_tiles] zeroed by the caller: flag(2) | lines(62); flag 1 = the tile's own
+                                         // line count, flag 2 = inclusive prefix over tiles 0..t
     unsigned int* ticket;                // zeroed by the caller
-    int64_t* totals;                     // [0] n_lines, [1] n_spans, [2] flags: 1 = capacity overflow, 2 = tile too dense
+    int64_t* totals;                     // [0] n_lines, [2] flags: 1 = capacity overflow, 2 = tile too dense
 };
 size_t onepass_smem_bytes(const OnePassDev&, uint32_t threads, uint32_t tile_units);
 // picks CTA size and tile size for the expected line density; `shrink` = number of too-dense retries so far

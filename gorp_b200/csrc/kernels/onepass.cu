@@ -115,11 +115,11 @@ __device__ __noinline__ uint32_t slow_chunk(const OnePassDev& a, uint32_t ent, u
     return ent;
 }
 
-// ---- named barriers: the CTA is kT worker threads (8 warps) + one IO warp
+// ---- named barriers: the CTA is kT worker threads (8 warps) + one look-back warp
 constexpr uint32_t kIoThreads = 32;
 constexpr uint32_t kBarWorkers = 1;  // workers only
-constexpr uint32_t kBarFull = 2;     // workers arrive, IO warp waits: the result stage holds a finished tile
-constexpr uint32_t kBarFree = 3;     // IO warp arrives, workers wait: the result stage may be overwritten
+constexpr uint32_t kBarCount = 2;    // workers arrive, look-back warp waits: the tile's line count is known (after phase A)
+constexpr uint32_t kBarBase = 3;     // look-back warp arrives, workers wait: the tile's first result row is known
 constexpr uint32_t kSortBins = 64;
 
 __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -147,11 +147,6 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t v, uint32_t* s_warp, uin
     return base + incl - v;
 }
 
-struct StageHdr {  // 32 bytes
-    long long tile;  // -1: no more tiles
-    uint32_t n_lines, n_spans, too_dense, pad[3];
-};
-
 __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t kT = blockDim.x - kIoThreads;  // worker threads
@@ -165,18 +160,16 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
     uint32_t* s_slots = reinterpret_cast<uint32_t*>(s_oext + ((A.n_outcomes + 3) & ~3u));
     uint16_t* s_text0 = reinterpret_cast<uint16_t*>(s_slots + A.n_slots * kT);
     uint16_t* s_text1 = s_text0 + kBuf + 8;
-    uint16_t* s_start = s_text1 + kBuf + 8;                     // [kT] line starts of the tile, in text order
-    uint16_t* s_perm = s_start + kT;                            // [kT] worker thread -> line of the tile (sorted by length)
-    StageHdr* st_hdr = reinterpret_cast<StageHdr*>(s_perm + kT);  // result stage, handed to the IO warp
-    int32_t* st_ext = reinterpret_cast<int32_t*>(st_hdr + 1);   // [kT]
-    uint32_t* st_spoff = reinterpret_cast<uint32_t*>(st_ext + kT);  // [kT] span offset inside the tile
-    int32_t* st_spans = reinterpret_cast<int32_t*>(st_spoff + kT);  // [kT * max_slots], packed in line order
-    uint16_t* st_start = reinterpret_cast<uint16_t*>(st_spans + kT * A.max_slots);  // [kT]
+    uint16_t* s_start = s_text1 + kBuf + 8;  // [kT] line starts of the tile, in text order
+    uint16_t* s_perm = s_start + kT;         // [kT] worker thread -> line of the tile (sorted by length)
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ uint32_t s_warp[16];
     __shared__ uint32_t s_bins[kSortBins];
     __shared__ uint32_t s_hist[kOnePassHistBins];
     __shared__ long long s_next_tile;
+    __shared__ long long s_cnt_tile, s_line_base;  // workers -> look-back warp: tile id (-1 = done); and back: first row
+    __shared__ uint32_t s_cnt_lines, s_cnt_dense;
+    __shared__ int s_skip_writes;
 
     const uint32_t rows_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_rows));
     const uint32_t text_abs0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_text0));
@@ -216,99 +209,57 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
     __syncthreads();
 
     if (threadIdx.x >= kT) {
-        // =============================================================== IO warp
-        // Per finished tile: publish its (lines, spans) aggregate, look back over the predecessors (decoupled
-        // look-back, 32 tiles per probe), publish the inclusive prefix, then copy the staged result rows out with
-        // coalesced stores. The workers are already on the next tile meanwhile.
+        // =============================================================== look-back warp
+        // As soon as the workers know how many lines START in the tile (phase A), publish that count, look back over
+        // the predecessor tiles (decoupled look-back, 32 tiles per probe) and hand the tile's first result row to
+        // the workers, who are walking the tile's lines meanwhile. Predecessors publish at the beginning of THEIR
+        // tile, so this never waits for a predecessor's walk.
         const uint32_t lane = threadIdx.x - kT;
         for (;;) {
-            bar_sync(kBarFull, kAll);
-            const long long tile = st_hdr->tile;
+            bar_sync(kBarCount, kAll);
+            const long long tile = s_cnt_tile;
             if (tile < 0) break;
-            const uint32_t n_t = st_hdr->n_lines, span_t = st_hdr->n_spans;
-            const bool too_dense = st_hdr->too_dense != 0;
-            const unsigned long long my_lines = n_t, my_spans = span_t;
-            unsigned long long pre_l = 0, pre_s = 0;
+            const unsigned long long my_lines = s_cnt_lines;
+            const bool too_dense = s_cnt_dense != 0;
+            unsigned long long pre_l = 0;
             if (tile > 0) {
-                if (lane == 0) st_release(P.tile_status + tile, kStAgg | my_lines | (my_spans << 20));
+                if (lane == 0) st_release(P.tile_status + tile, kStAgg | my_lines);
                 for (int64_t j = tile - 1;; j -= 32) {
                     const int64_t idx = j - lane;
                     unsigned long long v = kStPre;  // before tile 0: an empty inclusive prefix
                     if (idx >= 0) {
                         v = ld_acquire(P.tile_status + idx);
                         while ((v >> 62) == 0) {
-                            __nanosleep(64);
+                            __nanosleep(32);
                             v = ld_acquire(P.tile_status + idx);
                         }
                     }
                     const uint32_t pmask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
                     const uint32_t first = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1u : 32u;
-                    unsigned long long l = 0, s = 0;
-                    if (lane < first) {
-                        l = v & 0xFFFFFull;
-                        s = (v >> 20) & 0xFFFFFFFFull;
-                    } else if (lane == first && idx >= 0) {
-                        l = static_cast<unsigned long long>(P.tile_prefix[2 * idx]);
-                        s = static_cast<unsigned long long>(P.tile_prefix[2 * idx + 1]);
-                    }
+                    unsigned long long l = lane <= first ? (v & ~(3ull << 62)) : 0ull;  // aggregates, then one inclusive prefix
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        l += __shfl_xor_sync(0xffffffffu, l, o);
-                        s += __shfl_xor_sync(0xffffffffu, s, o);
-                    }
+                    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
                     pre_l += l;
-                    pre_s += s;
                     if (pmask) break;
                 }
             }
-            const long long line_base = static_cast<long long>(pre_l), span_base = static_cast<long long>(pre_s);
-            const long long line_end = line_base + static_cast<long long>(my_lines), span_end = span_base + static_cast<long long>(my_spans);
-            const bool over = line_end > P.cap_lines || span_end > P.cap_spans;
+            const long long line_base = static_cast<long long>(pre_l), line_end = line_base + static_cast<long long>(my_lines);
             if (lane == 0) {
-                P.tile_prefix[2 * tile] = line_end;
-                P.tile_prefix[2 * tile + 1] = span_end;
-                st_release(P.tile_status + tile, kStPre);
+                st_release(P.tile_status + tile, kStPre | static_cast<unsigned long long>(line_end));
+                const bool over = line_end > P.cap_lines;
                 if (too_dense) atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 2ull);
                 if (over) atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 1ull);
                 if (tile == P.n_tiles - 1) {
                     P.totals[0] = line_end;
-                    P.totals[1] = span_end;
-                }
-            }
-            if (!over && !too_dense) {
-                const int64_t t0 = tile * T;
-                for (uint32_t j = lane; j < n_t; j += 32) {
-                    const long long row = line_base + j;
-                    const int32_t e = st_ext[j];
-                    P.ext_id[row] = e;
-                    P.line_off[row] = t0 + st_start[j];
-                    P.span_off[row] = span_base + st_spoff[j];
-                    const uint32_t bin = e >= 0 ? static_cast<uint32_t>(e) : (e == -1 ? P.n_ext : P.n_ext + 1);
-                    if (smem_hist) atomicAdd(&s_hist[bin], 1u);
-                    else atomicAdd(P.hist + bin, 1ull);
-                }
-                int32_t* dst = P.spans + span_base;
-                if ((span_base & 3) == 0) {
-                    const uint32_t n4 = span_t >> 2;
-                    for (uint32_t i = lane; i < n4; i += 32) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(st_spans)[i];
-                    for (uint32_t i = (n4 << 2) + lane; i < span_t; i += 32) dst[i] = st_spans[i];
-                } else {  // span counts are even (2 per group): always 8-byte aligned
-                    const uint32_t n2 = span_t >> 1;
-                    for (uint32_t i = lane; i < n2; i += 32) reinterpret_cast<int2*>(dst)[i] = reinterpret_cast<const int2*>(st_spans)[i];
-                }
-                if (tile == P.n_tiles - 1 && lane == 0) {
                     // line i spans [line_off[i], line_off[i+1] - 1): a text that does not end in '\n' gets n_units + 1
-                    P.line_off[line_end] = P.n_units + (P.text[P.n_units - 1] == 0x0A ? 0 : 1);
-                    P.span_off[line_end] = span_end;
+                    if (!over) P.line_off[line_end] = P.n_units + (P.text[P.n_units - 1] == 0x0A ? 0 : 1);
                 }
+                s_line_base = line_base;
+                s_skip_writes = (over || too_dense) ? 1 : 0;
             }
             __syncwarp();
-            bar_arrive(kBarFree, kAll);
-        }
-        if (smem_hist) {
-            __syncwarp();
-            for (uint32_t i = lane; i < n_bins; i += 32)
-                if (s_hist[i]) atomicAdd(P.hist + i, static_cast<unsigned long long>(s_hist[i]));
+            __threadfence_block();
+            bar_arrive(kBarBase, kAll);
         }
         return;
     }
@@ -319,9 +270,9 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
     const uint32_t slot_stride = kT * 4;
     const uint32_t fin_ent = (A.fin_base * row_q) << 18;
     const uint32_t inv_row_q = 65536u / row_q + 1u;
+    const uint32_t stride = P.span_stride;
     int64_t tile = s_next_tile;
     uint32_t buf = 0, phase = 0;  // phase bit b = parity to wait for on barrier b
-    uint32_t iter = 0;
 
     while (tile < P.n_tiles) {
         bar_sync(kBarWorkers, kT);  // everyone has read s_next_tile; the other text buffer is no longer being read
@@ -369,6 +320,13 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
         uint32_t my = block_scan(static_cast<uint32_t>(__popcll(nl_mask)), s_warp, &n_t, kT) + extra;
         n_t += extra;
         const bool too_dense = n_t > kT;
+        if (threadIdx.x == 0) {
+            s_cnt_tile = tile;
+            s_cnt_lines = too_dense ? 0u : n_t;
+            s_cnt_dense = too_dense ? 1u : 0u;
+        }
+        __threadfence_block();
+        bar_arrive(kBarCount, kAll);  // the look-back for this tile runs while the lines are walked
         if (!too_dense) {
             if (extra && threadIdx.x == 0) s_start[0] = 0;
             const uint32_t u0 = threadIdx.x * per;
@@ -402,11 +360,11 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
         bar_sync(kBarWorkers, kT);
 
         // ---- B: one line per thread through the one-pass automaton
-        uint32_t outcome = 0, line = 0;
+        uint32_t outcome = 0, line = 0, rel = 0;
         if (have_line) {
             line = s_perm[threadIdx.x];
             for (uint32_t k = 0; k < A.n_init; ++k) sts32(slot_abs + __ldg(A.init_slots + k) * slot_stride, 0xFFFFFFFFu);
-            const uint32_t rel = s_start[line];
+            rel = s_start[line];
             uint32_t q = rel & ~7u;
             const uint32_t lo = rel & 7u;
             uint32_t ent = lo ? ((A.skip_base + lo - 1) * row_q) << 18 : 0u;
@@ -431,60 +389,41 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
             outcome = (((ent >> 18) - A.fin_base * row_q) * inv_row_q) >> 16;  // exact: a multiple of row_q below 2^14
         }
 
-        // ---- C: stage the tile's result rows for the IO warp (span counts: 2*groups for MATCH and CAPTURE_FAIL)
-        int32_t ext = -1;
-        uint32_t cnt = 0;
-        if (have_line) {
-            ext = s_oext[outcome];
-            if (ext != -1) cnt = __ldg(P.slots_per_ext + (ext >= 0 ? ext : -2 - ext));
-        }
-        if (iter > 0) bar_sync(kBarFree, kAll);  // the IO warp has copied the previous tile out
-        if (have_line) {
-            st_ext[line] = ext;
-            st_spoff[line] = cnt;
-        }
-        bar_sync(kBarWorkers, kT);
-        uint32_t span_t;
-        {
-            const bool row = !too_dense && threadIdx.x < n_t;
-            const uint32_t c = row ? st_spoff[threadIdx.x] : 0u;
-            const uint32_t excl = block_scan(c, s_warp, &span_t, kT);
-            if (row) {
-                st_spoff[threadIdx.x] = excl;
-                st_start[threadIdx.x] = s_start[threadIdx.x];
-            }
-        }
-        bar_sync(kBarWorkers, kT);
-        if (cnt) {
-            int32_t* out = st_spans + st_spoff[line];
+        // ---- C: result rows. Row = (first row of the tile, from the look-back warp) + line index inside the tile.
+        bar_sync(kBarBase, kAll);
+        if (have_line && !s_skip_writes) {
+            const int64_t row = s_line_base + line;
+            const int32_t ext = s_oext[outcome];
+            P.ext_id[row] = ext;
+            P.line_off[row] = t0 + rel;
+            int32_t* out = P.spans + row * stride;
+            uint32_t k = 0;
             if (ext >= 0) {
+                const uint32_t cnt = __ldg(P.slots_per_ext + ext);
                 const uint32_t* res = s_res + outcome * A.max_slots;
-                for (uint32_t k = 0; k < cnt; ++k) {
+                for (; k < cnt; ++k) {
                     int32_t val = -1;
                     for (uint32_t packed = res[k]; packed; packed >>= 8)
                         val = max(val, static_cast<int32_t>(lds32(slot_abs + (packed & 0xFFu) * slot_stride)));
                     out[k] = val;
                 }
-            } else {
-                for (uint32_t k = 0; k < cnt; ++k) out[k] = -1;
             }
+            for (; k < stride; ++k) out[k] = -1;
+            const uint32_t bin = ext >= 0 ? static_cast<uint32_t>(ext) : (ext == -1 ? P.n_ext : P.n_ext + 1);
+            if (smem_hist) atomicAdd(&s_hist[bin], 1u);
+            else atomicAdd(P.hist + bin, 1ull);
         }
-        if (threadIdx.x == 0) {
-            st_hdr->tile = tile;
-            st_hdr->n_lines = too_dense ? 0u : n_t;
-            st_hdr->n_spans = span_t;
-            st_hdr->too_dense = too_dense ? 1u : 0u;
-        }
-        __threadfence_block();
-        bar_arrive(kBarFull, kAll);
         tile = s_next_tile;
         buf ^= 1;
-        ++iter;
     }
-    if (iter > 0) bar_sync(kBarFree, kAll);
-    if (threadIdx.x == 0) st_hdr->tile = -1;
+    if (threadIdx.x == 0) s_cnt_tile = -1;
     __threadfence_block();
-    bar_arrive(kBarFull, kAll);
+    bar_arrive(kBarCount, kAll);
+    if (smem_hist) {
+        bar_sync(kBarWorkers, kT);
+        for (uint32_t i = threadIdx.x; i < n_bins; i += kT)
+            if (s_hist[i]) atomicAdd(P.hist + i, static_cast<unsigned long long>(s_hist[i]));
+    }
 }
 
 }  // namespace
@@ -495,8 +434,7 @@ size_t onepass_smem_bytes(const OnePassDev& a, uint32_t threads, uint32_t tile_u
     b += static_cast<size_t>((a.n_outcomes + 3) & ~3u) * 4;
     b += static_cast<size_t>(a.n_slots) * threads * 4;
     b += 2 * static_cast<size_t>(tile_units + kOnePassOverhang + 8) * 2;
-    b += static_cast<size_t>(threads) * (2 + 2);                           // s_start, s_perm
-    b += 32 + static_cast<size_t>(threads) * (4 + 4 + 2 + 4 * a.max_slots);  // result stage
+    b += static_cast<size_t>(threads) * (2 + 2);  // s_start, s_perm
     return b + 128;
 }
 

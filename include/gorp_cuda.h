@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GORP_ABI_VERSION 1
+#define GORP_ABI_VERSION 2
 
 typedef enum gorp_status {
     GORP_OK = 0,
@@ -54,16 +54,18 @@ typedef struct gorp_engine gorp_engine;
 typedef struct gorp_result {
     int64_t n_lines;
     int32_t n_extractions;
-    int32_t reserved;
+    int32_t span_stride;      /* int32 entries per result row of `spans` = 2 * (groups of the widest extraction) */
     const int32_t* ext_id;    /* [n_lines] */
     const int64_t* line_off;  /* [n_lines+1] start of each line in the caller's text; line i spans
                                  [line_off[i], line_off[i+1] - sep) with sep = 1 for gorp_extract_text ('\n'
                                  separated; line_off[n_lines] = n_units (+1 when the text does not end in '\n'))
                                  and sep = 0 for gorp_extract_lines (a copy of the caller's offsets) */
-    const int64_t* span_off;  /* [n_lines+1] CSR into spans, counted in int32 entries: line i owns
-                                 2 * n_groups(ext_id[i]) entries (none for MISS / capture failure) */
-    const int32_t* spans;     /* (start, end) pairs in UTF-16 units relative to the start of the line, in group
-                                 order == extractor-name order; (-1,-1) when a group did not participate */
+    const int32_t* spans;     /* [n_lines * span_stride] one fixed-size row per line: row i starts at i * span_stride
+                                 and holds 2 * n_groups(ext_id[i]) valid entries = (start, end) pairs in UTF-16 units
+                                 relative to the start of the line, in group order == extractor-name order; (-1,-1)
+                                 when a group did not participate; the rest of the row, and the whole row of a MISS
+                                 or capture-failed line, is -1. Fixed rows (instead of a CSR) keep the device path
+                                 free of a span-offset prefix sum and let Java index rows directly. */
     const int64_t* histogram; /* [n_extractions + 2]: lines per extraction, then MISS, then capture failures */
     void* owner;              /* internal */
 } gorp_result;
@@ -121,9 +123,10 @@ void gorp_result_release(gorp_engine* e, gorp_result* r);
 
 typedef struct gorp_device_result {
     int64_t n_lines;
+    int32_t span_stride;
+    int32_t reserved;
     const int32_t* d_ext_id;
     const int64_t* d_line_off;
-    const int64_t* d_span_off;
     const int32_t* d_spans;
     const int64_t* d_histogram;
     const int64_t* d_n_lines; /* device scalar */

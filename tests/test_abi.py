@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported():
     for n in names:
         assert hasattr(_ffi.lib, n), n
     assert sorted(_ffi.SYMBOLS) == names
-    assert _ffi.lib.gorp_abi_version() == 1
+    assert _ffi.lib.gorp_abi_version() == 2
 
 
 def test_blob_roundtrip_and_corruption():

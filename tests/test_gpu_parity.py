@@ -13,18 +13,6 @@ from tests.test_host_compile import ALL_DEFS, FUZZ_PATTERNS, TRICKY_LINES
 pytestmark = pytest.mark.gpu
 
 
-def dense_spans(batch, width):
-    """CSR spans of an ExtractionBatch -> [n, width] matrix padded with -1 (oracle layout)."""
-    n = batch.n_lines
-    out = np.full((n, max(width, 1)), -1, dtype=np.int32)
-    cnt = (batch.span_off[1:] - batch.span_off[:-1]).astype(np.int64)
-    if n and cnt.sum():
-        rows = np.repeat(np.arange(n), cnt)
-        cols = np.arange(int(cnt.sum())) - np.repeat(batch.span_off[:-1], cnt)
-        out[rows, cols] = batch.spans
-    return out[:, :width]
-
-
 def check_against_oracle(definition, text=None, lines=None, gorp=None):
     g = gorp or DefinitionReader.reader(definition).read()
     o = gorp_oracle.Gorp(definition)
@@ -44,12 +32,10 @@ def check_against_oracle(definition, text=None, lines=None, gorp=None):
         assert b.n_lines == len(starts)
         assert (b.line_off[:-1] == starts).all() and (b.line_off[1:] - 1 == ends).all()
     assert (b.ext_id == oe).all(), np.flatnonzero(b.ext_id != oe)[:10]
-    # span counts: 2*groups for matched AND capture-failed lines (the latter all -1), 0 for misses
-    ng = np.asarray([len(x.extractor_names) for x in o.extractions], dtype=np.int64)
-    e_of = np.where(oe >= 0, oe, np.where(oe <= -2, -2 - oe, 0))
-    want_cnt = np.where(oe == -1, 0, 2 * ng[e_of])
-    assert ((b.span_off[1:] - b.span_off[:-1]) == want_cnt).all()
-    assert (dense_spans(b, 2 * G) == osp).all()
+    # one fixed row of 2 * (widest extraction's groups) entries per line: 2*groups valid entries for a matched line,
+    # -1 everywhere else (padding, MISS rows, capture-failed rows) -- exactly the oracle's layout
+    assert b.span_stride == 2 * G and b.spans.shape == (b.n_lines, 2 * G)
+    assert (b.spans == osp[:, :2 * G]).all(), np.flatnonzero((b.spans != osp[:, :2 * G]).any(axis=1))[:10]
     E = len(o.extractions)
     hist = np.zeros(E + 2, dtype=np.int64)
     np.add.at(hist, np.where(oe >= 0, oe, np.where(oe == -1, E, E + 1)), 1)
@@ -183,19 +169,18 @@ def test_full_size_properties():
     assert b.n_lines == reps * b1.n_lines
     assert (b.histogram == reps * b1.histogram).all()
     assert (b.ext_id.reshape(reps, -1) == b1.ext_id[None, :]).all()
-    assert (b.spans.reshape(reps, -1) == b1.spans[None, :]).all()
-    assert (np.diff(b.line_off) > 0).all() and (np.diff(b.span_off) >= 0).all()
+    assert (b.spans.reshape(reps, b1.n_lines, -1) == b1.spans[None, :, :]).all()
+    assert (np.diff(b.line_off) > 0).all()
 
 
-TIERS = {"onepass": {}, "twopass_fused": {"GORP_FORCE_TWOPASS": "1"}, "unfused_fast": {"GORP_FORCE_UNFUSED": "1"},
-         "general": {"GORP_FORCE_GENERAL": "1"}}
+TIERS = {"onepass": {}, "twopass_fast": {"GORP_FORCE_TWOPASS": "1"}, "general": {"GORP_FORCE_GENERAL": "1"}}
 
 
 @pytest.mark.parametrize("tier", list(TIERS))
 def test_every_kernel_tier_text_form(tier, monkeypatch):
     """The text form takes the fastest tier the definition allows; force each tier in turn (the engine reads the
     GORP_FORCE_* switches when it is created) and hold all of them to the same oracle."""
-    for k in ("GORP_FORCE_TWOPASS", "GORP_FORCE_UNFUSED", "GORP_FORCE_GENERAL"):
+    for k in ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL"):
         monkeypatch.delenv(k, raising=False)
     for k, v in TIERS[tier].items():
         monkeypatch.setenv(k, v)
