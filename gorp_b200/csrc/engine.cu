@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -116,7 +118,7 @@ struct DeviceCtx {
     DevBuf tile_state;
     // per-call scratch, serialised by `mu`
     std::mutex mu;
-    DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, spans, hist, scalars;
+    DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, spans, hist, scalars, debug;
     // per-kernel device time: CUDA events on the launching stream, accumulated over timed calls
     cudaEvent_t ev[kMaxTimed + 1]{};
     const char* ev_name[kMaxTimed]{};
@@ -507,12 +509,35 @@ bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
         P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 8 + 8);
         CK(cudaMemsetAsync(st, 0, state_bytes, stream));
         CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
+        const bool debug = std::getenv("GORP_ONEPASS_DEBUG") != nullptr;
+        const int grid = k0_onepass_grid(L, P, threads);
+        if (debug) {
+            c.debug.reserve(static_cast<size_t>(grid) * 24 * 8);
+            CK(cudaMemsetAsync(c.debug.p, 0, static_cast<size_t>(grid) * 24 * 8, stream));
+            P.debug = c.debug.as<long long>();
+        }
         k0_onepass_extract(L, P, threads);
         tm.mark("k0_onepass_extract", 1);
         CK(cudaGetLastError());
         int64_t totals[3] = {0, 0, 0};
         CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        if (debug) {  // mean cycles per tile and phase, first and last worker warp
+            std::vector<long long> h(static_cast<size_t>(grid) * 24);
+            CK(cudaMemcpy(h.data(), c.debug.p, h.size() * 8, cudaMemcpyDeviceToHost));
+            static const char* kPhase[11] = {"top_barrier", "ticket+tail+tma_wait", "barrier", "newline_masks", "scan+starts",
+                                             "sort", "walk", "walk_barrier", "stage_rows", "base_barrier", "copy_out"};
+            for (int w = 0; w < 2; ++w) {
+                double acc[12] = {0};
+                for (int b = 0; b < grid; ++b)
+                    for (int i = 0; i < 12; ++i) acc[i] += static_cast<double>(h[(static_cast<size_t>(b) * 2 + w) * 12 + i]);
+                acc[11] = std::floor(acc[11] / 4);  // tiles (the low bits are debris of value consumption)
+                std::fprintf(stderr, "[onepass debug] %s warp, tile=%u units, %d CTAs, %.0f tiles/CTA; cycles per tile:", w ? "last" : "first",
+                             tile, grid, acc[11] / grid);
+                for (int i = 0; i < 11; ++i) std::fprintf(stderr, " %s=%.0f", kPhase[i], acc[i] / std::max(acc[11], 1.0));
+                std::fprintf(stderr, "\n");
+            }
+        }
         if (totals[2] & 2) {  // a tile held more line starts than the CTA has worker threads: smaller tiles
             ++c.onepass_shrink;
             continue;

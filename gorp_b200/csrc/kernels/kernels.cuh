@@ -160,7 +160,9 @@ struct OnePassParams {
                                          // line count, flag 2 = inclusive prefix over tiles 0..t
     unsigned int* ticket;                // zeroed by the caller
     int64_t* totals;                     // [0] n_lines, [2] flags: 1 = capacity overflow, 2 = tile too dense
+    long long* debug;                    // optional [grid * 2 * 10] per-phase cycle counters (GORP_ONEPASS_DEBUG=1)
 };
+int k0_onepass_grid(const Launch&, const OnePassParams&, uint32_t threads);
 size_t onepass_smem_bytes(const OnePassDev&, uint32_t threads, uint32_t tile_units);
 // picks CTA size and tile size for the expected line density; `shrink` = number of too-dense retries so far
 bool k0_onepass_plan(const OnePassDev&, double lines_per_unit, uint32_t shrink, uint32_t* threads, uint32_t* tile_units);

@@ -115,6 +115,16 @@ __device__ __noinline__ uint32_t slow_chunk(const OnePassDev& a, uint32_t ent, u
     return ent;
 }
 
+// bit k (k < 4) = unit k of the pair of words (a, b) is '\n' (0x000A). Low and high bytes are gathered with PRMT, a
+// unit is '\n' iff (low ^ 0x0A) | high == 0; exact zero-byte test, then the four flag bits (7, 15, 23, 31) are
+// compressed with one multiply.
+__device__ __forceinline__ uint32_t nl_bits4(uint32_t a, uint32_t b) {
+    const uint32_t lo = __byte_perm(a, b, 0x6420), hi = __byte_perm(a, b, 0x7531);
+    const uint32_t t = (lo ^ 0x0A0A0A0Au) | hi;
+    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);  // 0x80 in every zero byte of t
+    return (((z >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+
 // ---- named barriers: the CTA is kT worker threads (8 warps) + one look-back warp
 constexpr uint32_t kIoThreads = 32;
 constexpr uint32_t kBarWorkers = 1;  // workers only
@@ -157,7 +167,8 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
     uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem);
     uint32_t* s_res = s_rows + A.n_rows * A.width;
     int32_t* s_oext = reinterpret_cast<int32_t*>(s_res + ((A.n_outcomes * A.max_slots + 3) & ~3u));
-    uint32_t* s_slots = reinterpret_cast<uint32_t*>(s_oext + ((A.n_outcomes + 3) & ~3u));
+    uint32_t* s_ocnt = reinterpret_cast<uint32_t*>(s_oext + ((A.n_outcomes + 3) & ~3u));  // valid span entries per outcome
+    uint32_t* s_slots = s_ocnt + ((A.n_outcomes + 3) & ~3u);
     uint16_t* s_text0 = reinterpret_cast<uint16_t*>(s_slots + A.n_slots * kT);
     uint16_t* s_text1 = s_text0 + kBuf + 8;
     uint16_t* s_start = s_text1 + kBuf + 8;  // [kT] line starts of the tile, in text order
@@ -182,14 +193,20 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
         s_rows[i] = (((raw >> 16) * row_q) << 18) | ((raw & 0xFFFFu) * kT);
     }
     for (uint32_t i = threadIdx.x; i < A.n_outcomes * A.max_slots; i += kAll) s_res[i] = __ldg(A.out_res + i);
-    for (uint32_t i = threadIdx.x; i < A.n_outcomes; i += kAll) s_oext[i] = __ldg(A.out_ext + i);
+    for (uint32_t i = threadIdx.x; i < A.n_outcomes; i += kAll) {
+        const int32_t e = __ldg(A.out_ext + i);
+        s_oext[i] = e;
+        s_ocnt[i] = e >= 0 ? __ldg(P.slots_per_ext + e) : 0u;
+    }
+    __shared__ uint32_t s_init[16];
+    for (uint32_t i = threadIdx.x; i < A.n_init && i < 16; i += kAll) s_init[i] = __ldg(A.init_slots + i);
     const uint32_t n_bins = P.n_ext + 2;
     const bool smem_hist = n_bins <= kOnePassHistBins;
     for (uint32_t i = threadIdx.x; i < kOnePassHistBins; i += kAll) s_hist[i] = 0;
 
     auto issue_load = [&](int64_t tile, uint32_t b) {  // worker thread 0 only
         const int64_t t0 = tile * T;
-        const int64_t avail = P.n_units - t0 < kBuf ? P.n_units - t0 : kBuf;
+        const int64_t avail = P.n_units - t0 < kBuf + 8 ? P.n_units - t0 : kBuf + 8;
         const uint32_t bulk_units = static_cast<uint32_t>(avail) & ~7u;
         if (bulk_units) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -273,19 +290,31 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
     const uint32_t stride = P.span_stride;
     int64_t tile = s_next_tile;
     uint32_t buf = 0, phase = 0;  // phase bit b = parity to wait for on barrier b
+    // thread 0 takes the ticket of the tile after the next one early (its latency hides behind the result rows)
+    long long ticket_ahead = threadIdx.x == 0 && tile < P.n_tiles ? static_cast<long long>(atomicAdd(P.ticket, 1u)) : 0;
+    // optional per-phase cycle accounting (GORP_ONEPASS_DEBUG=1): thread 0 and the first thread of the last worker warp
+    const bool dbg = P.debug != nullptr && (threadIdx.x == 0 || threadIdx.x == kT - 32);
+    long long dbg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, dbg_prev = dbg ? clock64() : 0;
+#define GORP_PH(i)                         \
+    if (dbg) {                             \
+        const long long t_ = clock64();    \
+        dbg_acc[i] += t_ - dbg_prev;       \
+        dbg_prev = t_;                     \
+    }
 
     while (tile < P.n_tiles) {
         bar_sync(kBarWorkers, kT);  // everyone has read s_next_tile; the other text buffer is no longer being read
+        GORP_PH(0)
         if (threadIdx.x == 0) {
-            const long long nx = atomicAdd(P.ticket, 1u);
+            const long long nx = ticket_ahead;
             s_next_tile = nx;
             if (nx < P.n_tiles) issue_load(nx, buf ^ 1);
         }
         const int64_t t0 = tile * T;
         const uint32_t text_abs = buf ? text_abs1 : text_abs0;
         uint16_t* s_text = buf ? s_text1 : s_text0;
-        const int64_t avail = P.n_units - t0 < kBuf ? P.n_units - t0 : kBuf;  // > 0
-        const uint32_t bulk_units = static_cast<uint32_t>(avail) & ~7u;
+        const int64_t avail = P.n_units - t0 < kBuf + 8 ? P.n_units - t0 : kBuf + 8;  // > 0
+        const uint32_t bulk_units = static_cast<uint32_t>(avail) & ~7u;  // == kBuf + 8 except at the end of the text
         for (uint32_t i = bulk_units + threadIdx.x; i < kBuf + 8; i += kT)
             s_text[i] = i < avail ? __ldg(P.text + t0 + i) : static_cast<uint16_t>(0x0A);
         if (threadIdx.x < kSortBins) s_bins[threadIdx.x] = 0;
@@ -293,7 +322,9 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
             mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
             phase ^= 1u << buf;
         }
+        GORP_PH(1)
         bar_sync(kBarWorkers, kT);
+        GORP_PH(2)
 
         // ---- A: line starts owned by this tile = (position of a '\n' in [t0, t0+T)) + 1, if < n_units
         const uint32_t per = P.per;  // units per thread, multiple of 8, <= 64
@@ -302,19 +333,13 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
             const uint32_t u0 = threadIdx.x * per;
             for (uint32_t j = 0; j < per / 8; ++j) {
                 const uint4 v = lds128(text_abs + (u0 + j * 8) * 2);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                uint32_t m8 = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t m = __vcmpeq2(w[k], 0x000A000Au);
-                    m8 |= ((m & 1u) | ((m >> 15) & 2u)) << (k * 2);
-                }
-                nl_mask |= static_cast<unsigned long long>(m8) << (j * 8);
+                nl_mask |= static_cast<unsigned long long>(nl_bits4(v.x, v.y) | (nl_bits4(v.z, v.w) << 4)) << (j * 8);
             }
             // a '\n' at position p starts a line only if p + 1 < n_units (the padding beyond the text is '\n' too)
             const int64_t room = P.n_units - 1 - (t0 + u0);
             if (room < static_cast<int64_t>(per)) nl_mask = room <= 0 ? 0ull : (nl_mask & ((1ull << room) - 1ull));
         }
+        GORP_PH(3)
         const uint32_t extra = tile == 0 ? 1u : 0u;  // the line at offset 0
         uint32_t n_t;
         uint32_t my = block_scan(static_cast<uint32_t>(__popcll(nl_mask)), s_warp, &n_t, kT) + extra;
@@ -337,6 +362,7 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
             }
         }
         bar_sync(kBarWorkers, kT);
+        GORP_PH(4)
 
         // ---- A': counting sort of the tile's lines by the number of 16-byte chunks they span, so that the 32 lines
         // of a warp take (almost) the same number of loop iterations. The tile's last line ends beyond the tile:
@@ -353,17 +379,28 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
             rank = atomicAdd(&s_bins[key], 1u);
         }
         bar_sync(kBarWorkers, kT);
-        if (have_line) {
-            for (uint32_t b = 0; b < key; ++b) rank += s_bins[b];
-            s_perm[rank] = static_cast<uint16_t>(threadIdx.x);
+        {   // exclusive prefix over the 64 bins, redundantly per warp: lane l owns bins 2l and 2l+1
+            const uint32_t lane = threadIdx.x & 31u;
+            const uint32_t b0 = s_bins[2 * lane], b1 = s_bins[2 * lane + 1];
+            uint32_t incl = b0 + b1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t excl = incl - (b0 + b1);
+            const uint32_t e = __shfl_sync(0xffffffffu, excl, key >> 1), f = __shfl_sync(0xffffffffu, b0, key >> 1);
+            if (have_line) s_perm[rank + e + ((key & 1u) ? f : 0u)] = static_cast<uint16_t>(threadIdx.x);
         }
         bar_sync(kBarWorkers, kT);
+        GORP_PH(5)
 
         // ---- B: one line per thread through the one-pass automaton
         uint32_t outcome = 0, line = 0, rel = 0;
         if (have_line) {
             line = s_perm[threadIdx.x];
-            for (uint32_t k = 0; k < A.n_init; ++k) sts32(slot_abs + __ldg(A.init_slots + k) * slot_stride, 0xFFFFFFFFu);
+            for (uint32_t k = 0; k < A.n_init; ++k)
+                sts32(slot_abs + (k < 16 ? s_init[k] : __ldg(A.init_slots + k)) * slot_stride, 0xFFFFFFFFu);
             rel = s_start[line];
             uint32_t q = rel & ~7u;
             const uint32_t lo = rel & 7u;
@@ -390,32 +427,79 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
         }
 
         // ---- C: result rows. Row = (first row of the tile, from the look-back warp) + line index inside the tile.
-        bar_sync(kBarBase, kAll);
-        if (have_line && !s_skip_writes) {
-            const int64_t row = s_line_base + line;
-            const int32_t ext = s_oext[outcome];
-            P.ext_id[row] = ext;
-            P.line_off[row] = t0 + rel;
-            int32_t* out = P.spans + row * stride;
-            uint32_t k = 0;
-            if (ext >= 0) {
-                const uint32_t cnt = __ldg(P.slots_per_ext + ext);
-                const uint32_t* res = s_res + outcome * A.max_slots;
-                for (; k < cnt; ++k) {
+        // Once every walk is over this tile's text buffer is dead: the rows are staged in it in line order and, when
+        // the look-back warp has delivered the first row, copied out with coalesced (vector) stores. Rows too wide
+        // to be staged go out directly.
+        GORP_PH(6)
+        const bool staged = (kT * 4u * (1u + stride)) <= (kBuf + 8u) * 2u;
+        int32_t* st_ext = reinterpret_cast<int32_t*>(s_text);
+        int32_t* st_spans = st_ext + kT;
+        if (staged) bar_sync(kBarWorkers, kT);
+        else bar_sync(kBarBase, kAll);
+        if (threadIdx.x == 0 && s_next_tile < P.n_tiles) ticket_ahead = static_cast<long long>(atomicAdd(P.ticket, 1u));
+        if (dbg) dbg_acc[11] += st_ext[0] & 1;  // consume a value: the clock below is read after the barrier
+        GORP_PH(7)
+        int32_t ext = -1;
+        if (have_line) {
+            ext = s_oext[outcome];
+            const uint32_t cnt = s_ocnt[outcome];
+            const uint32_t* res = s_res + outcome * A.max_slots;
+            const uint32_t* my_slots = s_slots + threadIdx.x;
+            int32_t* out = staged ? st_spans + line * stride : P.spans + (s_line_base + line) * stride;
+            if (staged || !s_skip_writes) {
+                for (uint32_t k = 0; k < stride; ++k) {
                     int32_t val = -1;
-                    for (uint32_t packed = res[k]; packed; packed >>= 8)
-                        val = max(val, static_cast<int32_t>(lds32(slot_abs + (packed & 0xFFu) * slot_stride)));
+                    for (uint32_t packed = k < cnt ? res[k] : 0u; packed; packed >>= 8)
+                        val = max(val, static_cast<int32_t>(my_slots[(packed & 0xFFu) * kT]));
                     out[k] = val;
                 }
+                if (staged) {
+                    st_ext[line] = ext;
+                } else {
+                    P.ext_id[s_line_base + line] = ext;
+                    P.line_off[s_line_base + line] = t0 + rel;
+                }
             }
-            for (; k < stride; ++k) out[k] = -1;
-            const uint32_t bin = ext >= 0 ? static_cast<uint32_t>(ext) : (ext == -1 ? P.n_ext : P.n_ext + 1);
-            if (smem_hist) atomicAdd(&s_hist[bin], 1u);
-            else atomicAdd(P.hist + bin, 1ull);
         }
+        // histogram: one shared-memory atomic per distinct outcome of the warp
+        if (smem_hist) {
+            const uint32_t bin = !have_line ? 0xFFFFFFFFu : ext >= 0 ? static_cast<uint32_t>(ext) : (ext == -1 ? P.n_ext : P.n_ext + 1);
+            const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+            if (have_line && (threadIdx.x & 31u) == static_cast<uint32_t>(__ffs(peers)) - 1u) atomicAdd(&s_hist[bin], static_cast<uint32_t>(__popc(peers)));
+        } else if (have_line) {
+            atomicAdd(P.hist + (ext >= 0 ? static_cast<uint32_t>(ext) : (ext == -1 ? P.n_ext : P.n_ext + 1)), 1ull);
+        }
+        GORP_PH(8)
+        if (staged) {
+            bar_sync(kBarBase, kAll);
+            const bool skip_writes = s_skip_writes != 0;
+            const int64_t line_base = s_line_base;
+            if (dbg) dbg_acc[11] += line_base & 1;
+            GORP_PH(9)
+            if (!skip_writes && !too_dense) {
+                if (threadIdx.x < n_t) {
+                    P.ext_id[line_base + threadIdx.x] = st_ext[threadIdx.x];
+                    P.line_off[line_base + threadIdx.x] = t0 + s_start[threadIdx.x];
+                }
+                const uint32_t total = n_t * stride;
+                int32_t* dst = P.spans + line_base * stride;
+                if (((line_base * stride) & 3) == 0) {
+                    const uint32_t n4 = total >> 2;
+                    for (uint32_t i = threadIdx.x; i < n4; i += kT) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(st_spans)[i];
+                    for (uint32_t i = (n4 << 2) + threadIdx.x; i < total; i += kT) dst[i] = st_spans[i];
+                } else {
+                    for (uint32_t i = threadIdx.x; i < total; i += kT) dst[i] = st_spans[i];
+                }
+            }
+        }
+        GORP_PH(10)
+        dbg_acc[11] += 4;
         tile = s_next_tile;
         buf ^= 1;
     }
+    if (dbg)
+        for (int i = 0; i < 12; ++i) P.debug[(blockIdx.x * 2 + (threadIdx.x ? 1 : 0)) * 12 + i] = dbg_acc[i];
+#undef GORP_PH
     if (threadIdx.x == 0) s_cnt_tile = -1;
     __threadfence_block();
     bar_arrive(kBarCount, kAll);
@@ -431,7 +515,7 @@ __global__ void __launch_bounds__(512) onepass_kernel(OnePassParams P) {
 size_t onepass_smem_bytes(const OnePassDev& a, uint32_t threads, uint32_t tile_units) {
     size_t b = static_cast<size_t>(a.n_rows) * a.width * 4;
     b += static_cast<size_t>((a.n_outcomes * a.max_slots + 3) & ~3u) * 4;
-    b += static_cast<size_t>((a.n_outcomes + 3) & ~3u) * 4;
+    b += 2 * static_cast<size_t>((a.n_outcomes + 3) & ~3u) * 4;
     b += static_cast<size_t>(a.n_slots) * threads * 4;
     b += 2 * static_cast<size_t>(tile_units + kOnePassOverhang + 8) * 2;
     b += static_cast<size_t>(threads) * (2 + 2);  // s_start, s_perm
@@ -465,17 +549,22 @@ bool k0_onepass_plan(const OnePassDev& a, double lines_per_unit, uint32_t shrink
     return true;
 }
 
-void k0_onepass_extract(const Launch& L, const OnePassParams& P, uint32_t threads) {
+int k0_onepass_grid(const Launch& L, const OnePassParams& P, uint32_t threads) {
     const size_t smem = onepass_smem_bytes(P.a, threads, P.tile_units);
-    const int block = static_cast<int>(threads + 32);  // + the IO warp
+    const int block = static_cast<int>(threads + 32);  // + the look-back warp
     cudaFuncSetAttribute(onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onepass_kernel, block, smem);
     if (per_sm < 1) per_sm = 1;
     const int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
     int g = static_cast<int>(P.n_tiles < cap ? P.n_tiles : cap);
-    if (g < 1) g = 1;
-    onepass_kernel<<<g, block, smem, L.stream>>>(P);
+    return g < 1 ? 1 : g;
+}
+
+void k0_onepass_extract(const Launch& L, const OnePassParams& P, uint32_t threads) {
+    const size_t smem = onepass_smem_bytes(P.a, threads, P.tile_units);
+    const int g = k0_onepass_grid(L, P, threads);
+    onepass_kernel<<<g, static_cast<int>(threads + 32), smem, L.stream>>>(P);
 }
 
 }  // namespace gorp
