@@ -108,6 +108,8 @@ struct DeviceCtx {
     TdfaFastDev cap_fast{};
     CapDev cap{};
     OnePassDev onepass{};
+    OnePassDev chunkwalk{};      // same automaton, table variant of kernels/chunkwalk.cu
+    bool force_tiles = false;    // GORP_FORCE_TILES=1: the TMA-staged tile kernel instead of the chunk-walk kernel
     uint32_t onepass_shrink = 0;  // too-dense retries remembered across calls
     uint32_t* d_slots = nullptr;
     uint32_t n_ext = 0;
@@ -175,6 +177,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     if (const char* f = std::getenv("GORP_FORCE_GENERAL")) c.force_general = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TWOPASS")) c.force_twopass = f[0] == '1';
+    if (const char* f = std::getenv("GORP_FORCE_TILES")) c.force_tiles = f[0] == '1';
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
     // combined DFA
     const size_t S = m.dfa.n_states, C = m.dfa.n_classes;
@@ -423,6 +426,42 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     c.onepass.init_slots = upload(init, c.owned);
                     c.onepass.n_init = static_cast<uint32_t>(init.size());
                     c.onepass.enabled = 1;
+                    // chunk-walk variant of the table (kernels/chunkwalk.cu): a dead automaton keeps scanning to the
+                    // line's '\n' (row DEADSCAN) because the thread goes on with the next line from there
+                    //   rows [0,Sx) states, Sx = DEADSCAN, [Sx+1, Sx+16) SKIP_1..15 (32-byte loads), [Sx+16, ..) outcome rows
+                    {
+                        const uint32_t dscan = Sx, skip2 = Sx + 1, fin2 = Sx + 16, n_rows2 = fin2 + n_out;
+                        if (static_cast<uint64_t>(n_rows2) * width / 4 < (1u << 14)) {
+                            std::vector<uint32_t> rows2(static_cast<size_t>(n_rows2) * width, 0);
+                            for (uint32_t r = 0; r < n_rows2; ++r)
+                                for (uint32_t k = 0; k < width; ++k) {
+                                    uint32_t next = r, slot = 0;
+                                    if (r < Sx) {
+                                        if (k == 0x0A) {
+                                            next = fin2 + A.outcome_of[r];
+                                            slot = len_slot;
+                                        } else if (k < 128 || k - 128 < j_of_col.size()) {
+                                            const uint32_t j = k < 128 ? A.jcls[k] : j_of_col[k - 128];
+                                            const uint32_t ent = A.trans[static_cast<size_t>(r) * J + j];
+                                            if ((ent & 0xFFFFu) == 0xFFFFu) next = dscan;
+                                            else next = ent & 0xFFFFu, slot = ent >> 16;
+                                        } else {
+                                            next = dscan;  // padding column, never addressed
+                                        }
+                                    } else if (r == dscan) {
+                                        if (k == 0x0A) next = fin2, slot = len_slot;  // outcome 0 = MISS
+                                    } else if (r < fin2) {
+                                        next = r == skip2 ? 0u : r - 1;  // SKIP chain
+                                    }
+                                    rows2[static_cast<size_t>(r) * width + k] = (next << 16) | slot;
+                                }
+                            c.chunkwalk = c.onepass;
+                            c.chunkwalk.rows = upload(rows2, c.owned);
+                            c.chunkwalk.n_rows = n_rows2;
+                            c.chunkwalk.skip_base = skip2;
+                            c.chunkwalk.fin_base = fin2;
+                        }
+                    }
                 }
             }
         }
@@ -469,6 +508,73 @@ struct Timer {
         cudaEventRecord(c.ev[c.n_ev], s);
     }
 };
+
+// Text form through the chunk-walk one-pass kernel. Returns false when the batch has to take another path.
+bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
+                   int64_t& n_lines, gorp_device_result* out) {
+    if (n_units <= 0 || c.force_general || c.force_twopass || c.force_tiles || !c.chunkwalk.enabled) return false;
+    if (reinterpret_cast<uintptr_t>(d_text) & 31) return false;  // the walk uses 256-bit loads
+    uint32_t threads = 0;
+    if (!k0_chunkwalk_plan(c.chunkwalk, &threads)) return false;
+    Launch L{stream, c.sm_count};
+    c.hist.reserve((c.n_ext + 2) * 8);
+    bool exact = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        OnePassParams P{};
+        P.text = d_text;
+        P.n_units = n_units;
+        P.tile_units = threads * kChunkUnits;
+        P.per = kChunkUnits;
+        P.n_tiles = (n_units + P.tile_units - 1) / P.tile_units;
+        P.a = c.chunkwalk;
+        P.slots_per_ext = c.d_slots;
+        P.n_ext = c.n_ext;
+        P.span_stride = c.max_slots;
+        // look-back state: [status n_tiles][ticket (8 B)][totals 3 x int64]
+        const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 8 + 8 + 24;
+        c.tile_state.reserve(state_bytes);
+        int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
+        if (exact) cap_lines = n_lines + 16;
+        c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
+        c.line_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
+        c.spans.reserve((static_cast<size_t>(cap_lines) * c.max_slots + 4) * 4);
+        P.ext_id = c.ext_id.as<int32_t>();
+        P.line_off = c.line_off.as<int64_t>();
+        P.spans = c.spans.as<int32_t>();
+        P.hist = c.hist.as<unsigned long long>();
+        P.cap_lines = cap_lines;
+        unsigned char* st = c.tile_state.as<unsigned char>();
+        P.tile_status = reinterpret_cast<unsigned long long*>(st);
+        P.ticket = reinterpret_cast<unsigned int*>(st + static_cast<size_t>(P.n_tiles) * 8);
+        P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 8 + 8);
+        CK(cudaMemsetAsync(st, 0, state_bytes, stream));
+        CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
+        k0_chunkwalk_extract(L, P, threads);
+        tm.mark("k0_chunkwalk_extract", 1);
+        CK(cudaGetLastError());
+        int64_t totals[3] = {0, 0, 0};
+        CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        n_lines = totals[0];
+        c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
+        if (totals[2] & 1) {  // capacity overflow: rerun once with the exact size
+            exact = true;
+            continue;
+        }
+        CK(cudaMemcpyAsync(d_scalars, P.totals, 8, cudaMemcpyDeviceToDevice, stream));
+        if (out) {
+            out->n_lines = n_lines;
+            out->span_stride = static_cast<int32_t>(c.max_slots);
+            out->d_ext_id = P.ext_id;
+            out->d_line_off = P.line_off;
+            out->d_spans = P.spans;
+            out->d_histogram = c.hist.as<int64_t>();
+            out->d_n_lines = d_scalars;
+        }
+        return true;
+    }
+    return false;
+}
 
 // Text form through the one-pass kernel. Returns false when the batch has to take another path.
 bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
@@ -574,6 +680,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     const int64_t* d_line_off;
     int sep;
     bool ends_with_nl = true;
+    if (!d_off && run_chunkwalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off) {
         sep = 1;

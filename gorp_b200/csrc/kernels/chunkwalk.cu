@@ -1,0 +1,425 @@
+// K0c — one-pass "chunk owner" extraction kernel (sm_100a): every UTF-16 unit is looked at once, no shared-memory
+// staging of the text, no barrier inside the walk.
+//
+// The automaton is the one of host/fused.hpp (combined DFA x capture automata folded into one table, see
+// kernels/onepass.cu for the per-unit step):
+//
+//   per unit :  ent = LDS[row(ent) + 4*unit]              one shared-memory lookup, the only dependent chain
+//               STS slot(ent)[thread] = position          "last position at which command list `slot` fired"
+//   per line :  the '\n' column leads to the absorbing row of the line's OUTCOME (MISS | MATCH e | CAPTURE_FAIL e)
+//
+// Work decomposition: the text is cut into fixed chunks of kChunkUnits units, one per thread; a CTA takes a tile of
+// blockDim.x consecutive chunks by in-order ticket. A thread owns the lines whose PRECEDING '\n' lies in its chunk
+// (thread 0 of tile 0 also owns the line at offset 0) and walks them one after the other straight from global
+// memory with 256-bit loads (its chunk is a private sequential stream: one 32-byte sector per load, so nothing
+// depends on L1 retention), running past the end of its chunk to finish its last line. All threads therefore walk about
+// kChunkUnits units whatever the line lengths are, so the lanes of a warp stay busy without any sorting, and the
+// only block-wide steps are one scan of the per-chunk line counts at the start of the tile (newline pre-scan, done
+// per warp with coalesced loads: iteration i of a warp covers exactly the chunk of lane i) and the decoupled
+// look-back of the tile's first result row, done by warp 0 while the other warps are already walking. Result rows go
+// out when a line ends, batched every 2 loop iterations so that the lanes of a warp that have a finished line write
+// together; two banks of op slots per thread keep the finished line's positions alive meanwhile. Slots hold
+// tile-relative positions and are cleared once per tile: a value below the line's own start is "not written", so no
+// per-line initialisation is needed. Occupancy: the table + slots are the only shared memory (no text buffers), which is
+// what lets 32 warps per SM hide the lookup latency — the measured reason this beats the TMA-staged tile kernel.
+#include "device_common.cuh"
+
+namespace gorp {
+
+namespace {
+
+using namespace dev;
+
+constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62;
+
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// 8 units at text position `pos` (a multiple of 8); units at or beyond n_units read as '\n'
+__device__ __forceinline__ uint4 load_chunk(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units) {
+    if (pos + 8 <= n_units) return __ldg(reinterpret_cast<const uint4*>(text + pos));
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t p0 = pos + 2 * j, p1 = p0 + 1;
+        const uint32_t lo = p0 < n_units ? __ldg(text + p0) : 0x0Au;
+        const uint32_t hi = p1 < n_units ? __ldg(text + p1) : 0x0Au;
+        w[j] = lo | (hi << 16);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct Units16 {
+    uint4 a, b;
+};
+// 16 units at text position `pos` (a multiple of 16); units at or beyond n_units read as '\n'
+__device__ __forceinline__ Units16 load_units16(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units) {
+    Units16 r;
+    if (pos + 16 <= n_units) {
+        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+                     : "l"(text + pos));
+    } else {
+        r.a = load_chunk(text, pos, n_units);
+        r.b = load_chunk(text, pos + 8, n_units);
+    }
+    return r;
+}
+
+// bit k (k < 4) = unit k of the pair of words (a, b) is '\n' (0x000A). Low and high bytes are gathered with PRMT, a
+// unit is '\n' iff (low ^ 0x0A) | high == 0; exact zero-byte test, then the four flag bits (7, 15, 23, 31) are
+// compressed with one multiply.
+__device__ __forceinline__ uint32_t nl_bits4(uint32_t a, uint32_t b) {
+    const uint32_t lo = __byte_perm(a, b, 0x6420), hi = __byte_perm(a, b, 0x7531);
+    const uint32_t t = (lo ^ 0x0A0A0A0Au) | hi;
+    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);  // 0x80 in every zero byte of t
+    return (((z >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+
+// Entry layout in shared memory (rewritten from the raw table when the CTA starts):
+//   bits 31..18  next row, in units of 16 bytes from the start of the row area
+//   bits 13..0   op slot, in units of 4 bytes from the start of the slot bank (slot id * blockDim)
+// so that  next lookup address = (ent >> 14) + (rows_abs + 4*unit)   is a single LEA.HI on the dependent chain.
+template <int kByte>
+__device__ __forceinline__ void one_step(uint32_t& ent, uint32_t w, uint32_t rows_abs, uint32_t slot_abs, uint32_t pos) {
+    uint32_t b, a;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(b), "r"(rows_abs));
+    ent = lds32((ent >> 14) + a);
+    uint32_t m, sa;
+    asm("and.b32 %0, %1, 0x3FFF;" : "=r"(m) : "r"(ent));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(sa) : "r"(m), "r"(slot_abs));
+    sts32(sa, pos);
+}
+
+// A chunk that holds a unit >= 0x80: unit by unit through the column map (global, L1/L2 resident). A high surrogate
+// followed by a low surrogate takes the PAIR column (java.util.regex consumes the pair as one character).
+__device__ __noinline__ uint32_t slow_chunk(const OnePassDev& a, uint32_t ent, uint4 v, const uint16_t* __restrict__ text,
+                                            int64_t q, int64_t n_units, uint32_t rows_abs, uint32_t slot_abs, uint32_t pos,
+                                            uint32_t fin_ent) {
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        if (ent >= fin_ent) break;
+        const uint32_t u = unit_at(v, k);
+        uint32_t col = u;
+        if (u >= 0x80u) {
+            col = __ldg(a.xcol + u);
+            if ((u & 0xFC00u) == 0xD800u) {
+                const int64_t p1 = q + k + 1;
+                const uint32_t nx = k < 7 ? unit_at(v, k + 1) : (p1 < n_units ? __ldg(text + p1) : 0x0Au);
+                if ((nx & 0xFC00u) == 0xDC00u) col = __ldg(a.pair_col + col);
+            }
+        }
+        ent = lds32((ent >> 14) + rows_abs + col * 4);
+        sts32(slot_abs + ((ent & 0x3FFFu) << 2), pos + k);
+    }
+    return ent;
+}
+
+struct Pending {  // a finished line whose result row has not been written yet
+    uint32_t outcome, idx, bank_abs;
+    uint32_t start;  // tile-relative
+};
+
+__global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t kT = blockDim.x;
+    const OnePassDev& A = P.a;
+    constexpr uint32_t C = kChunkUnits;
+    // ---- carve shared memory (every area 16-byte aligned)
+    uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* s_res = s_rows + A.n_rows * A.width;
+    int32_t* s_oext = reinterpret_cast<int32_t*>(s_res + ((A.n_outcomes * A.max_slots + 3) & ~3u));
+    uint32_t* s_ocnt = reinterpret_cast<uint32_t*>(s_oext + ((A.n_outcomes + 3) & ~3u));  // valid span entries per outcome
+    uint32_t* s_slots = s_ocnt + ((A.n_outcomes + 3) & ~3u);  // [2 banks][n_slots][kT]
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_hist[kOnePassHistBins];
+    __shared__ long long s_tile, s_base;
+    __shared__ int s_skip_writes;
+    __shared__ unsigned int s_flag;  // (tile + 1) once s_base / s_skip_writes of the tile are valid
+
+    const uint32_t rows_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_rows));
+    const uint32_t row_q = A.width / 4;  // row size in 16-byte units
+    for (uint32_t i = threadIdx.x; i < A.n_rows * A.width; i += kT) {
+        const uint32_t raw = __ldg(A.rows + i);
+        s_rows[i] = (((raw >> 16) * row_q) << 18) | ((raw & 0xFFFFu) * kT);
+    }
+    for (uint32_t i = threadIdx.x; i < A.n_outcomes * A.max_slots; i += kT) s_res[i] = __ldg(A.out_res + i);
+    for (uint32_t i = threadIdx.x; i < A.n_outcomes; i += kT) {
+        const int32_t e = __ldg(A.out_ext + i);
+        s_oext[i] = e;
+        s_ocnt[i] = e >= 0 ? __ldg(P.slots_per_ext + e) : 0u;
+    }
+    const uint32_t n_bins = P.n_ext + 2;
+    const bool smem_hist = n_bins <= kOnePassHistBins;
+    for (uint32_t i = threadIdx.x; i < kOnePassHistBins; i += kT) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_flag = 0;
+
+    const uint32_t slot_abs0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_slots)) + threadIdx.x * 4;
+    const uint32_t slot_stride = kT * 4, bank_bytes = A.n_slots * slot_stride;
+    const uint32_t fin_ent = (A.fin_base * row_q) << 18;
+    const uint32_t inv_row_q = 65536u / row_q + 1u;
+    const uint32_t stride = P.span_stride;
+    const uint32_t len_off = (A.n_slots - 1) * slot_stride;  // the LEN slot is the last one
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = kT >> 5;
+    bool base_known = false;
+    int64_t row0 = 0;  // first result row of this thread in the current tile
+    bool skip_writes = false;
+
+    // writes the result row of a finished line
+    auto flush = [&](const Pending& pd, int64_t tile, int64_t tile0) {
+        if (!base_known) {
+            while (*reinterpret_cast<volatile unsigned int*>(&s_flag) != static_cast<unsigned int>(tile + 1)) {
+            }
+            __threadfence_block();
+            row0 += *reinterpret_cast<volatile long long*>(&s_base);
+            skip_writes = *reinterpret_cast<volatile int*>(&s_skip_writes) != 0;
+            base_known = true;
+        }
+        const int32_t ext = s_oext[pd.outcome];
+        const uint32_t bin = ext >= 0 ? static_cast<uint32_t>(ext) : (ext == -1 ? P.n_ext : P.n_ext + 1);
+        if (smem_hist) atomicAdd(&s_hist[bin], 1u);
+        else atomicAdd(P.hist + bin, 1ull);
+        if (skip_writes) return;
+        const int64_t row = row0 + pd.idx;
+        P.ext_id[row] = ext;
+        P.line_off[row] = tile0 + pd.start;
+        const uint32_t cnt = s_ocnt[pd.outcome];
+        const uint32_t* res = s_res + pd.outcome * A.max_slots;
+        int32_t* out = P.spans + row * stride;
+        // a boundary = the latest of its (<= 4) op slots; slots hold tile-relative positions, anything below the
+        // line's start is a left-over of an earlier line (or the per-tile clear value): the group did not participate
+        auto value = [&](uint32_t packed) {
+            if (!packed) return -1;
+            int32_t val = static_cast<int32_t>(lds32(pd.bank_abs + (packed & 0xFFu) * slot_stride));
+            for (packed >>= 8; packed; packed >>= 8)
+                val = max(val, static_cast<int32_t>(lds32(pd.bank_abs + (packed & 0xFFu) * slot_stride)));
+            return val < static_cast<int32_t>(pd.start) ? -1 : val - static_cast<int32_t>(pd.start);
+        };
+        if ((stride & 3u) == 0) {
+            for (uint32_t k = 0; k < stride; k += 4) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(res + k);  // entries >= cnt of a row are 0
+                *reinterpret_cast<int4*>(out + k) = make_int4(value(r4.x), value(r4.y), value(r4.z), value(r4.w));
+            }
+        } else {
+            for (uint32_t k = 0; k < stride; ++k) out[k] = value(k < cnt ? res[k] : 0u);
+        }
+    };
+
+    for (;;) {
+        __syncthreads();  // the previous tile no longer uses s_tile / s_warp; table setup done (first iteration)
+        if (threadIdx.x == 0) s_tile = static_cast<long long>(atomicAdd(P.ticket, 1u));
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        // ---- newline pre-scan, per warp with coalesced loads: iteration i reads the 32 x 16 bytes of lane i's chunk;
+        // a '\n' at position p counts when it starts a line (p + 1 < n_units). Lane i keeps the count and the first.
+        const int64_t tile0 = tile * kT * static_cast<int64_t>(C);
+        uint32_t cnt = 0, first = 0;
+        {
+            const int64_t wbase = tile0 + static_cast<int64_t>(warp) * 32 * C;
+            const bool inside = wbase + 32 * static_cast<int64_t>(C) + 1 <= P.n_units;
+            if (wbase < P.n_units) {
+#pragma unroll 4
+                for (uint32_t i = 0; i < 32; ++i) {
+                    const int64_t p = wbase + i * C + lane * 8;
+                    uint32_t m;
+                    if (inside) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.text + p));
+                        m = nl_bits4(v.x, v.y) | (nl_bits4(v.z, v.w) << 4);
+                    } else {
+                        const uint4 v = load_chunk(P.text, p, P.n_units);
+                        m = nl_bits4(v.x, v.y) | (nl_bits4(v.z, v.w) << 4);
+                        const int64_t room = P.n_units - 1 - p;  // positions (relative to p) that count: [0, room)
+                        m = room <= 0 ? 0u : (room < 8 ? m & ((1u << static_cast<uint32_t>(room)) - 1u) : m);
+                    }
+                    const uint32_t tot = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(m)));
+                    const uint32_t has = __ballot_sync(0xffffffffu, m != 0);
+                    const uint32_t fl = has ? static_cast<uint32_t>(__ffs(has)) - 1u : 0u;
+                    const uint32_t mf = __shfl_sync(0xffffffffu, m, fl);
+                    if (lane == i) {
+                        cnt = tot;
+                        first = fl * 8 + static_cast<uint32_t>(__ffs(mf)) - 1u;
+                    }
+                }
+            }
+        }
+        const bool line0 = tile == 0 && threadIdx.x == 0 && P.n_units > 0;  // the line at offset 0
+        const uint32_t mine = cnt + (line0 ? 1u : 0u);
+
+        // ---- block scan of the line counts; warp 0 then resolves the tile's first row by decoupled look-back
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+        for (uint32_t w = 0; w < n_warps; ++w) {
+            const uint32_t x = s_warp[w];
+            if (w < warp) wbase += x;
+            total += x;
+        }
+        row0 = wbase + incl - mine;
+        base_known = false;
+        if (warp == 0) {
+            unsigned long long pre = 0;
+            if (tile > 0) {
+                if (lane == 0) st_release(P.tile_status + tile, kStAgg | static_cast<unsigned long long>(total));
+                for (int64_t j = tile - 1;; j -= 32) {
+                    const int64_t idx = j - lane;
+                    unsigned long long v = kStPre;  // before tile 0: an empty inclusive prefix
+                    if (idx >= 0) {
+                        v = ld_acquire(P.tile_status + idx);
+                        while ((v >> 62) == 0) {
+                            __nanosleep(32);
+                            v = ld_acquire(P.tile_status + idx);
+                        }
+                    }
+                    const uint32_t pmask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                    const uint32_t firstp = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1u : 32u;
+                    unsigned long long l = lane <= firstp ? (v & ~(3ull << 62)) : 0ull;  // aggregates, then one inclusive prefix
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+                    pre += l;
+                    if (pmask) break;
+                }
+            }
+            if (lane == 0) {
+                const long long line_end = static_cast<long long>(pre) + total;
+                st_release(P.tile_status + tile, kStPre | static_cast<unsigned long long>(line_end));
+                const bool over = line_end > P.cap_lines;
+                if (over) atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 1ull);
+                if (tile == P.n_tiles - 1) {
+                    P.totals[0] = line_end;
+                    // line i spans [line_off[i], line_off[i+1] - 1): a text that does not end in '\n' gets n_units + 1
+                    if (!over) P.line_off[line_end] = P.n_units + (P.text[P.n_units - 1] == 0x0A ? 0 : 1);
+                }
+                s_base = static_cast<long long>(pre);
+                s_skip_writes = over ? 1 : 0;
+                __threadfence_block();
+                *reinterpret_cast<volatile unsigned int*>(&s_flag) = static_cast<unsigned int>(tile + 1);
+            }
+            __syncwarp();
+        }
+
+        // ---- walk the owned lines one after the other; positions are tile-relative (pos = unit - tile0)
+        for (uint32_t k = 0; k < 2 * A.n_slots; ++k) sts32(slot_abs0 + k * slot_stride, 0x80000000u);  // "never written"
+        if (mine) {
+            const uint32_t c_end = (threadIdx.x + 1) * C;  // tile-relative end of the chunk
+            const int64_t n_rel = P.n_units - tile0;       // tile-relative end of the text
+            uint32_t start = line0 ? 0u : threadIdx.x * C + first + 1;
+            uint32_t bank_abs = slot_abs0;
+            Pending pd{0, 0, 0, 0};
+            bool pending = false;
+            uint32_t idx = 0, it = 0;
+            uint32_t q = start & ~15u;
+            uint32_t lo = start & 15u;
+            uint32_t ent = lo ? ((A.skip_base + lo - 1) * row_q) << 18 : 0u;
+            bool active = true;
+            while (active) {
+                const Units16 u = load_units16(P.text, tile0 + q, P.n_units);
+                if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                    one_step<0>(ent, u.a.x, rows_abs, bank_abs, q);
+                    one_step<2>(ent, u.a.x, rows_abs, bank_abs, q + 1);
+                    one_step<0>(ent, u.a.y, rows_abs, bank_abs, q + 2);
+                    one_step<2>(ent, u.a.y, rows_abs, bank_abs, q + 3);
+                    one_step<0>(ent, u.a.z, rows_abs, bank_abs, q + 4);
+                    one_step<2>(ent, u.a.z, rows_abs, bank_abs, q + 5);
+                    one_step<0>(ent, u.a.w, rows_abs, bank_abs, q + 6);
+                    one_step<2>(ent, u.a.w, rows_abs, bank_abs, q + 7);
+                    one_step<0>(ent, u.b.x, rows_abs, bank_abs, q + 8);
+                    one_step<2>(ent, u.b.x, rows_abs, bank_abs, q + 9);
+                    one_step<0>(ent, u.b.y, rows_abs, bank_abs, q + 10);
+                    one_step<2>(ent, u.b.y, rows_abs, bank_abs, q + 11);
+                    one_step<0>(ent, u.b.z, rows_abs, bank_abs, q + 12);
+                    one_step<2>(ent, u.b.z, rows_abs, bank_abs, q + 13);
+                    one_step<0>(ent, u.b.w, rows_abs, bank_abs, q + 14);
+                    one_step<2>(ent, u.b.w, rows_abs, bank_abs, q + 15);
+                } else {
+                    ent = slow_chunk(A, ent, u.a, P.text, tile0 + q, P.n_units, rows_abs, bank_abs, q, fin_ent);
+                    ent = slow_chunk(A, ent, u.b, P.text, tile0 + q + 8, P.n_units, rows_abs, bank_abs, q + 8, fin_ent);
+                }
+                q += 16;
+                if (ent >= fin_ent) {  // the line ended inside these 16 units
+                    if (pending) flush(pd, tile, tile0);  // rare: two line ends within 2 iterations
+                    pd.outcome = (((ent >> 18) - A.fin_base * row_q) * inv_row_q) >> 16;  // exact: a multiple of row_q below 2^14
+                    pd.idx = idx++;
+                    pd.bank_abs = bank_abs;
+                    pd.start = start;
+                    pending = true;
+                    const uint32_t nl = lds32(bank_abs + len_off);  // tile-relative position of the terminating '\n'
+                    if (nl < c_end && static_cast<int64_t>(nl) + 1 < n_rel) {
+                        start = nl + 1;
+                        q = start & ~15u;
+                        lo = start & 15u;
+                        ent = lo ? ((A.skip_base + lo - 1) * row_q) << 18 : 0u;
+                        bank_abs = bank_abs == slot_abs0 ? slot_abs0 + bank_bytes : slot_abs0;
+                    } else {
+                        active = false;
+                    }
+                }
+                if ((++it & 1u) == 0 && pending) {
+                    flush(pd, tile, tile0);
+                    pending = false;
+                }
+            }
+            if (pending) flush(pd, tile, tile0);
+        }
+    }
+    if (smem_hist) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_bins; i += kT)
+            if (s_hist[i]) atomicAdd(P.hist + i, static_cast<unsigned long long>(s_hist[i]));
+    }
+}
+
+}  // namespace
+
+size_t chunkwalk_smem_bytes(const OnePassDev& a, uint32_t threads) {
+    size_t b = static_cast<size_t>(a.n_rows) * a.width * 4;
+    b += static_cast<size_t>((a.n_outcomes * a.max_slots + 3) & ~3u) * 4;
+    b += 2 * static_cast<size_t>((a.n_outcomes + 3) & ~3u) * 4;
+    b += 2 * static_cast<size_t>(a.n_slots) * threads * 4;
+    return b + 128;
+}
+
+bool k0_chunkwalk_plan(const OnePassDev& a, uint32_t* threads) {
+    if (!a.enabled) return false;
+    for (uint32_t kT : {512u, 256u, 128u}) {
+        if (static_cast<uint64_t>(a.n_slots) * kT > 0x3FFFu) continue;  // slot offsets are 14 bits of the table entry
+        const size_t smem = chunkwalk_smem_bytes(a, kT);
+        if (smem * (1024 / kT) <= 220 * 1024 || (kT == 128 && smem <= 220 * 1024)) {  // 32 warps per SM where it fits
+            *threads = kT;
+            return true;
+        }
+    }
+    return false;
+}
+
+int k0_chunkwalk_grid(const Launch& L, const OnePassParams& P, uint32_t threads) {
+    const size_t smem = chunkwalk_smem_bytes(P.a, threads);
+    cudaFuncSetAttribute(chunkwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunkwalk_kernel, static_cast<int>(threads), smem);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
+    int g = static_cast<int>(P.n_tiles < cap ? P.n_tiles : cap);
+    return g < 1 ? 1 : g;
+}
+
+void k0_chunkwalk_extract(const Launch& L, const OnePassParams& P, uint32_t threads) {
+    const size_t smem = chunkwalk_smem_bytes(P.a, threads);
+    const int g = k0_chunkwalk_grid(L, P, threads);
+    chunkwalk_kernel<<<g, static_cast<int>(threads), smem, L.stream>>>(P);
+}
+
+}  // namespace gorp

@@ -168,6 +168,14 @@ size_t onepass_smem_bytes(const OnePassDev&, uint32_t threads, uint32_t tile_uni
 bool k0_onepass_plan(const OnePassDev&, double lines_per_unit, uint32_t shrink, uint32_t* threads, uint32_t* tile_units);
 void k0_onepass_extract(const Launch&, const OnePassParams&, uint32_t threads);
 
+// K0c: chunk-walk one-pass kernel (text form) — see kernels/chunkwalk.cu. Uses OnePassParams (tile_units = threads *
+// kChunkUnits, per = kChunkUnits) with the DEADSCAN variant of the table.
+constexpr uint32_t kChunkUnits = 256;  // units per thread chunk
+size_t chunkwalk_smem_bytes(const OnePassDev&, uint32_t threads);
+bool k0_chunkwalk_plan(const OnePassDev&, uint32_t* threads);
+int k0_chunkwalk_grid(const Launch&, const OnePassParams&, uint32_t threads);
+void k0_chunkwalk_extract(const Launch&, const OnePassParams&, uint32_t threads);
+
 // K3: per-extraction histogram (E entries, then MISS, then capture failures).
 void k3_histogram(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist);
 
