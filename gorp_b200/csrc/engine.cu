@@ -524,7 +524,8 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
         P.text = d_text;
         P.n_units = n_units;
         P.tile_units = threads * kChunkUnits;
-        P.per = kChunkUnits;
+        P.per = 0;
+        if (const char* f = std::getenv("GORP_CW_PREFETCH")) P.per = static_cast<uint32_t>(std::atoi(f));
         P.n_tiles = (n_units + P.tile_units - 1) / P.tile_units;
         P.a = c.chunkwalk;
         P.slots_per_ext = c.d_slots;
@@ -549,6 +550,10 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
         P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 8 + 8);
         CK(cudaMemsetAsync(st, 0, state_bytes, stream));
         CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
+        if (std::getenv("GORP_ONEPASS_DEBUG"))
+            std::fprintf(stderr, "[chunkwalk debug] threads=%u grid=%d smem=%zu tiles=%lld n_slots=%u rows=%u\n", threads,
+                         k0_chunkwalk_grid(L, P, threads), chunkwalk_smem_bytes(P.a, threads), static_cast<long long>(P.n_tiles),
+                         P.a.n_slots, P.a.n_rows);
         k0_chunkwalk_extract(L, P, threads);
         tm.mark("k0_chunkwalk_extract", 1);
         CK(cudaGetLastError());

@@ -150,7 +150,12 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
         const uint32_t raw = __ldg(A.rows + i);
         s_rows[i] = (((raw >> 16) * row_q) << 18) | ((raw & 0xFFFFu) * kT);
     }
-    for (uint32_t i = threadIdx.x; i < A.n_outcomes * A.max_slots; i += kT) s_res[i] = __ldg(A.out_res + i);
+    // group boundary recipes: 0 = no writer; a single writer becomes 0x80000000 | byte offset of its slot inside a
+    // bank; several writers stay packed one slot id per byte
+    for (uint32_t i = threadIdx.x; i < A.n_outcomes * A.max_slots; i += kT) {
+        const uint32_t packed = __ldg(A.out_res + i);
+        s_res[i] = packed && packed < 256u ? 0x80000000u | (packed * kT * 4u) : packed;
+    }
     for (uint32_t i = threadIdx.x; i < A.n_outcomes; i += kT) {
         const int32_t e = __ldg(A.out_ext + i);
         s_oext[i] = e;
@@ -190,16 +195,21 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
         const int64_t row = row0 + pd.idx;
         P.ext_id[row] = ext;
         P.line_off[row] = tile0 + pd.start;
-        const uint32_t cnt = s_ocnt[pd.outcome];
         const uint32_t* res = s_res + pd.outcome * A.max_slots;
         int32_t* out = P.spans + row * stride;
         // a boundary = the latest of its (<= 4) op slots; slots hold tile-relative positions, anything below the
         // line's start is a left-over of an earlier line (or the per-tile clear value): the group did not participate
-        auto value = [&](uint32_t packed) {
-            if (!packed) return -1;
-            int32_t val = static_cast<int32_t>(lds32(pd.bank_abs + (packed & 0xFFu) * slot_stride));
-            for (packed >>= 8; packed; packed >>= 8)
-                val = max(val, static_cast<int32_t>(lds32(pd.bank_abs + (packed & 0xFFu) * slot_stride)));
+        auto value = [&](uint32_t recipe) {
+            int32_t val;
+            if (!recipe) {
+                val = -1;
+            } else if (recipe & 0x80000000u) {
+                val = static_cast<int32_t>(lds32(pd.bank_abs + (recipe & 0x7FFFFFFFu)));
+            } else {
+                val = static_cast<int32_t>(lds32(pd.bank_abs + (recipe & 0xFFu) * slot_stride));
+                for (recipe >>= 8; recipe; recipe >>= 8)
+                    val = max(val, static_cast<int32_t>(lds32(pd.bank_abs + (recipe & 0xFFu) * slot_stride)));
+            }
             return val < static_cast<int32_t>(pd.start) ? -1 : val - static_cast<int32_t>(pd.start);
         };
         if ((stride & 3u) == 0) {
@@ -208,19 +218,26 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
                 *reinterpret_cast<int4*>(out + k) = make_int4(value(r4.x), value(r4.y), value(r4.z), value(r4.w));
             }
         } else {
-            for (uint32_t k = 0; k < stride; ++k) out[k] = value(k < cnt ? res[k] : 0u);
+            for (uint32_t k = 0; k < stride; ++k) out[k] = value(res[k]);
         }
     };
 
+    // thread 0 takes the ticket of the NEXT tile while the current one is processed (hides the atomic's latency)
+    long long ticket_ahead = threadIdx.x == 0 ? static_cast<long long>(atomicAdd(P.ticket, 1u)) : 0;
     for (;;) {
         __syncthreads();  // the previous tile no longer uses s_tile / s_warp; table setup done (first iteration)
-        if (threadIdx.x == 0) s_tile = static_cast<long long>(atomicAdd(P.ticket, 1u));
+        if (threadIdx.x == 0) s_tile = ticket_ahead;
         __syncthreads();
         const int64_t tile = s_tile;
         if (tile >= P.n_tiles) break;
+        if (threadIdx.x == 0) ticket_ahead = static_cast<long long>(atomicAdd(P.ticket, 1u));
         // ---- newline pre-scan, per warp with coalesced loads: iteration i reads the 32 x 16 bytes of lane i's chunk;
         // a '\n' at position p counts when it starts a line (p + 1 < n_units). Lane i keeps the count and the first.
         const int64_t tile0 = tile * kT * static_cast<int64_t>(C);
+        if (!(P.per & 1u)) {  // start fetching this tile's chunks now; the pre-scan consumes them in order (GORP_CW_PREFETCH=1: off)
+            const int64_t n0 = tile0 + static_cast<int64_t>(threadIdx.x) * C;
+            if (n0 + C <= P.n_units) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.text + n0), "n"(C * 2) : "memory");
+        }
         uint32_t cnt = 0, first = 0;
         {
             const int64_t wbase = tile0 + static_cast<int64_t>(warp) * 32 * C;
@@ -394,15 +411,24 @@ size_t chunkwalk_smem_bytes(const OnePassDev& a, uint32_t threads) {
 
 bool k0_chunkwalk_plan(const OnePassDev& a, uint32_t* threads) {
     if (!a.enabled) return false;
-    for (uint32_t kT : {512u, 256u, 128u}) {
+    // the CTA size that keeps the most warps resident per SM (ties: the larger CTA, fewer table copies)
+    uint32_t best = 0, best_warps = 0;
+    for (uint32_t kT : {512u, 384u, 256u, 128u}) {
         if (static_cast<uint64_t>(a.n_slots) * kT > 0x3FFFu) continue;  // slot offsets are 14 bits of the table entry
         const size_t smem = chunkwalk_smem_bytes(a, kT);
-        if (smem * (1024 / kT) <= 220 * 1024 || (kT == 128 && smem <= 220 * 1024)) {  // 32 warps per SM where it fits
-            *threads = kT;
-            return true;
+        if (smem > 226 * 1024) continue;
+        cudaFuncSetAttribute(chunkwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunkwalk_kernel, static_cast<int>(kT), smem) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
         }
+        const uint32_t warps = static_cast<uint32_t>(per_sm) * kT / 32;
+        if (warps > best_warps) best = kT, best_warps = warps;
     }
-    return false;
+    if (!best) return false;
+    *threads = best;
+    return true;
 }
 
 int k0_chunkwalk_grid(const Launch& L, const OnePassParams& P, uint32_t threads) {
