@@ -107,12 +107,21 @@ def test_fuzz_small_alphabet(definition):
     check_against_oracle(definition, lines=lines)
 
 
-@pytest.mark.parametrize("name,n", [("simple", 300000), ("readme", 300000)])
+@pytest.mark.parametrize("name,n", [("simple", 300000), ("readme", 300000), ("weblog", 60000), ("syslog200", 60000),
+                                    ("utf16mix", 60000)])
 def test_config_corpora(name, n):
+    """The five BASELINE.json configs (prefixes the oracle finishes in seconds): #1 simple.grp, #2 README, #3 nginx /
+    Apache definition with parametric templates, #4 200 extractions (combined DFA > shared memory, L2-resident
+    table), #5 non-ASCII UTF-16 + divergence characters + 10 KB outliers."""
     d, gen = corpus.CONFIGS[name]
     text = gen(n)
     _, b, oe = check_against_oracle(d, text=text)
     assert b.n_lines == n and (oe >= 0).sum() > n // 3
+    if name == "utf16mix":
+        assert (oe <= -2).sum() > 0, "config #5 must exercise the DFA-accepts / java.util.regex-rejects outcome"
+        assert int(np.diff(b.line_off).max()) > 5000
+    if name == "syslog200":
+        assert len(set(oe[oe >= 0].tolist())) == 200
 
 
 def test_edge_cases():

@@ -49,6 +49,17 @@ def test_tables_reproduce_oracle(case):
     compare_host_tables(case[0], [c[0] for c in case[1]] + TRICKY_LINES)
 
 
+@pytest.mark.parametrize("name", ["weblog", "syslog200", "utf16mix"])
+def test_config_definitions_reproduce_oracle(name):
+    """Configs #3-#5 (gorp_b200/corpus.py): host tables vs oracle on generated lines + the tricky lines."""
+    from gorp_b200 import corpus
+    d, _ = corpus.CONFIGS[name]
+    gen = {"weblog": corpus.weblog_lines, "syslog200": corpus.syslog200_lines, "utf16mix": corpus.utf16_mix_lines}[name]
+    stats = compare_host_tables(d, gen(1200) + TRICKY_LINES, need_fused=False)
+    if name == "syslog200":
+        assert stats[0] * (stats[1] + 1) * 2 > 227 * 1024, "config #4's combined DFA must outgrow shared memory"
+
+
 @pytest.mark.parametrize("case", ALL_DEFS)
 def test_one_pass_automaton_reproduces_oracle(case):
     """host/fused.hpp: DFA x capture automata folded into one automaton, interpreted as kernels/onepass.cu runs it."""
