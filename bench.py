@@ -33,8 +33,15 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "log lines/sec and input GB/s per B200 (match+capture)"
-WORKLOAD = "config#2 README Put/Get/OtherRequest 3-extraction definition, synthetic access-log lines"
-BLOCK_LINES = 1_000_000
+# --workload: BASELINE.json configs; the headline (default) is config #2, the one the metric is quoted on for 1 GPU
+WORKLOADS = {
+    "readme": ("config#2 README Put/Get/OtherRequest 3-extraction definition, synthetic access-log lines", 1_000_000),
+    "simple": ("config#1 samples/simple.grp, synthetic matching/non-matching lines", 1_000_000),
+    "weblog": ("config#3 ~20-extraction nginx/Apache access+error definition with parametric templates, mixed line lengths", 200_000),
+    "syslog200": ("config#4 200-extraction definition, combined DFA outgrows shared memory (L2-resident table)", 200_000),
+    "utf16mix": ("config#5 nginx/Apache definition, non-ASCII UTF-16 + divergence characters + 10 KB outlier lines", 200_000),
+}
+WORKLOAD, BLOCK_LINES = WORKLOADS["readme"]
 
 
 def hbm_peak():
@@ -92,9 +99,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_block(rank):
+def make_block(rank, workload="readme"):
     from gorp_b200 import corpus
-    return corpus.readme_corpus(BLOCK_LINES, seed=0x5EED0002 + rank)
+    return corpus.CONFIGS[workload][1](BLOCK_LINES, seed=0x5EED0000 + {"simple": 1, "readme": 2, "weblog": 3, "syslog200": 4, "utf16mix": 5}[workload] + 16 * rank)
+
+
+def definition_of(workload):
+    from gorp_b200 import corpus
+    return corpus.CONFIGS[workload][0]
 
 
 def run_reference(args, rank, world):
@@ -104,11 +116,11 @@ def run_reference(args, rank, world):
     from gorp_b200 import corpus
     from oracle import gorp_oracle
     cores = os.cpu_count() or 1
-    block = make_block(0)
+    block = make_block(0, args.workload)
     reps = max(1, args.ref_lines // BLOCK_LINES)
     text = np.tile(block, reps)
     starts, ends = gorp_oracle.split_lines(text)
-    o = gorp_oracle.Gorp(corpus.README_DEF)
+    o = gorp_oracle.Gorp(definition_of(args.workload))
     o.extract_batch(block, gorp_oracle.split_lines(block), threads=cores)  # build + page-in
     for _ in range(args.warmup):
         o.extract_batch(text, (starts, ends), threads=cores)
@@ -142,7 +154,10 @@ def main():
     ap.add_argument("--cpu-lines", type=int, default=16_000_000)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only")
+    ap.add_argument("--workload", default="readme", choices=sorted(WORKLOADS), help="BASELINE.json config (default: #2, the headline)")
     args = ap.parse_args()
+    global WORKLOAD, BLOCK_LINES
+    WORKLOAD, BLOCK_LINES = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,14 +179,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- workload: seeded block tiled to lines_per_gpu in HBM
-    block = make_block(rank)
+    block = make_block(rank, args.workload)
     reps = max(1, args.lines_per_gpu // BLOCK_LINES)
     n_lines = reps * BLOCK_LINES
     d_block = torch.from_numpy(block.view(np.int16)).to(dev)
     d_text = d_block.repeat(reps)
     n_units = d_text.numel()
     in_bytes = n_units * 2
-    blob = Blob.from_definition(corpus.README_DEF)
+    blob = Blob.from_definition(definition_of(args.workload))
     eng = C.c_void_p()
     devs = (C.c_int * 1)(local_rank)
     _check(lib.gorp_engine_create(blob._ptr, blob.length, devs, 1, C.byref(eng)))
@@ -275,7 +290,7 @@ def main():
         creps = max(1, args.cpu_lines // BLOCK_LINES)
         ctext = np.tile(block, creps)
         cst = gorp_oracle.split_lines(ctext)
-        o = gorp_oracle.Gorp(corpus.README_DEF)
+        o = gorp_oracle.Gorp(definition_of(args.workload))
         o.extract_batch(block, gorp_oracle.split_lines(block), threads=cores)
         t0 = time.perf_counter()
         o.extract_batch(ctext, cst, threads=cores)

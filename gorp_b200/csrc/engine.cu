@@ -80,6 +80,18 @@ struct DevBuf {
         }
         cap = want;
     }
+    // grows to at least `bytes`, keeping the first `keep` bytes (device-to-device copy on `stream`, then waits)
+    void grow_keep(size_t bytes, size_t keep, cudaStream_t stream) {
+        if (bytes <= cap) return;
+        DevBuf bigger;
+        bigger.reserve(bytes);
+        if (p && keep) {
+            CK(cudaMemcpyAsync(bigger.p, p, keep, cudaMemcpyDeviceToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
+        std::swap(p, bigger.p);
+        std::swap(cap, bigger.cap);
+    }
     template <class T>
     T* as() const { return static_cast<T*>(p); }
     ~DevBuf() {
@@ -118,6 +130,11 @@ struct DeviceCtx {
     bool force_twopass = false;  // GORP_FORCE_TWOPASS=1: never use the one-pass automaton kernel (K1 -> K2 -> K4 instead)
     double lines_per_unit = 1.0 / 24.0;  // running estimate that sizes the one-pass kernel's tiles and output arrays
     DevBuf tile_state;
+    // host-buffer calls are pipelined in pieces: H2D of piece k+1 (s_in) overlaps the kernels of piece k (stream) and
+    // the D2H of the rows of piece k-1 (s_out); the rows of all pieces accumulate in acc_*
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2]{}, ev_free[2]{}, ev_rows = nullptr;
+    DevBuf textbuf[2], offbuf[2], acc_ext, acc_off, acc_spans, acc_hist;
     // per-call scratch, serialised by `mu`
     std::mutex mu;
     DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, spans, hist, scalars, debug;
@@ -135,20 +152,28 @@ struct DeviceCtx {
         for (void* p : owned) cudaFree(p);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : ev_in)
+            if (e) cudaEventDestroy(e);
+        for (auto& e : ev_free)
+            if (e) cudaEventDestroy(e);
+        if (ev_rows) cudaEventDestroy(ev_rows);
         if (stream) cudaStreamDestroy(stream);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
     }
 };
 
 struct HostResult {  // pinned host arrays behind a gorp_result
     void* p[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t cap[4] = {0, 0, 0, 0};
-    void reserve(int i, size_t bytes) {
+    void reserve(int i, size_t bytes, size_t keep = 0) {  // keeps the first `keep` bytes when it has to grow
         if (bytes <= cap[i]) return;
-        if (p[i]) cudaFreeHost(p[i]);
-        p[i] = nullptr;
-        cap[i] = 0;
+        void* q = nullptr;
         size_t want = bytes + bytes / 8 + 64;
-        CK(cudaMallocHost(&p[i], want));
+        CK(cudaMallocHost(&q, want));
+        if (p[i] && keep) std::memcpy(q, p[i], keep);
+        if (p[i]) cudaFreeHost(p[i]);
+        p[i] = q;
         cap[i] = want;
     }
     ~HostResult() {
@@ -175,6 +200,11 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     CK(cudaGetDeviceProperties(&prop, c.device));
     c.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking));
+    for (auto& e : c.ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : c.ev_free) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_rows, cudaEventDisableTiming));
     if (const char* f = std::getenv("GORP_FORCE_GENERAL")) c.force_general = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TWOPASS")) c.force_twopass = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TILES")) c.force_tiles = f[0] == '1';
@@ -705,6 +735,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         CK(cudaStreamSynchronize(stream));
         n_lines = total_nl + (last_unit != 0x0A ? 1 : 0);
         ends_with_nl = last_unit == 0x0A;
+        if (n_units > 0) c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
         c.line_off.reserve(static_cast<size_t>(total_nl + 3) * 8);
         k1_scatter_newlines(L, d_text, n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
         k1_finish(L, d_text, n_units, c.tile_base.as<int64_t>() + n_tiles, c.line_off.as<int64_t>(), d_n_lines);
@@ -762,23 +793,164 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     return n_lines;
 }
 
+// ------------------------------------------------------------------ host-buffer calls: pieces, pipelining, devices
+constexpr int64_t kPieceUnits = 32ll << 20;  // 64 MB of text per piece
+constexpr int kTextPad = 32;                 // units in front of a staged piece (aligned chunk reads of the lines form)
+
+struct Piece {
+    int64_t u0, u1;  // units [u0, u1) of the caller's text
+    int64_t l0, l1;  // lines [l0, l1) of the caller's offsets (lines form only)
+};
+
+// Cuts the batch into pieces of about kPieceUnits that end after a '\n' (text form) / at a string boundary (lines form).
+std::vector<Piece> plan_pieces(const uint16_t* text, int64_t n_units, const int64_t* off, int64_t n_lines, int64_t piece_units) {
+    std::vector<Piece> v;
+    if (off) {
+        int64_t l = 0;
+        while (l < n_lines) {
+            const int64_t* it = std::upper_bound(off + l + 1, off + n_lines + 1, off[l] + piece_units);
+            int64_t l1 = (it - off) - 1;
+            if (l1 <= l) l1 = l + 1;
+            if (l1 > n_lines) l1 = n_lines;
+            v.push_back({off[l], off[l1], l, l1});
+            l = l1;
+        }
+        if (v.empty()) v.push_back({0, 0, 0, 0});
+    } else {
+        int64_t u = 0;
+        while (u < n_units) {
+            int64_t cut = std::min(u + piece_units, n_units);
+            while (cut < n_units && text[cut - 1] != 0x0A) ++cut;
+            v.push_back({u, cut, 0, 0});
+            u = cut;
+        }
+        if (v.empty()) v.push_back({0, 0, 0, 0});
+    }
+    return v;
+}
+
+struct DeviceRun {  // what one device produced for its pieces
+    int64_t n_rows = 0;
+    int32_t stride = 0;
+    std::string error;
+    int status = GORP_OK;
+};
+
+// Processes pieces [p0, p1) on device context c. Rows accumulate in c.acc_*; when `hr` is given (single-device call) the
+// rows of every finished piece are copied to the host arrays at once, overlapping the next pieces.
+void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const int64_t* off, const std::vector<Piece>& pieces, size_t p0,
+                size_t p1, HostResult* hr, DeviceRun& run) {
+    std::lock_guard<std::mutex> lock(c.mu);
+    CK(cudaSetDevice(c.device));
+    Launch L{c.stream, c.sm_count};
+    const size_t E2 = e->def.extractions.size() + 2;
+    const uint32_t stride = e->match_only ? 0u : c.max_slots;
+    int64_t units_total = 0, lines_total = 0;
+    size_t max_units = 0, max_lines = 0;
+    for (size_t k = p0; k < p1; ++k) {
+        units_total += pieces[k].u1 - pieces[k].u0;
+        lines_total += pieces[k].l1 - pieces[k].l0;
+        max_units = std::max<size_t>(max_units, pieces[k].u1 - pieces[k].u0);
+        max_lines = std::max<size_t>(max_lines, pieces[k].l1 - pieces[k].l0);
+    }
+    const int n_buf = p1 - p0 > 1 ? 2 : 1;
+    for (int b = 0; b < n_buf; ++b) {
+        c.textbuf[b].reserve((max_units + kTextPad + 64) * 2);
+        if (off) c.offbuf[b].reserve((max_lines + 1) * 8);
+    }
+    // row capacity: exact for the lines form; for the text form sized for the first piece from the running density
+    // estimate, then (below) for the whole range from the density actually seen
+    const int64_t units_first = pieces[p0].u1 - pieces[p0].u0;
+    int64_t cap_rows = off ? lines_total : static_cast<int64_t>(static_cast<double>(units_first) * c.lines_per_unit * 1.25) + 4096;
+    auto reserve_rows = [&](int64_t rows, int64_t keep) {
+        c.acc_ext.grow_keep(static_cast<size_t>(rows + 1) * 4, static_cast<size_t>(keep) * 4, c.stream);
+        c.acc_off.grow_keep(static_cast<size_t>(rows + 2) * 8, static_cast<size_t>(keep + 1) * 8, c.stream);
+        c.acc_spans.grow_keep((static_cast<size_t>(rows) * stride + 4) * 4, static_cast<size_t>(keep) * stride * 4, c.stream);
+        if (hr) {
+            hr->reserve(0, static_cast<size_t>(rows + 1) * 4, static_cast<size_t>(keep) * 4);
+            hr->reserve(1, static_cast<size_t>(rows + 2) * 8, static_cast<size_t>(keep + 1) * 8);
+            hr->reserve(2, (static_cast<size_t>(rows) * stride + 4) * 4, static_cast<size_t>(keep) * stride * 4);
+        }
+    };
+    reserve_rows(cap_rows, 0);
+    c.acc_hist.reserve(E2 * 8);
+    CK(cudaMemsetAsync(c.acc_hist.p, 0, E2 * 8, c.stream));
+
+    auto stage = [&](size_t k) {  // H2D of piece k on s_in
+        const Piece& pc = pieces[k];
+        const int b = static_cast<int>((k - p0) & 1);
+        const int64_t units = pc.u1 - pc.u0;
+        const int64_t lead = off ? kTextPad + (pc.u0 & 15) : 0;  // keeps (device address - unit index) a multiple of 32 bytes
+        if (k >= p0 + 2) CK(cudaStreamWaitEvent(c.s_in, c.ev_free[b], 0));  // the gather of piece k-2 still reads this buffer's offsets
+        if (units)
+            CK(cudaMemcpyAsync(c.textbuf[b].as<uint16_t>() + lead, text + pc.u0, static_cast<size_t>(units) * 2, cudaMemcpyHostToDevice, c.s_in));
+        if (off)
+            CK(cudaMemcpyAsync(c.offbuf[b].p, off + pc.l0, static_cast<size_t>(pc.l1 - pc.l0 + 1) * 8, cudaMemcpyHostToDevice, c.s_in));
+        CK(cudaEventRecord(c.ev_in[b], c.s_in));
+    };
+
+    int64_t rows = 0;
+    stage(p0);
+    for (size_t k = p0; k < p1; ++k) {
+        const Piece& pc = pieces[k];
+        const int b = static_cast<int>((k - p0) & 1);
+        if (k + 1 < p1) stage(k + 1);  // the other buffer: its previous piece was computed (this thread waited for it)
+        CK(cudaStreamWaitEvent(c.stream, c.ev_in[b], 0));
+        const int64_t units = pc.u1 - pc.u0;
+        gorp_device_result dr{};
+        int64_t nl;
+        if (off) {
+            const uint16_t* vbase = c.textbuf[b].as<uint16_t>() + kTextPad + (pc.u0 & 15) - pc.u0;  // text[i] lives at vbase + i
+            nl = run_pipeline(c, vbase, 0, c.offbuf[b].as<int64_t>(), pc.l1 - pc.l0, c.stream, false, &dr);
+        } else {
+            nl = run_pipeline(c, c.textbuf[b].as<uint16_t>(), units, nullptr, 0, c.stream, false, &dr);
+        }
+        if (rows + nl > cap_rows) {  // the density estimate was too low: grow, keeping the rows gathered so far
+            if (hr) CK(cudaStreamSynchronize(c.s_out));
+            cap_rows = std::max<int64_t>(rows + nl, static_cast<int64_t>(static_cast<double>(rows + nl) / std::max<int64_t>(pc.u1 - pieces[p0].u0, 1) *
+                                                                         static_cast<double>(units_total) * 1.1) + 4096);
+            reserve_rows(cap_rows, rows);
+        }
+        // gather: rows [rows, rows + nl) of the batch
+        if (nl) CK(cudaMemcpyAsync(c.acc_ext.as<int32_t>() + rows, dr.d_ext_id, static_cast<size_t>(nl) * 4, cudaMemcpyDeviceToDevice, c.stream));
+        k_bias_copy(L, c.acc_off.as<int64_t>() + rows, dr.d_line_off, nl + 1, off ? 0 : pc.u0);
+        if (nl && stride)
+            CK(cudaMemcpyAsync(c.acc_spans.as<int32_t>() + static_cast<size_t>(rows) * stride, dr.d_spans, static_cast<size_t>(nl) * stride * 4,
+                               cudaMemcpyDeviceToDevice, c.stream));
+        k_accumulate(L, c.acc_hist.as<int64_t>(), dr.d_histogram, static_cast<int>(E2));
+        c.launches += 2;
+        CK(cudaEventRecord(c.ev_free[b], c.stream));
+        if (hr) {
+            CK(cudaEventRecord(c.ev_rows, c.stream));
+            CK(cudaStreamWaitEvent(c.s_out, c.ev_rows, 0));
+            if (nl) CK(cudaMemcpyAsync(static_cast<int32_t*>(hr->p[0]) + rows, c.acc_ext.as<int32_t>() + rows, static_cast<size_t>(nl) * 4, cudaMemcpyDeviceToHost, c.s_out));
+            CK(cudaMemcpyAsync(static_cast<int64_t*>(hr->p[1]) + rows, c.acc_off.as<int64_t>() + rows, static_cast<size_t>(nl + 1) * 8, cudaMemcpyDeviceToHost, c.s_out));
+            if (nl && stride)
+                CK(cudaMemcpyAsync(static_cast<int32_t*>(hr->p[2]) + static_cast<size_t>(rows) * stride, c.acc_spans.as<int32_t>() + static_cast<size_t>(rows) * stride,
+                                   static_cast<size_t>(nl) * stride * 4, cudaMemcpyDeviceToHost, c.s_out));
+        }
+        rows += nl;
+    }
+    if (hr) {
+        hr->reserve(3, E2 * 8);
+        CK(cudaStreamWaitEvent(c.s_out, c.ev_rows, 0));
+        CK(cudaMemcpyAsync(hr->p[3], c.acc_hist.p, E2 * 8, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        CK(cudaStreamSynchronize(c.s_out));
+    } else {
+        CK(cudaStreamSynchronize(c.stream));
+    }
+    run.n_rows = rows;
+    run.stride = static_cast<int32_t>(stride);
+}
+
 int extract_host(gorp_engine* e, const uint16_t* text, int64_t n_units, const int64_t* off, int64_t n_lines, gorp_result* out) {
     if (!e || !out || (!text && n_units > 0) || n_units < 0 || n_lines < 0) return fail(GORP_E_ARG, "bad argument");
     if (e->devs.empty()) return fail(GORP_E_CUDA, "engine has no CUDA device");
     return guarded([&]() -> int {
-        DeviceCtx& c = *e->devs[0];
-        std::lock_guard<std::mutex> lock(c.mu);
-        CK(cudaSetDevice(c.device));
-        c.text.reserve(static_cast<size_t>(n_units) * 2 + 32);
-        if (n_units) CK(cudaMemcpyAsync(c.text.p, text, static_cast<size_t>(n_units) * 2, cudaMemcpyHostToDevice, c.stream));
-        const int64_t* d_off = nullptr;
-        if (off) {
-            c.off_in.reserve(static_cast<size_t>(n_lines + 1) * 8);
-            CK(cudaMemcpyAsync(c.off_in.p, off, static_cast<size_t>(n_lines + 1) * 8, cudaMemcpyHostToDevice, c.stream));
-            d_off = c.off_in.as<int64_t>();
-        }
-        gorp_device_result dr{};
-        const int64_t nl = run_pipeline(c, c.text.as<uint16_t>(), n_units, d_off, n_lines, c.stream, false, &dr);
+        int64_t piece_units = kPieceUnits;
+        if (const char* f = std::getenv("GORP_PIECE_UNITS")) piece_units = std::max<int64_t>(std::atoll(f), 1024);
+        const std::vector<Piece> pieces = plan_pieces(text, n_units, off, n_lines, piece_units);
         std::unique_ptr<HostResult> hr;
         {
             std::lock_guard<std::mutex> pl(e->pool_mu);
@@ -788,20 +960,67 @@ int extract_host(gorp_engine* e, const uint16_t* text, int64_t n_units, const in
             }
         }
         if (!hr) hr = std::make_unique<HostResult>();
-        const size_t n_spans = static_cast<size_t>(nl) * static_cast<size_t>(dr.span_stride);
         const size_t E2 = e->def.extractions.size() + 2;
-        hr->reserve(0, static_cast<size_t>(nl + 1) * 4);
-        hr->reserve(1, static_cast<size_t>(nl + 1) * 8);
-        hr->reserve(2, (n_spans + 1) * 4);
-        hr->reserve(3, E2 * 8);
-        if (nl) CK(cudaMemcpyAsync(hr->p[0], dr.d_ext_id, static_cast<size_t>(nl) * 4, cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaMemcpyAsync(hr->p[1], dr.d_line_off, static_cast<size_t>(nl + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
-        if (n_spans) CK(cudaMemcpyAsync(hr->p[2], dr.d_spans, n_spans * 4, cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaMemcpyAsync(hr->p[3], dr.d_histogram, E2 * 8, cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaStreamSynchronize(c.stream));
+        const size_t G = std::min(e->devs.size(), pieces.size());
+        int64_t nl = 0;
+        int32_t stride = 0;
+        if (G <= 1) {
+            DeviceRun run;
+            run_pieces(e, *e->devs[0], text, off, pieces, 0, pieces.size(), hr.get(), run);
+            nl = run.n_rows;
+            stride = run.stride;
+        } else {
+            // contiguous ranges of pieces per device (lines shard as contiguous ranges: no data crosses devices); one
+            // host thread per device; the rows are copied out once every device's row base is known
+            std::vector<DeviceRun> runs(G);
+            std::vector<size_t> first(G + 1);
+            for (size_t d = 0; d <= G; ++d) first[d] = pieces.size() * d / G;
+            std::vector<std::thread> th;
+            for (size_t d = 0; d < G; ++d)
+                th.emplace_back([&, d]() {
+                    runs[d].status = guarded([&]() -> int {
+                        run_pieces(e, *e->devs[d], text, off, pieces, first[d], first[d + 1], nullptr, runs[d]);
+                        return GORP_OK;
+                    });
+                    if (runs[d].status != GORP_OK) runs[d].error = g_error;
+                });
+            for (auto& t : th) t.join();
+            for (size_t d = 0; d < G; ++d)
+                if (runs[d].status != GORP_OK) return fail(runs[d].status, runs[d].error);
+            std::vector<int64_t> base(G + 1, 0);
+            for (size_t d = 0; d < G; ++d) base[d + 1] = base[d] + runs[d].n_rows;
+            nl = base[G];
+            stride = runs[0].stride;
+            hr->reserve(0, static_cast<size_t>(nl + 1) * 4);
+            hr->reserve(1, static_cast<size_t>(nl + 2) * 8);
+            hr->reserve(2, (static_cast<size_t>(nl) * stride + 4) * 4);
+            hr->reserve(3, E2 * 8);
+            std::vector<int64_t> hist(G * E2);
+            for (size_t d = 0; d < G; ++d) {
+                DeviceCtx& c = *e->devs[d];
+                std::lock_guard<std::mutex> lock(c.mu);
+                CK(cudaSetDevice(c.device));
+                const int64_t n = runs[d].n_rows;
+                if (n) CK(cudaMemcpyAsync(static_cast<int32_t*>(hr->p[0]) + base[d], c.acc_ext.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c.stream));
+                CK(cudaMemcpyAsync(static_cast<int64_t*>(hr->p[1]) + base[d], c.acc_off.p, static_cast<size_t>(n + (d + 1 == G ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, c.stream));
+                if (n && stride)
+                    CK(cudaMemcpyAsync(static_cast<int32_t*>(hr->p[2]) + static_cast<size_t>(base[d]) * stride, c.acc_spans.p, static_cast<size_t>(n) * stride * 4,
+                                       cudaMemcpyDeviceToHost, c.stream));
+                CK(cudaMemcpyAsync(hist.data() + d * E2, c.acc_hist.p, E2 * 8, cudaMemcpyDeviceToHost, c.stream));
+            }
+            for (size_t d = 0; d < G; ++d) {
+                CK(cudaSetDevice(e->devs[d]->device));
+                CK(cudaStreamSynchronize(e->devs[d]->stream));
+            }
+            int64_t* h = static_cast<int64_t*>(hr->p[3]);
+            for (size_t i = 0; i < E2; ++i) {
+                h[i] = 0;
+                for (size_t d = 0; d < G; ++d) h[i] += hist[d * E2 + i];
+            }
+        }
         out->n_lines = nl;
         out->n_extractions = static_cast<int32_t>(e->def.extractions.size());
-        out->span_stride = dr.span_stride;
+        out->span_stride = stride;
         out->ext_id = static_cast<const int32_t*>(hr->p[0]);
         out->line_off = static_cast<const int64_t*>(hr->p[1]);
         out->spans = static_cast<const int32_t*>(hr->p[2]);

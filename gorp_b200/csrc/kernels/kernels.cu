@@ -343,6 +343,17 @@ __global__ void __launch_bounds__(kThreads) histogram_kernel(const int32_t* __re
     }
 }
 
+// dst[i] = src[i] + bias (result assembly of a pipelined batch: piece-relative line offsets -> batch offsets)
+__global__ void __launch_bounds__(kThreads) bias_copy_kernel(int64_t* __restrict__ dst, const int64_t* __restrict__ src, int64_t n, int64_t bias) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * kThreads)
+        dst[i] = src[i] + bias;
+}
+
+__global__ void accumulate_kernel(int64_t* __restrict__ dst, const int64_t* __restrict__ src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
 int blocks_for(int64_t n, int per_block) { return static_cast<int>((n + per_block - 1) / per_block); }
 
 }  // namespace
@@ -408,6 +419,17 @@ void k4_tdfa_capture(const Launch& L, const CapDev& c, const uint16_t* text, con
     if (n_lines <= 0) return;
     int g = persistent_grid(L, reinterpret_cast<const void*>(tdfa_capture_kernel), 0, n_lines);
     tdfa_capture_kernel<<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_stride, ext_id, spans);
+}
+
+void k_bias_copy(const Launch& L, int64_t* dst, const int64_t* src, int64_t n, int64_t bias) {
+    if (n <= 0) return;
+    const int64_t want = (n + kThreads - 1) / kThreads, cap = static_cast<int64_t>(L.sm_count) * 8;
+    bias_copy_kernel<<<static_cast<int>(want < cap ? want : cap), kThreads, 0, L.stream>>>(dst, src, n, bias);
+}
+
+void k_accumulate(const Launch& L, int64_t* dst, const int64_t* src, int n) {
+    if (n <= 0) return;
+    accumulate_kernel<<<(n + 255) / 256, 256, 0, L.stream>>>(dst, src, n);
 }
 
 void k3_histogram(const Launch& L, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist) {

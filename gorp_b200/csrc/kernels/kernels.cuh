@@ -176,6 +176,10 @@ bool k0_chunkwalk_plan(const OnePassDev&, uint32_t* threads);
 int k0_chunkwalk_grid(const Launch&, const OnePassParams&, uint32_t threads);
 void k0_chunkwalk_extract(const Launch&, const OnePassParams&, uint32_t threads);
 
+// result assembly of a batch that is pipelined in pieces: dst[i] = src[i] + bias ; dst[i] += src[i]
+void k_bias_copy(const Launch&, int64_t* dst, const int64_t* src, int64_t n, int64_t bias);
+void k_accumulate(const Launch&, int64_t* dst, const int64_t* src, int n);
+
 // K3: per-extraction histogram (E entries, then MISS, then capture failures).
 void k3_histogram(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist);
 

@@ -216,3 +216,37 @@ def test_every_kernel_tier_text_form(tier, monkeypatch):
     text = np.concatenate([np.concatenate((np.asarray(jdkre.to_units(s), dtype=np.uint16), [10])) for s in lines]).astype(np.uint16)
     check_against_oracle(V.README_DEF, text=text)
     check_against_oracle(V.README_DEF, text=text[:-1])  # last line not terminated
+
+
+def test_host_calls_pipelined_in_pieces(monkeypatch):
+    """gorp_extract_text / gorp_extract_lines cut a batch into line-aligned pieces (H2D of the next piece overlaps the
+    kernels and the D2H of the previous ones); tiny pieces here, so every seam, the row-capacity growth and the
+    lines-form staging get exercised."""
+    d, gen = corpus.CONFIGS["readme"]
+    text = gen(50000, seed=5)
+    for piece in ("1024", "70000", "1000000"):
+        monkeypatch.setenv("GORP_PIECE_UNITS", piece)
+        g, b, _ = check_against_oracle(d, text=text)
+        check_against_oracle(d, text=text[:-1], gorp=g)
+    monkeypatch.setenv("GORP_PIECE_UNITS", "3000")
+    lines = corpus.weblog_lines(4000, seed=3) + ["", "x" * 9000, ""]
+    check_against_oracle(corpus.WEBLOG_DEF, lines=lines)
+    check_against_oracle(corpus.WEBLOG_DEF, text=corpus.lines_to_text(lines))
+
+
+def test_multi_device_engine(monkeypatch):
+    """One engine over several GPUs: contiguous line-aligned ranges per device, rows concatenated in device order."""
+    from gorp_b200 import _ffi
+    n = _ffi.lib.gorp_device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("GORP_PIECE_UNITS", "200000")
+    d, gen = corpus.CONFIGS["readme"]
+    g = DefinitionReader.reader(d).read(devices=list(range(n)))
+    text = gen(120000, seed=9)
+    check_against_oracle(d, text=text, gorp=g)
+    check_against_oracle(d, text=text[:-1], gorp=g)
+    lines = corpus.weblog_lines(5000, seed=4)
+    g3 = DefinitionReader.reader(corpus.WEBLOG_DEF).read(devices=list(range(n)))
+    check_against_oracle(corpus.WEBLOG_DEF, lines=lines, gorp=g3)
+    check_against_oracle(corpus.WEBLOG_DEF, text=corpus.lines_to_text(lines), gorp=g3)
