@@ -193,8 +193,24 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     dres = _ffi.DeviceResult()
 
+    # N > 1: the one (optional) collective of the path — all-reduce of the per-extraction histogram (E + 2 int64) over
+    # NCCL, every step, inside the timed region
+    from gorp_b200 import sharding
+    n_bins = blob.info()[2] + 2
+    d_hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
+    cudart = None
+    if world > 1:
+        try:
+            from cuda.bindings import runtime as cudart
+        except Exception:  # noqa: BLE001
+            from cuda import cudart
+
     def step(flags=0):
         _check(lib.gorp_extract_text_device(eng, 0, d_text.data_ptr(), n_units, stream, flags, C.byref(dres)))
+        if world > 1:
+            (err,) = cudart.cudaMemcpyAsync(d_hist.data_ptr(), dres.d_histogram, n_bins * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, stream)
+            assert int(err) == 0, err
+            sharding.allreduce_histogram(d_hist)
 
     def barrier():
         if world > 1:
@@ -221,6 +237,8 @@ def main():
     barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:  # every rank holds the job-wide histogram: its sum is the job's line count
+        assert int(d_hist.sum().item()) == n_lines * world, (int(d_hist.sum().item()), n_lines * world)
     _check(lib.gorp_kernel_times(eng, 0, names, tot, 16, C.byref(cnt), C.byref(calls), C.byref(launches), 1))
     kern = {names[i].decode(): tot[i] / max(calls.value, 1) for i in range(cnt.value)}
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -309,7 +327,8 @@ def main():
             "config": {"workload": WORKLOAD, "lines_per_gpu": n_lines, "units_per_gpu": n_units,
                        "bytes_per_gpu": in_bytes, "block": "%d-line seeded block tiled %dx in HBM" % (BLOCK_LINES, reps),
                        "l2": "input (%.1f GB) is far larger than L2, no flush needed" % (in_bytes / 1e9),
-                       "parallelism": "lines sharded per GPU, no collective"},
+                       "parallelism": "lines sharded per GPU as contiguous ranges, tables replicated; no data-path collective"
+                                      + (", one NCCL all-reduce of the %d-bin histogram per step" % n_bins if world > 1 else "")},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches.value),
         }))
