@@ -566,6 +566,7 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
         c.tile_state.reserve(state_bytes);
         int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
         if (exact) cap_lines = n_lines + 16;
+        if (const char* f = std::getenv("GORP_PAD_ROWS")) cap_lines += std::atoll(f);
         c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
         c.line_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
         c.spans.reserve((static_cast<size_t>(cap_lines) * c.max_slots + 4) * 4);
@@ -581,15 +582,41 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
         CK(cudaMemsetAsync(st, 0, state_bytes, stream));
         CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
         if (std::getenv("GORP_ONEPASS_DEBUG"))
-            std::fprintf(stderr, "[chunkwalk debug] threads=%u grid=%d smem=%zu tiles=%lld n_slots=%u rows=%u\n", threads,
-                         k0_chunkwalk_grid(L, P, threads), chunkwalk_smem_bytes(P.a, threads), static_cast<long long>(P.n_tiles),
-                         P.a.n_slots, P.a.n_rows);
+            std::fprintf(stderr, "[chunkwalk debug] threads=%u grid=%d smem=%zu tiles=%lld n_slots=%u rows=%u cap_lines=%lld text=%p ext=%p off=%p spans=%p state=%p\n",
+                         threads, k0_chunkwalk_grid(L, P, threads), chunkwalk_smem_bytes(P.a, threads), static_cast<long long>(P.n_tiles),
+                         P.a.n_slots, P.a.n_rows, static_cast<long long>(cap_lines), static_cast<const void*>(d_text), static_cast<void*>(P.ext_id),
+                         static_cast<void*>(P.line_off), static_cast<void*>(P.spans), static_cast<void*>(st));
+        const bool debug = std::getenv("GORP_ONEPASS_DEBUG") != nullptr;
+        const int grid = k0_chunkwalk_grid(L, P, threads);
+        if (debug) {
+            c.debug.reserve(static_cast<size_t>(grid) * 4 * 8);
+            CK(cudaMemsetAsync(c.debug.p, 0, static_cast<size_t>(grid) * 4 * 8, stream));
+            P.debug = c.debug.as<long long>();
+        }
         k0_chunkwalk_extract(L, P, threads);
         tm.mark("k0_chunkwalk_extract", 1);
         CK(cudaGetLastError());
         int64_t totals[3] = {0, 0, 0};
         CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        if (debug) {  // CTAs per SM, tiles per CTA, spread of the CTA run times
+            std::vector<long long> h(static_cast<size_t>(grid) * 4);
+            CK(cudaMemcpy(h.data(), c.debug.p, h.size() * 8, cudaMemcpyDeviceToHost));
+            std::vector<int> per_sm(1024, 0);
+            long long t_min = h[2], t_max = h[3], tiles_min = h[1], tiles_max = h[1], late = 0;
+            for (int b = 0; b < grid; ++b) {
+                ++per_sm[h[b * 4] & 1023];
+                t_min = std::min(t_min, h[b * 4 + 2]);
+                t_max = std::max(t_max, h[b * 4 + 3]);
+                tiles_min = std::min(tiles_min, h[b * 4 + 1]);
+                tiles_max = std::max(tiles_max, h[b * 4 + 1]);
+            }
+            for (int b = 0; b < grid; ++b) late += (h[b * 4 + 2] - t_min) > 100000 ? 1 : 0;  // started > 100 us after the first
+            int sm1 = 0, sm2 = 0, sm3 = 0;
+            for (int v : per_sm) sm1 += v == 1, sm2 += v == 2, sm3 += v > 2;
+            std::fprintf(stderr, "[chunkwalk debug] kernel span %.3f ms; SMs with 1/2/>2 CTAs: %d/%d/%d; tiles per CTA %lld..%lld; CTAs started late: %lld\n",
+                         (t_max - t_min) / 1e6, sm1, sm2, sm3, tiles_min, tiles_max, late);
+        }
         n_lines = totals[0];
         c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
         if (totals[2] & 1) {  // capacity overflow: rerun once with the exact size

@@ -62,7 +62,8 @@ struct Units16 {
 __device__ __forceinline__ Units16 load_units16(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units) {
     Units16 r;
     if (pos + 16 <= n_units) {
-        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        // the walk is the last use of these 32 bytes: L2 evict-first keeps the not-yet-walked text of the tiles in flight
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
                      : "l"(text + pos));
     } else {
@@ -212,7 +213,14 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
             }
             return val < static_cast<int32_t>(pd.start) ? -1 : val - static_cast<int32_t>(pd.start);
         };
-        if ((stride & 3u) == 0) {
+        if ((stride & 7u) == 0) {  // 32-byte aligned rows: one 256-bit streaming store per 8 entries
+            for (uint32_t k = 0; k < stride; k += 8) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(res + k), r5 = *reinterpret_cast<const uint4*>(res + k + 4);
+                asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + k), "r"(value(r4.x)), "r"(value(r4.y)),
+                             "r"(value(r4.z)), "r"(value(r4.w)), "r"(value(r5.x)), "r"(value(r5.y)), "r"(value(r5.z)), "r"(value(r5.w))
+                             : "memory");
+            }
+        } else if ((stride & 3u) == 0) {
             for (uint32_t k = 0; k < stride; k += 4) {
                 const uint4 r4 = *reinterpret_cast<const uint4*>(res + k);  // entries >= cnt of a row are 0
                 *reinterpret_cast<int4*>(out + k) = make_int4(value(r4.x), value(r4.y), value(r4.z), value(r4.w));
@@ -224,12 +232,31 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
 
     // thread 0 takes the ticket of the NEXT tile while the current one is processed (hides the atomic's latency)
     long long ticket_ahead = threadIdx.x == 0 ? static_cast<long long>(atomicAdd(P.ticket, 1u)) : 0;
+    long long dbg_t0 = 0, dbg_tiles = 0;
+    if (P.debug && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+    // All CTAs start together, and a tile is a memory-bound burst (prefetch + pre-scan) followed by a long compute
+    // phase (the walk): CTAs that stay in lock-step alternate between fighting for HBM and leaving it idle (measured:
+    // a stable mode that is 1.4x slower). Spread the phases once, at the start: each CTA delays its first tile by a
+    // pseudo-random fraction of a tile time. Skipped for small batches, where the delay would not pay off.
+    if (!(P.per & 2u) && P.n_tiles >= 8ll * gridDim.x) {
+        if (threadIdx.x == 0) {
+            const unsigned long long delay_ns = static_cast<unsigned long long>((blockIdx.x * 2654435761u) >> 27) * 2500ull;  // 0 .. 77.5 us
+            unsigned long long t_start, t_now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+            do {
+                __nanosleep(2000);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+            } while (t_now - t_start < delay_ns);
+        }
+        __syncthreads();
+    }
     for (;;) {
         __syncthreads();  // the previous tile no longer uses s_tile / s_warp; table setup done (first iteration)
         if (threadIdx.x == 0) s_tile = ticket_ahead;
         __syncthreads();
         const int64_t tile = s_tile;
         if (tile >= P.n_tiles) break;
+        ++dbg_tiles;
         if (threadIdx.x == 0) ticket_ahead = static_cast<long long>(atomicAdd(P.ticket, 1u));
         // ---- newline pre-scan, per warp with coalesced loads: iteration i reads the 32 x 16 bytes of lane i's chunk;
         // a '\n' at position p counts when it starts a line (p + 1 < n_units). Lane i keeps the count and the first.
@@ -391,6 +418,16 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
             }
             if (pending) flush(pd, tile, tile0);
         }
+    }
+    if (P.debug && threadIdx.x == 0) {  // GORP_ONEPASS_DEBUG: where and how long this CTA ran
+        long long t1;
+        uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.debug[blockIdx.x * 4 + 0] = smid;
+        P.debug[blockIdx.x * 4 + 1] = dbg_tiles;
+        P.debug[blockIdx.x * 4 + 2] = dbg_t0;
+        P.debug[blockIdx.x * 4 + 3] = t1;
     }
     if (smem_hist) {
         __syncthreads();
