@@ -60,21 +60,34 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
-    def start(self):
+    def launch(self):
+        """Start nvidia-smi early (it needs ~0.1-0.3 s to come up); only the samples taken between start() and stop()
+        are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+
+            def pump():
+                for ln in self.proc.stdout:
+                    self.lines.append((time.perf_counter(), ln))
+            self.t = threading.Thread(target=pump, daemon=True)
             self.t.start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def start(self):
+        if self.proc is None:
+            self.launch()
+        self.t0 = time.perf_counter()
+
     def stop(self):
+        self.t1 = time.perf_counter()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)  # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -83,7 +96,10 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if self.t0 <= t <= self.t1 + 0.06]
+        if not inside and self.lines:  # region shorter than the sampling period: the sample closest to it
+            inside = [min(self.lines, key=lambda x: abs(x[0] - self.t1))[1]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -145,7 +161,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lines-per-gpu", type=int, default=100_000_000)
@@ -154,6 +170,7 @@ def main():
     ap.add_argument("--cpu-lines", type=int, default=16_000_000)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics: do not run nvidia-smi beside the timed region")
     ap.add_argument("--workload", default="readme", choices=sorted(WORKLOADS), help="BASELINE.json config (default: #2, the headline)")
     args = ap.parse_args()
     global WORKLOAD, BLOCK_LINES
@@ -198,12 +215,16 @@ def main():
     from gorp_b200 import sharding
     n_bins = blob.info()[2] + 2
     d_hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
-    cudart = None
-    if world > 1:
-        try:
-            from cuda.bindings import runtime as cudart
-        except Exception:  # noqa: BLE001
-            from cuda import cudart
+    try:
+        from cuda.bindings import runtime as cudart
+    except Exception:  # noqa: BLE001
+        from cuda import cudart
+    # the batch is the seeded block tiled `reps` times: its histogram must be reps x the block's (checked after warm-up,
+    # an end-to-end sanity check of the timed path at full size; the parity tests proper are tests/ -m gpu)
+    res0 = _ffi.Result()
+    _check(lib.gorp_extract_text(eng, block.ctypes.data, block.size, C.byref(res0)))
+    block_hist = np.ctypeslib.as_array(res0.histogram, (n_bins,)).copy()
+    lib.gorp_result_release(eng, C.byref(res0))
 
     def step(flags=0):
         _check(lib.gorp_extract_text_device(eng, 0, d_text.data_ptr(), n_units, stream, flags, C.byref(dres)))
@@ -217,16 +238,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if not args.no_clock_sampler:
+        sampler.launch()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     assert dres.n_lines == n_lines, (dres.n_lines, n_lines)
+    (err,) = cudart.cudaMemcpyAsync(d_hist.data_ptr(), dres.d_histogram, n_bins * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, stream)
+    assert int(err) == 0, err
+    assert (d_hist.cpu().numpy() == reps * block_hist).all(), (d_hist.cpu().numpy().tolist(), (reps * block_hist).tolist())
     names = (C.c_char_p * 16)()
     tot = (C.c_double * 16)()
     cnt, calls, launches = C.c_int(), C.c_int64(), C.c_int64()
     _check(lib.gorp_kernel_times(eng, 0, names, tot, 16, C.byref(cnt), C.byref(calls), C.byref(launches), 1))
 
-    sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -318,19 +318,35 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
             unsigned long long pre = 0;
             if (tile > 0) {
                 if (lane == 0) st_release(P.tile_status + tile, kStAgg | static_cast<unsigned long long>(total));
-                for (int64_t j = tile - 1;; j -= 32) {
-                    const int64_t idx = j - lane;
-                    unsigned long long v = kStPre;  // before tile 0: an empty inclusive prefix
-                    if (idx >= 0) {
-                        v = ld_acquire(P.tile_status + idx);
-                        while ((v >> 62) == 0) {
+                // 128 predecessors per probe (4 independent acquire loads per lane): lane l looks at the tiles at distance
+                // 4l+1 .. 4l+4. All resident CTAs publish their aggregate at about the same time, so the nearest
+                // inclusive prefix can be a whole generation (grid size) away; wide probes keep that to 2-3 round trips.
+                for (int64_t j = tile - 1;; j -= 128) {
+                    unsigned long long v[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int64_t idx = j - (lane * 4 + m);
+                        v[m] = idx >= 0 ? ld_acquire(P.tile_status + idx) : kStPre;  // before tile 0: an empty inclusive prefix
+                    }
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int64_t idx = j - (lane * 4 + m);
+                        while ((v[m] >> 62) == 0) {
                             __nanosleep(32);
-                            v = ld_acquire(P.tile_status + idx);
+                            v[m] = ld_acquire(P.tile_status + idx);
                         }
                     }
-                    const uint32_t pmask = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                    unsigned long long part = 0;  // aggregates up to and including the lane's nearest inclusive prefix
+                    bool has = false;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        if (!has) {
+                            part += v[m] & ~(3ull << 62);
+                            has = (v[m] >> 62) == 2;
+                        }
+                    const uint32_t pmask = __ballot_sync(0xffffffffu, has);
                     const uint32_t firstp = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1u : 32u;
-                    unsigned long long l = lane <= firstp ? (v & ~(3ull << 62)) : 0ull;  // aggregates, then one inclusive prefix
+                    unsigned long long l = lane <= firstp ? part : 0ull;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
                     pre += l;
@@ -411,7 +427,10 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
                         active = false;
                     }
                 }
-                if ((++it & 1u) == 0 && pending) {
+                // rows go out every other iteration, once the tile's first row is known (no waiting here: the row can stay
+                // pending until the thread's next line ends)
+                if ((++it & 1u) == 0 && pending &&
+                    (base_known || *reinterpret_cast<volatile unsigned int*>(&s_flag) == static_cast<unsigned int>(tile + 1))) {
                     flush(pd, tile, tile0);
                     pending = false;
                 }

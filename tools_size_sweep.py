@@ -21,14 +21,18 @@ for arg in sys.argv[1:]:
     n_units = d_text.numel()
     ts = []
     flush = torch.empty(64 << 20, dtype=torch.int32, device=dev) if os.environ.get("SWEEP_FLUSH") else None
-    for i in range(6):
+    for i in range(int(os.environ.get('SWEEP_CALLS', '6'))):
         if flush is not None:
             flush.fill_(i)
             torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _check(lib.gorp_extract_text_device(eng, 0, d_text.data_ptr(), n_units, stream, 0, C.byref(dres)))
-        e1.record(); torch.cuda.synchronize()
-        ts.append(round(e0.elapsed_time(e1), 2))
+        _check(lib.gorp_extract_text_device(eng, 0, d_text.data_ptr(), n_units, stream, int(os.environ.get("SWEEP_FLAGS", "0")), C.byref(dres)))
+        e1.record()
+        if not os.environ.get("SWEEP_NOSYNC"):
+            torch.cuda.synchronize()
+        ts.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = [round(a.elapsed_time(b), 2) for a, b in ts]
     print("%3d M lines (alloc %3d)" % (reps, alloc), "ms per call:", ts, "x%.2f of 0.125 ms/Mline" % (min(ts[1:]) / (reps * 0.125)), flush=True)
     del d_text, d_all
