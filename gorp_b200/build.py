@@ -20,7 +20,8 @@ HOST_SOURCES = [os.path.join(CSRC, "host", f) for f in
                 ("common.cpp", "definition.cpp", "automata.cpp", "capture.cpp", "model.cpp", "fused.cpp")]
 CUDA_SOURCES = [os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "kernels", "kernels.cu"),
                 os.path.join(CSRC, "kernels", "fast.cu"), os.path.join(CSRC, "kernels", "onepass.cu"),
-                os.path.join(CSRC, "kernels", "chunkwalk.cu")]
+                os.path.join(CSRC, "kernels", "chunkwalk.cu"), os.path.join(CSRC, "kernels", "dfawalk.cu"),
+                os.path.join(CSRC, "kernels", "capwalk.cu")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-Wall", "-shared", "-I", os.path.join(ROOT, "include")]
 

@@ -121,6 +121,11 @@ struct DeviceCtx {
     CapDev cap{};
     OnePassDev onepass{};
     OnePassDev chunkwalk{};      // same automaton, table variant of kernels/chunkwalk.cu
+    DfaWalkDev dfawalk{};        // class-indexed combined DFA of kernels/dfawalk.cu (text form, any definition)
+    CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
+    bool force_k4 = false;       // GORP_FORCE_K4=1: one-line-per-thread capture kernels (K4) instead of the bucketed K4b
+    DevBuf perm, items, buckets;
+    bool force_k1k2 = false;     // GORP_FORCE_K1K2=1: newline index + DFA scan as separate kernels (K1, K2) instead of K0d
     bool force_tiles = false;    // GORP_FORCE_TILES=1: the TMA-staged tile kernel instead of the chunk-walk kernel
     uint32_t onepass_shrink = 0;  // too-dense retries remembered across calls
     uint32_t* d_slots = nullptr;
@@ -208,6 +213,8 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     if (const char* f = std::getenv("GORP_FORCE_GENERAL")) c.force_general = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TWOPASS")) c.force_twopass = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TILES")) c.force_tiles = f[0] == '1';
+    if (const char* f = std::getenv("GORP_FORCE_K1K2")) c.force_k1k2 = f[0] == '1';
+    if (const char* f = std::getenv("GORP_FORCE_K4")) c.force_k4 = f[0] == '1';
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
     // combined DFA
     const size_t S = m.dfa.n_states, C = m.dfa.n_classes;
@@ -274,6 +281,43 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
             c.dfa_direct.accept_first = c.dfa.accept_first;
             c.dfa_direct.n_classes = static_cast<uint32_t>(C);
             c.dfa_direct.enabled = 1;
+        }
+    }
+    // chunk-walk DFA tier: class-indexed u16 rows + DEADSCAN / SKIP / FIN rows (see kernels.cuh: DfaWalkDev)
+    {
+        const size_t E = m.n_groups.size();
+        const size_t K = C + 1, NL = C, dscan = S, fin_base = S + 16, R = fin_base + 1 + E;
+        if (R <= 0xFFFF && K * 2 <= 0xFFFF) {
+            std::vector<uint16_t> rows(((R * K + 7) / 8) * 8, 0);
+            for (size_t r = 0; r < R; ++r)
+                for (size_t k = 0; k < K; ++k) {
+                    size_t nx;
+                    if (r < S) {
+                        if (k == NL) {
+                            nx = fin_base + 1 + m.dfa.accept_first[r];
+                        } else {
+                            const int32_t t = m.dfa.trans[r * C + k];
+                            nx = t < 0 ? dscan : static_cast<size_t>(t);
+                        }
+                    } else if (r == dscan) {
+                        nx = k == NL ? fin_base : dscan;
+                    } else if (r < fin_base) {
+                        nx = r == S + 1 ? 0 : r - 1;  // SKIP chain (swallows any unit, '\n' included)
+                    } else {
+                        nx = r;  // FIN: absorbing
+                    }
+                    rows[r * K + k] = static_cast<uint16_t>(nx);
+                }
+            std::vector<uint16_t> cls128(128), xcls(m.dfa.classmap);
+            for (size_t u = 0; u < 128; ++u) cls128[u] = static_cast<uint16_t>(2 * (u == 0x0A ? NL : m.dfa.classmap[u]));
+            c.dfawalk.table = upload(rows, c.owned);
+            c.dfawalk.n_rows = static_cast<uint32_t>(R);
+            c.dfawalk.K = static_cast<uint32_t>(K);
+            c.dfawalk.n_states = static_cast<uint32_t>(S);
+            c.dfawalk.fin_base = static_cast<uint32_t>(fin_base);
+            c.dfawalk.cls128 = upload(cls128, c.owned);
+            c.dfawalk.xcls = upload(xcls, c.owned);
+            c.dfawalk.enabled = 1;
         }
     }
     // capture automata
@@ -368,6 +412,55 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                 c.cap_fast.n_regs = max_regs;
                 c.cap_fast.ext = upload(fext, c.owned);
                 c.cap_fast.enabled = 1;
+            }
+        }
+        // bucketed capture tier: one table per extraction, read through L1/L2 (kernels.cuh: CapImgDev)
+        if (E <= kCapMaxBuckets) {
+            const uint32_t Cn = m.symbols.n_classes, K = Cn + 1, NL = Cn, row_bytes = K * 4;
+            uint32_t max_regs = 0;
+            for (size_t e = 0; e < E; ++e) max_regs = std::max(max_regs, m.tdfas[e].n_regs);
+            std::vector<uint32_t> cls128(128), image;
+            for (uint32_t u = 0; u < 128; ++u) cls128[u] = (u == 0x0A ? NL : m.symbols.classmap[u]) * 4;
+            std::vector<CapImgExt> fext(E);
+            bool ok = max_regs < 63;
+            for (size_t e = 0; e < E && ok; ++e) {
+                const Tdfa& t = m.tdfas[e];
+                const uint32_t Sx = t.n_states, rows = 2 * Sx + 17;
+                if (static_cast<uint64_t>(rows) * row_bytes >= (1u << 26) || (image.size() + static_cast<size_t>(rows) * K) * 4 >= (1ull << 31)) {
+                    ok = false;
+                    break;
+                }
+                fext[e] = {static_cast<uint32_t>(image.size() * 4), row_bytes, Sx, (Sx + 15) * row_bytes, (Sx + 16) * row_bytes,
+                           (Sx + 17) * row_bytes};
+                const size_t base = image.size();
+                image.resize(base + static_cast<size_t>(rows) * K);
+                auto put = [&](uint32_t r, uint32_t k, uint32_t next_row, uint32_t slot) {
+                    image[base + static_cast<size_t>(r) * K + k] = ((next_row * row_bytes) << 6) | slot;
+                };
+                for (uint32_t r = 0; r < rows; ++r)
+                    for (uint32_t k = 0; k < K; ++k) {
+                        if (r < Sx) {
+                            if (k == NL) { put(r, k, Sx + 17 + r, max_regs); continue; }
+                            const uint32_t ent = t.trans[static_cast<size_t>(r) * Cn + k];
+                            const uint32_t nx = ent & 0xFFFFu, ol = ent >> 16;
+                            if (nx == 0xFFFFu) { put(r, k, Sx + 15, max_regs); continue; }
+                            const uint32_t o0 = t.op_off[ol], o1 = t.op_off[ol + 1];
+                            if (o1 == o0) put(r, k, nx, max_regs);
+                            else if (o1 - o0 == 1 && (t.ops[o0] & 0xFF) == 0xFF) put(r, k, nx, t.ops[o0] >> 8);
+                            else put(r, k, Sx + 16, max_regs);  // SLOW: replayed through the general tables
+                        } else if (r < Sx + 15) {
+                            put(r, k, r == Sx ? 0u : r - 1, max_regs);  // SKIP chain
+                        } else {
+                            put(r, k, r, max_regs);  // DEAD / SLOW / FRZ: absorbing
+                        }
+                    }
+            }
+            if (ok) {
+                c.capimg.image = upload(image, c.owned);
+                c.capimg.cls128 = upload(cls128, c.owned);
+                c.capimg.ext = upload(fext, c.owned);
+                c.capimg.n_regs = max_regs;
+                c.capimg.enabled = capwalk_smem_bytes(c.capimg) <= 200 * 1024 ? 1u : 0u;
             }
         }
         // one-pass tier: DFA x capture automata folded into one automaton (host/fused.hpp, kernels/onepass.cu)
@@ -731,6 +824,62 @@ bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
     return false;
 }
 
+// Text form, newline index + combined DFA through the chunk-walk DFA kernel (K0d): fills c.line_off / c.ext_id.
+// Returns false when the batch has to take K1 + K2 instead.
+bool run_dfawalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
+                 int64_t& n_lines, bool& ends_with_nl) {
+    if (n_units <= 0 || c.force_general || c.force_k1k2 || !c.dfawalk.enabled) return false;
+    if (reinterpret_cast<uintptr_t>(d_text) & 31) return false;  // the walk uses 256-bit loads
+    uint32_t threads = 0;
+    bool in_smem = false;
+    if (!k0_dfawalk_plan(c.dfawalk, &threads, &in_smem)) return false;
+    Launch L{stream, c.sm_count};
+    bool exact = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        DfaWalkParams P{};
+        P.text = d_text;
+        P.n_units = n_units;
+        const int64_t tile_units = static_cast<int64_t>(threads) * kChunkUnits;
+        P.n_tiles = (n_units + tile_units - 1) / tile_units;
+        P.a = c.dfawalk;
+        P.stage_rows = kDfaWalkStagePerThread * threads;
+        const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 8 + 8 + 24;
+        c.tile_state.reserve(state_bytes);
+        int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
+        if (exact) cap_lines = n_lines + 16;
+        c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
+        c.line_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
+        P.ext_id = c.ext_id.as<int32_t>();
+        P.line_off = c.line_off.as<int64_t>();
+        P.cap_lines = cap_lines;
+        unsigned char* st = c.tile_state.as<unsigned char>();
+        P.tile_status = reinterpret_cast<unsigned long long*>(st);
+        P.ticket = reinterpret_cast<unsigned int*>(st + static_cast<size_t>(P.n_tiles) * 8);
+        P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 8 + 8);
+        CK(cudaMemsetAsync(st, 0, state_bytes, stream));
+        if (std::getenv("GORP_ONEPASS_DEBUG"))
+            std::fprintf(stderr, "[dfawalk debug] threads=%u grid=%d smem=%zu (table %s) tiles=%lld rows=%u K=%u cap_lines=%lld\n", threads,
+                         k0_dfawalk_grid(L, P, threads, in_smem), dfawalk_smem_bytes(P.a, threads, in_smem), in_smem ? "in smem" : "global",
+                         static_cast<long long>(P.n_tiles), P.a.n_rows, P.a.K, static_cast<long long>(cap_lines));
+        k0_dfawalk_scan(L, P, threads, in_smem);
+        tm.mark("k0_dfawalk_scan", 1);
+        CK(cudaGetLastError());
+        int64_t totals[3] = {0, 0, 0};
+        CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        n_lines = totals[0];
+        ends_with_nl = totals[1] != 0;
+        c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
+        if (totals[2] & 1) {  // capacity overflow: rerun once with the exact size
+            exact = true;
+            continue;
+        }
+        CK(cudaMemcpyAsync(d_scalars, P.totals, 8, cudaMemcpyDeviceToDevice, stream));
+        return true;
+    }
+    return false;
+}
+
 // Runs the device pipeline. Text form when d_off == nullptr. Caller holds c.mu and has set the device.
 // Returns n_lines (synchronises once for the text form to size the per-line arrays).
 int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, const int64_t* d_off, int64_t n_lines,
@@ -744,7 +893,12 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     bool ends_with_nl = true;
     if (!d_off && run_chunkwalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
-    if (!d_off) {
+    bool scanned = false;  // ext_id already holds the combined-DFA result
+    if (!d_off && run_dfawalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, ends_with_nl)) {
+        sep = 1;
+        scanned = true;
+        d_line_off = c.line_off.as<int64_t>();
+    } else if (!d_off) {
         sep = 1;
         const int64_t n_tiles = (n_units + kNlTile - 1) / kNlTile;
         c.tile_counts.reserve(static_cast<size_t>(n_tiles + 1) * 4);
@@ -779,7 +933,8 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     // every line but (possibly) the last is terminated by '\n' in the text form: fast tiers; an unterminated last line
     // goes through the general kernels
     const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
-    if (sep == 1 && c.dfa_direct.enabled && !c.force_general) {
+    if (scanned) {
+    } else if (sep == 1 && c.dfa_direct.enabled && !c.force_general) {
         k2_dfa_direct(L, c.dfa_direct, d_text, d_line_off, n_fast, c.ext_id.as<int32_t>());
         if (n_fast < n_lines) k2_dfa_scan(L, c.dfa, d_text, d_line_off + n_fast, sep, 1, c.ext_id.as<int32_t>() + n_fast);
         tm.mark("k2_dfa_scan", n_fast < n_lines ? 2 : 1);
@@ -790,7 +945,43 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     // result rows of `spans`: max_slots entries per line, no offsets needed
     const uint32_t stride = c.max_slots;
     c.spans.reserve((nl * stride + 4) * 4);
-    if (!c.cap.match_only && stride > 0) {
+    bool hist_done = false;
+    if (!c.cap.match_only && stride > 0 && sep == 1 && c.capimg.enabled && !c.force_general && !c.force_k4 && n_lines > 0 &&
+        n_lines < (1ll << 32)) {
+        // K4b: histogram -> buckets by extraction -> one warp per work item (kernels/capwalk.cu)
+        const uint32_t E = c.n_ext;
+        CK(cudaMemsetAsync(c.hist.p, 0, (E + 2) * 8, stream));
+        k3_histogram(L, c.ext_id.as<int32_t>(), n_lines, E, c.hist.as<unsigned long long>());
+        tm.mark("k3_histogram", 1);
+        hist_done = true;
+        const size_t max_items = nl / kCapItemLines + E + 1;
+        c.perm.reserve(nl * 4 + 16);
+        c.items.reserve(max_items * sizeof(CapItem));
+        c.buckets.reserve((2 * static_cast<size_t>(E) + 4) * 4);
+        uint32_t* bucket_base = c.buckets.as<uint32_t>();
+        uint32_t* cursor = bucket_base + E + 1;
+        uint32_t* n_items = cursor + E;
+        uint32_t* item_ticket = n_items + 1;
+        k4b_bucket(L, c.ext_id.as<int32_t>(), n_lines, E, c.hist.as<unsigned long long>(), bucket_base, cursor, c.perm.as<uint32_t>(),
+                   c.items.as<CapItem>(), n_items, item_ticket, c.spans.as<int32_t>(), stride);
+        tm.mark("k4b_bucket", 2);
+        CapWalkParams W{};
+        W.text = d_text;
+        W.n_units = n_units;
+        W.line_off = d_line_off;
+        W.perm = c.perm.as<uint32_t>();
+        W.items = c.items.as<CapItem>();
+        W.n_items = n_items;
+        W.item_ticket = item_ticket;
+        W.img = c.capimg;
+        W.cap = c.cap;
+        W.span_stride = stride;
+        W.ext_id = c.ext_id.as<int32_t>();
+        W.spans = c.spans.as<int32_t>();
+        W.hist = c.hist.as<unsigned long long>();
+        k4b_capwalk(L, W);
+        tm.mark("k4b_capwalk", 1);
+    } else if (!c.cap.match_only && stride > 0) {
         if (sep == 1 && c.cap_fast.enabled && !c.force_general) {
             k4_tdfa_fast(L, c.cap_fast, c.cap, d_text, n_units, d_line_off, n_fast, stride, c.ext_id.as<int32_t>(), c.spans.as<int32_t>());
             if (n_fast < n_lines)
@@ -804,9 +995,11 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     } else {
         tm.mark("k4_tdfa_capture", 0);
     }
-    CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
-    k3_histogram(L, c.ext_id.as<int32_t>(), n_lines, c.n_ext, c.hist.as<unsigned long long>());
-    tm.mark("k3_histogram", 1);
+    if (!hist_done) {
+        CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
+        k3_histogram(L, c.ext_id.as<int32_t>(), n_lines, c.n_ext, c.hist.as<unsigned long long>());
+        tm.mark("k3_histogram", 1);
+    }
     CK(cudaGetLastError());
     if (out) {
         out->n_lines = n_lines;

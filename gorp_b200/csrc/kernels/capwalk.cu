@@ -1,0 +1,296 @@
+// K4b — capture half of the text form, bucketed by extraction (sm_100a). Stands in for
+// JDKRegexpCookedExtraction.match/_constructMatch (reference jdkre/JDKRegexpCookedExtraction.java:36-59) on the lines
+// the combined DFA assigned to an extraction.
+//
+//   bucket_plan     histogram (K3) -> bucket bases, cursors, work items (extraction e, <= kCapItemLines lines of it)
+//   bucket_scatter  line ids grouped by extraction (CTA-local counting, one global atomic per CTA and non-empty
+//                   bucket); rows of MISS lines are filled with -1 here
+//   capwalk         one WARP per work item: all lanes run the capture automaton of the same extraction (the lanes of a
+//                   warp then touch the same few table rows, so the L1 gathers stay cheap and the tables never have
+//                   to fit shared memory), every lane walks one line at a time in 32-byte blocks and pulls its next
+//                   line from the item when it finishes one (ballot-ranked, no atomics), so lanes stay busy
+//                   whatever the line lengths are. Tag registers live in shared memory, [register][thread].
+//
+// Table image per extraction (engine.cu builds it from host/capture.hpp: Tdfa), rows of K = classes + 1 u32 entries
+// (last column = '\n'):  [0,S) states | S..S+14 = SKIP_1..15 | S+15 = DEAD | S+16 = SLOW (trap: the block is replayed
+// through the general tables) | S+17+s = FRZ(s), reached at the line's '\n' from state s, absorbing.
+// Entry = (byte offset of the next row inside the extraction's table) << 6 | register slot to set to the current
+// position (slot n_regs = the per-thread dummy).
+#include "device_common.cuh"
+
+namespace gorp {
+
+namespace {
+
+using namespace dev;
+
+constexpr int kBucketThreads = 256;
+constexpr int kBucketSeg = 4096;  // lines per CTA of the scatter pass
+
+// ------------------------------------------------------------------ bucket plan (one CTA)
+__global__ void __launch_bounds__(1024) bucket_plan_kernel(const unsigned long long* __restrict__ hist, uint32_t n_ext,
+                                                           uint32_t* __restrict__ bucket_base /* [E+1] */,
+                                                           uint32_t* __restrict__ cursor /* [E] */, CapItem* __restrict__ items,
+                                                           uint32_t* __restrict__ n_items_out, uint32_t* __restrict__ item_ticket) {
+    __shared__ uint32_t s_item_base[kCapMaxBuckets + 1];
+    __shared__ uint32_t s_base[kCapMaxBuckets + 1];
+    for (uint32_t e = threadIdx.x; e < n_ext; e += blockDim.x) s_base[e] = static_cast<uint32_t>(hist[e]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0, irun = 0;
+        for (uint32_t e = 0; e < n_ext; ++e) {
+            const uint32_t n = s_base[e];
+            s_base[e] = run;
+            s_item_base[e] = irun;
+            run += n;
+            irun += (n + kCapItemLines - 1) / kCapItemLines;
+        }
+        s_base[n_ext] = run;
+        s_item_base[n_ext] = irun;
+        *n_items_out = irun;
+        *item_ticket = 0;
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e <= n_ext; e += blockDim.x) {
+        bucket_base[e] = s_base[e];
+        if (e < n_ext) {
+            cursor[e] = s_base[e];
+            const uint32_t b0 = s_base[e], b1 = s_base[e + 1];
+            uint32_t k = s_item_base[e];
+            for (uint32_t b = b0; b < b1; b += kCapItemLines, ++k) {
+                const uint32_t end = b + kCapItemLines < b1 ? b + kCapItemLines : b1;
+                items[k] = CapItem{e, b, end};
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ bucket scatter
+__global__ void __launch_bounds__(kBucketThreads) bucket_scatter_kernel(const int32_t* __restrict__ ext_id, int64_t n_lines, uint32_t n_ext,
+                                                                        uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm,
+                                                                        int32_t* __restrict__ spans, uint32_t span_stride) {
+    __shared__ uint32_t s_cnt[kCapMaxBuckets];
+    __shared__ uint32_t s_pos[kCapMaxBuckets];
+    for (int64_t seg0 = static_cast<int64_t>(blockIdx.x) * kBucketSeg; seg0 < n_lines; seg0 += static_cast<int64_t>(gridDim.x) * kBucketSeg) {
+        for (uint32_t i = threadIdx.x; i < n_ext; i += kBucketThreads) s_cnt[i] = 0;
+        __syncthreads();
+        const int64_t seg1 = seg0 + kBucketSeg < n_lines ? seg0 + kBucketSeg : n_lines;
+        int32_t mine[kBucketSeg / kBucketThreads];
+        uint32_t rank[kBucketSeg / kBucketThreads];
+#pragma unroll
+        for (int k = 0; k < kBucketSeg / kBucketThreads; ++k) {
+            const int64_t line = seg0 + k * kBucketThreads + threadIdx.x;
+            mine[k] = line < seg1 ? ext_id[line] : -1;
+            rank[k] = mine[k] >= 0 ? atomicAdd(&s_cnt[mine[k]], 1u) : 0u;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_ext; i += kBucketThreads) {
+            const uint32_t n = s_cnt[i];
+            s_pos[i] = n ? atomicAdd(cursor + i, n) : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kBucketSeg / kBucketThreads; ++k) {
+            const int64_t line = seg0 + k * kBucketThreads + threadIdx.x;
+            if (line >= seg1) continue;
+            if (mine[k] >= 0) {
+                perm[s_pos[mine[k]] + rank[k]] = static_cast<uint32_t>(line);
+            } else {  // MISS: the row is all -1
+                int32_t* out = spans + line * span_stride;
+                for (uint32_t s = 0; s < span_stride; ++s) out[s] = -1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ capture walk
+__device__ __forceinline__ uint32_t ldg32_off(const unsigned char* __restrict__ base, uint32_t off) {
+    return __ldg(reinterpret_cast<const uint32_t*>(base + off));
+}
+
+template <int kByte>
+__device__ __forceinline__ void cw_step(uint32_t& st, uint32_t w, uint32_t cls_abs, const unsigned char* __restrict__ tab, uint32_t reg_abs,
+                                        uint32_t reg_stride, uint32_t pos) {
+    uint32_t b, a;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(b), "r"(cls_abs));
+    const uint32_t c4 = lds32(a);
+    const uint32_t ent = ldg32_off(tab, st + c4);
+    st = ent >> 6;
+    uint32_t sa;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(ent & 63u), "r"(reg_stride), "r"(reg_abs));
+    sts32(sa, pos);
+}
+
+// 16 units through the general tables (units >= 0x80, surrogate pairs, transitions with several register commands).
+// `q` = text position of the block, `a` = text position of the line start; units at or beyond n_units read as '\n'.
+// `st` is a row byte offset of the extraction's image on entry and exit.
+__device__ __noinline__ uint32_t cw_slow16(const CapDev& c, const ExtDev& x, const CapImgExt& fx, uint32_t st,
+                                           const uint16_t* __restrict__ text, int64_t q, int64_t a, int64_t n_units, uint32_t reg_abs,
+                                           uint32_t reg_stride) {
+    const uint32_t S = fx.n_states;
+    uint32_t row = st / fx.row_bytes;
+    const uint32_t n_cols = c.n_classes + 1;
+    const uint32_t* __restrict__ tr = c.tdfa_trans + x.trans_off;
+    const uint32_t* __restrict__ opo = c.tdfa_op_off + x.opoff_off;
+    const uint16_t* __restrict__ ops = c.tdfa_ops + x.ops_off;
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+        if (row >= S + 15) break;  // DEAD / FRZ
+        const int64_t p = q + k;
+        const uint32_t u = p < n_units ? __ldg(text + p) : 0x0Au;
+        if (row >= S) {  // SKIP_j
+            row = row == S ? 0u : row - 1;
+            continue;
+        }
+        if (u == 0x0Au) {
+            row = S + 17 + row;
+            break;
+        }
+        const uint32_t pos = static_cast<uint32_t>(p - a);
+        uint32_t sym = __ldg(c.cls + u);
+        // a high surrogate followed by a low surrogate is ONE java.util.regex character
+        if ((u & 0xFC00u) == 0xD800u && p + 1 < n_units && (__ldg(text + p + 1) & 0xFC00u) == 0xDC00u) sym = c.pair_hi_class;
+        const uint32_t ent = __ldg(tr + row * n_cols + sym);
+        const uint32_t ol = ent >> 16;
+        if (ol) {
+            const uint32_t o0 = __ldg(opo + ol), o1 = __ldg(opo + ol + 1);
+            for (uint32_t i = o0; i < o1; ++i) {
+                const uint32_t op = __ldg(ops + i);
+                const uint32_t src = op & 0xFFu;
+                const uint32_t val = src == 0xFFu ? pos : lds32(reg_abs + src * reg_stride);
+                sts32(reg_abs + (op >> 8) * reg_stride, val);
+            }
+        }
+        row = ent & 0xFFFFu;
+        if (row == S) row = S + 15;  // the general table's dead row index is S
+    }
+    return row * fx.row_bytes;
+}
+
+__global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkParams P) {
+    extern __shared__ __align__(16) uint32_t s_mem[];  // [cls128][registers: (n_regs + 1) x blockDim]
+    for (uint32_t i = threadIdx.x; i < 128; i += kCapWalkThreads) s_mem[i] = __ldg(P.img.cls128 + i);
+    __syncthreads();
+    const uint32_t cls_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_mem));
+    const uint32_t reg_stride = kCapWalkThreads * 4;
+    const uint32_t reg_abs = cls_abs + 512 + threadIdx.x * 4;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n_items = *P.n_items;
+    const uint32_t stride = P.span_stride;
+
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(P.item_ticket, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const CapItem it = P.items[item];
+        const uint32_t e = it.ext;
+        const CapImgExt fx = P.img.ext[e];
+        const ExtDev x = P.cap.ext[e];
+        const unsigned char* __restrict__ tab = reinterpret_cast<const unsigned char*>(P.img.image) + fx.tab_off;
+        uint32_t cursor = it.begin;  // warp-uniform: next unassigned entry of the item
+
+        // per-lane line state
+        bool active = false;
+        uint32_t line = 0;
+        int64_t a = 0, q = 0;
+        uint32_t st = fx.dead_off;
+        for (;;) {
+            // lanes without a line take the next ones of the item
+            const uint32_t want = __ballot_sync(0xffffffffu, !active);
+            if (want) {
+                const uint32_t idx = cursor + static_cast<uint32_t>(__popc(want & lt_mask));
+                if (!active && idx < it.end) {
+                    line = __ldg(P.perm + idx);
+                    a = __ldg(P.line_off + line);
+                    q = a & ~int64_t(15);
+                    const uint32_t lo = static_cast<uint32_t>(a - q);
+                    st = lo ? (fx.n_states + lo - 1) * fx.row_bytes : 0u;
+                    active = true;
+                }
+                cursor += static_cast<uint32_t>(__popc(want));
+                if (cursor > it.end) cursor = it.end;
+            }
+            if (!__any_sync(0xffffffffu, active)) break;
+            if (active) {
+                const Units16 u = load_units16(P.text, q, P.n_units);
+                const uint32_t st0 = st;
+                const uint32_t pos = static_cast<uint32_t>(q - a);  // negative while skipping: only ever stored to the dummy register
+                if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                    cw_step<0>(st, u.a.x, cls_abs, tab, reg_abs, reg_stride, pos);
+                    cw_step<2>(st, u.a.x, cls_abs, tab, reg_abs, reg_stride, pos + 1);
+                    cw_step<0>(st, u.a.y, cls_abs, tab, reg_abs, reg_stride, pos + 2);
+                    cw_step<2>(st, u.a.y, cls_abs, tab, reg_abs, reg_stride, pos + 3);
+                    cw_step<0>(st, u.a.z, cls_abs, tab, reg_abs, reg_stride, pos + 4);
+                    cw_step<2>(st, u.a.z, cls_abs, tab, reg_abs, reg_stride, pos + 5);
+                    cw_step<0>(st, u.a.w, cls_abs, tab, reg_abs, reg_stride, pos + 6);
+                    cw_step<2>(st, u.a.w, cls_abs, tab, reg_abs, reg_stride, pos + 7);
+                    cw_step<0>(st, u.b.x, cls_abs, tab, reg_abs, reg_stride, pos + 8);
+                    cw_step<2>(st, u.b.x, cls_abs, tab, reg_abs, reg_stride, pos + 9);
+                    cw_step<0>(st, u.b.y, cls_abs, tab, reg_abs, reg_stride, pos + 10);
+                    cw_step<2>(st, u.b.y, cls_abs, tab, reg_abs, reg_stride, pos + 11);
+                    cw_step<0>(st, u.b.z, cls_abs, tab, reg_abs, reg_stride, pos + 12);
+                    cw_step<2>(st, u.b.z, cls_abs, tab, reg_abs, reg_stride, pos + 13);
+                    cw_step<0>(st, u.b.w, cls_abs, tab, reg_abs, reg_stride, pos + 14);
+                    cw_step<2>(st, u.b.w, cls_abs, tab, reg_abs, reg_stride, pos + 15);
+                    if (st == fx.slow_off) st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
+                } else {
+                    st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
+                }
+                q += 16;
+                if (st >= fx.dead_off) {  // the line is finished: DEAD (rejected) or FRZ(s)
+                    int32_t* out = P.spans + static_cast<int64_t>(line) * stride;
+                    bool ok = st >= fx.frz_off;
+                    uint32_t s = 0;
+                    if (ok) {
+                        s = (st - fx.frz_off) / fx.row_bytes;
+                        ok = __ldg(P.cap.tdfa_accepting + x.acc_off + s) != 0;
+                    }
+                    if (ok) {
+                        const uint8_t* __restrict__ fin = P.cap.tdfa_fin + x.fin_off + s * x.n_slots;
+                        const int32_t len = static_cast<int32_t>(__ldg(P.line_off + line + 1) - 1 - a);
+                        for (uint32_t k = 0; k < x.n_slots; ++k) {
+                            const uint32_t r = __ldg(fin + k);
+                            out[k] = r == 0xFFu ? -1 : (r == 0xFEu ? len : static_cast<int32_t>(lds32(reg_abs + r * reg_stride)));
+                        }
+                        for (uint32_t k = x.n_slots; k < stride; ++k) out[k] = -1;
+                    } else {  // the combined DFA accepted, java.util.regex does not: capture failure (Gorp.java:173-177)
+                        P.ext_id[line] = -2 - static_cast<int32_t>(e);
+                        for (uint32_t k = 0; k < stride; ++k) out[k] = -1;
+                        atomicAdd(P.hist + e, ~0ull);  // -1
+                        atomicAdd(P.hist + P.cap.n_ext + 1, 1ull);
+                    }
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void k4b_bucket(const Launch& L, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, const unsigned long long* hist,
+                uint32_t* bucket_base, uint32_t* cursor, uint32_t* perm, CapItem* items, uint32_t* n_items, uint32_t* item_ticket,
+                int32_t* spans, uint32_t span_stride) {
+    bucket_plan_kernel<<<1, 1024, 0, L.stream>>>(hist, n_ext, bucket_base, cursor, items, n_items, item_ticket);
+    if (n_lines <= 0) return;
+    const int64_t want = (n_lines + kBucketSeg - 1) / kBucketSeg, cap = static_cast<int64_t>(L.sm_count) * 8;
+    bucket_scatter_kernel<<<static_cast<int>(want < cap ? want : cap), kBucketThreads, 0, L.stream>>>(ext_id, n_lines, n_ext, cursor, perm, spans,
+                                                                                                     span_stride);
+}
+
+size_t capwalk_smem_bytes(const CapImgDev& img) { return 512 + static_cast<size_t>(img.n_regs + 1) * kCapWalkThreads * 4; }
+
+void k4b_capwalk(const Launch& L, const CapWalkParams& P) {
+    const size_t smem = capwalk_smem_bytes(P.img);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(capwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, capwalk_kernel, kCapWalkThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    capwalk_kernel<<<L.sm_count * per_sm, kCapWalkThreads, smem, L.stream>>>(P);
+}
+
+}  // namespace gorp

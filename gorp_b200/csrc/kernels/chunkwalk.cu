@@ -30,59 +30,6 @@ namespace {
 
 using namespace dev;
 
-constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62;
-
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// 8 units at text position `pos` (a multiple of 8); units at or beyond n_units read as '\n'
-__device__ __forceinline__ uint4 load_chunk(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units) {
-    if (pos + 8 <= n_units) return __ldg(reinterpret_cast<const uint4*>(text + pos));
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int64_t p0 = pos + 2 * j, p1 = p0 + 1;
-        const uint32_t lo = p0 < n_units ? __ldg(text + p0) : 0x0Au;
-        const uint32_t hi = p1 < n_units ? __ldg(text + p1) : 0x0Au;
-        w[j] = lo | (hi << 16);
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-struct Units16 {
-    uint4 a, b;
-};
-// 16 units at text position `pos` (a multiple of 16); units at or beyond n_units read as '\n'
-__device__ __forceinline__ Units16 load_units16(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units) {
-    Units16 r;
-    if (pos + 16 <= n_units) {
-        // the walk is the last use of these 32 bytes: L2 evict-first keeps the not-yet-walked text of the tiles in flight
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
-                     : "l"(text + pos));
-    } else {
-        r.a = load_chunk(text, pos, n_units);
-        r.b = load_chunk(text, pos + 8, n_units);
-    }
-    return r;
-}
-
-// bit k (k < 4) = unit k of the pair of words (a, b) is '\n' (0x000A). Low and high bytes are gathered with PRMT, a
-// unit is '\n' iff (low ^ 0x0A) | high == 0; exact zero-byte test, then the four flag bits (7, 15, 23, 31) are
-// compressed with one multiply.
-__device__ __forceinline__ uint32_t nl_bits4(uint32_t a, uint32_t b) {
-    const uint32_t lo = __byte_perm(a, b, 0x6420), hi = __byte_perm(a, b, 0x7531);
-    const uint32_t t = (lo ^ 0x0A0A0A0Au) | hi;
-    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);  // 0x80 in every zero byte of t
-    return (((z >> 7) * 0x00204081u) >> 21) & 0xFu;
-}
-
 // Entry layout in shared memory (rewritten from the raw table when the CTA starts):
 //   bits 31..18  next row, in units of 16 bytes from the start of the row area
 //   bits 13..0   op slot, in units of 4 bytes from the start of the slot bank (slot id * blockDim)

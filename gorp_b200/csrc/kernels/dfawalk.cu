@@ -1,0 +1,374 @@
+// K0d — chunk-walk DFA kernel (sm_100a): newline index + combined-DFA scan of the text form in ONE pass over the text,
+// for definitions whose one-pass product automaton (host/fused.hpp) is not available. Stands in for
+// PolyMatcher.match + Automata.step/accept (reference autom/PolyMatcher.java:123-133, autom/Automata.java:133-139)
+// and the first-index dispatch of Gorp.java:166-167; the capture half runs afterwards, bucketed by extraction
+// (kernels/capwalk.cu).
+//
+// Work decomposition = kernels/chunkwalk.cu: the text is cut into chunks of kChunkUnits units, one per thread; a CTA
+// takes a tile of blockDim.x consecutive chunks by in-order ticket; a thread owns the lines whose preceding '\n' lies
+// in its chunk and walks them one after the other with 256-bit loads, so every lane walks about kChunkUnits units
+// whatever the line lengths are. Differences:
+//   * the automaton is the class-indexed combined DFA (u16 next-row entries, K = classes + 1 columns, the last column
+//     is '\n'); it lives in shared memory when it fits, otherwise it is read through L1/L2 (template kSmem);
+//       rows [0,S) states | S = DEADSCAN (dead, keeps scanning to the line's '\n') | S+1..S+15 = SKIP_1..15 (units that
+//       precede the line in its first 32-byte block) | fin_base = S+16: FIN(-1), FIN(0..E-1) absorbing outcome rows
+//   * a finished line is only (extraction id, start): rows are staged in shared memory by tile-local row index and go
+//     out after the walk with fully coalesced stores, once the tile's first row is known (decoupled look-back by warp 0
+//     during the walk).
+#include "device_common.cuh"
+
+namespace gorp {
+
+namespace {
+
+using namespace dev;
+
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// newline mask of 16 units (bit k = unit k is '\n')
+__device__ __forceinline__ uint32_t nl_mask16(const Units16& u) {
+    return nl_bits4(u.a.x, u.a.y) | (nl_bits4(u.a.z, u.a.w) << 4) | (nl_bits4(u.b.x, u.b.y) << 8) | (nl_bits4(u.b.z, u.b.w) << 12);
+}
+
+// exclusive prefix of the tile's line count over all earlier tiles (decoupled look-back, called by every lane of warp 0;
+// publishes the tile's aggregate first). 128 predecessors per probe: see kernels/chunkwalk.cu.
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* tile_status, int64_t tile, uint32_t total,
+                                                                 uint32_t lane) {
+    unsigned long long pre = 0;
+    if (tile == 0) return 0;
+    if (lane == 0) st_release(tile_status + tile, kStAgg | static_cast<unsigned long long>(total));
+    for (int64_t j = tile - 1;; j -= 128) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int64_t idx = j - (lane * 4 + m);
+            v[m] = idx >= 0 ? ld_acquire(tile_status + idx) : kStPre;  // before tile 0: an empty inclusive prefix
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int64_t idx = j - (lane * 4 + m);
+            while ((v[m] >> 62) == 0) {
+                __nanosleep(32);
+                v[m] = ld_acquire(tile_status + idx);
+            }
+        }
+        unsigned long long part = 0;  // aggregates up to and including the lane's nearest inclusive prefix
+        bool has = false;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (!has) {
+                part += v[m] & ~(3ull << 62);
+                has = (v[m] >> 62) == 2;
+            }
+        const uint32_t pmask = __ballot_sync(0xffffffffu, has);
+        const uint32_t firstp = pmask ? static_cast<uint32_t>(__ffs(pmask)) - 1u : 32u;
+        unsigned long long l = lane <= firstp ? part : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        pre += l;
+        if (pmask) break;
+    }
+    return pre;
+}
+
+template <bool kSmem>
+__device__ __forceinline__ uint32_t dw_next(uint32_t st, uint32_t cx, uint32_t row_bytes, const unsigned char* __restrict__ tab_g) {
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(st), "r"(row_bytes), "r"(cx));
+    if (kSmem) return lds16(a);
+    return __ldg(reinterpret_cast<const uint16_t*>(tab_g + a));
+}
+
+// one step on an ASCII unit held in byte kByte (0 or 2) of w. s_cx[unit] = byte offset of the unit's column inside a
+// row (+ the shared-memory address of the table when kSmem), so the dependent chain is one IMAD + one load.
+template <bool kSmem, int kByte>
+__device__ __forceinline__ uint32_t dw_step(uint32_t st, uint32_t w, uint32_t cx_abs, uint32_t row_bytes,
+                                            const unsigned char* __restrict__ tab_g) {
+    uint32_t b, a;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(b), "r"(cx_abs));
+    return dw_next<kSmem>(st, lds32(a), row_bytes, tab_g);
+}
+
+// 8 units that hold a unit >= 0x80: unit by unit through the full class map (global, L1/L2 resident)
+template <bool kSmem>
+__device__ __noinline__ uint32_t dw_slow8(const DfaWalkDev& A, uint32_t st, uint4 v, uint32_t cx_abs, uint32_t tab_abs, uint32_t row_bytes,
+                                          const unsigned char* __restrict__ tab_g) {
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        if (st >= A.fin_base) break;
+        const uint32_t u = unit_at(v, k);
+        const uint32_t cx = u < 0x80u ? lds32(cx_abs + u * 4) : (kSmem ? tab_abs : 0u) + 2u * __ldg(A.xcls + u);
+        st = dw_next<kSmem>(st, cx, row_bytes, tab_g);
+    }
+    return st;
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t kT = blockDim.x;
+    const DfaWalkDev& A = P.a;
+    constexpr uint32_t C = kChunkUnits;
+    const uint32_t row_bytes = A.K * 2;
+    const uint32_t table_bytes = kSmem ? ((A.n_rows * row_bytes + 15u) & ~15u) : 0u;
+    // ---- carve shared memory: [table][cx 128 x u32][staged ext][staged start]
+    uint32_t* s_cx = reinterpret_cast<uint32_t*>(smem + table_bytes);
+    int32_t* s_sext = reinterpret_cast<int32_t*>(s_cx + 128);
+    uint32_t* s_sstart = reinterpret_cast<uint32_t*>(s_sext + P.stage_rows);
+    __shared__ uint32_t s_warp[32];
+    __shared__ long long s_tile, s_base;
+    __shared__ int s_skip_writes;
+    __shared__ unsigned int s_flag;  // (tile + 1) once s_base / s_skip_writes of the tile are valid
+
+    const uint32_t tab_abs = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const uint32_t cx_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_cx));
+    const unsigned char* __restrict__ tab_g = reinterpret_cast<const unsigned char*>(A.table);
+    if (kSmem) {
+        const uint32_t n16 = (A.n_rows * row_bytes + 15u) / 16u;  // the global copy is padded to 16 bytes
+        const uint4* src = reinterpret_cast<const uint4*>(A.table);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (uint32_t i = threadIdx.x; i < n16; i += kT) dst[i] = __ldg(src + i);
+    }
+    for (uint32_t i = threadIdx.x; i < 128; i += kT) s_cx[i] = (kSmem ? tab_abs : 0u) + __ldg(A.cls128 + i);
+    if (threadIdx.x == 0) s_flag = 0;
+
+    const uint32_t fin_base = A.fin_base, skip0 = A.n_states;  // SKIP_k = skip0 + k
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = kT >> 5;
+
+    long long ticket_ahead = threadIdx.x == 0 ? static_cast<long long>(atomicAdd(P.ticket, 1u)) : 0;
+    for (;;) {
+        __syncthreads();  // the previous tile no longer uses s_tile / s_warp / the staging area; table setup done
+        if (threadIdx.x == 0) s_tile = ticket_ahead;
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        if (threadIdx.x == 0) ticket_ahead = static_cast<long long>(atomicAdd(P.ticket, 1u));
+        const int64_t tile0 = tile * kT * static_cast<int64_t>(C);
+        {  // start fetching this tile's chunks now; the pre-scan consumes them in order
+            const int64_t n0 = tile0 + static_cast<int64_t>(threadIdx.x) * C;
+            if (n0 + C <= P.n_units) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.text + n0), "n"(C * 2) : "memory");
+        }
+        // ---- newline pre-scan, per warp with coalesced loads: iteration i reads the 32 x 16 bytes of lane i's chunk;
+        // a '\n' at position p counts when it starts a line (p + 1 < n_units). Lane i keeps the count and the first.
+        uint32_t cnt = 0, first = 0;
+        {
+            const int64_t wbase = tile0 + static_cast<int64_t>(warp) * 32 * C;
+            const bool inside = wbase + 32 * static_cast<int64_t>(C) + 1 <= P.n_units;
+            if (wbase < P.n_units) {
+#pragma unroll 4
+                for (uint32_t i = 0; i < 32; ++i) {
+                    const int64_t p = wbase + i * C + lane * 8;
+                    uint32_t m;
+                    if (inside) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.text + p));
+                        m = nl_bits4(v.x, v.y) | (nl_bits4(v.z, v.w) << 4);
+                    } else {
+                        const uint4 v = load_chunk(P.text, p, P.n_units);
+                        m = nl_bits4(v.x, v.y) | (nl_bits4(v.z, v.w) << 4);
+                        const int64_t room = P.n_units - 1 - p;  // positions (relative to p) that count: [0, room)
+                        m = room <= 0 ? 0u : (room < 8 ? m & ((1u << static_cast<uint32_t>(room)) - 1u) : m);
+                    }
+                    const uint32_t tot = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(m)));
+                    const uint32_t has = __ballot_sync(0xffffffffu, m != 0);
+                    const uint32_t fl = has ? static_cast<uint32_t>(__ffs(has)) - 1u : 0u;
+                    const uint32_t mf = __shfl_sync(0xffffffffu, m, fl);
+                    if (lane == i) {
+                        cnt = tot;
+                        first = fl * 8 + static_cast<uint32_t>(__ffs(mf)) - 1u;
+                    }
+                }
+            }
+        }
+        const bool line0 = tile == 0 && threadIdx.x == 0 && P.n_units > 0;  // the line at offset 0
+        const uint32_t mine = cnt + (line0 ? 1u : 0u);
+
+        // ---- block scan of the line counts; warp 0 then resolves the tile's first row by decoupled look-back
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wsum = 0, total = 0;
+        for (uint32_t w = 0; w < n_warps; ++w) {
+            const uint32_t x = s_warp[w];
+            if (w < warp) wsum += x;
+            total += x;
+        }
+        const uint32_t row0 = wsum + incl - mine;  // tile-local index of this thread's first row
+        if (warp == 0) {
+            const unsigned long long pre = lookback_exclusive(P.tile_status, tile, total, lane);
+            if (lane == 0) {
+                const long long line_end = static_cast<long long>(pre) + total;
+                st_release(P.tile_status + tile, kStPre | static_cast<unsigned long long>(line_end));
+                const bool over = line_end > P.cap_lines;
+                if (over) atomicOr(reinterpret_cast<unsigned long long*>(P.totals + 2), 1ull);
+                if (tile == P.n_tiles - 1) {
+                    P.totals[0] = line_end;
+                    P.totals[1] = P.text[P.n_units - 1] == 0x0A ? 1 : 0;
+                    // line i spans [line_off[i], line_off[i+1] - 1): a text that does not end in '\n' gets n_units + 1
+                    if (!over) P.line_off[line_end] = P.n_units + (P.text[P.n_units - 1] == 0x0A ? 0 : 1);
+                }
+                s_base = static_cast<long long>(pre);
+                s_skip_writes = over ? 1 : 0;
+                __threadfence_block();
+                *reinterpret_cast<volatile unsigned int*>(&s_flag) = static_cast<unsigned int>(tile + 1);
+            }
+            __syncwarp();
+        }
+
+        // ---- walk the owned lines one after the other; positions are tile-relative
+        if (mine) {
+            const uint32_t c_end = (threadIdx.x + 1) * C;  // tile-relative end of the chunk
+            const int64_t n_rel = P.n_units - tile0;       // tile-relative end of the text
+            uint32_t start = line0 ? 0u : threadIdx.x * C + first + 1;
+            uint32_t q = start & ~15u;
+            uint32_t lo = start & 15u;
+            uint32_t st = lo ? skip0 + lo : 0u;
+            uint32_t row = row0;
+            for (;;) {
+                const Units16 u = load_units16(P.text, tile0 + q, P.n_units);
+                if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                    st = dw_step<kSmem, 0>(st, u.a.x, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.a.x, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.a.y, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.a.y, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.a.z, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.a.z, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.a.w, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.a.w, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.b.x, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.b.x, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.b.y, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.b.y, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.b.z, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.b.z, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.b.w, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.b.w, cx_abs, row_bytes, tab_g);
+                } else {
+                    st = dw_slow8<kSmem>(A, st, u.a, cx_abs, tab_abs, row_bytes, tab_g);
+                    st = dw_slow8<kSmem>(A, st, u.b, cx_abs, tab_abs, row_bytes, tab_g);
+                }
+                if (st >= fin_base) {  // the line ended inside these 16 units: at its first '\n' at or after `start`
+                    uint32_t m = nl_mask16(u);
+                    if (q < start) m &= ~0u << (start - q);
+                    const uint32_t nl = q + static_cast<uint32_t>(__ffs(m)) - 1u;  // tile-relative position of the '\n'
+                    const int32_t ext = static_cast<int32_t>(st - fin_base) - 1;
+                    if (row < P.stage_rows) {
+                        s_sext[row] = ext;
+                        s_sstart[row] = start;
+                    } else {  // denser tile than the staging area: this row goes out directly
+                        while (*reinterpret_cast<volatile unsigned int*>(&s_flag) != static_cast<unsigned int>(tile + 1)) {
+                        }
+                        __threadfence_block();
+                        if (!*reinterpret_cast<volatile int*>(&s_skip_writes)) {
+                            const int64_t g = *reinterpret_cast<volatile long long*>(&s_base) + row;
+                            P.ext_id[g] = ext;
+                            P.line_off[g] = tile0 + start;
+                        }
+                    }
+                    ++row;
+                    if (nl < c_end && static_cast<int64_t>(nl) + 1 < n_rel) {
+                        start = nl + 1;
+                        q = start & ~15u;
+                        lo = start & 15u;
+                        st = lo ? skip0 + lo : 0u;
+                        continue;
+                    }
+                    break;
+                }
+                q += 16;
+            }
+        }
+        // ---- coalesced copy-out of the staged rows
+        __syncthreads();
+        {
+            while (*reinterpret_cast<volatile unsigned int*>(&s_flag) != static_cast<unsigned int>(tile + 1)) {
+            }
+            __threadfence_block();
+            if (!*reinterpret_cast<volatile int*>(&s_skip_writes)) {
+                const int64_t base = *reinterpret_cast<volatile long long*>(&s_base);
+                const uint32_t n = total < P.stage_rows ? total : P.stage_rows;
+                for (uint32_t i = threadIdx.x; i < n; i += kT) {
+                    P.ext_id[base + i] = s_sext[i];
+                    P.line_off[base + i] = tile0 + s_sstart[i];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+size_t dfawalk_smem_bytes(const DfaWalkDev& a, uint32_t threads, bool in_smem) {
+    size_t b = in_smem ? ((static_cast<size_t>(a.n_rows) * a.K * 2 + 15) & ~size_t(15)) : 0;
+    b += 128 * 4;
+    b += static_cast<size_t>(kDfaWalkStagePerThread) * threads * 8;
+    return b + 128;
+}
+
+// picks table placement and CTA size: the table goes to shared memory when that still leaves >= 16 resident warps per SM
+bool k0_dfawalk_plan(const DfaWalkDev& a, uint32_t* threads, bool* in_smem) {
+    if (!a.enabled) return false;
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool sm = pass == 0;
+        uint32_t best = 0, best_warps = 0;
+        for (uint32_t kT : {1024u, 512u, 256u}) {
+            const size_t smem = dfawalk_smem_bytes(a, kT, sm);
+            if (smem > 226 * 1024) continue;
+            int per_sm = 0;
+            cudaError_t e;
+            if (sm) {
+                cudaFuncSetAttribute(dfawalk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<true>, static_cast<int>(kT), smem);
+            } else {
+                cudaFuncSetAttribute(dfawalk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<false>, static_cast<int>(kT), smem);
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            const uint32_t warps = static_cast<uint32_t>(per_sm) * kT / 32;
+            if (warps > best_warps) best = kT, best_warps = warps;
+        }
+        if (best && (best_warps >= 16 || !sm)) {
+            *threads = best;
+            *in_smem = sm;
+            return true;
+        }
+    }
+    return false;
+}
+
+int k0_dfawalk_grid(const Launch& L, const DfaWalkParams& P, uint32_t threads, bool in_smem) {
+    const size_t smem = dfawalk_smem_bytes(P.a, threads, in_smem);
+    int per_sm = 1;
+    if (in_smem) {
+        cudaFuncSetAttribute(dfawalk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<true>, static_cast<int>(threads), smem);
+    } else {
+        cudaFuncSetAttribute(dfawalk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<false>, static_cast<int>(threads), smem);
+    }
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
+    const int g = static_cast<int>(P.n_tiles < cap ? P.n_tiles : cap);
+    return g < 1 ? 1 : g;
+}
+
+void k0_dfawalk_scan(const Launch& L, const DfaWalkParams& P, uint32_t threads, bool in_smem) {
+    const size_t smem = dfawalk_smem_bytes(P.a, threads, in_smem);
+    const int g = k0_dfawalk_grid(L, P, threads, in_smem);
+    if (in_smem) dfawalk_kernel<true><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
+    else dfawalk_kernel<false><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
+}
+
+}  // namespace gorp

@@ -176,6 +176,80 @@ bool k0_chunkwalk_plan(const OnePassDev&, uint32_t* threads);
 int k0_chunkwalk_grid(const Launch&, const OnePassParams&, uint32_t threads);
 void k0_chunkwalk_extract(const Launch&, const OnePassParams&, uint32_t threads);
 
+// K0d: chunk-walk DFA kernel (text form, any definition) — see kernels/dfawalk.cu. Newline index + combined DFA in one
+// pass: writes line_off[0..n] and ext_id (>= 0 | -1); the capture half follows (kernels/capwalk.cu).
+struct DfaWalkDev {
+    const uint16_t* table;       // [n_rows * K] next row (global copy, padded to 16 bytes; copied to shared memory
+                                 // when it fits). Rows: [0,S) states, S = DEADSCAN, S+1..S+15 = SKIP_1..15,
+                                 // fin_base = S+16: FIN(-1), then FIN(0..E-1). Column K-1 = '\n'.
+    uint32_t n_rows, K;
+    uint32_t n_states, fin_base;
+    const uint16_t* cls128;      // [128] ASCII unit -> byte offset of its column inside a row (2 * column)
+    const uint16_t* xcls;        // [65536] unit -> column (units >= 0x80)
+    uint32_t enabled;
+};
+struct DfaWalkParams {
+    const uint16_t* text;
+    int64_t n_units, n_tiles;    // tiles of blockDim * kChunkUnits units
+    DfaWalkDev a;
+    int32_t* ext_id;
+    int64_t* line_off;
+    int64_t cap_lines;
+    uint32_t stage_rows;         // rows staged in shared memory per tile (kDfaWalkStagePerThread * blockDim)
+    unsigned long long* tile_status;  // [n_tiles] zeroed by the caller (decoupled look-back, as OnePassParams)
+    unsigned int* ticket;        // zeroed by the caller
+    int64_t* totals;             // [0] n_lines, [1] 1 = the text ends with '\n', [2] flags: 1 = capacity overflow
+};
+constexpr uint32_t kDfaWalkStagePerThread = 6;
+size_t dfawalk_smem_bytes(const DfaWalkDev&, uint32_t threads, bool in_smem);
+bool k0_dfawalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem);
+int k0_dfawalk_grid(const Launch&, const DfaWalkParams&, uint32_t threads, bool in_smem);
+void k0_dfawalk_scan(const Launch&, const DfaWalkParams&, uint32_t threads, bool in_smem);
+
+// K4b: capture half of the text form, bucketed by extraction — see kernels/capwalk.cu.
+constexpr uint32_t kCapItemLines = 1024;   // lines per work item (one warp walks one item)
+constexpr uint32_t kCapMaxBuckets = 4096;  // extractions the bucket kernels hold in shared memory
+constexpr int kCapWalkThreads = 256;
+struct CapItem {
+    uint32_t ext, begin, end;    // entries [begin, end) of `perm` are lines of extraction `ext`
+};
+struct CapImgExt {               // per-extraction table inside the image (byte offsets)
+    uint32_t tab_off;            // of the table inside the image
+    uint32_t row_bytes;          // K * 4
+    uint32_t n_states;
+    uint32_t dead_off;           // (S+15) * row_bytes ; everything >= dead_off ends the walk of a line
+    uint32_t slow_off;           // (S+16) * row_bytes
+    uint32_t frz_off;            // (S+17) * row_bytes
+};
+struct CapImgDev {
+    const uint32_t* image;       // all tables
+    const uint32_t* cls128;      // [128] ASCII unit -> class * 4 ('\n' -> the last column)
+    const CapImgExt* ext;        // [E]
+    uint32_t n_regs;             // widest register file; slot n_regs = the per-thread dummy
+    uint32_t enabled;
+};
+struct CapWalkParams {
+    const uint16_t* text;
+    int64_t n_units;
+    const int64_t* line_off;
+    const uint32_t* perm;        // line ids grouped by extraction
+    const CapItem* items;
+    const uint32_t* n_items;
+    uint32_t* item_ticket;
+    CapImgDev img;
+    CapDev cap;                  // general tables (slow path, final states)
+    uint32_t span_stride;
+    int32_t* ext_id;
+    int32_t* spans;
+    unsigned long long* hist;    // [E+2]: a capture failure moves one count from bin e to bin E+1
+};
+// hist (K3 layout) -> bucket_base[E+1], cursor[E], items (<= n_lines / kCapItemLines + E), perm; MISS rows := -1
+void k4b_bucket(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, const unsigned long long* hist,
+                uint32_t* bucket_base, uint32_t* cursor, uint32_t* perm, CapItem* items, uint32_t* n_items, uint32_t* item_ticket,
+                int32_t* spans, uint32_t span_stride);
+size_t capwalk_smem_bytes(const CapImgDev&);
+void k4b_capwalk(const Launch&, const CapWalkParams&);
+
 // result assembly of a batch that is pipelined in pieces: dst[i] = src[i] + bias ; dst[i] += src[i]
 void k_bias_copy(const Launch&, int64_t* dst, const int64_t* src, int64_t n, int64_t bias);
 void k_accumulate(const Launch&, int64_t* dst, const int64_t* src, int n);

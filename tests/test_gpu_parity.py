@@ -182,15 +182,20 @@ def test_full_size_properties():
     assert (np.diff(b.line_off) > 0).all()
 
 
-TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"}, "twopass_fast": {"GORP_FORCE_TWOPASS": "1"},
+TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
+         "dfawalk_capwalk": {"GORP_FORCE_TWOPASS": "1"},
+         "dfawalk_k4": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K4": "1"},
+         "k1k2_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1"},
+         "twopass_fast": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1", "GORP_FORCE_K4": "1"},
          "general": {"GORP_FORCE_GENERAL": "1"}}
+_TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES", "GORP_FORCE_K1K2", "GORP_FORCE_K4")
 
 
 @pytest.mark.parametrize("tier", list(TIERS))
 def test_every_kernel_tier_text_form(tier, monkeypatch):
     """The text form takes the fastest tier the definition allows; force each tier in turn (the engine reads the
     GORP_FORCE_* switches when it is created) and hold all of them to the same oracle."""
-    for k in ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES"):
+    for k in _TIER_ENV:
         monkeypatch.delenv(k, raising=False)
     for k, v in TIERS[tier].items():
         monkeypatch.setenv(k, v)
