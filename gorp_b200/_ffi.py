@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgorpcuda.so")
+LIB_PATH = os.environ.get("GORP_LIB") or os.path.join(HERE, "libgorpcuda.so")  # GORP_LIB: A/B runs against another build
 
 if not os.path.exists(LIB_PATH):
     raise ImportError("gorp_b200: %s not found — run `python -m gorp_b200.build` (there is no CPU fallback)" % LIB_PATH)

@@ -109,6 +109,10 @@ T* upload(const std::vector<T>& v, std::vector<void*>& owned) {
 }
 
 constexpr int kMaxTimed = 12;
+// The decoupled look-back words are the only hot read-write global data of the one-pass kernels. They get 2 MB pages of
+// their own: when this buffer came out of the pool of the engine's small table allocations, k0_chunkwalk_extract ran
+// 15-30 % slower (same SASS, same box; measured A/B, profiles/README.md round 1e).
+constexpr size_t kTileStateMinBytes = 4u << 20;
 
 struct DeviceCtx {
     int device = 0;
@@ -125,6 +129,7 @@ struct DeviceCtx {
     CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
     bool force_k4 = false;       // GORP_FORCE_K4=1: one-line-per-thread capture kernels (K4) instead of the bucketed K4b
     DevBuf perm, items, buckets;
+    int dfa_tier = 0;            // GORP_DFA_TIER: 0 = by line length, 1 = chunk-owner walk (K0d), 2 = line index + lane queue (K1 + K2b)
     bool force_k1k2 = false;     // GORP_FORCE_K1K2=1: newline index + DFA scan as separate kernels (K1, K2) instead of K0d
     bool force_tiles = false;    // GORP_FORCE_TILES=1: the TMA-staged tile kernel instead of the chunk-walk kernel
     uint32_t onepass_shrink = 0;  // too-dense retries remembered across calls
@@ -215,6 +220,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     if (const char* f = std::getenv("GORP_FORCE_TILES")) c.force_tiles = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_K1K2")) c.force_k1k2 = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_K4")) c.force_k4 = f[0] == '1';
+    if (const char* f = std::getenv("GORP_DFA_TIER")) c.dfa_tier = std::atoi(f);
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
     // combined DFA
     const size_t S = m.dfa.n_states, C = m.dfa.n_classes;
@@ -287,7 +293,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     {
         const size_t E = m.n_groups.size();
         const size_t K = C + 1, NL = C, dscan = S, fin_base = S + 16, R = fin_base + 1 + E;
-        if (R <= 0xFFFF && K * 2 <= 0xFFFF) {
+        if (R <= 0xFFFF && K * 2 <= 0xFFFF && !std::getenv("GORP_SKIP_NEWTABLES")) {
             std::vector<uint16_t> rows(((R * K + 7) / 8) * 8, 0);
             for (size_t r = 0; r < R; ++r)
                 for (size_t k = 0; k < K; ++k) {
@@ -415,7 +421,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
             }
         }
         // bucketed capture tier: one table per extraction, read through L1/L2 (kernels.cuh: CapImgDev)
-        if (E <= kCapMaxBuckets) {
+        if (E <= kCapMaxBuckets && !std::getenv("GORP_SKIP_NEWTABLES")) {
             const uint32_t Cn = m.symbols.n_classes, K = Cn + 1, NL = Cn, row_bytes = K * 4;
             uint32_t max_regs = 0;
             for (size_t e = 0; e < E; ++e) max_regs = std::max(max_regs, m.tdfas[e].n_regs);
@@ -656,7 +662,7 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
         P.span_stride = c.max_slots;
         // look-back state: [status n_tiles][ticket (8 B)][totals 3 x int64]
         const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 8 + 8 + 24;
-        c.tile_state.reserve(state_bytes);
+        c.tile_state.reserve(std::max<size_t>(state_bytes, kTileStateMinBytes));
         int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
         if (exact) cap_lines = n_lines + 16;
         if (const char* f = std::getenv("GORP_PAD_ROWS")) cap_lines += std::atoll(f);
@@ -753,7 +759,7 @@ bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
         P.span_stride = c.max_slots;
         // look-back state: [status n_tiles][ticket (8 B)][totals 3 x int64]
         const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 8 + 8 + 24;
-        c.tile_state.reserve(state_bytes);
+        c.tile_state.reserve(std::max<size_t>(state_bytes, kTileStateMinBytes));
         int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
         if (exact) cap_lines = n_lines + 16;
         c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
@@ -844,7 +850,7 @@ bool run_dfawalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
         P.a = c.dfawalk;
         P.stage_rows = kDfaWalkStagePerThread * threads;
         const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 8 + 8 + 24;
-        c.tile_state.reserve(state_bytes);
+        c.tile_state.reserve(std::max<size_t>(state_bytes, kTileStateMinBytes));
         int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
         if (exact) cap_lines = n_lines + 16;
         c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
@@ -894,7 +900,10 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     if (!d_off && run_chunkwalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     bool scanned = false;  // ext_id already holds the combined-DFA result
-    if (!d_off && run_dfawalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, ends_with_nl)) {
+    // long or ragged lines: a line index (K1) + lanes that pull lines dynamically (K2b) beats the chunk-owner walk (K0d),
+    // whose threads are stuck with whatever lines start in their chunk
+    const bool by_lines = c.dfa_tier == 2 || (c.dfa_tier == 0 && c.lines_per_unit < 1.0 / 100.0);
+    if (!d_off && !by_lines && run_dfawalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, ends_with_nl)) {
         sep = 1;
         scanned = true;
         d_line_off = c.line_off.as<int64_t>();
@@ -933,7 +942,22 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     // every line but (possibly) the last is terminated by '\n' in the text form: fast tiers; an unterminated last line
     // goes through the general kernels
     const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
+    uint32_t lw_threads = 0;
+    bool lw_smem = false;
     if (scanned) {
+    } else if (sep == 1 && !c.force_general && !c.force_k1k2 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0 &&
+               k2b_linewalk_plan(c.dfawalk, &lw_threads, &lw_smem)) {
+        LineWalkParams W{};
+        W.text = d_text;
+        W.n_units = n_units;
+        W.line_off = d_line_off;
+        W.n_lines = n_lines;
+        W.a = c.dfawalk;
+        W.ext_id = c.ext_id.as<int32_t>();
+        W.item_ticket = reinterpret_cast<unsigned int*>(d_n_lines + 4);
+        CK(cudaMemsetAsync(W.item_ticket, 0, 4, stream));
+        k2b_linewalk_scan(L, W, lw_threads, lw_smem);
+        tm.mark("k2b_linewalk_scan", 1);
     } else if (sep == 1 && c.dfa_direct.enabled && !c.force_general) {
         k2_dfa_direct(L, c.dfa_direct, d_text, d_line_off, n_fast, c.ext_id.as<int32_t>());
         if (n_fast < n_lines) k2_dfa_scan(L, c.dfa, d_text, d_line_off + n_fast, sep, 1, c.ext_id.as<int32_t>() + n_fast);
@@ -976,6 +1000,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         W.img = c.capimg;
         W.cap = c.cap;
         W.span_stride = stride;
+        if (const char* f = std::getenv("GORP_CAP_FLAGS")) W.flags = static_cast<uint32_t>(std::atoi(f));
         W.ext_id = c.ext_id.as<int32_t>();
         W.spans = c.spans.as<int32_t>();
         W.hist = c.hist.as<unsigned long long>();

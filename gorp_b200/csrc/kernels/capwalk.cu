@@ -177,13 +177,38 @@ __global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkPara
     const uint32_t reg_stride = kCapWalkThreads * 4;
     const uint32_t reg_abs = cls_abs + 512 + threadIdx.x * 4;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t reg_abs_warp = reg_abs - lane * 4;  // registers of lane 0 of this warp
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_items = *P.n_items;
     const uint32_t stride = P.span_stride;
 
+    // Work items are handed out to a CTA in batches of one item per warp (consecutive items = the same extraction most
+    // of the time), so the warps of a CTA read the same capture tables and those stay L1-resident: a warp-wide gather is
+    // as slow as its slowest lane, one L1 miss among 32 lanes costs the whole warp an L2 round trip.
+    // s_q = (first item of the batch << 32) | items of the batch already taken
+    __shared__ unsigned long long s_q;
+    constexpr uint32_t kBatch = kCapWalkThreads / 32;
+    if (threadIdx.x == 0) s_q = static_cast<unsigned long long>(kBatch);  // an empty batch: the first taker refills
+    __syncthreads();
     for (;;) {
         uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(P.item_ticket, 1u);
+        if (lane == 0) {
+            for (;;) {
+                const unsigned long long old = atomicAdd(&s_q, 1ull);
+                const uint32_t k = static_cast<uint32_t>(old), base = static_cast<uint32_t>(old >> 32);
+                if (k < kBatch) {
+                    item = base + k;
+                    break;
+                }
+                if (k == kBatch) {  // this warp refills
+                    const uint32_t nb = atomicAdd(P.item_ticket, kBatch);
+                    atomicExch(&s_q, (static_cast<unsigned long long>(nb) << 32) | 1ull);
+                    item = nb;
+                    break;
+                }
+                while (static_cast<uint32_t>(*reinterpret_cast<volatile unsigned long long*>(&s_q)) > kBatch) __nanosleep(64);
+            }
+        }
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         const CapItem it = P.items[item];
@@ -191,32 +216,57 @@ __global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkPara
         const CapImgExt fx = P.img.ext[e];
         const ExtDev x = P.cap.ext[e];
         const unsigned char* __restrict__ tab = reinterpret_cast<const unsigned char*>(P.img.image) + fx.tab_off;
-        uint32_t cursor = it.begin;  // warp-uniform: next unassigned entry of the item
+        uint32_t cursor = it.begin;  // warp-uniform: next unclaimed entry of the item
 
-        // per-lane line state
+        // per-lane state: the line being walked, and the NEXT line of the lane, claimed one line ahead so that its
+        // id (perm) and start (line_off) are loaded long before they are needed
         bool active = false;
-        uint32_t line = 0;
+        uint32_t line = 0, len = 0;
         int64_t a = 0, q = 0;
         uint32_t st = fx.dead_off;
+        uint32_t nstage = 0;  // 0 = no next line, 1 = id requested, 2 = start and end requested
+        uint32_t nline = 0;
+        int64_t na = 0, nb = 0;
         for (;;) {
-            // lanes without a line take the next ones of the item
-            const uint32_t want = __ballot_sync(0xffffffffu, !active);
-            if (want) {
-                const uint32_t idx = cursor + static_cast<uint32_t>(__popc(want & lt_mask));
-                if (!active && idx < it.end) {
-                    line = __ldg(P.perm + idx);
-                    a = __ldg(P.line_off + line);
-                    q = a & ~int64_t(15);
-                    const uint32_t lo = static_cast<uint32_t>(a - q);
-                    st = lo ? (fx.n_states + lo - 1) * fx.row_bytes : 0u;
-                    active = true;
+            if (!active && nstage) {  // start the claimed line
+                if (nstage == 1) {
+                    na = __ldg(P.line_off + nline);
+                    nb = __ldg(P.line_off + nline + 1);
                 }
-                cursor += static_cast<uint32_t>(__popc(want));
-                if (cursor > it.end) cursor = it.end;
+                line = nline;
+                a = na;
+                len = static_cast<uint32_t>(nb - 1 - na);
+                q = a & ~int64_t(15);
+                const uint32_t lo = static_cast<uint32_t>(a - q);
+                st = lo ? (fx.n_states + lo - 1) * fx.row_bytes : 0u;
+                active = true;
+                nstage = 0;
+                // the lines of a bucket are scattered over the text: ask L2 for the rest of the line in whole 128-byte
+                // lines now (the first one comes with the first block load)
+                const char* t8 = reinterpret_cast<const char*>(P.text);
+                const int64_t p_end = (nb < P.n_units ? nb : P.n_units) * 2;
+                int64_t p = ((a * 2) & ~int64_t(127)) + 128;
+                for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
+            } else if (nstage == 1) {
+                na = __ldg(P.line_off + nline);
+                nb = __ldg(P.line_off + nline + 1);
+                nstage = 2;
             }
-            if (!__any_sync(0xffffffffu, active)) break;
+            if (cursor < it.end) {  // lanes without a next line claim the next entries of the item
+                const uint32_t want = __ballot_sync(0xffffffffu, nstage == 0);
+                if (want) {
+                    const uint32_t idx = cursor + static_cast<uint32_t>(__popc(want & lt_mask));
+                    if (nstage == 0 && idx < it.end) {
+                        nline = __ldg(P.perm + idx);
+                        nstage = 1;
+                    }
+                    cursor += static_cast<uint32_t>(__popc(want));
+                }
+            }
+            if (!__any_sync(0xffffffffu, active || nstage != 0)) break;
+            bool finished = false;
             if (active) {
-                const Units16 u = load_units16(P.text, q, P.n_units);
+                const Units16 u = P.flags & 1u ? load_units16(P.text, q, P.n_units) : load_units16_keep(P.text, q, P.n_units);
                 const uint32_t st0 = st;
                 const uint32_t pos = static_cast<uint32_t>(q - a);  // negative while skipping: only ever stored to the dummy register
                 if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
@@ -241,29 +291,40 @@ __global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkPara
                     st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
                 }
                 q += 16;
-                if (st >= fx.dead_off) {  // the line is finished: DEAD (rejected) or FRZ(s)
-                    int32_t* out = P.spans + static_cast<int64_t>(line) * stride;
-                    bool ok = st >= fx.frz_off;
-                    uint32_t s = 0;
-                    if (ok) {
-                        s = (st - fx.frz_off) / fx.row_bytes;
-                        ok = __ldg(P.cap.tdfa_accepting + x.acc_off + s) != 0;
+                finished = st >= fx.dead_off;  // DEAD (rejected) or FRZ(s)
+            }
+            uint32_t fmeta = 0xFFFFFFFFu;  // final capture state of an accepted line
+            if (finished) {
+                active = false;
+                if (st >= fx.frz_off) {
+                    const uint32_t s = (st - fx.frz_off) / fx.row_bytes;
+                    if (__ldg(P.cap.tdfa_accepting + x.acc_off + s) != 0) fmeta = s;
+                }
+            }
+            // result rows of the lines that ended in this iteration: the whole warp writes each row (lane k = entry k)
+            uint32_t fin_mask = __ballot_sync(0xffffffffu, finished);
+            __syncwarp();  // the finished lanes' tag registers are read by the other lanes below
+            while (fin_mask) {
+                const uint32_t src = static_cast<uint32_t>(__ffs(fin_mask)) - 1u;
+                fin_mask &= fin_mask - 1u;
+                const uint32_t f_line = __shfl_sync(0xffffffffu, line, src);
+                const uint32_t f_meta = __shfl_sync(0xffffffffu, fmeta, src);
+                const int32_t f_len = static_cast<int32_t>(__shfl_sync(0xffffffffu, len, src));
+                int32_t* out = P.spans + static_cast<int64_t>(f_line) * stride;
+                if (f_meta != 0xFFFFFFFFu) {
+                    const uint8_t* __restrict__ fin = P.cap.tdfa_fin + x.fin_off + f_meta * x.n_slots;
+                    const uint32_t src_regs = reg_abs_warp + src * 4;
+                    for (uint32_t k = lane; k < stride; k += 32) {
+                        const uint32_t r = k < x.n_slots ? __ldg(fin + k) : 0xFFu;
+                        out[k] = r == 0xFFu ? -1 : (r == 0xFEu ? f_len : static_cast<int32_t>(lds32(src_regs + r * reg_stride)));
                     }
-                    if (ok) {
-                        const uint8_t* __restrict__ fin = P.cap.tdfa_fin + x.fin_off + s * x.n_slots;
-                        const int32_t len = static_cast<int32_t>(__ldg(P.line_off + line + 1) - 1 - a);
-                        for (uint32_t k = 0; k < x.n_slots; ++k) {
-                            const uint32_t r = __ldg(fin + k);
-                            out[k] = r == 0xFFu ? -1 : (r == 0xFEu ? len : static_cast<int32_t>(lds32(reg_abs + r * reg_stride)));
-                        }
-                        for (uint32_t k = x.n_slots; k < stride; ++k) out[k] = -1;
-                    } else {  // the combined DFA accepted, java.util.regex does not: capture failure (Gorp.java:173-177)
-                        P.ext_id[line] = -2 - static_cast<int32_t>(e);
-                        for (uint32_t k = 0; k < stride; ++k) out[k] = -1;
+                } else {  // the combined DFA accepted, java.util.regex does not: capture failure (Gorp.java:173-177)
+                    for (uint32_t k = lane; k < stride; k += 32) out[k] = -1;
+                    if (lane == 0) {
+                        P.ext_id[f_line] = -2 - static_cast<int32_t>(e);
                         atomicAdd(P.hist + e, ~0ull);  // -1
                         atomicAdd(P.hist + P.cap.n_ext + 1, 1ull);
                     }
-                    active = false;
                 }
             }
         }

@@ -305,6 +305,106 @@ __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
     }
 }
 
+// ------------------------------------------------------------------ K2b: the same automaton over an existing line index
+// Lines come from line_off (K1); a WARP takes work items of kLineItemLines consecutive lines, every lane walks one line
+// at a time in 32-byte blocks and claims its next line one line ahead (ballot-ranked, no atomics), so lanes stay busy
+// whatever the line lengths are (long or ragged lines, 10 KB outliers) — the case the chunk-owner walk above handles
+// badly, because there a thread's work is fixed by where the lines happen to start.
+template <bool kSmem>
+__global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t kT = blockDim.x;
+    const DfaWalkDev& A = P.a;
+    const uint32_t row_bytes = A.K * 2;
+    const uint32_t table_bytes = kSmem ? ((A.n_rows * row_bytes + 15u) & ~15u) : 0u;
+    uint32_t* s_cx = reinterpret_cast<uint32_t*>(smem + table_bytes);
+    const uint32_t tab_abs = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const uint32_t cx_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_cx));
+    const unsigned char* __restrict__ tab_g = reinterpret_cast<const unsigned char*>(A.table);
+    if (kSmem) {
+        const uint32_t n16 = (A.n_rows * row_bytes + 15u) / 16u;
+        const uint4* src = reinterpret_cast<const uint4*>(A.table);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (uint32_t i = threadIdx.x; i < n16; i += kT) dst[i] = __ldg(src + i);
+    }
+    for (uint32_t i = threadIdx.x; i < 128; i += kT) s_cx[i] = (kSmem ? tab_abs : 0u) + __ldg(A.cls128 + i);
+    __syncthreads();
+    const uint32_t fin_base = A.fin_base, skip0 = A.n_states;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int64_t n_items = (P.n_lines + kLineItemLines - 1) / kLineItemLines;
+
+    for (;;) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(P.item_ticket, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        int64_t cursor = static_cast<int64_t>(item) * kLineItemLines;  // warp-uniform: next unclaimed line of the item
+        const int64_t end = cursor + kLineItemLines < P.n_lines ? cursor + kLineItemLines : P.n_lines;
+        bool active = false, has_next = false;
+        int64_t line = 0, nline = 0, q = 0, na = 0, nb = 0;
+        uint32_t st = 0;
+        for (;;) {
+            if (!active && has_next) {  // start the claimed line
+                line = nline;
+                q = na & ~int64_t(15);
+                const uint32_t lo = static_cast<uint32_t>(na - q);
+                st = lo ? skip0 + lo : 0u;
+                active = true;
+                has_next = false;
+                // ask L2 for the rest of the line in whole 128-byte lines (the first one comes with the first block load)
+                const char* t8 = reinterpret_cast<const char*>(P.text);
+                const int64_t p_end = (nb < P.n_units ? nb : P.n_units) * 2;
+                int64_t p = ((na * 2) & ~int64_t(127)) + 128;
+                for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
+            }
+            if (cursor < end) {  // lanes without a next line claim the next lines of the item
+                const uint32_t want = __ballot_sync(0xffffffffu, !has_next);
+                if (want) {
+                    const int64_t idx = cursor + __popc(want & lt_mask);
+                    if (!has_next && idx < end) {
+                        nline = idx;
+                        na = __ldg(P.line_off + idx);
+                        nb = __ldg(P.line_off + idx + 1);
+                        has_next = true;
+                    }
+                    cursor += __popc(want);
+                }
+            }
+            if (!__any_sync(0xffffffffu, active || has_next)) break;
+            if (active) {
+                const Units16 u = load_units16(P.text, q, P.n_units);
+                if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                    st = dw_step<kSmem, 0>(st, u.a.x, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.a.x, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.a.y, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.a.y, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.a.z, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.a.z, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.a.w, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.a.w, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.b.x, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.b.x, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.b.y, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.b.y, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.b.z, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.b.z, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 0>(st, u.b.w, cx_abs, row_bytes, tab_g);
+                    st = dw_step<kSmem, 2>(st, u.b.w, cx_abs, row_bytes, tab_g);
+                } else {
+                    st = dw_slow8<kSmem>(A, st, u.a, cx_abs, tab_abs, row_bytes, tab_g);
+                    st = dw_slow8<kSmem>(A, st, u.b, cx_abs, tab_abs, row_bytes, tab_g);
+                }
+                q += 16;
+                if (st >= fin_base) {  // reached the line's '\n' (or the end of the text)
+                    P.ext_id[line] = static_cast<int32_t>(st - fin_base) - 1;
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 size_t dfawalk_smem_bytes(const DfaWalkDev& a, uint32_t threads, bool in_smem) {
@@ -369,6 +469,31 @@ void k0_dfawalk_scan(const Launch& L, const DfaWalkParams& P, uint32_t threads, 
     const int g = k0_dfawalk_grid(L, P, threads, in_smem);
     if (in_smem) dfawalk_kernel<true><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
     else dfawalk_kernel<false><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
+}
+
+size_t linewalk_smem_bytes(const DfaWalkDev& a, bool in_smem) {
+    return (in_smem ? ((static_cast<size_t>(a.n_rows) * a.K * 2 + 15) & ~size_t(15)) : 0) + 128 * 4 + 128;
+}
+
+bool k2b_linewalk_plan(const DfaWalkDev& a, uint32_t* threads, bool* in_smem) {
+    if (!a.enabled) return false;
+    *threads = 768;  // two CTAs per SM (48 warps) when the table leaves room for them
+    *in_smem = linewalk_smem_bytes(a, true) <= 200 * 1024;
+    return true;
+}
+
+void k2b_linewalk_scan(const Launch& L, const LineWalkParams& P, uint32_t threads, bool in_smem) {
+    const size_t smem = linewalk_smem_bytes(P.a, in_smem);
+    int per_sm = 1;
+    if (in_smem) {
+        cudaFuncSetAttribute(linewalk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linewalk_kernel<true>, static_cast<int>(threads), smem);
+        linewalk_kernel<true><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), static_cast<int>(threads), smem, L.stream>>>(P);
+    } else {
+        cudaFuncSetAttribute(linewalk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linewalk_kernel<false>, static_cast<int>(threads), smem);
+        linewalk_kernel<false><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), static_cast<int>(threads), smem, L.stream>>>(P);
+    }
 }
 
 }  // namespace gorp

@@ -206,6 +206,21 @@ bool k0_dfawalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem);
 int k0_dfawalk_grid(const Launch&, const DfaWalkParams&, uint32_t threads, bool in_smem);
 void k0_dfawalk_scan(const Launch&, const DfaWalkParams&, uint32_t threads, bool in_smem);
 
+// K2b: the K0d automaton over an existing line index (K1), lanes pull lines dynamically — see kernels/dfawalk.cu.
+// Every line must be terminated by '\n' in the text or end at n_units.
+constexpr uint32_t kLineItemLines = 1024;
+struct LineWalkParams {
+    const uint16_t* text;
+    int64_t n_units;
+    const int64_t* line_off;
+    int64_t n_lines;
+    DfaWalkDev a;
+    int32_t* ext_id;
+    unsigned int* item_ticket;   // zeroed by the caller
+};
+bool k2b_linewalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem);
+void k2b_linewalk_scan(const Launch&, const LineWalkParams&, uint32_t threads, bool in_smem);
+
 // K4b: capture half of the text form, bucketed by extraction — see kernels/capwalk.cu.
 constexpr uint32_t kCapItemLines = 1024;   // lines per work item (one warp walks one item)
 constexpr uint32_t kCapMaxBuckets = 4096;  // extractions the bucket kernels hold in shared memory
@@ -239,6 +254,7 @@ struct CapWalkParams {
     CapImgDev img;
     CapDev cap;                  // general tables (slow path, final states)
     uint32_t span_stride;
+    uint32_t flags;              // diagnostics (GORP_CAP_FLAGS): 1 = text loads bypass L1 and are L2 evict-first
     int32_t* ext_id;
     int32_t* spans;
     unsigned long long* hist;    // [E+2]: a capture failure moves one count from bin e to bin E+1

@@ -88,6 +88,10 @@ extern "C" int ht_run_fused(const void* blob, size_t len, const uint16_t* text, 
             stats[2] = A.n_jcls;
             stats[3] = A.n_op_slots;
             stats[4] = static_cast<uint32_t>(A.outcomes.size());
+            uint32_t multi = 0;
+            for (uint32_t r : A.res) multi += (r >> 8) != 0;
+            stats[5] = multi;  // group boundaries with more than one writer slot
+            stats[6] = static_cast<uint32_t>(A.res.size());
         }
         if (!A.available) {
             std::snprintf(err, errlen, "%s", A.why_not.c_str());

@@ -109,12 +109,17 @@ def test_fuzz_small_alphabet(definition):
 
 @pytest.mark.parametrize("name,n", [("simple", 300000), ("readme", 300000), ("weblog", 60000), ("syslog200", 60000),
                                     ("utf16mix", 60000)])
-def test_config_corpora(name, n):
+def test_config_corpora(name, n, monkeypatch):
     """The five BASELINE.json configs (prefixes the oracle finishes in seconds): #1 simple.grp, #2 README, #3 nginx /
     Apache definition with parametric templates, #4 200 extractions (combined DFA > shared memory, L2-resident
     table), #5 non-ASCII UTF-16 + divergence characters + 10 KB outliers."""
     d, gen = corpus.CONFIGS[name]
     text = gen(n)
+    if name in ("weblog", "syslog200", "utf16mix"):  # both DFA tiers of the big-definition path (K0d / K1 + K2b)
+        for tier in ("1", "2"):
+            monkeypatch.setenv("GORP_DFA_TIER", tier)
+            check_against_oracle(d, text=text)
+        monkeypatch.delenv("GORP_DFA_TIER")
     _, b, oe = check_against_oracle(d, text=text)
     assert b.n_lines == n and (oe >= 0).sum() > n // 3
     if name == "utf16mix":
@@ -183,12 +188,13 @@ def test_full_size_properties():
 
 
 TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
-         "dfawalk_capwalk": {"GORP_FORCE_TWOPASS": "1"},
-         "dfawalk_k4": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K4": "1"},
+         "dfawalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1"},
+         "linewalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2"},
+         "dfawalk_k4": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1", "GORP_FORCE_K4": "1"},
          "k1k2_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1"},
          "twopass_fast": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1", "GORP_FORCE_K4": "1"},
          "general": {"GORP_FORCE_GENERAL": "1"}}
-_TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES", "GORP_FORCE_K1K2", "GORP_FORCE_K4")
+_TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES", "GORP_FORCE_K1K2", "GORP_FORCE_K4", "GORP_DFA_TIER")
 
 
 @pytest.mark.parametrize("tier", list(TIERS))
