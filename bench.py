@@ -257,10 +257,22 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    per_step = []
     for _ in range(args.steps):
         step(_ffi.FLAG_TIME_KERNELS)
+        if os.environ.get("GORP_BENCH_PER_STEP"):  # diagnostics only: an event per step
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            per_step.append(ev)
     e1.record()
     barrier()
+    if per_step:
+        prev = e0
+        ts = []
+        for ev in per_step:
+            ts.append(round(prev.elapsed_time(ev), 2))
+            prev = ev
+        print("[bench] ms per step:", ts, file=sys.stderr)
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:  # every rank holds the job-wide histogram: its sum is the job's line count

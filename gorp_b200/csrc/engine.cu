@@ -292,13 +292,17 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     // chunk-walk DFA tier: class-indexed u16 rows + DEADSCAN / SKIP / FIN rows (see kernels.cuh: DfaWalkDev)
     {
         const size_t E = m.n_groups.size();
-        const size_t K = C + 1, NL = C, dscan = S, fin_base = S + 16, R = fin_base + 1 + E;
+        // K = classes + '\n' column, padded to an odd count: the rows of lanes that read the same column then fall into
+        // different shared-memory banks
+        const size_t NL = C, K = (C + 1) | 1, dscan = S, fin_base = S + 16, R = fin_base + 1 + E;
         if (R <= 0xFFFF && K * 2 <= 0xFFFF && !std::getenv("GORP_SKIP_NEWTABLES")) {
             std::vector<uint16_t> rows(((R * K + 7) / 8) * 8, 0);
             for (size_t r = 0; r < R; ++r)
                 for (size_t k = 0; k < K; ++k) {
                     size_t nx;
-                    if (r < S) {
+                    if (k > NL) {
+                        nx = r;  // padding column, never addressed
+                    } else if (r < S) {
                         if (k == NL) {
                             nx = fin_base + 1 + m.dfa.accept_first[r];
                         } else {
@@ -422,7 +426,8 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
         }
         // bucketed capture tier: one table per extraction, read through L1/L2 (kernels.cuh: CapImgDev)
         if (E <= kCapMaxBuckets && !std::getenv("GORP_SKIP_NEWTABLES")) {
-            const uint32_t Cn = m.symbols.n_classes, K = Cn + 1, NL = Cn, row_bytes = K * 4;
+            // K = classes + '\n' column, padded to an odd count (shared-memory banks, as for the DFA table)
+            const uint32_t Cn = m.symbols.n_classes, NL = Cn, K = (Cn + 1) | 1, row_bytes = K * 4;
             uint32_t max_regs = 0;
             for (size_t e = 0; e < E; ++e) max_regs = std::max(max_regs, m.tdfas[e].n_regs);
             std::vector<uint32_t> cls128(128), image;
@@ -436,6 +441,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     ok = false;
                     break;
                 }
+                while (image.size() % 4) image.push_back(0);  // 16-byte aligned tables (copied to shared memory with 128-bit loads)
                 fext[e] = {static_cast<uint32_t>(image.size() * 4), row_bytes, Sx, (Sx + 15) * row_bytes, (Sx + 16) * row_bytes,
                            (Sx + 17) * row_bytes};
                 const size_t base = image.size();
@@ -445,6 +451,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                 };
                 for (uint32_t r = 0; r < rows; ++r)
                     for (uint32_t k = 0; k < K; ++k) {
+                        if (k > NL) { put(r, k, r, max_regs); continue; }  // padding column, never addressed
                         if (r < Sx) {
                             if (k == NL) { put(r, k, Sx + 17 + r, max_regs); continue; }
                             const uint32_t ent = t.trans[static_cast<size_t>(r) * Cn + k];
@@ -462,10 +469,21 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     }
             }
             if (ok) {
+                image.resize(image.size() + 8, 0);  // the last table may be read 16 bytes at a time
                 c.capimg.image = upload(image, c.owned);
                 c.capimg.cls128 = upload(cls128, c.owned);
                 c.capimg.ext = upload(fext, c.owned);
                 c.capimg.n_regs = max_regs;
+                // shared memory for the table of the extraction a CTA works on: the largest table that still leaves room
+                // for two CTAs per SM (larger tables are read through L1/L2)
+                const size_t fixed = 512 + static_cast<size_t>(max_regs + 1) * kCapWalkThreads * 4;
+                const size_t budget = fixed + 1024 < 110 * 1024 ? 110 * 1024 - fixed - 1024 : 0;
+                size_t best = 0;
+                for (size_t e = 0; e < E; ++e) {
+                    const size_t tb = static_cast<size_t>(2 * m.tdfas[e].n_states + 17) * row_bytes;
+                    if (tb <= budget) best = std::max(best, tb);
+                }
+                c.capimg.smem_table_bytes = static_cast<uint32_t>((best + 15) & ~size_t(15));
                 c.capimg.enabled = capwalk_smem_bytes(c.capimg) <= 200 * 1024 ? 1u : 0u;
             }
         }
@@ -1000,7 +1018,8 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         W.img = c.capimg;
         W.cap = c.cap;
         W.span_stride = stride;
-        if (const char* f = std::getenv("GORP_CAP_FLAGS")) W.flags = static_cast<uint32_t>(std::atoi(f));
+        W.smem_table_bytes = c.capimg.smem_table_bytes;
+        if (const char* f = std::getenv("GORP_CAP_FLAGS")) W.smem_table_bytes = (std::atoi(f) & 2) ? 0u : W.smem_table_bytes;
         W.ext_id = c.ext_id.as<int32_t>();
         W.spans = c.spans.as<int32_t>();
         W.hist = c.hist.as<unsigned long long>();

@@ -109,14 +109,15 @@ __device__ __forceinline__ uint32_t ldg32_off(const unsigned char* __restrict__ 
     return __ldg(reinterpret_cast<const uint32_t*>(base + off));
 }
 
-template <int kByte>
-__device__ __forceinline__ void cw_step(uint32_t& st, uint32_t w, uint32_t cls_abs, const unsigned char* __restrict__ tab, uint32_t reg_abs,
-                                        uint32_t reg_stride, uint32_t pos) {
+// kSmemTab: the extraction's table was copied to shared memory (tab_abs); otherwise it is read through L1/L2 (tab)
+template <bool kSmemTab, int kByte>
+__device__ __forceinline__ void cw_step(uint32_t& st, uint32_t w, uint32_t cls_abs, uint32_t tab_abs, const unsigned char* __restrict__ tab,
+                                        uint32_t reg_abs, uint32_t reg_stride, uint32_t pos) {
     uint32_t b, a;
     asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
     asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(b), "r"(cls_abs));
     const uint32_t c4 = lds32(a);
-    const uint32_t ent = ldg32_off(tab, st + c4);
+    const uint32_t ent = kSmemTab ? lds32(tab_abs + st + c4) : ldg32_off(tab, st + c4);
     st = ent >> 6;
     uint32_t sa;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(ent & 63u), "r"(reg_stride), "r"(reg_abs));
@@ -169,165 +170,172 @@ __device__ __noinline__ uint32_t cw_slow16(const CapDev& c, const ExtDev& x, con
     return row * fx.row_bytes;
 }
 
-__global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkParams P) {
-    extern __shared__ __align__(16) uint32_t s_mem[];  // [cls128][registers: (n_regs + 1) x blockDim]
-    for (uint32_t i = threadIdx.x; i < 128; i += kCapWalkThreads) s_mem[i] = __ldg(P.img.cls128 + i);
-    __syncthreads();
-    const uint32_t cls_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_mem));
+// One work item (lines of one extraction) walked by all warps of the CTA: lanes claim lines from the CTA's cursor.
+template <bool kSmemTab>
+__device__ __forceinline__ void cw_item(const CapWalkParams& P, const CapItem& it, uint32_t* s_cursor, uint4* s_fin, uint32_t cls_abs,
+                                        uint32_t tab_abs, uint32_t reg_abs, uint32_t reg_abs_warp, uint32_t lane) {
+    const uint32_t e = it.ext;
+    const CapImgExt fx = P.img.ext[e];
+    const ExtDev x = P.cap.ext[e];
+    const unsigned char* __restrict__ tab = reinterpret_cast<const unsigned char*>(P.img.image) + fx.tab_off;
     const uint32_t reg_stride = kCapWalkThreads * 4;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t stride = P.span_stride;
+    const uint32_t inv_stride = 65536u / stride + 1u;  // i / stride == (i * inv_stride) >> 16 for i < 32 * stride <= 2048
+    bool exhausted = false;  // warp-uniform: the item has no unclaimed line left
+
+    // per-lane state: the line being walked, and the NEXT line of the lane, claimed one line ahead so that its id
+    // (perm), start and end (line_off) are loaded long before they are needed
+    bool active = false;
+    uint32_t line = 0, len = 0;
+    int64_t a = 0, q = 0;
+    uint32_t st = fx.dead_off;
+    uint32_t nstage = 0;  // 0 = no next line, 1 = id requested, 2 = start and end requested
+    uint32_t nline = 0;
+    int64_t na = 0, nb = 0;
+    for (;;) {
+        if (!active && nstage) {  // start the claimed line
+            if (nstage == 1) {
+                na = __ldg(P.line_off + nline);
+                nb = __ldg(P.line_off + nline + 1);
+            }
+            line = nline;
+            a = na;
+            len = static_cast<uint32_t>(nb - 1 - na);
+            q = a & ~int64_t(15);
+            const uint32_t lo = static_cast<uint32_t>(a - q);
+            st = lo ? (fx.n_states + lo - 1) * fx.row_bytes : 0u;
+            active = true;
+            nstage = 0;
+            // the lines of a bucket are scattered over the text: ask L2 for the rest of the line in whole 128-byte lines
+            // now (the first one comes with the first block load)
+            const char* t8 = reinterpret_cast<const char*>(P.text);
+            const int64_t p_end = (nb < P.n_units ? nb : P.n_units) * 2;
+            int64_t p = ((a * 2) & ~int64_t(127)) + 128;
+            for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
+        } else if (nstage == 1) {
+            na = __ldg(P.line_off + nline);
+            nb = __ldg(P.line_off + nline + 1);
+            nstage = 2;
+        }
+        if (!exhausted) {  // lanes without a next line claim the next entries of the item
+            const uint32_t want = __ballot_sync(0xffffffffu, nstage == 0);
+            if (want) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(s_cursor, static_cast<uint32_t>(__popc(want)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t idx = base + static_cast<uint32_t>(__popc(want & lt_mask));
+                if (nstage == 0 && idx < it.end) {
+                    nline = __ldg(P.perm + idx);
+                    nstage = 1;
+                }
+                exhausted = base + static_cast<uint32_t>(__popc(want)) >= it.end;
+            }
+        }
+        if (!__any_sync(0xffffffffu, active || nstage != 0)) break;
+        bool finished = false;
+        if (active) {
+            const Units16 u = load_units16(P.text, q, P.n_units);
+            const uint32_t st0 = st;
+            const uint32_t pos = static_cast<uint32_t>(q - a);  // negative while skipping: only ever stored to the dummy register
+            if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                cw_step<kSmemTab, 0>(st, u.a.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos);
+                cw_step<kSmemTab, 2>(st, u.a.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 1);
+                cw_step<kSmemTab, 0>(st, u.a.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 2);
+                cw_step<kSmemTab, 2>(st, u.a.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 3);
+                cw_step<kSmemTab, 0>(st, u.a.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 4);
+                cw_step<kSmemTab, 2>(st, u.a.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 5);
+                cw_step<kSmemTab, 0>(st, u.a.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 6);
+                cw_step<kSmemTab, 2>(st, u.a.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 7);
+                cw_step<kSmemTab, 0>(st, u.b.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 8);
+                cw_step<kSmemTab, 2>(st, u.b.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 9);
+                cw_step<kSmemTab, 0>(st, u.b.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 10);
+                cw_step<kSmemTab, 2>(st, u.b.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 11);
+                cw_step<kSmemTab, 0>(st, u.b.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 12);
+                cw_step<kSmemTab, 2>(st, u.b.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 13);
+                cw_step<kSmemTab, 0>(st, u.b.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 14);
+                cw_step<kSmemTab, 2>(st, u.b.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 15);
+                if (st == fx.slow_off) st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
+            } else {
+                st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
+            }
+            q += 16;
+            finished = st >= fx.dead_off;  // DEAD (rejected) or FRZ(s)
+        }
+        uint32_t fmeta = 0xFFFFFFFFu;  // final capture state of an accepted line
+        if (finished) {
+            active = false;
+            if (st >= fx.frz_off) {
+                const uint32_t s = (st - fx.frz_off) / fx.row_bytes;
+                if (__ldg(P.cap.tdfa_accepting + x.acc_off + s) != 0) fmeta = s;
+            }
+        }
+        // result rows of the lines that ended in this iteration, written by the whole warp: the finished lanes post
+        // (line, final state, length, lane) in the warp's staging area, then lane i writes entry i % stride of row i / stride
+        const uint32_t fin_mask = __ballot_sync(0xffffffffu, finished);
+        if (fin_mask) {
+            if (finished) {
+                s_fin[__popc(fin_mask & lt_mask)] = make_uint4(line, fmeta, len, lane);
+                if (fmeta == 0xFFFFFFFFu) {  // the combined DFA accepted, java.util.regex does not (Gorp.java:173-177)
+                    P.ext_id[line] = -2 - static_cast<int32_t>(e);
+                    atomicAdd(P.hist + e, ~0ull);  // -1
+                    atomicAdd(P.hist + P.cap.n_ext + 1, 1ull);
+                }
+            }
+            __syncwarp();  // staging area and the finished lanes' tag registers are read by the other lanes
+            const uint32_t total = static_cast<uint32_t>(__popc(fin_mask)) * stride;
+            for (uint32_t i = lane; i < total; i += 32) {
+                const uint32_t j = (i * inv_stride) >> 16, k = i - j * stride;
+                const uint4 f = s_fin[j];
+                int32_t val = -1;
+                if (f.y != 0xFFFFFFFFu && k < x.n_slots) {
+                    const uint32_t r = __ldg(P.cap.tdfa_fin + x.fin_off + f.y * x.n_slots + k);
+                    if (r == 0xFEu) val = static_cast<int32_t>(f.z);
+                    else if (r != 0xFFu) val = static_cast<int32_t>(lds32(reg_abs_warp + f.w * 4 + r * reg_stride));
+                }
+                P.spans[static_cast<int64_t>(f.x) * stride + k] = val;
+            }
+            __syncwarp();  // the staging area is rewritten in the next iteration
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCapWalkThreads, 3) capwalk_kernel(CapWalkParams P) {
+    extern __shared__ __align__(16) uint32_t s_mem[];  // [cls128][registers: (n_regs + 1) x blockDim][table of the item]
+    __shared__ uint32_t s_item, s_cursor, s_loaded;
+    __shared__ uint4 s_fin_all[kCapWalkThreads];  // per warp: the lines that finished in the current iteration
+    for (uint32_t i = threadIdx.x; i < 128; i += kCapWalkThreads) s_mem[i] = __ldg(P.img.cls128 + i);
+    if (threadIdx.x == 0) s_loaded = 0xFFFFFFFFu;
+    const uint32_t cls_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_mem));
     const uint32_t reg_abs = cls_abs + 512 + threadIdx.x * 4;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t reg_abs_warp = reg_abs - lane * 4;  // registers of lane 0 of this warp
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t tab_words0 = 128 + (P.img.n_regs + 1) * kCapWalkThreads;
+    const uint32_t tab_abs = cls_abs + tab_words0 * 4;
     const uint32_t n_items = *P.n_items;
-    const uint32_t stride = P.span_stride;
-
-    // Work items are handed out to a CTA in batches of one item per warp (consecutive items = the same extraction most
-    // of the time), so the warps of a CTA read the same capture tables and those stay L1-resident: a warp-wide gather is
-    // as slow as its slowest lane, one L1 miss among 32 lanes costs the whole warp an L2 round trip.
-    // s_q = (first item of the batch << 32) | items of the batch already taken
-    __shared__ unsigned long long s_q;
-    constexpr uint32_t kBatch = kCapWalkThreads / 32;
-    if (threadIdx.x == 0) s_q = static_cast<unsigned long long>(kBatch);  // an empty batch: the first taker refills
-    __syncthreads();
     for (;;) {
-        uint32_t item = 0;
-        if (lane == 0) {
-            for (;;) {
-                const unsigned long long old = atomicAdd(&s_q, 1ull);
-                const uint32_t k = static_cast<uint32_t>(old), base = static_cast<uint32_t>(old >> 32);
-                if (k < kBatch) {
-                    item = base + k;
-                    break;
-                }
-                if (k == kBatch) {  // this warp refills
-                    const uint32_t nb = atomicAdd(P.item_ticket, kBatch);
-                    atomicExch(&s_q, (static_cast<unsigned long long>(nb) << 32) | 1ull);
-                    item = nb;
-                    break;
-                }
-                while (static_cast<uint32_t>(*reinterpret_cast<volatile unsigned long long*>(&s_q)) > kBatch) __nanosleep(64);
-            }
-        }
-        item = __shfl_sync(0xffffffffu, item, 0);
+        __syncthreads();  // the previous item is finished (its table and s_item / s_cursor are free)
+        if (threadIdx.x == 0) s_item = atomicAdd(P.item_ticket, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
         if (item >= n_items) break;
         const CapItem it = P.items[item];
-        const uint32_t e = it.ext;
-        const CapImgExt fx = P.img.ext[e];
-        const ExtDev x = P.cap.ext[e];
-        const unsigned char* __restrict__ tab = reinterpret_cast<const unsigned char*>(P.img.image) + fx.tab_off;
-        uint32_t cursor = it.begin;  // warp-uniform: next unclaimed entry of the item
-
-        // per-lane state: the line being walked, and the NEXT line of the lane, claimed one line ahead so that its
-        // id (perm) and start (line_off) are loaded long before they are needed
-        bool active = false;
-        uint32_t line = 0, len = 0;
-        int64_t a = 0, q = 0;
-        uint32_t st = fx.dead_off;
-        uint32_t nstage = 0;  // 0 = no next line, 1 = id requested, 2 = start and end requested
-        uint32_t nline = 0;
-        int64_t na = 0, nb = 0;
-        for (;;) {
-            if (!active && nstage) {  // start the claimed line
-                if (nstage == 1) {
-                    na = __ldg(P.line_off + nline);
-                    nb = __ldg(P.line_off + nline + 1);
-                }
-                line = nline;
-                a = na;
-                len = static_cast<uint32_t>(nb - 1 - na);
-                q = a & ~int64_t(15);
-                const uint32_t lo = static_cast<uint32_t>(a - q);
-                st = lo ? (fx.n_states + lo - 1) * fx.row_bytes : 0u;
-                active = true;
-                nstage = 0;
-                // the lines of a bucket are scattered over the text: ask L2 for the rest of the line in whole 128-byte
-                // lines now (the first one comes with the first block load)
-                const char* t8 = reinterpret_cast<const char*>(P.text);
-                const int64_t p_end = (nb < P.n_units ? nb : P.n_units) * 2;
-                int64_t p = ((a * 2) & ~int64_t(127)) + 128;
-                for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
-            } else if (nstage == 1) {
-                na = __ldg(P.line_off + nline);
-                nb = __ldg(P.line_off + nline + 1);
-                nstage = 2;
-            }
-            if (cursor < it.end) {  // lanes without a next line claim the next entries of the item
-                const uint32_t want = __ballot_sync(0xffffffffu, nstage == 0);
-                if (want) {
-                    const uint32_t idx = cursor + static_cast<uint32_t>(__popc(want & lt_mask));
-                    if (nstage == 0 && idx < it.end) {
-                        nline = __ldg(P.perm + idx);
-                        nstage = 1;
-                    }
-                    cursor += static_cast<uint32_t>(__popc(want));
-                }
-            }
-            if (!__any_sync(0xffffffffu, active || nstage != 0)) break;
-            bool finished = false;
-            if (active) {
-                const Units16 u = P.flags & 1u ? load_units16(P.text, q, P.n_units) : load_units16_keep(P.text, q, P.n_units);
-                const uint32_t st0 = st;
-                const uint32_t pos = static_cast<uint32_t>(q - a);  // negative while skipping: only ever stored to the dummy register
-                if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
-                    cw_step<0>(st, u.a.x, cls_abs, tab, reg_abs, reg_stride, pos);
-                    cw_step<2>(st, u.a.x, cls_abs, tab, reg_abs, reg_stride, pos + 1);
-                    cw_step<0>(st, u.a.y, cls_abs, tab, reg_abs, reg_stride, pos + 2);
-                    cw_step<2>(st, u.a.y, cls_abs, tab, reg_abs, reg_stride, pos + 3);
-                    cw_step<0>(st, u.a.z, cls_abs, tab, reg_abs, reg_stride, pos + 4);
-                    cw_step<2>(st, u.a.z, cls_abs, tab, reg_abs, reg_stride, pos + 5);
-                    cw_step<0>(st, u.a.w, cls_abs, tab, reg_abs, reg_stride, pos + 6);
-                    cw_step<2>(st, u.a.w, cls_abs, tab, reg_abs, reg_stride, pos + 7);
-                    cw_step<0>(st, u.b.x, cls_abs, tab, reg_abs, reg_stride, pos + 8);
-                    cw_step<2>(st, u.b.x, cls_abs, tab, reg_abs, reg_stride, pos + 9);
-                    cw_step<0>(st, u.b.y, cls_abs, tab, reg_abs, reg_stride, pos + 10);
-                    cw_step<2>(st, u.b.y, cls_abs, tab, reg_abs, reg_stride, pos + 11);
-                    cw_step<0>(st, u.b.z, cls_abs, tab, reg_abs, reg_stride, pos + 12);
-                    cw_step<2>(st, u.b.z, cls_abs, tab, reg_abs, reg_stride, pos + 13);
-                    cw_step<0>(st, u.b.w, cls_abs, tab, reg_abs, reg_stride, pos + 14);
-                    cw_step<2>(st, u.b.w, cls_abs, tab, reg_abs, reg_stride, pos + 15);
-                    if (st == fx.slow_off) st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
-                } else {
-                    st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
-                }
-                q += 16;
-                finished = st >= fx.dead_off;  // DEAD (rejected) or FRZ(s)
-            }
-            uint32_t fmeta = 0xFFFFFFFFu;  // final capture state of an accepted line
-            if (finished) {
-                active = false;
-                if (st >= fx.frz_off) {
-                    const uint32_t s = (st - fx.frz_off) / fx.row_bytes;
-                    if (__ldg(P.cap.tdfa_accepting + x.acc_off + s) != 0) fmeta = s;
-                }
-            }
-            // result rows of the lines that ended in this iteration: the whole warp writes each row (lane k = entry k)
-            uint32_t fin_mask = __ballot_sync(0xffffffffu, finished);
-            __syncwarp();  // the finished lanes' tag registers are read by the other lanes below
-            while (fin_mask) {
-                const uint32_t src = static_cast<uint32_t>(__ffs(fin_mask)) - 1u;
-                fin_mask &= fin_mask - 1u;
-                const uint32_t f_line = __shfl_sync(0xffffffffu, line, src);
-                const uint32_t f_meta = __shfl_sync(0xffffffffu, fmeta, src);
-                const int32_t f_len = static_cast<int32_t>(__shfl_sync(0xffffffffu, len, src));
-                int32_t* out = P.spans + static_cast<int64_t>(f_line) * stride;
-                if (f_meta != 0xFFFFFFFFu) {
-                    const uint8_t* __restrict__ fin = P.cap.tdfa_fin + x.fin_off + f_meta * x.n_slots;
-                    const uint32_t src_regs = reg_abs_warp + src * 4;
-                    for (uint32_t k = lane; k < stride; k += 32) {
-                        const uint32_t r = k < x.n_slots ? __ldg(fin + k) : 0xFFu;
-                        out[k] = r == 0xFFu ? -1 : (r == 0xFEu ? f_len : static_cast<int32_t>(lds32(src_regs + r * reg_stride)));
-                    }
-                } else {  // the combined DFA accepted, java.util.regex does not: capture failure (Gorp.java:173-177)
-                    for (uint32_t k = lane; k < stride; k += 32) out[k] = -1;
-                    if (lane == 0) {
-                        P.ext_id[f_line] = -2 - static_cast<int32_t>(e);
-                        atomicAdd(P.hist + e, ~0ull);  // -1
-                        atomicAdd(P.hist + P.cap.n_ext + 1, 1ull);
-                    }
-                }
-            }
+        const CapImgExt fx = P.img.ext[it.ext];
+        // the extraction's table goes to shared memory when it fits: a warp-wide gather through L1 is as slow as its
+        // slowest lane (one L1 miss among 32 lanes costs the whole warp an L2 round trip), LDS has no such tail
+        const uint32_t tab_bytes = fx.frz_off + fx.n_states * fx.row_bytes;  // (2S + 17) rows
+        const bool in_smem = tab_bytes <= P.smem_table_bytes;
+        if (in_smem && s_loaded != it.ext) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(P.img.image) + fx.tab_off);
+            uint4* dst = reinterpret_cast<uint4*>(s_mem + tab_words0);
+            for (uint32_t i = threadIdx.x; i < (tab_bytes + 15) / 16; i += kCapWalkThreads) dst[i] = __ldg(src + i);
         }
+        if (threadIdx.x == 0) s_cursor = it.begin;
+        __syncthreads();
+        if (threadIdx.x == 0 && in_smem) s_loaded = it.ext;
+        uint4* s_fin = s_fin_all + (threadIdx.x & ~31u);
+        if (in_smem) cw_item<true>(P, it, &s_cursor, s_fin, cls_abs, tab_abs, reg_abs, reg_abs_warp, lane);
+        else cw_item<false>(P, it, &s_cursor, s_fin, cls_abs, tab_abs, reg_abs, reg_abs_warp, lane);
     }
 }
 
@@ -343,7 +351,9 @@ void k4b_bucket(const Launch& L, const int32_t* ext_id, int64_t n_lines, uint32_
                                                                                                      span_stride);
 }
 
-size_t capwalk_smem_bytes(const CapImgDev& img) { return 512 + static_cast<size_t>(img.n_regs + 1) * kCapWalkThreads * 4; }
+size_t capwalk_smem_bytes(const CapImgDev& img) {
+    return 512 + static_cast<size_t>(img.n_regs + 1) * kCapWalkThreads * 4 + img.smem_table_bytes;
+}
 
 void k4b_capwalk(const Launch& L, const CapWalkParams& P) {
     const size_t smem = capwalk_smem_bytes(P.img);

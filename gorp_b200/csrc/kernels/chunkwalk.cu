@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
     uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem);
     uint32_t* s_res = s_rows + A.n_rows * A.width;
     int32_t* s_oext = reinterpret_cast<int32_t*>(s_res + ((A.n_outcomes * A.max_slots + 3) & ~3u));
-    uint32_t* s_ocnt = reinterpret_cast<uint32_t*>(s_oext + ((A.n_outcomes + 3) & ~3u));  // valid span entries per outcome
-    uint32_t* s_slots = s_ocnt + ((A.n_outcomes + 3) & ~3u);  // [2 banks][n_slots][kT]
+    uint32_t* s_obin = reinterpret_cast<uint32_t*>(s_oext + ((A.n_outcomes + 3) & ~3u));  // histogram bin per outcome
+    uint32_t* s_slots = s_obin + ((A.n_outcomes + 3) & ~3u);  // [2 banks][n_slots][kT]
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_hist[kOnePassHistBins];
     __shared__ long long s_tile, s_base;
@@ -98,16 +98,16 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
         const uint32_t raw = __ldg(A.rows + i);
         s_rows[i] = (((raw >> 16) * row_q) << 18) | ((raw & 0xFFFFu) * kT);
     }
-    // group boundary recipes: 0 = no writer; a single writer becomes 0x80000000 | byte offset of its slot inside a
-    // bank; several writers stay packed one slot id per byte
+    // group boundary recipes: 0 = no writer; one writer: byte offset of its slot inside a bank (slot ids start at 1);
+    // several writers: bit 31 | one slot id per byte (ids < 128 here: the plan keeps n_slots * blockDim below 2^14)
     for (uint32_t i = threadIdx.x; i < A.n_outcomes * A.max_slots; i += kT) {
         const uint32_t packed = __ldg(A.out_res + i);
-        s_res[i] = packed && packed < 256u ? 0x80000000u | (packed * kT * 4u) : packed;
+        s_res[i] = packed < 256u ? packed * kT * 4u : 0x80000000u | packed;
     }
     for (uint32_t i = threadIdx.x; i < A.n_outcomes; i += kT) {
         const int32_t e = __ldg(A.out_ext + i);
         s_oext[i] = e;
-        s_ocnt[i] = e >= 0 ? __ldg(P.slots_per_ext + e) : 0u;
+        s_obin[i] = e >= 0 ? static_cast<uint32_t>(e) : (e == -1 ? P.n_ext : P.n_ext + 1);  // histogram bin of the outcome
     }
     const uint32_t n_bins = P.n_ext + 2;
     const bool smem_hist = n_bins <= kOnePassHistBins;
@@ -135,41 +135,48 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
             skip_writes = *reinterpret_cast<volatile int*>(&s_skip_writes) != 0;
             base_known = true;
         }
-        const int32_t ext = s_oext[pd.outcome];
-        const uint32_t bin = ext >= 0 ? static_cast<uint32_t>(ext) : (ext == -1 ? P.n_ext : P.n_ext + 1);
+        const uint32_t bin = s_obin[pd.outcome];
         if (smem_hist) atomicAdd(&s_hist[bin], 1u);
         else atomicAdd(P.hist + bin, 1ull);
         if (skip_writes) return;
         const int64_t row = row0 + pd.idx;
-        P.ext_id[row] = ext;
+        P.ext_id[row] = s_oext[pd.outcome];
         P.line_off[row] = tile0 + pd.start;
         const uint32_t* res = s_res + pd.outcome * A.max_slots;
         int32_t* out = P.spans + row * stride;
-        // a boundary = the latest of its (<= 4) op slots; slots hold tile-relative positions, anything below the
-        // line's start is a left-over of an earlier line (or the per-tile clear value): the group did not participate
-        auto value = [&](uint32_t recipe) {
-            int32_t val;
-            if (!recipe) {
-                val = -1;
-            } else if (recipe & 0x80000000u) {
-                val = static_cast<int32_t>(lds32(pd.bank_abs + (recipe & 0x7FFFFFFFu)));
-            } else {
-                val = static_cast<int32_t>(lds32(pd.bank_abs + (recipe & 0xFFu) * slot_stride));
-                for (recipe >>= 8; recipe; recipe >>= 8)
-                    val = max(val, static_cast<int32_t>(lds32(pd.bank_abs + (recipe & 0xFFu) * slot_stride)));
-            }
-            return val < static_cast<int32_t>(pd.start) ? -1 : val - static_cast<int32_t>(pd.start);
+        const int32_t start = static_cast<int32_t>(pd.start);
+        // a boundary = the position held by its writer slot; slots hold tile-relative positions, anything below the line's
+        // start is a left-over of an earlier line (or the per-tile clear value): the group did not participate
+        auto single = [&](uint32_t recipe) {  // recipe 0 reads the dummy slot: discarded
+            const int32_t val = static_cast<int32_t>(lds32(pd.bank_abs + recipe));
+            return (recipe == 0u || val < start) ? -1 : val - start;
+        };
+        auto value = [&](uint32_t recipe) {  // several writers: the latest of them
+            if (!(recipe & 0x80000000u)) return single(recipe);
+            recipe &= 0x7FFFFFFFu;
+            int32_t val = static_cast<int32_t>(lds32(pd.bank_abs + (recipe & 0xFFu) * slot_stride));
+            for (recipe >>= 8; recipe; recipe >>= 8)
+                val = max(val, static_cast<int32_t>(lds32(pd.bank_abs + (recipe & 0xFFu) * slot_stride)));
+            return val < start ? -1 : val - start;
         };
         if ((stride & 7u) == 0) {  // 32-byte aligned rows: one 256-bit streaming store per 8 entries
             for (uint32_t k = 0; k < stride; k += 8) {
                 const uint4 r4 = *reinterpret_cast<const uint4*>(res + k), r5 = *reinterpret_cast<const uint4*>(res + k + 4);
-                asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + k), "r"(value(r4.x)), "r"(value(r4.y)),
-                             "r"(value(r4.z)), "r"(value(r4.w)), "r"(value(r5.x)), "r"(value(r5.y)), "r"(value(r5.z)), "r"(value(r5.w))
+                int32_t v0, v1, v2, v3, v4, v5, v6, v7;
+                if (!((r4.x | r4.y | r4.z | r4.w | r5.x | r5.y | r5.z | r5.w) & 0x80000000u)) {
+                    v0 = single(r4.x), v1 = single(r4.y), v2 = single(r4.z), v3 = single(r4.w);
+                    v4 = single(r5.x), v5 = single(r5.y), v6 = single(r5.z), v7 = single(r5.w);
+                } else {
+                    v0 = value(r4.x), v1 = value(r4.y), v2 = value(r4.z), v3 = value(r4.w);
+                    v4 = value(r5.x), v5 = value(r5.y), v6 = value(r5.z), v7 = value(r5.w);
+                }
+                asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + k), "r"(v0), "r"(v1), "r"(v2), "r"(v3),
+                             "r"(v4), "r"(v5), "r"(v6), "r"(v7)
                              : "memory");
             }
         } else if ((stride & 3u) == 0) {
             for (uint32_t k = 0; k < stride; k += 4) {
-                const uint4 r4 = *reinterpret_cast<const uint4*>(res + k);  // entries >= cnt of a row are 0
+                const uint4 r4 = *reinterpret_cast<const uint4*>(res + k);  // entries beyond the outcome's own are "no writer"
                 *reinterpret_cast<int4*>(out + k) = make_int4(value(r4.x), value(r4.y), value(r4.z), value(r4.w));
             }
         } else {
@@ -183,9 +190,12 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
     if (P.debug && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     // All CTAs start together, and a tile is a memory-bound burst (prefetch + pre-scan) followed by a long compute
     // phase (the walk): CTAs that stay in lock-step alternate between fighting for HBM and leaving it idle (measured:
-    // a stable mode that is 1.4x slower). Spread the phases once, at the start: each CTA delays its first tile by a
-    // pseudo-random fraction of a tile time. Skipped for small batches, where the delay would not pay off.
-    if (!(P.per & 2u) && P.n_tiles >= 8ll * gridDim.x) {
+    // a stable mode that is 1.4x slower). Spreading the phases once, at the start (each CTA delays its first tile by a
+    // pseudo-random fraction of a tile time) removed that mode when the look-back was narrow; with the 128-wide probes
+    // and rows that stay pending it does the opposite: the early CTAs block on the look-back of predecessors that are
+    // still sleeping and are released together. Measured per launch (100 M lines): with the delay 12.0 ms or 17.6 ms at
+    // random, without it 11.85 ms every time (profiles/README.md, round 1e). Kept as a diagnostic switch.
+    if ((P.per & 2u) && P.n_tiles >= 8ll * gridDim.x) {  // off by default (GORP_CW_PREFETCH=2 turns it on), see above
         if (threadIdx.x == 0) {
             const unsigned long long delay_ns = static_cast<unsigned long long>((blockIdx.x * 2654435761u) >> 27) * 2500ull;  // 0 .. 77.5 us
             unsigned long long t_start, t_now;

@@ -222,7 +222,7 @@ bool k2b_linewalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem);
 void k2b_linewalk_scan(const Launch&, const LineWalkParams&, uint32_t threads, bool in_smem);
 
 // K4b: capture half of the text form, bucketed by extraction — see kernels/capwalk.cu.
-constexpr uint32_t kCapItemLines = 1024;   // lines per work item (one warp walks one item)
+constexpr uint32_t kCapItemLines = 4096;   // lines per work item (one CTA walks one item)
 constexpr uint32_t kCapMaxBuckets = 4096;  // extractions the bucket kernels hold in shared memory
 constexpr int kCapWalkThreads = 256;
 struct CapItem {
@@ -241,6 +241,7 @@ struct CapImgDev {
     const uint32_t* cls128;      // [128] ASCII unit -> class * 4 ('\n' -> the last column)
     const CapImgExt* ext;        // [E]
     uint32_t n_regs;             // widest register file; slot n_regs = the per-thread dummy
+    uint32_t smem_table_bytes;   // shared memory set aside for the table of the extraction a CTA is working on
     uint32_t enabled;
 };
 struct CapWalkParams {
@@ -254,7 +255,7 @@ struct CapWalkParams {
     CapImgDev img;
     CapDev cap;                  // general tables (slow path, final states)
     uint32_t span_stride;
-    uint32_t flags;              // diagnostics (GORP_CAP_FLAGS): 1 = text loads bypass L1 and are L2 evict-first
+    uint32_t smem_table_bytes;   // = img.smem_table_bytes, or 0 to read every table through L1/L2 (GORP_CAP_FLAGS=2)
     int32_t* ext_id;
     int32_t* spans;
     unsigned long long* hist;    // [E+2]: a capture failure moves one count from bin e to bin E+1

@@ -137,3 +137,25 @@ extern "C" int ht_run_fused(const void* blob, size_t len, const uint16_t* text, 
         return -1;
     }
 }
+
+// per-extraction capture automaton sizes: out[4*e..] = states, classes, registers, slots. Returns the extraction count.
+extern "C" int ht_tdfa_sizes(const void* blob, size_t len, uint32_t* out, int cap, char* err, int errlen) {
+    try {
+        CompiledDefinition def = parse_blob(blob, len);
+        DeviceModel m = build_device_model(def);
+        int n = 0;
+        for (auto& t : m.tdfas) {
+            if (n < cap) {
+                out[4 * n] = t.n_states;
+                out[4 * n + 1] = t.n_classes;
+                out[4 * n + 2] = t.n_regs;
+                out[4 * n + 3] = t.n_slots;
+            }
+            ++n;
+        }
+        return n;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
