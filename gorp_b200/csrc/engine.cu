@@ -221,6 +221,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     if (const char* f = std::getenv("GORP_FORCE_K1K2")) c.force_k1k2 = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_K4")) c.force_k4 = f[0] == '1';
     if (const char* f = std::getenv("GORP_DFA_TIER")) c.dfa_tier = std::atoi(f);
+    if (const char* f = std::getenv("GORP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(std::atoi(f)));  // diagnostics
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
     // combined DFA
     const size_t S = m.dfa.n_states, C = m.dfa.n_classes;
@@ -477,10 +478,10 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                 // shared memory for the table of the extraction a CTA works on: the largest table that still leaves room
                 // for two CTAs per SM (larger tables are read through L1/L2)
                 const size_t fixed = 512 + static_cast<size_t>(max_regs + 1) * kCapWalkThreads * 4;
-                const size_t budget = fixed + 1024 < 110 * 1024 ? 110 * 1024 - fixed - 1024 : 0;
+                const size_t budget = fixed + 5 * 1024 < 110 * 1024 ? 110 * 1024 - fixed - 5 * 1024 : 0;
                 size_t best = 0;
                 for (size_t e = 0; e < E; ++e) {
-                    const size_t tb = static_cast<size_t>(2 * m.tdfas[e].n_states + 17) * row_bytes;
+                    const size_t tb = static_cast<size_t>(m.tdfas[e].n_states + 17) * row_bytes;  // without the FRZ rows
                     if (tb <= budget) best = std::max(best, tb);
                 }
                 c.capimg.smem_table_bytes = static_cast<uint32_t>((best + 15) & ~size_t(15));
@@ -973,6 +974,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         W.a = c.dfawalk;
         W.ext_id = c.ext_id.as<int32_t>();
         W.item_ticket = reinterpret_cast<unsigned int*>(d_n_lines + 4);
+        if (const char* f = std::getenv("GORP_WALK_FLAGS")) W.flags = static_cast<uint32_t>(std::atoi(f));
         CK(cudaMemsetAsync(W.item_ticket, 0, 4, stream));
         k2b_linewalk_scan(L, W, lw_threads, lw_smem);
         tm.mark("k2b_linewalk_scan", 1);
@@ -1019,6 +1021,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         W.cap = c.cap;
         W.span_stride = stride;
         W.smem_table_bytes = c.capimg.smem_table_bytes;
+        if (const char* f = std::getenv("GORP_WALK_FLAGS")) W.flags = static_cast<uint32_t>(std::atoi(f));
         if (const char* f = std::getenv("GORP_CAP_FLAGS")) W.smem_table_bytes = (std::atoi(f) & 2) ? 0u : W.smem_table_bytes;
         W.ext_id = c.ext_id.as<int32_t>();
         W.spans = c.spans.as<int32_t>();

@@ -111,14 +111,20 @@ __device__ __forceinline__ uint32_t ldg32_off(const unsigned char* __restrict__ 
 
 // kSmemTab: the extraction's table was copied to shared memory (tab_abs); otherwise it is read through L1/L2 (tab)
 template <bool kSmemTab, int kByte>
-__device__ __forceinline__ void cw_step(uint32_t& st, uint32_t w, uint32_t cls_abs, uint32_t tab_abs, const unsigned char* __restrict__ tab,
-                                        uint32_t reg_abs, uint32_t reg_stride, uint32_t pos) {
+__device__ __forceinline__ void cw_step(uint32_t& st, uint32_t& fin, uint32_t dead_off, uint32_t w, uint32_t cls_abs, uint32_t tab_abs,
+                                        const unsigned char* __restrict__ tab, uint32_t reg_abs, uint32_t reg_stride, uint32_t pos) {
     uint32_t b, a;
     asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
     asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(b), "r"(cls_abs));
     const uint32_t c4 = lds32(a);
-    const uint32_t ent = kSmemTab ? lds32(tab_abs + st + c4) : ldg32_off(tab, st + c4);
+    uint32_t ent;
+    if (kSmemTab) {  // the shared-memory copy has no FRZ rows: ids beyond DEAD read the DEAD row, `fin` keeps the highest id seen
+        ent = lds32(tab_abs + min(st, dead_off) + c4);
+    } else {
+        ent = ldg32_off(tab, st + c4);
+    }
     st = ent >> 6;
+    if (kSmemTab) fin = max(fin, st);
     uint32_t sa;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(ent & 63u), "r"(reg_stride), "r"(reg_abs));
     sts32(sa, pos);
@@ -212,7 +218,8 @@ __device__ __forceinline__ void cw_item(const CapWalkParams& P, const CapItem& i
             const char* t8 = reinterpret_cast<const char*>(P.text);
             const int64_t p_end = (nb < P.n_units ? nb : P.n_units) * 2;
             int64_t p = ((a * 2) & ~int64_t(127)) + 128;
-            for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
+            if (!(P.flags & 2u))
+                for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
         } else if (nstage == 1) {
             na = __ldg(P.line_off + nline);
             nb = __ldg(P.line_off + nline + 1);
@@ -235,26 +242,28 @@ __device__ __forceinline__ void cw_item(const CapWalkParams& P, const CapItem& i
         if (!__any_sync(0xffffffffu, active || nstage != 0)) break;
         bool finished = false;
         if (active) {
-            const Units16 u = load_units16(P.text, q, P.n_units);
+            const Units16 u = P.flags & 1u ? load_units16(P.text, q, P.n_units) : load_units16_l2keep(P.text, q, P.n_units);
             const uint32_t st0 = st;
+            uint32_t fin = 0;
             const uint32_t pos = static_cast<uint32_t>(q - a);  // negative while skipping: only ever stored to the dummy register
             if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
-                cw_step<kSmemTab, 0>(st, u.a.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos);
-                cw_step<kSmemTab, 2>(st, u.a.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 1);
-                cw_step<kSmemTab, 0>(st, u.a.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 2);
-                cw_step<kSmemTab, 2>(st, u.a.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 3);
-                cw_step<kSmemTab, 0>(st, u.a.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 4);
-                cw_step<kSmemTab, 2>(st, u.a.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 5);
-                cw_step<kSmemTab, 0>(st, u.a.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 6);
-                cw_step<kSmemTab, 2>(st, u.a.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 7);
-                cw_step<kSmemTab, 0>(st, u.b.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 8);
-                cw_step<kSmemTab, 2>(st, u.b.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 9);
-                cw_step<kSmemTab, 0>(st, u.b.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 10);
-                cw_step<kSmemTab, 2>(st, u.b.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 11);
-                cw_step<kSmemTab, 0>(st, u.b.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 12);
-                cw_step<kSmemTab, 2>(st, u.b.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 13);
-                cw_step<kSmemTab, 0>(st, u.b.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 14);
-                cw_step<kSmemTab, 2>(st, u.b.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 15);
+                cw_step<kSmemTab, 0>(st, fin, fx.dead_off, u.a.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos);
+                cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.a.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 1);
+                cw_step<kSmemTab, 0>(st, fin, fx.dead_off, u.a.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 2);
+                cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.a.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 3);
+                cw_step<kSmemTab, 0>(st, fin, fx.dead_off, u.a.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 4);
+                cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.a.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 5);
+                cw_step<kSmemTab, 0>(st, fin, fx.dead_off, u.a.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 6);
+                cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.a.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 7);
+                cw_step<kSmemTab, 0>(st, fin, fx.dead_off, u.b.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 8);
+                cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.b.x, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 9);
+                cw_step<kSmemTab, 0>(st, fin, fx.dead_off, u.b.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 10);
+                cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.b.y, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 11);
+                cw_step<kSmemTab, 0>(st, fin, fx.dead_off, u.b.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 12);
+                cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.b.z, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 13);
+                cw_step<kSmemTab, 0>(st, fin, fx.dead_off, u.b.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 14);
+                cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.b.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 15);
+                if (kSmemTab && fin >= fx.dead_off) st = fin;  // SLOW and FRZ ids do not survive the steps that follow them
                 if (st == fx.slow_off) st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
             } else {
                 st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
@@ -300,7 +309,7 @@ __device__ __forceinline__ void cw_item(const CapWalkParams& P, const CapItem& i
     }
 }
 
-__global__ void __launch_bounds__(kCapWalkThreads, 3) capwalk_kernel(CapWalkParams P) {
+__global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkParams P) {
     extern __shared__ __align__(16) uint32_t s_mem[];  // [cls128][registers: (n_regs + 1) x blockDim][table of the item]
     __shared__ uint32_t s_item, s_cursor, s_loaded;
     __shared__ uint4 s_fin_all[kCapWalkThreads];  // per warp: the lines that finished in the current iteration
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(kCapWalkThreads, 3) capwalk_kernel(CapWalkPara
         const CapImgExt fx = P.img.ext[it.ext];
         // the extraction's table goes to shared memory when it fits: a warp-wide gather through L1 is as slow as its
         // slowest lane (one L1 miss among 32 lanes costs the whole warp an L2 round trip), LDS has no such tail
-        const uint32_t tab_bytes = fx.frz_off + fx.n_states * fx.row_bytes;  // (2S + 17) rows
+        const uint32_t tab_bytes = fx.frz_off;  // (S + 17) rows: states, SKIP, DEAD, SLOW (the FRZ rows stay behind)
         const bool in_smem = tab_bytes <= P.smem_table_bytes;
         if (in_smem && s_loaded != it.ext) {
             const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(P.img.image) + fx.tab_off);

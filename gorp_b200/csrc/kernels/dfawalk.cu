@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
                 const char* t8 = reinterpret_cast<const char*>(P.text);
                 const int64_t p_end = (nb < P.n_units ? nb : P.n_units) * 2;
                 int64_t p = ((na * 2) & ~int64_t(127)) + 128;
-                for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
+                if (!(P.flags & 2u))
+                    for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
             }
             if (cursor < end) {  // lanes without a next line claim the next lines of the item
                 const uint32_t want = __ballot_sync(0xffffffffu, !has_next);
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
             }
             if (!__any_sync(0xffffffffu, active || has_next)) break;
             if (active) {
-                const Units16 u = load_units16(P.text, q, P.n_units);
+                const Units16 u = P.flags & 1u ? load_units16(P.text, q, P.n_units) : load_units16_l2keep(P.text, q, P.n_units);
                 if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
                     st = dw_step<kSmem, 0>(st, u.a.x, cx_abs, row_bytes, tab_g);
                     st = dw_step<kSmem, 2>(st, u.a.x, cx_abs, row_bytes, tab_g);

@@ -159,3 +159,22 @@ extern "C" int ht_tdfa_sizes(const void* blob, size_t len, uint32_t* out, int ca
         return -1;
     }
 }
+
+// the compacted combined DFA (host/automata.hpp: CompactDfa): trans[S*C] (-1 dead) and accept_first[S]. Returns S, sets *n_classes.
+extern "C" int ht_compact_dfa(const void* blob, size_t len, int32_t* trans, int64_t cap, int32_t* accept_first, uint32_t* n_classes,
+                              char* err, int errlen) {
+    try {
+        CompiledDefinition def = parse_blob(blob, len);
+        DeviceModel m = build_device_model(def);
+        *n_classes = m.dfa.n_classes;
+        const int64_t n = static_cast<int64_t>(m.dfa.n_states) * m.dfa.n_classes;
+        if (trans && n <= cap) {
+            std::memcpy(trans, m.dfa.trans.data(), n * sizeof(int32_t));
+            std::memcpy(accept_first, m.dfa.accept_first.data(), m.dfa.n_states * sizeof(int32_t));
+        }
+        return static_cast<int>(m.dfa.n_states);
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
