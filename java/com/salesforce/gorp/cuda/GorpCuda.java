@@ -35,11 +35,11 @@ public final class GorpCuda implements AutoCloseable {
     private static final SymbolLookup LIB =
             SymbolLookup.libraryLookup(System.getProperty("gorp.cuda.lib", "libgorpcuda.so"), Arena.global());
 
-    // struct gorp_result { int64 n_lines; int32 n_extractions, reserved; 5 pointers; void* owner; }
+    // struct gorp_result (include/gorp_cuda.h, ABI v2): { int64 n_lines; int32 n_extractions, span_stride; 4 pointers; void* owner; }
     private static final StructLayout RESULT = MemoryLayout.structLayout(
-            JAVA_LONG.withName("n_lines"), JAVA_INT.withName("n_extractions"), JAVA_INT.withName("reserved"),
-            ADDRESS.withName("ext_id"), ADDRESS.withName("line_off"), ADDRESS.withName("span_off"),
-            ADDRESS.withName("spans"), ADDRESS.withName("histogram"), ADDRESS.withName("owner"));
+            JAVA_LONG.withName("n_lines"), JAVA_INT.withName("n_extractions"), JAVA_INT.withName("span_stride"),
+            ADDRESS.withName("ext_id"), ADDRESS.withName("line_off"), ADDRESS.withName("spans"),
+            ADDRESS.withName("histogram"), ADDRESS.withName("owner"));
 
     private static MethodHandle fn(String name, FunctionDescriptor d) {
         return LINKER.downcallHandle(LIB.find(name).orElseThrow(), d);
@@ -57,11 +57,15 @@ public final class GorpCuda implements AutoCloseable {
 
     private final Gorp gorp;
     private final CookedExtraction[] extractions;
+    private final int[] groups;  // capture groups per extraction (JDKRegexpCookedExtraction._constructMatch reads groupCount())
     private final MemorySegment engine;
 
     public GorpCuda(Gorp gorp, int... devices) throws Throwable {
         this.gorp = gorp;
         this.extractions = gorp.getExtractions().toArray(new CookedExtraction[0]);
+        this.groups = new int[extractions.length];
+        for (int i = 0; i < groups.length; ++i)
+            groups[i] = java.util.regex.Pattern.compile(extractions[i].getRegexpSource()).matcher("").groupCount();
         byte[] blob = DfaExport.export(gorp);
         try (Arena a = Arena.ofConfined()) {
             MemorySegment b = a.allocate(blob.length, 8);
@@ -140,9 +144,9 @@ public final class GorpCuda implements AutoCloseable {
 
     private List<ExtractionResult> materialise(MemorySegment res, LineSource src, long n, boolean safe) throws ExtractionException {
         MemorySegment extId = res.get(ADDRESS, 16).reinterpret(4 * Math.max(n, 1));
-        MemorySegment spanOff = res.get(ADDRESS, 32).reinterpret(8 * (n + 1));
-        long nSpans = n == 0 ? 0 : spanOff.getAtIndex(JAVA_LONG, n);
-        MemorySegment spans = res.get(ADDRESS, 40).reinterpret(4 * Math.max(nSpans, 1));
+        // one fixed row of span_stride int32 entries per line: (start, end) pairs of the matched extraction's groups
+        long stride = res.get(JAVA_INT, 12);
+        MemorySegment spans = res.get(ADDRESS, 32).reinterpret(4 * Math.max(n * stride, 1));
         List<ExtractionResult> out = new ArrayList<>((int) n);
         for (long i = 0; i < n; ++i) {
             int e = extId.getAtIndex(JAVA_INT, i);
@@ -155,8 +159,8 @@ public final class GorpCuda implements AutoCloseable {
                         "Internal error: high-level match for extraction #%d (%s) failed to match generated regexp: %s",
                         -2 - e, x.getName(), x.getRegexpDesc()));
             }
-            long s0 = spanOff.getAtIndex(JAVA_LONG, i), s1 = spanOff.getAtIndex(JAVA_LONG, i + 1);
-            String[] values = new String[(int) ((s1 - s0) / 2)];
+            long s0 = i * stride;
+            String[] values = new String[groups[e]];
             for (int g = 0; g < values.length; ++g) {
                 int a = spans.getAtIndex(JAVA_INT, s0 + 2L * g), b = spans.getAtIndex(JAVA_INT, s0 + 2L * g + 1);
                 values[g] = a < 0 ? null : input.substring(a, b);
