@@ -128,7 +128,7 @@ struct DeviceCtx {
     DfaWalkDev dfawalk{};        // class-indexed combined DFA of kernels/dfawalk.cu (text form, any definition)
     CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
     bool force_k4 = false;       // GORP_FORCE_K4=1: one-line-per-thread capture kernels (K4) instead of the bucketed K4b
-    DevBuf perm, items, buckets;
+    DevBuf perm, items, buckets, nl_masks;
     int dfa_tier = 0;            // GORP_DFA_TIER: 0 = by line length, 1 = chunk-owner walk (K0d), 2 = line index + lane queue (K1 + K2b)
     bool force_k1k2 = false;     // GORP_FORCE_K1K2=1: newline index + DFA scan as separate kernels (K1, K2) instead of K0d
     bool force_tiles = false;    // GORP_FORCE_TILES=1: the TMA-staged tile kernel instead of the chunk-walk kernel
@@ -932,7 +932,13 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         c.tile_counts.reserve(static_cast<size_t>(n_tiles + 1) * 4);
         c.tile_base.reserve(static_cast<size_t>(n_tiles + 2) * 8);
         c.scan_scratch.reserve(static_cast<size_t>(n_tiles / 4096 + 8) * 8);
-        k1_count_newlines(L, d_text, n_units, c.tile_counts.as<uint32_t>());
+        const bool with_masks = !c.force_k1k2 && !c.force_general;  // the count pass leaves the '\n' masks for the scatter pass
+        if (with_masks) {
+            c.nl_masks.reserve(static_cast<size_t>(n_tiles) * 256 * 4);
+            k1_count_newlines_masks(L, d_text, n_units, c.tile_counts.as<uint32_t>(), c.nl_masks.as<uint32_t>());
+        } else {
+            k1_count_newlines(L, d_text, n_units, c.tile_counts.as<uint32_t>());
+        }
         tm.mark("k1_count_newlines", 1);
         scan_u32_to_i64(L, c.tile_counts.as<uint32_t>(), n_tiles, c.tile_base.as<int64_t>(), c.scan_scratch.as<int64_t>());
         tm.mark("scan_tiles", 3);
@@ -946,7 +952,8 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         ends_with_nl = last_unit == 0x0A;
         if (n_units > 0) c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
         c.line_off.reserve(static_cast<size_t>(total_nl + 3) * 8);
-        k1_scatter_newlines(L, d_text, n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
+        if (with_masks) k1_scatter_masks(L, c.nl_masks.as<uint32_t>(), n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
+        else k1_scatter_newlines(L, d_text, n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
         k1_finish(L, d_text, n_units, c.tile_base.as<int64_t>() + n_tiles, c.line_off.as<int64_t>(), d_n_lines);
         tm.mark("k1_scatter_newlines", 2);
         d_line_off = c.line_off.as<int64_t>();

@@ -99,6 +99,10 @@ constexpr int kNlTile = 8192;
 void k1_count_newlines(const Launch&, const uint16_t* text, int64_t n_units, uint32_t* tile_counts);
 void k1_scatter_newlines(const Launch&, const uint16_t* text, int64_t n_units, const int64_t* tile_base,
                          int64_t* line_off /* entries 1.. */);
+// same pair with the '\n' masks (one u32 per 32 units, ceil(n_units / kNlTile) * 256 words) as a side product of the
+// count pass: the scatter pass then reads the masks instead of the text (one HBM pass over the text instead of two)
+void k1_count_newlines_masks(const Launch&, const uint16_t* text, int64_t n_units, uint32_t* tile_counts, uint32_t* masks);
+void k1_scatter_masks(const Launch&, const uint32_t* masks, int64_t n_units, const int64_t* tile_base, int64_t* line_off);
 void k1_finish(const Launch&, const uint16_t* text, int64_t n_units, const int64_t* total_newlines, int64_t* line_off,
                int64_t* n_lines_out);
 
