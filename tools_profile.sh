@@ -1,14 +1,15 @@
 #!/bin/bash
-# Profiling recipe (run under gpurun, 1 GPU): launch list of one bench step + full ncu capture of the hot kernels.
-# Usage: bash tools_profile.sh <tag> [lines] [kernel-regex]
-#   -> gpurun_out/<tag>_launches.csv, gpurun_out/<tag>_prof.ncu-rep
-set -x
+# Profiling recipe (run under gpurun, 1 GPU): launch lists of bench steps + full ncu captures of the hot kernels.
+# Usage: bash tools_profile.sh <tag>
+#   -> gpurun_out/<tag>_launches_<workload>.csv, gpurun_out/<tag>_prof_<workload>.ncu-rep
 TAG=${1:-prof}
-LINES=${2:-8000000}
-KREGEX=${3:-'onepass|fused|dfa_|tdfa_|nl_'}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --lines-per-gpu $LINES --skip-e2e --skip-cpu > gpurun_out/${TAG}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"$KREGEX" -s 3 -c 2 -f -o gpurun_out/${TAG}_prof \
-    python bench.py --steps 1 --warmup 3 --lines-per-gpu $LINES --skip-e2e --skip-cpu > gpurun_out/${TAG}_prof.log 2>&1
+for spec in "readme 8000000 chunkwalk" "syslog200 16000000 linewalk|capwalk|nl_" "weblog 16000000 linewalk|capwalk|nl_"; do
+    set -- $spec
+    W=$1; LINES=$2; KREGEX=$3
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_$W.csv \
+        python bench.py --workload $W --steps 2 --warmup 3 --lines-per-gpu $LINES --skip-e2e --skip-cpu > gpurun_out/${TAG}_launches_$W.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:"$KREGEX" -s 6 -c 4 -f -o gpurun_out/${TAG}_prof_$W \
+        python bench.py --workload $W --steps 1 --warmup 3 --lines-per-gpu $LINES --skip-e2e --skip-cpu > gpurun_out/${TAG}_prof_$W.log 2>&1
+done
 ls -la gpurun_out/
