@@ -42,6 +42,7 @@ WORKLOADS = {
     "utf16mix": ("config#5 nginx/Apache definition, non-ASCII UTF-16 + divergence characters + 10 KB outlier lines", 200_000),
 }
 WORKLOAD, BLOCK_LINES = WORKLOADS["readme"]
+NCU_DRAM_BYTES_PER_TEXT_BYTE = {"k0_chunkwalk_extract": (1.370340e9 + 0.319971e9) / (8_000_000 * 62.612088 * 2)}
 
 
 def hbm_peak():
@@ -333,8 +334,13 @@ def main():
         roof = None
         if dom:
             ach = in_bytes / (kern[dom] / 1e3) / 1e9
+            # DRAM bytes per launch from the committed ncu --set full capture of the same kernel (profiles/
+            # r1h_ncu_summary_readme.txt: 1.370 GB read + 0.320 GB written per 1.002 GB of text), scaled to this launch
+            traffic = NCU_DRAM_BYTES_PER_TEXT_BYTE.get(dom)
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": in_bytes,
+                    "traffic": traffic * in_bytes if traffic else None,
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per text byte (profiles/r1h_ncu_summary_readme.txt) x bytes of this launch" if traffic else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": in_bytes,
                     "kernel_ms": kern[dom], "all_kernels_ms": kern,
                     "whole_step_frac": (in_bytes / (ms_max / 1e3) / 1e9) / peak,
                     "whole_step_frac_of_8TBps": (in_bytes / (ms_max / 1e3) / 1e9) / 8000.0}
