@@ -162,13 +162,20 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
         if ((stride & 7u) == 0) {  // 32-byte aligned rows: one 256-bit streaming store per 8 entries
             for (uint32_t k = 0; k < stride; k += 8) {
                 const uint4 r4 = *reinterpret_cast<const uint4*>(res + k), r5 = *reinterpret_cast<const uint4*>(res + k + 4);
-                int32_t v0, v1, v2, v3, v4, v5, v6, v7;
-                if (!((r4.x | r4.y | r4.z | r4.w | r5.x | r5.y | r5.z | r5.w) & 0x80000000u)) {
-                    v0 = single(r4.x), v1 = single(r4.y), v2 = single(r4.z), v3 = single(r4.w);
-                    v4 = single(r5.x), v5 = single(r5.y), v6 = single(r5.z), v7 = single(r5.w);
-                } else {
-                    v0 = value(r4.x), v1 = value(r4.y), v2 = value(r4.z), v3 = value(r4.w);
-                    v4 = value(r5.x), v5 = value(r5.y), v6 = value(r5.z), v7 = value(r5.w);
+                // every entry through the single-writer path first (a several-writer recipe reads the dummy slot there),
+                // then only the several-writer entries again, one by one
+                auto fast = [&](uint32_t recipe) { return single(recipe & 0x80000000u ? 0u : recipe); };
+                int32_t v0 = fast(r4.x), v1 = fast(r4.y), v2 = fast(r4.z), v3 = fast(r4.w);
+                int32_t v4 = fast(r5.x), v5 = fast(r5.y), v6 = fast(r5.z), v7 = fast(r5.w);
+                if ((r4.x | r4.y | r4.z | r4.w | r5.x | r5.y | r5.z | r5.w) & 0x80000000u) {
+                    if (r4.x & 0x80000000u) v0 = value(r4.x);
+                    if (r4.y & 0x80000000u) v1 = value(r4.y);
+                    if (r4.z & 0x80000000u) v2 = value(r4.z);
+                    if (r4.w & 0x80000000u) v3 = value(r4.w);
+                    if (r5.x & 0x80000000u) v4 = value(r5.x);
+                    if (r5.y & 0x80000000u) v5 = value(r5.y);
+                    if (r5.z & 0x80000000u) v6 = value(r5.z);
+                    if (r5.w & 0x80000000u) v7 = value(r5.w);
                 }
                 asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + k), "r"(v0), "r"(v1), "r"(v2), "r"(v3),
                              "r"(v4), "r"(v5), "r"(v6), "r"(v7)
