@@ -130,6 +130,30 @@ __device__ __forceinline__ void cw_step(uint32_t& st, uint32_t& fin, uint32_t de
     sts32(sa, pos);
 }
 
+// one step on ANY unit (blocks that hold a unit >= 0x80): the class comes from the full class map, a high surrogate that
+// is followed by a low surrogate takes the PAIR_HI class (java.util.regex consumes the pair as one character)
+template <bool kSmemTab>
+__device__ __forceinline__ void cw_step_any(uint32_t& st, uint32_t& fin, uint32_t dead_off, uint32_t u, uint32_t nx, const CapDev& c,
+                                            uint32_t cls_abs, uint32_t tab_abs, const unsigned char* __restrict__ tab, uint32_t reg_abs,
+                                            uint32_t reg_stride, uint32_t pos) {
+    uint32_t c4;
+    if (u < 0x80u) {
+        c4 = lds32(cls_abs + u * 4);
+    } else {
+        c4 = 4u * __ldg(c.cls + u);
+        if ((u & 0xFC00u) == 0xD800u && (nx & 0xFC00u) == 0xDC00u) c4 = 4u * c.pair_hi_class;
+    }
+    uint32_t ent;
+    if (kSmemTab) {
+        ent = lds32(tab_abs + min(st, dead_off) + c4);
+    } else {
+        ent = ldg32_off(tab, st + c4);
+    }
+    st = ent >> 6;
+    if (kSmemTab) fin = max(fin, st);
+    sts32(reg_abs + (ent & 63u) * reg_stride, pos);
+}
+
 // 16 units through the general tables (units >= 0x80, surrogate pairs, transitions with several register commands).
 // `q` = text position of the block, `a` = text position of the line start; units at or beyond n_units read as '\n'.
 // `st` is a row byte offset of the extraction's image on entry and exit.
@@ -265,8 +289,19 @@ __device__ __forceinline__ void cw_item(const CapWalkParams& P, const CapItem& i
                 cw_step<kSmemTab, 2>(st, fin, fx.dead_off, u.b.w, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + 15);
                 if (kSmemTab && fin >= fx.dead_off) st = fin;  // SLOW and FRZ ids do not survive the steps that follow them
                 if (st == fx.slow_off) st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
-            } else {
-                st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
+            } else {  // a unit >= 0x80 in the block: same tables, classes through the full class map
+                const uint32_t w[8] = {u.a.x, u.a.y, u.a.z, u.a.w, u.b.x, u.b.y, u.b.z, u.b.w};
+                // the unit after the block: only a high surrogate in the block's last unit looks at it; units at or beyond
+                // n_units read as '\n' (the pair test of the general path: p + 1 < n_units)
+                const uint32_t after = ((w[7] >> 16) & 0xFC00u) == 0xD800u && q + 16 < P.n_units ? __ldg(P.text + q + 16) : 0x0Au;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t cu = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xFFFFu);
+                    const uint32_t nu = k == 15 ? after : ((k & 1) ? (w[(k + 1) >> 1] & 0xFFFFu) : (w[k >> 1] >> 16));
+                    cw_step_any<kSmemTab>(st, fin, fx.dead_off, cu, nu, P.cap, cls_abs, tab_abs, tab, reg_abs, reg_stride, pos + k);
+                }
+                if (kSmemTab && fin >= fx.dead_off) st = fin;
+                if (st == fx.slow_off) st = cw_slow16(P.cap, x, fx, st0, P.text, q, a, P.n_units, reg_abs, reg_stride);
             }
             q += 16;
             finished = st >= fx.dead_off;  // DEAD (rejected) or FRZ(s)
