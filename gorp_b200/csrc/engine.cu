@@ -293,9 +293,26 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     // chunk-walk DFA tier: class-indexed u16 rows + DEADSCAN / SKIP / FIN rows (see kernels.cuh: DfaWalkDev)
     {
         const size_t E = m.n_groups.size();
-        // K = classes + '\n' column, padded to an odd count: the rows of lanes that read the same column then fall into
-        // different shared-memory banks
-        const size_t NL = C, K = (C + 1) | 1, dscan = S, fin_base = S + 16, R = fin_base + 1 + E;
+        // Columns: the classes ordered by how often log text hits them (a static weight per ASCII character), then '\n'.
+        // A table that fits shared memory gets an odd column count (the rows of lanes that read the same column then
+        // fall into different banks); a larger one is read through L1/L2 and gets 32-byte aligned rows whose first
+        // sector holds the 16 hottest columns, so a warp-wide lookup touches fewer sectors and the hot set is smaller.
+        const size_t NL = C, dscan = S, fin_base = S + 16, R = fin_base + 1 + E;
+        const bool big = R * ((C + 1) | 1) * 2 > 200 * 1024;
+        const size_t K = big ? ((C + 1 + 15) / 16) * 16 : ((C + 1) | 1);
+        std::vector<uint32_t> weight(C, 0), col_of(C + 1), cls_of(C + 1);
+        for (uint32_t u = 0; u < 128; ++u) {
+            if (u == 0x0A) continue;
+            uint32_t w = 1;
+            if (u >= 'a' && u <= 'z') w = 8;
+            else if ((u >= '0' && u <= '9') || u == ' ') w = 6;
+            else if (u >= 'A' && u <= 'Z') w = 3;
+            else if (std::strchr(".-_/:=[](),'\"", static_cast<int>(u)) && u) w = 2;
+            weight[m.dfa.classmap[u]] += w;
+        }
+        for (size_t k = 0; k <= C; ++k) cls_of[k] = static_cast<uint32_t>(k);
+        std::stable_sort(cls_of.begin(), cls_of.begin() + C, [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+        for (size_t k = 0; k <= C; ++k) col_of[cls_of[k]] = static_cast<uint32_t>(k);  // class -> column; NL (class id C) stays last
         if (R <= 0xFFFF && K * 2 <= 0xFFFF && !std::getenv("GORP_SKIP_NEWTABLES")) {
             std::vector<uint16_t> rows(((R * K + 7) / 8) * 8, 0);
             for (size_t r = 0; r < R; ++r)
@@ -307,7 +324,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                         if (k == NL) {
                             nx = fin_base + 1 + m.dfa.accept_first[r];
                         } else {
-                            const int32_t t = m.dfa.trans[r * C + k];
+                            const int32_t t = m.dfa.trans[r * C + cls_of[k]];
                             nx = t < 0 ? dscan : static_cast<size_t>(t);
                         }
                     } else if (r == dscan) {
@@ -319,8 +336,9 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     }
                     rows[r * K + k] = static_cast<uint16_t>(nx);
                 }
-            std::vector<uint16_t> cls128(128), xcls(m.dfa.classmap);
-            for (size_t u = 0; u < 128; ++u) cls128[u] = static_cast<uint16_t>(2 * (u == 0x0A ? NL : m.dfa.classmap[u]));
+            std::vector<uint16_t> cls128(128), xcls(65536);
+            for (size_t u = 0; u < 65536; ++u) xcls[u] = static_cast<uint16_t>(col_of[m.dfa.classmap[u]]);
+            for (size_t u = 0; u < 128; ++u) cls128[u] = static_cast<uint16_t>(2 * (u == 0x0A ? NL : col_of[m.dfa.classmap[u]]));
             c.dfawalk.table = upload(rows, c.owned);
             c.dfawalk.n_rows = static_cast<uint32_t>(R);
             c.dfawalk.K = static_cast<uint32_t>(K);
