@@ -237,13 +237,6 @@ __device__ __forceinline__ void cw_item(const CapWalkParams& P, const CapItem& i
             st = lo ? (fx.n_states + lo - 1) * fx.row_bytes : 0u;
             active = true;
             nstage = 0;
-            // the lines of a bucket are scattered over the text: ask L2 for the rest of the line in whole 128-byte lines
-            // now (the first one comes with the first block load)
-            const char* t8 = reinterpret_cast<const char*>(P.text);
-            const int64_t p_end = (nb < P.n_units ? nb : P.n_units) * 2;
-            int64_t p = ((a * 2) & ~int64_t(127)) + 128;
-            if (!(P.flags & 2u))
-                for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
         } else if (nstage == 1) {
             na = __ldg(P.line_off + nline);
             nb = __ldg(P.line_off + nline + 1);

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
         int64_t cursor = static_cast<int64_t>(item) * kLineItemLines;  // warp-uniform: next unclaimed line of the item
         const int64_t end = cursor + kLineItemLines < P.n_lines ? cursor + kLineItemLines : P.n_lines;
         bool active = false, has_next = false;
-        int64_t line = 0, nline = 0, q = 0, na = 0, nb = 0;
+        int64_t line = 0, nline = 0, q = 0, na = 0;
         uint32_t st = 0;
         for (;;) {
             if (!active && has_next) {  // start the claimed line
@@ -352,12 +352,6 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
                 st = lo ? skip0 + lo : 0u;
                 active = true;
                 has_next = false;
-                // ask L2 for the rest of the line in whole 128-byte lines (the first one comes with the first block load)
-                const char* t8 = reinterpret_cast<const char*>(P.text);
-                const int64_t p_end = (nb < P.n_units ? nb : P.n_units) * 2;
-                int64_t p = ((na * 2) & ~int64_t(127)) + 128;
-                if (!(P.flags & 2u))
-                    for (int n = 0; n < 8 && p < p_end; ++n, p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(t8 + p));
             }
             if (cursor < end) {  // lanes without a next line claim the next lines of the item
                 const uint32_t want = __ballot_sync(0xffffffffu, !has_next);
@@ -366,7 +360,6 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
                     if (!has_next && idx < end) {
                         nline = idx;
                         na = __ldg(P.line_off + idx);
-                        nb = __ldg(P.line_off + idx + 1);
                         has_next = true;
                     }
                     cursor += __popc(want);

@@ -221,7 +221,7 @@ struct LineWalkParams {
     DfaWalkDev a;
     int32_t* ext_id;
     unsigned int* item_ticket;   // zeroed by the caller
-    uint32_t flags;              // GORP_WALK_FLAGS (diagnostics): 1 = text loads L2 evict-first, 2 = no L2 prefetch of the line
+    uint32_t flags;              // GORP_WALK_FLAGS (diagnostics): 1 = text loads L2 evict-first
 };
 bool k2b_linewalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem);
 void k2b_linewalk_scan(const Launch&, const LineWalkParams&, uint32_t threads, bool in_smem);
@@ -261,7 +261,7 @@ struct CapWalkParams {
     CapDev cap;                  // general tables (slow path, final states)
     uint32_t span_stride;
     uint32_t smem_table_bytes;   // = img.smem_table_bytes, or 0 to read every table through L1/L2 (GORP_CAP_FLAGS=2)
-    uint32_t flags;              // GORP_WALK_FLAGS (diagnostics): 1 = text loads L2 evict-first, 2 = no L2 prefetch of the line
+    uint32_t flags;              // GORP_WALK_FLAGS (diagnostics): 1 = text loads L2 evict-first
     int32_t* ext_id;
     int32_t* spans;
     unsigned long long* hist;    // [E+2]: a capture failure moves one count from bin e to bin E+1
