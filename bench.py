@@ -325,6 +325,34 @@ def main():
                "d2h_bytes_per_step": int(d2h), "lines_per_step_per_gpu": int(e2e_lines), "ms_per_step": float(tt.item()) * 1e3,
                "timing": "host wall clock around gorp_extract_text (it returns after the last D2H), max over ranks"}
         del h_text
+        # the same call fed with ISO-8859-1 bytes (what a JDK 9+ String with the LATIN1 coder holds; the synthetic corpus is
+        # ASCII): gorp_extract_text_latin1 widens on the device, the host-to-device copy moves half the bytes
+        if int(block.max()) < 256:
+            h8 = torch.empty(e2e_reps * block.size, dtype=torch.uint8).pin_memory()
+            h8_np = h8.numpy()
+            b8 = block.astype(np.uint8)
+            for r in range(e2e_reps):
+                h8_np[r * block.size:(r + 1) * block.size] = b8
+
+            def e2e8_step():
+                _check(lib.gorp_extract_text_latin1(eng, h8_np.ctypes.data, h8_np.size, C.byref(res)))
+                nl8 = res.n_lines
+                lib.gorp_result_release(eng, C.byref(res))
+                return nl8
+            assert e2e8_step() == nl
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e8_step()
+            torch.cuda.synchronize()
+            dt8 = (time.perf_counter() - t0) / args.e2e_steps
+            tt8 = torch.tensor([dt8], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt8, op=dist.ReduceOp.MAX)
+            e2e["latin1_input"] = {"value": e2e_lines * world / float(tt8.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h8_np.size),
+                                   "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt8.item()) * 1e3,
+                                   "call": "gorp_extract_text_latin1 (ISO-8859-1 bytes in, widened to UTF-16 on the device)"}
+            del h8
     except Exception as ex:  # noqa: BLE001
         e2e = {"value": None, "unit": "lines/s", "error": str(ex)[:200]}
 

@@ -48,7 +48,7 @@ class DeviceResult(C.Structure):
 SYMBOLS = [
     "gorp_abi_version", "gorp_last_error", "gorp_device_count", "gorp_compile_definition", "gorp_compile_patterns",
     "gorp_blob_free", "gorp_blob_get_info", "gorp_blob_get_extraction", "gorp_blob_get_extractor_name",
-    "gorp_blob_get_tables", "gorp_engine_create", "gorp_engine_destroy", "gorp_extract_lines", "gorp_extract_text",
+    "gorp_blob_get_tables", "gorp_engine_create", "gorp_engine_destroy", "gorp_extract_lines", "gorp_extract_text", "gorp_extract_text_latin1",
     "gorp_result_release", "gorp_extract_text_device", "gorp_extract_lines_device", "gorp_kernel_times",
 ]
 
@@ -72,6 +72,7 @@ lib.gorp_engine_destroy.argtypes = [C.c_void_p]
 lib.gorp_engine_destroy.restype = None
 lib.gorp_extract_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Result)]
 lib.gorp_extract_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Result)]
+lib.gorp_extract_text_latin1.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Result)]
 lib.gorp_result_release.argtypes = [C.c_void_p, C.POINTER(Result)]
 lib.gorp_result_release.restype = None
 lib.gorp_extract_text_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,

@@ -144,7 +144,7 @@ struct DeviceCtx {
     // the D2H of the rows of piece k-1 (s_out); the rows of all pieces accumulate in acc_*
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2]{}, ev_free[2]{}, ev_rows = nullptr;
-    DevBuf textbuf[2], offbuf[2], acc_ext, acc_off, acc_spans, acc_hist;
+    DevBuf textbuf[2], offbuf[2], bytebuf[2], acc_ext, acc_off, acc_spans, acc_hist;
     // per-call scratch, serialised by `mu`
     std::mutex mu;
     DevBuf text, off_in, line_off, tile_counts, tile_base, scan_scratch, ext_id, spans, hist, scalars, debug;
@@ -1095,7 +1095,8 @@ struct Piece {
 };
 
 // Cuts the batch into pieces of about kPieceUnits that end after a '\n' (text form) / at a string boundary (lines form).
-std::vector<Piece> plan_pieces(const uint16_t* text, int64_t n_units, const int64_t* off, int64_t n_lines, int64_t piece_units) {
+template <class Unit>
+std::vector<Piece> plan_pieces(const Unit* text, int64_t n_units, const int64_t* off, int64_t n_lines, int64_t piece_units) {
     std::vector<Piece> v;
     if (off) {
         int64_t l = 0;
@@ -1130,8 +1131,9 @@ struct DeviceRun {  // what one device produced for its pieces
 
 // Processes pieces [p0, p1) on device context c. Rows accumulate in c.acc_*; when `hr` is given (single-device call) the
 // rows of every finished piece are copied to the host arrays at once, overlapping the next pieces.
-void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const int64_t* off, const std::vector<Piece>& pieces, size_t p0,
-                size_t p1, HostResult* hr, DeviceRun& run) {
+// `text8` (ISO-8859-1 bytes, text form only) replaces `text`: the bytes are staged and widened to UTF-16 on the device.
+void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_t* text8, const int64_t* off, const std::vector<Piece>& pieces,
+                size_t p0, size_t p1, HostResult* hr, DeviceRun& run) {
     std::lock_guard<std::mutex> lock(c.mu);
     CK(cudaSetDevice(c.device));
     Launch L{c.stream, c.sm_count};
@@ -1148,6 +1150,7 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const int64_
     const int n_buf = p1 - p0 > 1 ? 2 : 1;
     for (int b = 0; b < n_buf; ++b) {
         c.textbuf[b].reserve((max_units + kTextPad + 64) * 2);
+        if (text8) c.bytebuf[b].reserve(max_units + 64);
         if (off) c.offbuf[b].reserve((max_lines + 1) * 8);
     }
     // row capacity: exact for the lines form; for the text form sized for the first piece from the running density
@@ -1174,7 +1177,9 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const int64_
         const int64_t units = pc.u1 - pc.u0;
         const int64_t lead = off ? kTextPad + (pc.u0 & 15) : 0;  // keeps (device address - unit index) a multiple of 32 bytes
         if (k >= p0 + 2) CK(cudaStreamWaitEvent(c.s_in, c.ev_free[b], 0));  // the gather of piece k-2 still reads this buffer's offsets
-        if (units)
+        if (units && text8)
+            CK(cudaMemcpyAsync(c.bytebuf[b].p, text8 + pc.u0, static_cast<size_t>(units), cudaMemcpyHostToDevice, c.s_in));
+        else if (units)
             CK(cudaMemcpyAsync(c.textbuf[b].as<uint16_t>() + lead, text + pc.u0, static_cast<size_t>(units) * 2, cudaMemcpyHostToDevice, c.s_in));
         if (off)
             CK(cudaMemcpyAsync(c.offbuf[b].p, off + pc.l0, static_cast<size_t>(pc.l1 - pc.l0 + 1) * 8, cudaMemcpyHostToDevice, c.s_in));
@@ -1195,6 +1200,10 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const int64_
             const uint16_t* vbase = c.textbuf[b].as<uint16_t>() + kTextPad + (pc.u0 & 15) - pc.u0;  // text[i] lives at vbase + i
             nl = run_pipeline(c, vbase, 0, c.offbuf[b].as<int64_t>(), pc.l1 - pc.l0, c.stream, false, &dr);
         } else {
+            if (text8) {
+                k_widen_latin1(L, c.bytebuf[b].as<uint8_t>(), c.textbuf[b].as<uint16_t>(), units);
+                c.launches += 1;
+            }
             nl = run_pipeline(c, c.textbuf[b].as<uint16_t>(), units, nullptr, 0, c.stream, false, &dr);
         }
         if (rows + nl > cap_rows) {  // the density estimate was too low: grow, keeping the rows gathered so far
@@ -1236,13 +1245,14 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const int64_
     run.stride = static_cast<int32_t>(stride);
 }
 
-int extract_host(gorp_engine* e, const uint16_t* text, int64_t n_units, const int64_t* off, int64_t n_lines, gorp_result* out) {
-    if (!e || !out || (!text && n_units > 0) || n_units < 0 || n_lines < 0) return fail(GORP_E_ARG, "bad argument");
+int extract_host(gorp_engine* e, const uint16_t* text, const uint8_t* text8, int64_t n_units, const int64_t* off, int64_t n_lines,
+                 gorp_result* out) {
+    if (!e || !out || (!text && !text8 && n_units > 0) || n_units < 0 || n_lines < 0) return fail(GORP_E_ARG, "bad argument");
     if (e->devs.empty()) return fail(GORP_E_CUDA, "engine has no CUDA device");
     return guarded([&]() -> int {
         int64_t piece_units = kPieceUnits;
         if (const char* f = std::getenv("GORP_PIECE_UNITS")) piece_units = std::max<int64_t>(std::atoll(f), 1024);
-        const std::vector<Piece> pieces = plan_pieces(text, n_units, off, n_lines, piece_units);
+        const std::vector<Piece> pieces = text8 ? plan_pieces(text8, n_units, off, n_lines, piece_units) : plan_pieces(text, n_units, off, n_lines, piece_units);
         std::unique_ptr<HostResult> hr;
         {
             std::lock_guard<std::mutex> pl(e->pool_mu);
@@ -1258,7 +1268,7 @@ int extract_host(gorp_engine* e, const uint16_t* text, int64_t n_units, const in
         int32_t stride = 0;
         if (G <= 1) {
             DeviceRun run;
-            run_pieces(e, *e->devs[0], text, off, pieces, 0, pieces.size(), hr.get(), run);
+            run_pieces(e, *e->devs[0], text, text8, off, pieces, 0, pieces.size(), hr.get(), run);
             nl = run.n_rows;
             stride = run.stride;
         } else {
@@ -1271,7 +1281,7 @@ int extract_host(gorp_engine* e, const uint16_t* text, int64_t n_units, const in
             for (size_t d = 0; d < G; ++d)
                 th.emplace_back([&, d]() {
                     runs[d].status = guarded([&]() -> int {
-                        run_pieces(e, *e->devs[d], text, off, pieces, first[d], first[d + 1], nullptr, runs[d]);
+                        run_pieces(e, *e->devs[d], text, text8, off, pieces, first[d], first[d + 1], nullptr, runs[d]);
                         return GORP_OK;
                     });
                     if (runs[d].status != GORP_OK) runs[d].error = g_error;
@@ -1556,11 +1566,15 @@ void gorp_engine_destroy(gorp_engine* e) { delete e; }
 
 int gorp_extract_lines(gorp_engine* e, const uint16_t* text, const int64_t* off, int64_t n_lines, gorp_result* out) {
     if (!off) return fail(GORP_E_ARG, "null offsets");
-    return extract_host(e, text, n_lines > 0 ? off[n_lines] : 0, off, n_lines, out);
+    return extract_host(e, text, nullptr, n_lines > 0 ? off[n_lines] : 0, off, n_lines, out);
 }
 
 int gorp_extract_text(gorp_engine* e, const uint16_t* text, int64_t n_units, gorp_result* out) {
-    return extract_host(e, text, n_units, nullptr, 0, out);
+    return extract_host(e, text, nullptr, n_units, nullptr, 0, out);
+}
+
+int gorp_extract_text_latin1(gorp_engine* e, const uint8_t* text, int64_t n_bytes, gorp_result* out) {
+    return extract_host(e, nullptr, text, n_bytes, nullptr, 0, out);
 }
 
 void gorp_result_release(gorp_engine* e, gorp_result* r) {

@@ -420,6 +420,25 @@ __global__ void accumulate_kernel(int64_t* __restrict__ dst, const int64_t* __re
     if (i < n) dst[i] += src[i];
 }
 
+// ISO-8859-1 bytes -> UTF-16 units (zero extension), 16 bytes in / 32 bytes out per thread and iteration. `dst` is 16-byte
+// aligned; `src` may sit at any address (a line-aligned piece of the caller's buffer copied to a 16-byte aligned
+// staging buffer starts at offset 0, so both are aligned here).
+__global__ void __launch_bounds__(kThreads) widen_latin1_kernel(const uint8_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t n) {
+    const int64_t n16 = n / 16;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < n16; i += static_cast<int64_t>(gridDim.x) * kThreads) {
+        const uint4 v = ld_stream(reinterpret_cast<const uint4*>(src) + i);
+        uint4 lo, hi;
+        lo.x = __byte_perm(v.x, 0, 0x4140), lo.y = __byte_perm(v.x, 0, 0x4342);
+        lo.z = __byte_perm(v.y, 0, 0x4140), lo.w = __byte_perm(v.y, 0, 0x4342);
+        hi.x = __byte_perm(v.z, 0, 0x4140), hi.y = __byte_perm(v.z, 0, 0x4342);
+        hi.z = __byte_perm(v.w, 0, 0x4140), hi.w = __byte_perm(v.w, 0, 0x4342);
+        reinterpret_cast<uint4*>(dst)[2 * i] = lo;
+        reinterpret_cast<uint4*>(dst)[2 * i + 1] = hi;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = n16 * 16 + threadIdx.x; i < n; i += kThreads) dst[i] = src[i];
+}
+
 int blocks_for(int64_t n, int per_block) { return static_cast<int>((n + per_block - 1) / per_block); }
 
 }  // namespace
@@ -501,6 +520,12 @@ void k_bias_copy(const Launch& L, int64_t* dst, const int64_t* src, int64_t n, i
     if (n <= 0) return;
     const int64_t want = (n + kThreads - 1) / kThreads, cap = static_cast<int64_t>(L.sm_count) * 8;
     bias_copy_kernel<<<static_cast<int>(want < cap ? want : cap), kThreads, 0, L.stream>>>(dst, src, n, bias);
+}
+
+void k_widen_latin1(const Launch& L, const uint8_t* src, uint16_t* dst, int64_t n) {
+    if (n <= 0) return;
+    const int64_t want = (n / 16 + kThreads - 1) / kThreads + 1, cap = static_cast<int64_t>(L.sm_count) * 8;
+    widen_latin1_kernel<<<static_cast<int>(want < cap ? want : cap), kThreads, 0, L.stream>>>(src, dst, n);
 }
 
 void k_accumulate(const Launch& L, int64_t* dst, const int64_t* src, int n) {

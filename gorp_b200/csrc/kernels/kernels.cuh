@@ -276,6 +276,8 @@ void k4b_capwalk(const Launch&, const CapWalkParams&);
 // result assembly of a batch that is pipelined in pieces: dst[i] = src[i] + bias ; dst[i] += src[i]
 void k_bias_copy(const Launch&, int64_t* dst, const int64_t* src, int64_t n, int64_t bias);
 void k_accumulate(const Launch&, int64_t* dst, const int64_t* src, int n);
+// dst[i] = src[i] (ISO-8859-1 byte -> UTF-16 unit); both 16-byte aligned
+void k_widen_latin1(const Launch&, const uint8_t* src, uint16_t* dst, int64_t n);
 
 // K3: per-extraction histogram (E entries, then MISS, then capture failures).
 void k3_histogram(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist);

@@ -111,6 +111,12 @@ void gorp_engine_destroy(gorp_engine* e);
 int gorp_extract_lines(gorp_engine* e, const uint16_t* text, const int64_t* off, int64_t n_lines, gorp_result* out);
 /* Gorp.extractAll(CharBuffer): split on U+000A only; a final line without '\n' counts; '\r' is data. */
 int gorp_extract_text(gorp_engine* e, const uint16_t* text, int64_t n_units, gorp_result* out);
+/* Same call for text held as ISO-8859-1 bytes, one byte per character — what a JDK 9+ String with the LATIN1 coder holds
+ * (java.lang.String compact strings; `String.getBytes(ISO_8859_1)` is a plain copy for such strings), i.e. the usual
+ * case for log text. The bytes are widened to UTF-16 on the device, so the host-to-device copy moves half the bytes of
+ * gorp_extract_text; results are identical to gorp_extract_text on the zero-extended text (spans and line_off count
+ * characters == UTF-16 units). Split on byte 0x0A. */
+int gorp_extract_text_latin1(gorp_engine* e, const uint8_t* text, int64_t n_bytes, gorp_result* out);
 void gorp_result_release(gorp_engine* e, gorp_result* r);
 
 /* --- device-resident variants: `d_text` (and `d_off`) already live in the HBM of the engine's device `dev_index`

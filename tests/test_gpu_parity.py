@@ -245,6 +245,35 @@ def test_host_calls_pipelined_in_pieces(monkeypatch):
     check_against_oracle(corpus.WEBLOG_DEF, text=corpus.lines_to_text(lines))
 
 
+def test_latin1_text_form(monkeypatch):
+    """gorp_extract_text_latin1: ISO-8859-1 bytes in, widened on the device; identical to the UTF-16 call on the
+    zero-extended text and to the oracle (including pieces whose seams fall anywhere in the byte buffer)."""
+    rng = np.random.default_rng(31)
+    for name, n in (("readme", 50000), ("weblog", 8000)):
+        d, gen = corpus.CONFIGS[name]
+        text = gen(n, seed=11)
+        assert int(text.max()) < 256
+        # sprinkle Latin-1 supplement characters (and the divergence characters that fit a byte: VT, BS, NEL, CR)
+        text = text.copy()
+        pos = rng.integers(0, len(text), size=n // 4)
+        pos = pos[text[pos] != 10]
+        text[pos] = rng.choice(np.array([0xE9, 0xFC, 0xA0, 0x85, 0x0B, 0x08, 0x0D, 0xFF], dtype=np.uint16), size=len(pos))
+        for piece in (None, "5000"):
+            if piece:
+                monkeypatch.setenv("GORP_PIECE_UNITS", piece)
+            g, b16, oe = check_against_oracle(d, text=text)
+            for t in (text, text[:-1]):
+                b16 = g.extract_batch_text(t)
+                b8 = g.extract_batch_text_latin1(t.astype(np.uint8))
+                assert b8.n_lines == b16.n_lines and b8.span_stride == b16.span_stride
+                assert (b8.ext_id == b16.ext_id).all() and (b8.line_off == b16.line_off).all()
+                assert (b8.spans == b16.spans).all() and (b8.histogram == b16.histogram).all()
+        monkeypatch.delenv("GORP_PIECE_UNITS", raising=False)
+    g = DefinitionReader.reader(V.README_DEF).read()
+    assert g.extract_batch_text_latin1(b"").n_lines == 0
+    assert g.extract_batch_text_latin1(b"[1]: GET 2ms /a").ext_id.tolist() == [1]
+
+
 def test_multi_device_engine(monkeypatch):
     """One engine over several GPUs: contiguous line-aligned ranges per device, rows concatenated in device order."""
     from gorp_b200 import _ffi
