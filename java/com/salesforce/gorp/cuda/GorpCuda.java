@@ -52,6 +52,8 @@ public final class GorpCuda implements AutoCloseable {
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
     private static final MethodHandle EXTRACT_TEXT = fn("gorp_extract_text",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+    private static final MethodHandle EXTRACT_TEXT_LATIN1 = fn("gorp_extract_text_latin1",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
     private static final MethodHandle RESULT_RELEASE = fn("gorp_result_release", FunctionDescriptor.ofVoid(ADDRESS, ADDRESS));
     private static final MethodHandle LAST_ERROR = fn("gorp_last_error", FunctionDescriptor.of(ADDRESS));
 
@@ -133,6 +135,39 @@ public final class GorpCuda implements AutoCloseable {
                 return materialise(res, i -> {
                     int s = (int) lineOff.getAtIndex(JAVA_LONG, i), e = (int) lineOff.getAtIndex(JAVA_LONG, i + 1) - 1;
                     return view.subSequence(s, e).toString();
+                }, n, false);
+            } finally {
+                RESULT_RELEASE.invokeExact(engine, res);
+            }
+        }
+    }
+
+    /**
+     * '\n'-separated log text held one byte per character (ISO-8859-1), e.g. a memory-mapped ASCII log file or
+     * {@code String.getBytes(ISO_8859_1)} of LATIN1-coded Strings: half the bytes cross PCIe, results are those of
+     * {@link #extractAll(CharBuffer)} on the same characters. A direct buffer is passed zero-copy.
+     */
+    public List<ExtractionResult> extractAllLatin1(java.nio.ByteBuffer text) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment seg;
+            if (text.isDirect()) {
+                seg = MemorySegment.ofBuffer(text);
+            } else {
+                seg = a.allocate(Math.max(text.remaining(), 1), 16);
+                MemorySegment.copy(MemorySegment.ofBuffer(text), 0, seg, 0, text.remaining());
+            }
+            final java.nio.ByteBuffer view = text.duplicate();
+            final int base = view.position();
+            MemorySegment res = a.allocate(RESULT);
+            check((int) EXTRACT_TEXT_LATIN1.invokeExact(engine, seg, (long) text.remaining(), res));
+            try {
+                long n = res.get(JAVA_LONG, 0);
+                MemorySegment lineOff = res.get(ADDRESS, 24).reinterpret(8 * (n + 1));
+                return materialise(res, i -> {
+                    int s = (int) lineOff.getAtIndex(JAVA_LONG, i), e = (int) lineOff.getAtIndex(JAVA_LONG, i + 1) - 1;
+                    byte[] b = new byte[e - s];
+                    view.get(base + s, b);
+                    return new String(b, java.nio.charset.StandardCharsets.ISO_8859_1);
                 }, n, false);
             } finally {
                 RESULT_RELEASE.invokeExact(engine, res);
