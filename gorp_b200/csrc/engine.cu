@@ -19,6 +19,7 @@
 
 #include "../../include/gorp_cuda.h"
 #include "host/fused.hpp"
+#include "host/walktables.hpp"
 #include "kernels/kernels.cuh"
 
 using namespace gorp;
@@ -290,62 +291,17 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
             c.dfa_direct.enabled = 1;
         }
     }
-    // chunk-walk DFA tier: class-indexed u16 rows + DEADSCAN / SKIP / FIN rows (see kernels.cuh: DfaWalkDev)
-    {
-        const size_t E = m.n_groups.size();
-        // Columns: the classes ordered by how often log text hits them (a static weight per ASCII character), then '\n'.
-        // A table that fits shared memory gets an odd column count (the rows of lanes that read the same column then
-        // fall into different banks); a larger one is read through L1/L2 and gets 32-byte aligned rows whose first
-        // sector holds the 16 hottest columns, so a warp-wide lookup touches fewer sectors and the hot set is smaller.
-        const size_t NL = C, dscan = S, fin_base = S + 16, R = fin_base + 1 + E;
-        const bool big = R * ((C + 1) | 1) * 2 > 200 * 1024;
-        const size_t K = big ? ((C + 1 + 15) / 16) * 16 : ((C + 1) | 1);
-        std::vector<uint32_t> weight(C, 0), col_of(C + 1), cls_of(C + 1);
-        for (uint32_t u = 0; u < 128; ++u) {
-            if (u == 0x0A) continue;
-            uint32_t w = 1;
-            if (u >= 'a' && u <= 'z') w = 8;
-            else if ((u >= '0' && u <= '9') || u == ' ') w = 6;
-            else if (u >= 'A' && u <= 'Z') w = 3;
-            else if (std::strchr(".-_/:=[](),'\"", static_cast<int>(u)) && u) w = 2;
-            weight[m.dfa.classmap[u]] += w;
-        }
-        for (size_t k = 0; k <= C; ++k) cls_of[k] = static_cast<uint32_t>(k);
-        std::stable_sort(cls_of.begin(), cls_of.begin() + C, [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
-        for (size_t k = 0; k <= C; ++k) col_of[cls_of[k]] = static_cast<uint32_t>(k);  // class -> column; NL (class id C) stays last
-        if (R <= 0xFFFF && K * 2 <= 0xFFFF && !std::getenv("GORP_SKIP_NEWTABLES")) {
-            std::vector<uint16_t> rows(((R * K + 7) / 8) * 8, 0);
-            for (size_t r = 0; r < R; ++r)
-                for (size_t k = 0; k < K; ++k) {
-                    size_t nx;
-                    if (k > NL) {
-                        nx = r;  // padding column, never addressed
-                    } else if (r < S) {
-                        if (k == NL) {
-                            nx = fin_base + 1 + m.dfa.accept_first[r];
-                        } else {
-                            const int32_t t = m.dfa.trans[r * C + cls_of[k]];
-                            nx = t < 0 ? dscan : static_cast<size_t>(t);
-                        }
-                    } else if (r == dscan) {
-                        nx = k == NL ? fin_base : dscan;
-                    } else if (r < fin_base) {
-                        nx = r == S + 1 ? 0 : r - 1;  // SKIP chain (swallows any unit, '\n' included)
-                    } else {
-                        nx = r;  // FIN: absorbing
-                    }
-                    rows[r * K + k] = static_cast<uint16_t>(nx);
-                }
-            std::vector<uint16_t> cls128(128), xcls(65536);
-            for (size_t u = 0; u < 65536; ++u) xcls[u] = static_cast<uint16_t>(col_of[m.dfa.classmap[u]]);
-            for (size_t u = 0; u < 128; ++u) cls128[u] = static_cast<uint16_t>(2 * (u == 0x0A ? NL : col_of[m.dfa.classmap[u]]));
-            c.dfawalk.table = upload(rows, c.owned);
-            c.dfawalk.n_rows = static_cast<uint32_t>(R);
-            c.dfawalk.K = static_cast<uint32_t>(K);
-            c.dfawalk.n_states = static_cast<uint32_t>(S);
-            c.dfawalk.fin_base = static_cast<uint32_t>(fin_base);
-            c.dfawalk.cls128 = upload(cls128, c.owned);
-            c.dfawalk.xcls = upload(xcls, c.owned);
+    // chunk-walk / line-walk DFA tier: class-indexed u16 rows + DEADSCAN / SKIP / FIN rows (host/walktables.hpp)
+    if (!std::getenv("GORP_SKIP_NEWTABLES")) {
+        const DfaWalkTable t = build_dfawalk_table(m);
+        if (t.available) {
+            c.dfawalk.table = upload(t.rows, c.owned);
+            c.dfawalk.n_rows = t.n_rows;
+            c.dfawalk.K = t.K;
+            c.dfawalk.n_states = t.n_states;
+            c.dfawalk.fin_base = t.fin_base;
+            c.dfawalk.cls128 = upload(t.cls128, c.owned);
+            c.dfawalk.xcls = upload(t.xcls, c.owned);
             c.dfawalk.enabled = 1;
         }
     }
@@ -443,65 +399,24 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                 c.cap_fast.enabled = 1;
             }
         }
-        // bucketed capture tier: one table per extraction, read through L1/L2 (kernels.cuh: CapImgDev)
-        if (E <= kCapMaxBuckets && !std::getenv("GORP_SKIP_NEWTABLES")) {
-            // K = classes + '\n' column, padded to an odd count (shared-memory banks, as for the DFA table)
-            const uint32_t Cn = m.symbols.n_classes, NL = Cn, K = (Cn + 1) | 1, row_bytes = K * 4;
-            uint32_t max_regs = 0;
-            for (size_t e = 0; e < E; ++e) max_regs = std::max(max_regs, m.tdfas[e].n_regs);
-            std::vector<uint32_t> cls128(128), image;
-            for (uint32_t u = 0; u < 128; ++u) cls128[u] = (u == 0x0A ? NL : m.symbols.classmap[u]) * 4;
-            std::vector<CapImgExt> fext(E);
-            bool ok = max_regs < 63;
-            for (size_t e = 0; e < E && ok; ++e) {
-                const Tdfa& t = m.tdfas[e];
-                const uint32_t Sx = t.n_states, rows = 2 * Sx + 17;
-                if (static_cast<uint64_t>(rows) * row_bytes >= (1u << 26) || (image.size() + static_cast<size_t>(rows) * K) * 4 >= (1ull << 31)) {
-                    ok = false;
-                    break;
-                }
-                while (image.size() % 4) image.push_back(0);  // 16-byte aligned tables (copied to shared memory with 128-bit loads)
-                fext[e] = {static_cast<uint32_t>(image.size() * 4), row_bytes, Sx, (Sx + 15) * row_bytes, (Sx + 16) * row_bytes,
-                           (Sx + 17) * row_bytes};
-                const size_t base = image.size();
-                image.resize(base + static_cast<size_t>(rows) * K);
-                auto put = [&](uint32_t r, uint32_t k, uint32_t next_row, uint32_t slot) {
-                    image[base + static_cast<size_t>(r) * K + k] = ((next_row * row_bytes) << 6) | slot;
-                };
-                for (uint32_t r = 0; r < rows; ++r)
-                    for (uint32_t k = 0; k < K; ++k) {
-                        if (k > NL) { put(r, k, r, max_regs); continue; }  // padding column, never addressed
-                        if (r < Sx) {
-                            if (k == NL) { put(r, k, Sx + 17 + r, max_regs); continue; }
-                            const uint32_t ent = t.trans[static_cast<size_t>(r) * Cn + k];
-                            const uint32_t nx = ent & 0xFFFFu, ol = ent >> 16;
-                            if (nx == 0xFFFFu) { put(r, k, Sx + 15, max_regs); continue; }
-                            const uint32_t o0 = t.op_off[ol], o1 = t.op_off[ol + 1];
-                            if (o1 == o0) put(r, k, nx, max_regs);
-                            else if (o1 - o0 == 1 && (t.ops[o0] & 0xFF) == 0xFF) put(r, k, nx, t.ops[o0] >> 8);
-                            else put(r, k, Sx + 16, max_regs);  // SLOW: replayed through the general tables
-                        } else if (r < Sx + 15) {
-                            put(r, k, r == Sx ? 0u : r - 1, max_regs);  // SKIP chain
-                        } else {
-                            put(r, k, r, max_regs);  // DEAD / SLOW / FRZ: absorbing
-                        }
-                    }
-            }
-            if (ok) {
-                image.resize(image.size() + 8, 0);  // the last table may be read 16 bytes at a time
-                c.capimg.image = upload(image, c.owned);
-                c.capimg.cls128 = upload(cls128, c.owned);
+        // bucketed capture tier: one table per extraction (host/walktables.hpp, kernels.cuh: CapImgDev)
+        if (!std::getenv("GORP_SKIP_NEWTABLES")) {
+            const CapImage img = build_cap_image(m, kCapMaxBuckets);
+            if (img.available) {
+                static_assert(sizeof(CapImageExt) == sizeof(CapImgExt), "host and device descriptors of a capture table must match");
+                std::vector<CapImgExt> fext(img.ext.size());
+                std::memcpy(fext.data(), img.ext.data(), fext.size() * sizeof(CapImgExt));
+                c.capimg.image = upload(img.image, c.owned);
+                c.capimg.cls128 = upload(img.cls128, c.owned);
                 c.capimg.ext = upload(fext, c.owned);
-                c.capimg.n_regs = max_regs;
+                c.capimg.n_regs = img.n_regs;
                 // shared memory for the table of the extraction a CTA works on: the largest table that still leaves room
                 // for two CTAs per SM (larger tables are read through L1/L2)
-                const size_t fixed = 512 + static_cast<size_t>(max_regs + 1) * kCapWalkThreads * 4;
+                const size_t fixed = 512 + static_cast<size_t>(img.n_regs + 1) * kCapWalkThreads * 4;
                 const size_t budget = fixed + 5 * 1024 < 110 * 1024 ? 110 * 1024 - fixed - 5 * 1024 : 0;
                 size_t best = 0;
-                for (size_t e = 0; e < E; ++e) {
-                    const size_t tb = static_cast<size_t>(m.tdfas[e].n_states + 17) * row_bytes;  // without the FRZ rows
-                    if (tb <= budget) best = std::max(best, tb);
-                }
+                for (const CapImageExt& x : img.ext)
+                    if (x.frz_off <= budget) best = std::max<size_t>(best, x.frz_off);  // (S + 17) rows: without the FRZ rows
                 c.capimg.smem_table_bytes = static_cast<uint32_t>((best + 15) & ~size_t(15));
                 c.capimg.enabled = capwalk_smem_bytes(c.capimg) <= 200 * 1024 ? 1u : 0u;
             }

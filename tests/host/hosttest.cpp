@@ -178,3 +178,123 @@ extern "C" int ht_compact_dfa(const void* blob, size_t len, int32_t* trans, int6
         return -1;
     }
 }
+
+// The big-definition text path interpreted the way kernels/dfawalk.cu (K0d / K2b) and kernels/capwalk.cu (K4b) run it:
+// '\n' split, combined DFA over the class-indexed table with SKIP / DEADSCAN / FIN rows in 16-unit blocks starting at
+// the aligned block that holds the line start, then the capture walk over the extraction's table image (smem_variant:
+// ids beyond DEAD read the DEAD row and the highest id seen survives; otherwise the physical FRZ rows), SLOW blocks
+// replayed through the general tables. Returns the line count, or -1 (err) / -2 (tables not available).
+#include "../../gorp_b200/csrc/host/walktables.hpp"
+
+extern "C" int64_t ht_run_walk(const void* blob, size_t len, const uint16_t* text, int64_t n_units, int smem_variant, int64_t cap_lines,
+                               int32_t* ext, int32_t* spans, int stride, char* err, int errlen) {
+    try {
+        CompiledDefinition def = parse_blob(blob, len);
+        DeviceModel m = build_device_model(def);
+        const DfaWalkTable D = build_dfawalk_table(m);
+        const CapImage I = build_cap_image(m, 4096);
+        if (!D.available || !I.available) return -2;
+        auto unit = [&](int64_t p) -> uint32_t { return p < n_units ? text[p] : 0x0Au; };
+        int64_t n_lines = 0, a = 0;
+        while (a < n_units) {
+            int64_t b = a;
+            while (b < n_units && text[b] != 0x0A) ++b;  // line = [a, b), its '\n' at b (virtual at n_units)
+            if (n_lines >= cap_lines) return -1;
+            // ---- DFA
+            int64_t q = a & ~int64_t(15);
+            uint32_t st = a - q ? D.n_states + static_cast<uint32_t>(a - q) : 0u;
+            while (st < D.fin_base) {
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t u = unit(q + k);
+                    const uint32_t col = u < 128 ? D.cls128[u] / 2u : D.xcls[u];
+                    st = D.rows[static_cast<size_t>(st) * D.K + col];
+                }
+                q += 16;
+            }
+            const int32_t e = static_cast<int32_t>(st - D.fin_base) - 1;
+            int32_t* out = spans + n_lines * stride;
+            for (int k = 0; k < stride; ++k) out[k] = -1;
+            ext[n_lines] = e;
+            if (e >= 0) {
+                // ---- capture
+                const CapImageExt& fx = I.ext[e];
+                const Tdfa& t = m.tdfas[e];
+                std::vector<int32_t> regs(I.n_regs + 1, -7);
+                const uint32_t S = fx.n_states, Cn = m.symbols.n_classes;
+                q = a & ~int64_t(15);
+                uint32_t cs = a - q ? (S + static_cast<uint32_t>(a - q) - 1) * fx.row_bytes : 0u;
+                while (cs < fx.dead_off) {
+                    const uint32_t st0 = cs;
+                    uint32_t fin = 0;
+                    for (int k = 0; k < 16; ++k) {
+                        const uint32_t u = unit(q + k);
+                        uint32_t c4;
+                        if (u < 128) {
+                            c4 = I.cls128[u];
+                        } else {
+                            c4 = 4u * m.symbols.classmap[u];
+                            if ((u & 0xFC00u) == 0xD800u && (unit(q + k + 1) & 0xFC00u) == 0xDC00u) c4 = 4u * m.symbols.pair_hi_class;
+                        }
+                        const uint32_t row = smem_variant ? std::min(cs, fx.dead_off) : cs;
+                        const uint32_t ent = I.image[(fx.tab_off + row + c4) / 4];
+                        cs = ent >> 6;
+                        fin = std::max(fin, cs);
+                        regs[ent & 63u] = static_cast<int32_t>(q + k - a);
+                    }
+                    if (smem_variant && fin >= fx.dead_off) cs = fin;
+                    if (cs == fx.slow_off) {  // replay the block through the general tables (kernels/capwalk.cu: cw_slow16)
+                        uint32_t row = st0 / fx.row_bytes;
+                        for (int k = 0; k < 16; ++k) {
+                            if (row >= S + 15) break;
+                            const int64_t p = q + k;
+                            const uint32_t u = unit(p);
+                            if (row >= S) {
+                                row = row == S ? 0u : row - 1;
+                                continue;
+                            }
+                            if (u == 0x0A) {
+                                row = S + 17 + row;
+                                break;
+                            }
+                            uint32_t sym = m.symbols.classmap[u];
+                            if ((u & 0xFC00u) == 0xD800u && p + 1 < n_units && (text[p + 1] & 0xFC00u) == 0xDC00u) sym = m.symbols.pair_hi_class;
+                            const uint32_t ent = t.trans[static_cast<size_t>(row) * Cn + sym];
+                            if ((ent & 0xFFFFu) == 0xFFFFu) {
+                                row = S + 15;
+                                continue;
+                            }
+                            const uint32_t ol = ent >> 16;
+                            for (uint32_t i = t.op_off[ol]; i < t.op_off[ol + 1]; ++i) {
+                                const uint32_t op = t.ops[i], src = op & 0xFFu;
+                                regs[op >> 8] = src == 0xFFu ? static_cast<int32_t>(p - a) : regs[src];
+                            }
+                            row = ent & 0xFFFFu;
+                        }
+                        cs = row * fx.row_bytes;
+                    }
+                    q += 16;
+                }
+                bool ok = cs >= fx.frz_off;
+                uint32_t s = 0;
+                if (ok) {
+                    s = (cs - fx.frz_off) / fx.row_bytes;
+                    ok = t.accepting[s] != 0;
+                }
+                if (!ok) {
+                    ext[n_lines] = -2 - e;
+                } else {
+                    for (uint32_t k = 0; k < t.n_slots && static_cast<int>(k) < stride; ++k) {
+                        const uint8_t f = t.fin[static_cast<size_t>(s) * t.n_slots + k];
+                        out[k] = f == 0xFF ? -1 : (f == 0xFE ? static_cast<int32_t>(b - a) : regs[f]);
+                    }
+                }
+            }
+            ++n_lines;
+            a = b + 1;
+        }
+        return n_lines;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}

@@ -46,3 +46,23 @@ def run(blob_bytes: bytes, text: np.ndarray, starts: np.ndarray, ends: np.ndarra
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return ext, spans[:, :stride], stats
+
+
+def run_walk(blob_bytes: bytes, text: np.ndarray, stride: int, smem_variant: bool):
+    """Interprets the tables of the big-definition text path (host/walktables.hpp) the way kernels/dfawalk.cu and
+    kernels/capwalk.cu walk them. Returns (ext, spans) or None when the tables are not available."""
+    lib = load()
+    text = np.ascontiguousarray(text, dtype=np.uint16)
+    cap = int((text == 10).sum()) + 2
+    ext = np.empty(cap, dtype=np.int32)
+    spans = np.full((cap, max(stride, 1)), -1, dtype=np.int32)
+    err = C.create_string_buffer(1024)
+    P = C.c_void_p
+    lib.ht_run_walk.restype = C.c_int64
+    n = lib.ht_run_walk(blob_bytes, C.c_size_t(len(blob_bytes)), P(text.ctypes.data), C.c_int64(len(text)), C.c_int(1 if smem_variant else 0),
+                        C.c_int64(cap), P(ext.ctypes.data), P(spans.ctypes.data), C.c_int(max(stride, 1)), err, C.c_int(1024))
+    if n == -2:
+        return None
+    if n < 0:
+        raise RuntimeError(err.value.decode())
+    return ext[:n], spans[:n, :stride]

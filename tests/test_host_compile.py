@@ -168,3 +168,38 @@ def test_product_dfa_language_vs_component_dfas():
                 break
         got = [] if p < 0 else al[p]
         assert got == want == m.match(jdkre.to_units(s)), s
+
+
+def compare_walk_tables(definition, lines, drop_last_newline=False):
+    """Tables of the big-definition text path (host/walktables.hpp: class-indexed DFA rows with SKIP / DEADSCAN / FIN,
+    per-extraction capture images with SKIP / DEAD / SLOW / FRZ) interpreted the way the kernels walk them — both the
+    shared-memory variant (no FRZ rows, highest id survives) and the L1/L2 variant — against the oracle."""
+    g = DefinitionReader.reader(definition).read()
+    o = gorp_oracle.Gorp(definition)
+    text, starts, ends = pack(lines)
+    if drop_last_newline:
+        text = text[:-1]
+    G = max(len(x.extractor_names) for x in o.extractions)
+    oe, osp = o.extract_batch(text, (starts, ends), threads=1)
+    for smem_variant in (True, False):
+        r = hostlib.run_walk(g.blob().bytes(), text, 2 * G, smem_variant)
+        assert r is not None
+        ext, spans = r
+        assert len(ext) == len(lines)
+        bad = [i for i in range(len(lines)) if ext[i] != oe[i] or (spans[i] != osp[i][:2 * G]).any()]
+        assert not bad, [(lines[i], int(ext[i]), int(oe[i]), spans[i].tolist(), osp[i].tolist()) for i in bad[:5]]
+
+
+@pytest.mark.parametrize("case", ALL_DEFS)
+def test_walk_tables_reproduce_oracle(case):
+    lines = [c[0] for c in case[1]] + TRICKY_LINES
+    compare_walk_tables(case[0], lines)
+    compare_walk_tables(case[0], [s for s in lines if s] + ["[1]: GET 2ms /tail"], drop_last_newline=True)
+
+
+@pytest.mark.parametrize("name", ["weblog", "syslog200", "utf16mix"])
+def test_walk_tables_on_config_definitions(name):
+    from gorp_b200 import corpus
+    d, _ = corpus.CONFIGS[name]
+    gen = {"weblog": corpus.weblog_lines, "syslog200": corpus.syslog200_lines, "utf16mix": corpus.utf16_mix_lines}[name]
+    compare_walk_tables(d, gen(800) + TRICKY_LINES)
