@@ -187,6 +187,21 @@ def test_full_size_properties():
     assert (np.diff(b.line_off) > 0).all()
 
 
+@pytest.mark.parametrize("name,n,reps", [("weblog", 40000, 40), ("syslog200", 40000, 40), ("utf16mix", 30000, 30)])
+def test_full_size_properties_big_definitions(name, n, reps):
+    """Configs #3-#5 at scale (1.2-1.6 M lines: many work items per extraction, many items per CTA): the results of a
+    tiled corpus are the tiled results of the block, which is checked line by line against the oracle."""
+    d, gen = corpus.CONFIGS[name]
+    block = gen(n, seed=321)
+    g, b1, _ = check_against_oracle(d, text=block)
+    b = g.extract_batch_text(np.tile(block, reps))
+    assert b.n_lines == reps * b1.n_lines
+    assert (b.histogram == reps * b1.histogram).all()
+    assert (b.ext_id.reshape(reps, -1) == b1.ext_id[None, :]).all()
+    assert (b.spans.reshape(reps, b1.n_lines, -1) == b1.spans[None, :, :]).all()
+    assert (np.diff(b.line_off).reshape(reps, -1) == np.diff(b1.line_off)[None, :]).all()
+
+
 TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
          "dfawalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1"},
          "linewalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2"},
