@@ -301,6 +301,9 @@ def test_multi_device_engine(monkeypatch):
     text = gen(120000, seed=9)
     check_against_oracle(d, text=text, gorp=g)
     check_against_oracle(d, text=text[:-1], gorp=g)
+    b16, b8 = g.extract_batch_text(text), g.extract_batch_text_latin1(text.astype(np.uint8))  # the corpus is ASCII
+    assert (b8.ext_id == b16.ext_id).all() and (b8.line_off == b16.line_off).all() and (b8.spans == b16.spans).all()
+    assert (b8.histogram == b16.histogram).all()
     lines = corpus.weblog_lines(5000, seed=4)
     g3 = DefinitionReader.reader(corpus.WEBLOG_DEF).read(devices=list(range(n)))
     check_against_oracle(corpus.WEBLOG_DEF, lines=lines, gorp=g3)
