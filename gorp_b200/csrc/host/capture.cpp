@@ -724,6 +724,71 @@ class TdfaBuilder {
 
 }  // namespace
 
+namespace {
+
+// Moore minimisation of the tagged automaton: two states are merged when they are indistinguishable for every input
+// suffix — same acceptance and final register recipe, and for every class the same command list and equivalent
+// successors. The command lists act on one global register file, so equal lists mean equal effects. Determinisation
+// with register maps leaves many such duplicates (states reached with different histories but the same future).
+void minimise_tdfa(Tdfa& t) {
+    const size_t S = t.n_states, C = t.n_classes, G = t.n_slots;
+    if (S < 2) return;
+    std::vector<uint32_t> block(S);
+    {
+        std::map<std::vector<uint8_t>, uint32_t> ids;
+        for (size_t s = 0; s < S; ++s) {
+            std::vector<uint8_t> key(t.fin.begin() + static_cast<long>(s * G), t.fin.begin() + static_cast<long>((s + 1) * G));
+            key.push_back(t.accepting[s]);
+            block[s] = ids.emplace(std::move(key), static_cast<uint32_t>(ids.size())).first->second;
+        }
+    }
+    size_t n_blocks = 0;
+    for (;;) {
+        std::map<std::vector<uint32_t>, uint32_t> ids;
+        std::vector<uint32_t> next_block(S);
+        std::vector<uint32_t> key(2 * C + 1);
+        for (size_t s = 0; s < S; ++s) {
+            key[0] = block[s];
+            for (size_t c = 0; c < C; ++c) {
+                const uint32_t ent = t.trans[s * C + c], nx = ent & 0xFFFFu;
+                key[1 + 2 * c] = nx == 0xFFFFu ? 0xFFFFFFFFu : block[nx];
+                key[2 + 2 * c] = nx == 0xFFFFu ? 0u : ent >> 16;
+            }
+            next_block[s] = ids.emplace(key, static_cast<uint32_t>(ids.size())).first->second;
+        }
+        const bool stable = ids.size() == n_blocks;
+        n_blocks = ids.size();
+        block.swap(next_block);
+        if (stable) break;
+    }
+    if (n_blocks == S) return;
+    // new ids in order of first occurrence (state 0 stays the start state), one representative per block
+    std::vector<uint32_t> id_of_block(n_blocks, 0xFFFFFFFFu), rep;
+    for (size_t s = 0; s < S; ++s)
+        if (id_of_block[block[s]] == 0xFFFFFFFFu) {
+            id_of_block[block[s]] = static_cast<uint32_t>(rep.size());
+            rep.push_back(static_cast<uint32_t>(s));
+        }
+    Tdfa m;
+    m.n_states = static_cast<uint32_t>(rep.size());
+    m.n_classes = t.n_classes;
+    m.n_regs = t.n_regs;
+    m.n_slots = t.n_slots;
+    m.op_off = t.op_off;
+    m.ops = t.ops;
+    for (uint32_t s : rep) {
+        for (size_t c = 0; c < C; ++c) {
+            const uint32_t ent = t.trans[static_cast<size_t>(s) * C + c], nx = ent & 0xFFFFu;
+            m.trans.push_back(nx == 0xFFFFu ? ent : (id_of_block[block[nx]] | (ent & 0xFFFF0000u)));
+        }
+        m.accepting.push_back(t.accepting[s]);
+        m.fin.insert(m.fin.end(), t.fin.begin() + static_cast<long>(s * G), t.fin.begin() + static_cast<long>((s + 1) * G));
+    }
+    t = std::move(m);
+}
+
+}  // namespace
+
 Tdfa build_tdfa(const CaptureProgram& p, const SymbolClasses& sc, size_t max_states, size_t max_regs) {
     if (max_states > 0xFFFE) max_states = 0xFFFE;
     if (max_regs > 250) max_regs = 250;
@@ -739,6 +804,7 @@ Tdfa build_tdfa(const CaptureProgram& p, const SymbolClasses& sc, size_t max_sta
         }
         t.n_regs += 1;
     }
+    minimise_tdfa(t);
     return t;
 }
 

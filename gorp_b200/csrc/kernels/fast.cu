@@ -122,7 +122,7 @@ void k2_dfa_direct(const Launch& L, const DfaDirectDev& d, const uint16_t* text,
                    int32_t* ext_id) {
     if (n_lines <= 0) return;
     const size_t smem = static_cast<size_t>(d.n_rows) * 512;
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
         cudaFuncSetAttribute(dfa_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfa_direct_kernel, kFastThreads, smem);
@@ -140,7 +140,7 @@ void k4_tdfa_fast(const Launch& L, const TdfaFastDev& f, const CapDev& c, const 
                   const int64_t* line_off, int64_t n_lines, uint32_t span_stride, int32_t* ext_id, int32_t* spans) {
     if (n_lines <= 0) return;
     const size_t smem = static_cast<size_t>(f.image_words) * 4 + static_cast<size_t>(f.n_regs + 2) * kCapThreads * 4;
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
         cudaFuncSetAttribute(tdfa_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdfa_fast_kernel, kCapThreads, smem);
