@@ -1456,6 +1456,7 @@ int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_d
         } else {
             model = build_device_model(eng->def);
             fused = build_fused(model);
+            finalize_device_model(model, fused);
         }
         int avail = 0;
         if (cudaGetDeviceCount(&avail) != cudaSuccess || avail == 0) {

@@ -724,8 +724,6 @@ class TdfaBuilder {
 
 }  // namespace
 
-namespace {
-
 // Moore minimisation of the tagged automaton: two states are merged when they are indistinguishable for every input
 // suffix — same acceptance and final register recipe, and for every class the same command list and equivalent
 // successors. The command lists act on one global register file, so equal lists mean equal effects. Determinisation
@@ -787,8 +785,6 @@ void minimise_tdfa(Tdfa& t) {
     t = std::move(m);
 }
 
-}  // namespace
-
 Tdfa build_tdfa(const CaptureProgram& p, const SymbolClasses& sc, size_t max_states, size_t max_regs) {
     if (max_states > 0xFFFE) max_states = 0xFFFE;
     if (max_regs > 250) max_regs = 250;
@@ -804,7 +800,6 @@ Tdfa build_tdfa(const CaptureProgram& p, const SymbolClasses& sc, size_t max_sta
         }
         t.n_regs += 1;
     }
-    minimise_tdfa(t);
     return t;
 }
 

@@ -51,4 +51,9 @@ struct Tdfa {
 // Throws UnsupportedError when the determinisation exceeds the limits.
 Tdfa build_tdfa(const CaptureProgram& p, const SymbolClasses& sc, size_t max_states = 60000, size_t max_regs = 250);
 
+// Merges the states of `t` that no input suffix can tell apart (same acceptance, final recipe, command lists and equivalent
+// successors). Used for the per-extraction tables of the bucketed capture walk; the one-pass product automaton
+// (host/fused.hpp) is minimised as a whole and is built from the unminimised automata.
+void minimise_tdfa(Tdfa& t);
+
 }  // namespace gorp

@@ -278,4 +278,9 @@ FusedAutomaton build_fused(const DeviceModel& m, size_t max_states, size_t max_o
     return A;
 }
 
+void finalize_device_model(DeviceModel& m, const FusedAutomaton& fused) {
+    if (fused.available) return;
+    for (Tdfa& t : m.tdfas) minimise_tdfa(t);
+}
+
 }  // namespace gorp

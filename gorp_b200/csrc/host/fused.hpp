@@ -49,4 +49,9 @@ struct FusedAutomaton {
 
 FusedAutomaton build_fused(const DeviceModel& m, size_t max_states = 2048, size_t max_op_slots = 120);
 
+// Last load-time step: a definition that does not get the one-pass automaton takes the index -> DFA -> bucket -> capture
+// path, whose per-extraction tables live in shared memory — their automata are minimised. (With the one-pass automaton
+// the per-extraction automata only serve the List<String> form and stay as built.)
+void finalize_device_model(DeviceModel& m, const FusedAutomaton& fused);
+
 }  // namespace gorp

@@ -14,6 +14,7 @@ extern "C" int ht_run(const void* blob, size_t len, const uint16_t* text, const 
     try {
         CompiledDefinition def = parse_blob(blob, len);
         DeviceModel m = build_device_model(def);
+        finalize_device_model(m, build_fused(m));  // what gorp_engine_create does
         if (stats) {
             stats[0] = m.dfa.n_states;
             stats[1] = m.dfa.n_classes;
@@ -143,6 +144,7 @@ extern "C" int ht_tdfa_sizes(const void* blob, size_t len, uint32_t* out, int ca
     try {
         CompiledDefinition def = parse_blob(blob, len);
         DeviceModel m = build_device_model(def);
+        finalize_device_model(m, build_fused(m));
         int n = 0;
         for (auto& t : m.tdfas) {
             if (n < cap) {
@@ -191,6 +193,7 @@ extern "C" int64_t ht_run_walk(const void* blob, size_t len, const uint16_t* tex
     try {
         CompiledDefinition def = parse_blob(blob, len);
         DeviceModel m = build_device_model(def);
+        finalize_device_model(m, build_fused(m));
         const DfaWalkTable D = build_dfawalk_table(m);
         const CapImage I = build_cap_image(m, 4096);
         if (!D.available || !I.available) return -2;
