@@ -9,12 +9,18 @@
 
 using namespace gorp;
 
+static int g_force_minimise = 0;
+// 1: ht_run minimises every capture automaton (host/capture.hpp: minimise_tdfa) whatever path the definition takes
+extern "C" void ht_set_force_minimise(int on) { g_force_minimise = on; }
+
 extern "C" int ht_run(const void* blob, size_t len, const uint16_t* text, const int64_t* starts, const int64_t* ends, int64_t n,
                       int32_t* ext, int32_t* spans, int stride, uint32_t* stats, char* err, int errlen) {
     try {
         CompiledDefinition def = parse_blob(blob, len);
         DeviceModel m = build_device_model(def);
         finalize_device_model(m, build_fused(m));  // what gorp_engine_create does
+        if (g_force_minimise)
+            for (Tdfa& t : m.tdfas) minimise_tdfa(t);
         if (stats) {
             stats[0] = m.dfa.n_states;
             stats[1] = m.dfa.n_classes;

@@ -203,3 +203,19 @@ def test_walk_tables_on_config_definitions(name):
     d, _ = corpus.CONFIGS[name]
     gen = {"weblog": corpus.weblog_lines, "syslog200": corpus.syslog200_lines, "utf16mix": corpus.utf16_mix_lines}[name]
     compare_walk_tables(d, gen(800) + TRICKY_LINES)
+
+
+def test_minimised_capture_automata_reproduce_oracle():
+    """minimise_tdfa (Moore minimisation of the tagged automata, used for the tables of the bucketed capture walk) on every
+    definition and fuzz pattern, including the small ones the engine leaves unminimised: same outcomes and spans."""
+    lib = hostlib.load()
+    lib.ht_set_force_minimise(1)
+    try:
+        for case in ALL_DEFS:
+            compare_host_tables(case[0], [c[0] for c in case[1]] + TRICKY_LINES)
+        rng = np.random.default_rng(3)
+        for definition in FUZZ_PATTERNS:
+            lines = ["".join(rng.choice(list("abcd: "), size=rng.integers(0, 24))) for _ in range(1500)]
+            compare_host_tables(definition, lines)
+    finally:
+        lib.ht_set_force_minimise(0)
