@@ -259,21 +259,23 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     per_step = []
+    gap_ms = float(os.environ.get("GORP_BENCH_GAP_MS", "0"))  # diagnostics only: idle time between steps
     for _ in range(args.steps):
+        if os.environ.get("GORP_BENCH_PER_STEP"):  # diagnostics only: a pair of events per step
+            if gap_ms:
+                torch.cuda.synchronize()
+                time.sleep(gap_ms / 1e3)
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         step(_ffi.FLAG_TIME_KERNELS)
-        if os.environ.get("GORP_BENCH_PER_STEP"):  # diagnostics only: an event per step
+        if os.environ.get("GORP_BENCH_PER_STEP"):
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
-            per_step.append(ev)
+            per_step.append((ev0, ev))
     e1.record()
     barrier()
     if per_step:
-        prev = e0
-        ts = []
-        for ev in per_step:
-            ts.append(round(prev.elapsed_time(ev), 2))
-            prev = ev
-        print("[bench] ms per step:", ts, file=sys.stderr)
+        print("[bench] ms per step:", [round(a.elapsed_time(b), 2) for a, b in per_step], file=sys.stderr)
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:  # every rank holds the job-wide histogram: its sum is the job's line count
