@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the gorp batch extraction path (BASELINE.json metric).
+"""bench.py — benchmark of the gorp batch extraction path (BASELINE.json metric) over all five BASELINE configs.
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A step = one pass of the hot path (newline index -> combined DFA -> capture -> span offsets -> histogram) over one
-batch of synthetic access-log text: config #2 of BASELINE.json (README Put/Get/OtherRequest definition, 100 M lines
-per GPU, a seeded 1 M-line block tiled in HBM). N > 1: one process per GPU (torchrun), lines sharded as independent
-contiguous ranges, no data-path collective ("weak" scaling: 100 M lines per GPU).
+A step = one pass of the hot path (newline index -> combined DFA -> capture -> result rows -> histogram) over one
+batch of synthetic log text resident in HBM. N > 1: one process per GPU (torchrun), lines sharded as independent
+contiguous ranges, tables replicated, no data-path collective ("weak" scaling: the same lines per GPU for every N).
 
-  value        whole-job lines/s with the text already resident in HBM (device-resident C-ABI entry point)
-  e2e          same metric through gorp_extract_text with HOST buffers: pinned host text -> H2D -> kernels ->
-               D2H of every result array, all inside the timed region
-  roofline     dominant kernel: algorithmic input bytes per launch / its CUDA-event time, vs measured HBM peak
+  value        config #2 (README definition, 100 M lines per GPU), whole-job lines/s, device-resident C-ABI entry point
+  configs[]    the same measurement for config #4 (200 extractions — the config the 40 %-of-HBM target is stated on),
+               #5, #3 and #1: {workload, lines, ms_per_step, value, roofline{kernel, frac, whole_step_frac, traffic},
+               parity{...}} — config #4 first
+  e2e          config #2 through gorp_extract_text with HOST buffers: pinned host text -> H2D -> kernels -> D2H of
+               every result array, all inside the timed region
+  roofline     dominant kernel of config #2: algorithmic input bytes per launch / its CUDA-event time vs measured HBM peak
   cpu_baseline the oracle's C restatement of the reference loop on the host cores (JVM unavailable here)
 
---impl reference times that CPU restatement alone (the reference is pure Java; no JVM exists in this image).
+Parity inside the bench (the parity tests proper are tests/ -m gpu): per config, the order-independent 64-bit hash of
+(line index, ext_id, spans) of the first block of lines computed from the GPU result must equal the hash computed
+from the CPU oracle's result for the same lines, and the batch histogram must equal the tiled block's.
+
+--impl reference times the CPU restatement alone (the reference is pure Java; no JVM exists in this image), same
+`config` as this arm, on a bounded sample of it per step.
 """
 from __future__ import annotations
 
@@ -38,11 +45,12 @@ WORKLOADS = {
     "readme": ("config#2 README Put/Get/OtherRequest 3-extraction definition, synthetic access-log lines", 1_000_000),
     "simple": ("config#1 samples/simple.grp, synthetic matching/non-matching lines", 1_000_000),
     "weblog": ("config#3 ~20-extraction nginx/Apache access+error definition with parametric templates, mixed line lengths", 200_000),
-    "syslog200": ("config#4 200-extraction definition, combined DFA outgrows shared memory (L2-resident table)", 200_000),
+    "syslog200": ("config#4 200-extraction definition, combined DFA outgrows shared memory", 200_000),
     "utf16mix": ("config#5 nginx/Apache definition, non-ASCII UTF-16 + divergence characters + 10 KB outlier lines", 200_000),
 }
-WORKLOAD, BLOCK_LINES = WORKLOADS["readme"]
-NCU_DRAM_BYTES_PER_TEXT_BYTE = {"k0_chunkwalk_extract": (1.370340e9 + 0.319971e9) / (8_000_000 * 62.612088 * 2)}
+SEED_OF = {"simple": 1, "readme": 2, "weblog": 3, "syslog200": 4, "utf16mix": 5}
+EXTRA_CONFIGS = ["syslog200", "utf16mix", "weblog", "simple"]  # configs[] order: the 40 %-target config first
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # written by tools_ncu_traffic.py from an ncu --set full capture
 
 
 def hbm_peak():
@@ -55,8 +63,16 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """{workload: {kernel: {"dram_bytes_per_text_byte": x, "source": file}}} from the committed ncu capture, or {}."""
+    try:
+        return json.load(open(TRAFFIC_FILE))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -116,9 +132,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_block(rank, workload="readme"):
+def make_block(rank, workload):
     from gorp_b200 import corpus
-    return corpus.CONFIGS[workload][1](BLOCK_LINES, seed=0x5EED0000 + {"simple": 1, "readme": 2, "weblog": 3, "syslog200": 4, "utf16mix": 5}[workload] + 16 * rank)
+    return corpus.CONFIGS[workload][1](WORKLOADS[workload][1], seed=0x5EED0000 + SEED_OF[workload] + 16 * rank)
 
 
 def definition_of(workload):
@@ -126,19 +142,40 @@ def definition_of(workload):
     return corpus.CONFIGS[workload][0]
 
 
+def config_dict(workload, lines_per_gpu, block_units, world, n_bins):
+    """The `config` object of a bench line; the reference arm prints the same object."""
+    desc, block_lines = WORKLOADS[workload]
+    reps = max(1, lines_per_gpu // block_lines)
+    n_units = reps * block_units
+    return {"workload": desc, "lines_per_gpu": reps * block_lines, "units_per_gpu": n_units, "bytes_per_gpu": n_units * 2,
+            "block": "%d-line seeded block (per-rank seed) tiled %dx in HBM" % (block_lines, reps),
+            "l2": "input (%.1f GB) is far larger than L2, no flush needed" % (n_units * 2 / 1e9),
+            "parallelism": "lines sharded per GPU as contiguous ranges, tables replicated; no data-path collective"
+                           + (", one NCCL all-reduce of the %d-bin histogram per step" % n_bins if world > 1 else "")}
+
+
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU algorithm (C restatement, all host threads) on a bounded sample per step."""
+    """Reference arm: the reference's CPU algorithm (C restatement, all host threads). Same config as the GPU arm; every
+    step processes a bounded sample of it (as many lines of the workload as keep the whole run within a few minutes)."""
     if rank != 0:
         return
-    from gorp_b200 import corpus
     from oracle import gorp_oracle
     cores = os.cpu_count() or 1
+    desc, block_lines = WORKLOADS[args.workload]
     block = make_block(0, args.workload)
-    reps = max(1, args.ref_lines // BLOCK_LINES)
+    o = gorp_oracle.Gorp(definition_of(args.workload))
+    bst = gorp_oracle.split_lines(block)
+    o.extract_batch(block, bst, threads=cores)  # build + page-in
+    t0 = time.perf_counter()
+    o.extract_batch(block, bst, threads=cores)
+    rate = block_lines / max(time.perf_counter() - t0, 1e-6)
+    total_lines = (args.lines_per_gpu // block_lines) * block_lines * world
+    budget = args.ref_budget_s / max(args.steps + args.warmup, 1)
+    sample_lines = total_lines if args.ref_lines == 0 else args.ref_lines
+    sample_lines = int(min(sample_lines, max(rate * budget * 0.8, block_lines)))
+    reps = max(1, sample_lines // block_lines)
     text = np.tile(block, reps)
     starts, ends = gorp_oracle.split_lines(text)
-    o = gorp_oracle.Gorp(definition_of(args.workload))
-    o.extract_batch(block, gorp_oracle.split_lines(block), threads=cores)  # build + page-in
     for _ in range(args.warmup):
         o.extract_batch(text, (starts, ends), threads=cores)
     t0 = time.perf_counter()
@@ -147,81 +184,52 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / args.steps
     n = len(starts)
     val = n / dt
-    sample = "%d lines (%.2f GB UTF-16) of the same synthetic workload per step" % (n, text.nbytes / 1e9)
+    n_bins = len(o.extractions) + 2
+    sample = "%d lines (%.2f GB UTF-16) of the config's %d lines per step, all %d host threads" % (n, text.nbytes / 1e9, total_lines, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "lines/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic", "input_gb_per_s": text.nbytes / dt / 1e9,
-        "config": {"workload": WORKLOAD, "lines_per_step": n, "note": "reference is pure Java and no JVM exists in this image: "
-                   "C restatement of Gorp.extract (oracle/gorp_oracle.c), one extract per line, static partition over host threads"},
+        "config": config_dict(args.workload, args.lines_per_gpu, block.size, world, n_bins),
+        "reference_note": "the reference is pure Java and no JVM exists in this image: C restatement of Gorp.extract "
+                          "(oracle/gorp_oracle.c), one extract per line, static partition over host threads; a rate metric, "
+                          "measured on a bounded sample of the config per step",
         "cpu_baseline": {"value": val, "unit": "lines/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lines-per-gpu", type=int, default=100_000_000)
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--ref-lines", type=int, default=16_000_000)
-    ap.add_argument("--cpu-lines", type=int, default=16_000_000)
-    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
-    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only")
-    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics: do not run nvidia-smi beside the timed region")
-    ap.add_argument("--workload", default="readme", choices=sorted(WORKLOADS), help="BASELINE.json config (default: #2, the headline)")
-    args = ap.parse_args()
-    global WORKLOAD, BLOCK_LINES
-    WORKLOAD, BLOCK_LINES = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+class Env:
+    pass
 
-    import torch
-    import torch.distributed as dist
-    from gorp_b200 import build as gbuild
-    gbuild.build()
-    from gorp_b200 import _ffi, corpus
-    from gorp_b200.api import Blob, _check
-    lib = _ffi.lib
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    # ---- workload: seeded block tiled to lines_per_gpu in HBM
-    block = make_block(rank, args.workload)
-    reps = max(1, args.lines_per_gpu // BLOCK_LINES)
-    n_lines = reps * BLOCK_LINES
+def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None, keep=False):
+    """One config, device-resident: returns the result dict (and, with keep=True, the engine / block for the e2e leg)."""
+    torch, dist, lib, _ffi, Blob, _check, cudart = env.torch, env.dist, env.lib, env.ffi, env.Blob, env.check, env.cudart
+    from gorp_b200 import parityhash, sharding
+    from oracle import gorp_oracle
+    rank, world, dev = env.rank, env.world, env.dev
+    desc, block_lines = WORKLOADS[workload]
+    block = make_block(rank, workload)
+    reps = max(1, lines_per_gpu // block_lines)
+    n_lines = reps * block_lines
     d_block = torch.from_numpy(block.view(np.int16)).to(dev)
     d_text = d_block.repeat(reps)
+    del d_block
     n_units = d_text.numel()
     in_bytes = n_units * 2
-    blob = Blob.from_definition(definition_of(args.workload))
+    blob = Blob.from_definition(definition_of(workload))
+    n_bins = blob.info()[2] + 2
     eng = C.c_void_p()
-    devs = (C.c_int * 1)(local_rank)
+    devs = (C.c_int * 1)(env.local_rank)
+    t0 = time.perf_counter()
     _check(lib.gorp_engine_create(blob._ptr, blob.length, devs, 1, C.byref(eng)))
+    create_s = time.perf_counter() - t0
     stream = torch.cuda.current_stream().cuda_stream
     dres = _ffi.DeviceResult()
-
-    # N > 1: the one (optional) collective of the path — all-reduce of the per-extraction histogram (E + 2 int64) over
-    # NCCL, every step, inside the timed region
-    from gorp_b200 import sharding
-    n_bins = blob.info()[2] + 2
     d_hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
-    try:
-        from cuda.bindings import runtime as cudart
-    except Exception:  # noqa: BLE001
-        from cuda import cudart
-    # the batch is the seeded block tiled `reps` times: its histogram must be reps x the block's (checked after warm-up,
-    # an end-to-end sanity check of the timed path at full size; the parity tests proper are tests/ -m gpu)
+
+    # the block through the host-buffer call: its histogram (the tiled batch must give reps x that)
     res0 = _ffi.Result()
     _check(lib.gorp_extract_text(eng, block.ctypes.data, block.size, C.byref(res0)))
     block_hist = np.ctypeslib.as_array(res0.histogram, (n_bins,)).copy()
@@ -230,6 +238,7 @@ def main():
     def step(flags=0):
         _check(lib.gorp_extract_text_device(eng, 0, d_text.data_ptr(), n_units, stream, flags, C.byref(dres)))
         if world > 1:
+            # the one (optional) collective of the path: all-reduce of the per-extraction histogram, every step
             (err,) = cudart.cudaMemcpyAsync(d_hist.data_ptr(), dres.d_histogram, n_bins * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, stream)
             assert int(err) == 0, err
             sharding.allreduce_histogram(d_hist)
@@ -239,28 +248,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if not args.no_clock_sampler:
-        sampler.launch()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
     assert dres.n_lines == n_lines, (dres.n_lines, n_lines)
     (err,) = cudart.cudaMemcpyAsync(d_hist.data_ptr(), dres.d_histogram, n_bins * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, stream)
     assert int(err) == 0, err
     assert (d_hist.cpu().numpy() == reps * block_hist).all(), (d_hist.cpu().numpy().tolist(), (reps * block_hist).tolist())
+    # parity at full size: hash of the first block's rows (GPU result of the timed path) == hash of the oracle's rows
+    ext_t, sp_t = parityhash.device_results(dres, dev)
+    first_line = rank * n_lines
+    gpu_prefix = parityhash.hash_torch(first_line, ext_t[:block_lines], sp_t[:block_lines])
+    gpu_total = parityhash.hash_torch(first_line, ext_t, sp_t)
+    o = gorp_oracle.Gorp(definition_of(workload))
+    cores = os.cpu_count() or 1
+    bst = gorp_oracle.split_lines(block)
+    oe, osp = o.extract_batch(block, bst, threads=cores)
+    stride = int(dres.span_stride)
+    cpu_prefix = parityhash.hash_numpy(first_line, oe, osp[:, :stride])
+    assert gpu_prefix == cpu_prefix, "parity hash mismatch on %s: gpu %x cpu %x" % (workload, gpu_prefix, cpu_prefix)
+    del ext_t, sp_t
     names = (C.c_char_p * 16)()
     tot = (C.c_double * 16)()
     cnt, calls, launches = C.c_int(), C.c_int64(), C.c_int64()
     _check(lib.gorp_kernel_times(eng, 0, names, tot, 16, C.byref(cnt), C.byref(calls), C.byref(launches), 1))
 
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     per_step = []
     gap_ms = float(os.environ.get("GORP_BENCH_GAP_MS", "0"))  # diagnostics only: idle time between steps
-    for _ in range(args.steps):
+    for _ in range(steps):
         if os.environ.get("GORP_BENCH_PER_STEP"):  # diagnostics only: a pair of events per step
             if gap_ms:
                 torch.cuda.synchronize()
@@ -275,22 +295,79 @@ def main():
     e1.record()
     barrier()
     if per_step:
-        print("[bench] ms per step:", [round(a.elapsed_time(b), 2) for a, b in per_step], file=sys.stderr)
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
+        print("[bench] %s ms per step:" % workload, [round(a.elapsed_time(b), 2) for a, b in per_step], file=sys.stderr)
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1) / steps
     if world > 1:  # every rank holds the job-wide histogram: its sum is the job's line count
         assert int(d_hist.sum().item()) == n_lines * world, (int(d_hist.sum().item()), n_lines * world)
     _check(lib.gorp_kernel_times(eng, 0, names, tot, 16, C.byref(cnt), C.byref(calls), C.byref(launches), 1))
-    kern = {names[i].decode(): tot[i] / max(calls.value, 1) for i in range(cnt.value)}
+    kern = {}
+    for i in range(cnt.value):  # a kernel that is marked twice in one call (retry) adds up
+        kern[names[i].decode()] = kern.get(names[i].decode(), 0.0) + tot[i] / max(calls.value, 1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    h = torch.tensor([gpu_total & 0xFFFFFFFF, gpu_total >> 32], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # 64-bit modular sum over ranks: 32-bit halves, carried
+        dist.all_reduce(h, op=dist.ReduceOp.SUM)
     ms_max = float(t.item())
+    lo, hi = int(h[0].item()), int(h[1].item())
+    corpus_hash = (lo + (hi << 32)) & ((1 << 64) - 1)
     total_lines = n_lines * world
-    value = total_lines / (ms_max / 1e3)
+    peak, peak_src = hbm_peak()
+    dom = max(kern, key=kern.get) if kern else None
+    roof = None
+    if dom:
+        ach = in_bytes / (kern[dom] / 1e3) / 1e9
+        tr = ncu_traffic().get(workload, {})
+        per_kernel = {k: v["dram_bytes_per_text_byte"] * in_bytes for k, v in tr.items() if k in kern}
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": per_kernel.get(dom),
+                "traffic_step": sum(per_kernel.values()) if per_kernel and len(per_kernel) == len(kern) else None,
+                "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum per text byte (%s) x bytes of this launch"
+                                   % tr[dom]["source"]) if dom in tr else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": in_bytes,
+                "kernel_ms": kern[dom], "all_kernels_ms": kern,
+                "whole_step_frac": (in_bytes / (ms_max / 1e3) / 1e9) / peak,
+                "whole_step_frac_of_8TBps": (in_bytes / (ms_max / 1e3) / 1e9) / 8000.0}
+    out = {"workload": desc, "key": workload, "lines": total_lines, "lines_per_gpu": n_lines, "bytes_per_gpu": in_bytes,
+           "ms_per_step": ms_max, "value": total_lines / (ms_max / 1e3), "unit": "lines/s",
+           "input_gb_per_s": in_bytes * world / (ms_max / 1e3) / 1e9, "steps": steps, "roofline": roof,
+           "parity": {"prefix_lines_per_rank": block_lines, "prefix_hash_gpu": "%016x" % gpu_prefix,
+                      "prefix_hash_cpu_oracle": "%016x" % cpu_prefix, "prefix_equal": True,
+                      "corpus_hash": "%016x" % corpus_hash, "histogram_equals_tiled_block": True,
+                      "what": "order-independent 64-bit hash of (global line index, ext_id, spans) — gorp_b200/parityhash.py"},
+           "gpu_launches": int(launches.value), "engine_create_s": create_s,
+           "config": config_dict(workload, lines_per_gpu, block.size, world, n_bins)}
+    # CPU baseline on rank 0: bounded sample of the same workload
+    if rank == 0 and not env.args.skip_cpu:
+        creps = max(1, env.args.cpu_lines // block_lines)
+        ctext = np.tile(block, creps)
+        cst = gorp_oracle.split_lines(ctext)
+        t0 = time.perf_counter()
+        o.extract_batch(ctext, cst, threads=cores)
+        cdt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        o.extract_batch(block, bst, threads=1)
+        cdt1 = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(cst[0]) / cdt, "unit": "lines/s", "cores": cores, "kind": "port",
+                               "sample": "%d lines (%.2f GB) of the same workload, all %d host threads; 1 thread: %.0f lines/s"
+                                         % (len(cst[0]), ctext.nbytes / 1e9, cores, block_lines / cdt1),
+                               "note": "C restatement of the reference's Gorp.extract loop (JVM unavailable in this image)"}
+    if keep:
+        return out, clocks, (eng, block, reps, n_units, in_bytes, barrier)
+    del d_text
+    lib.gorp_engine_destroy(eng)
+    torch.cuda.empty_cache()
+    return out, clocks, None
 
-    # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H inside the timed region)
-    e2e = None
+
+def e2e_run(env, kept, workload):
+    """config #2 end to end through the host-buffer C ABI (H2D + kernels + D2H inside the timed region)."""
+    torch, dist, lib, _ffi, _check = env.torch, env.dist, env.lib, env.ffi, env.check
+    eng, block, reps, n_units, in_bytes, barrier = kept
+    block_lines = WORKLOADS[workload][1]
+    world, dev, args = env.world, env.dev, env.args
     try:
         if args.skip_e2e:
             raise RuntimeError("skipped (--skip-e2e)")
@@ -300,7 +377,7 @@ def main():
                 avail_gb = int(ln.split()[1]) / 1e6
         per_rank_gb = in_bytes / 1e9 * 1.6
         e2e_reps = reps if avail_gb > per_rank_gb * world * 1.5 + 16 else max(1, int(reps * (avail_gb - 16) / (per_rank_gb * world * 1.5)))
-        e2e_lines = e2e_reps * BLOCK_LINES
+        e2e_lines = e2e_reps * block_lines
         h_text = torch.empty(e2e_reps * block.size, dtype=torch.int16).pin_memory()
         h_np = h_text.numpy().view(np.uint16)
         for r in range(e2e_reps):
@@ -325,6 +402,7 @@ def main():
         d2h = nl * 4 + (nl + 1) * 8 + ns * 4 + 5 * 8
         e2e = {"value": e2e_lines * world / float(tt.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h_np.size * 2),
                "d2h_bytes_per_step": int(d2h), "lines_per_step_per_gpu": int(e2e_lines), "ms_per_step": float(tt.item()) * 1e3,
+               "h2d_gb_per_s_per_gpu": h_np.size * 2 / float(tt.item()) / 1e9,
                "timing": "host wall clock around gorp_extract_text (it returns after the last D2H), max over ranks"}
         # the same call fed with ISO-8859-1 bytes (what a JDK 9+ String with the LATIN1 coder holds; the synthetic corpus is
         # ASCII): gorp_extract_text_latin1 widens on the device, the host-to-device copy moves half the bytes
@@ -355,54 +433,81 @@ def main():
         del h_text
     except Exception as ex:  # noqa: BLE001
         e2e = {"value": None, "unit": "lines/s", "error": str(ex)[:200]}
+    return e2e
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lines-per-gpu", type=int, default=100_000_000)
+    ap.add_argument("--config-lines-per-gpu", type=int, default=40_000_000, help="lines per GPU of the configs[] entries")
+    ap.add_argument("--config-steps", type=int, default=10)
+    ap.add_argument("--configs", default=",".join(EXTRA_CONFIGS), help="comma-separated extra configs ('' = none)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-lines", type=int, default=0, help="reference arm: lines per step (0 = the config's, bounded by --ref-budget-s)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: wall-clock budget of the whole run")
+    ap.add_argument("--cpu-lines", type=int, default=16_000_000)
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics: do not run nvidia-smi beside the timed region")
+    ap.add_argument("--workload", default="readme", choices=sorted(WORKLOADS), help="BASELINE.json config of `value` (default: #2, the headline)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gorp_b200 import build as gbuild
+    gbuild.build()
+    from gorp_b200 import _ffi
+    from gorp_b200.api import Blob, _check
+    try:
+        from cuda.bindings import runtime as cudart
+    except Exception:  # noqa: BLE001
+        from cuda import cudart
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    env = Env()
+    env.torch, env.dist, env.lib, env.ffi, env.Blob, env.check, env.cudart = torch, dist, _ffi.lib, _ffi, Blob, _check, cudart
+    env.rank, env.local_rank, env.world, env.dev, env.args = rank, local_rank, world, dev, args
+
+    sampler = ClockSampler(local_rank)
+    if not args.no_clock_sampler:
+        sampler.launch()
+    head, clocks, kept = device_config_run(env, args.workload, args.lines_per_gpu, args.steps, args.warmup, sampler=sampler, keep=True)
+    e2e = e2e_run(env, kept, args.workload)
+    env.lib.gorp_engine_destroy(kept[0])
+    kept = None
+    torch.cuda.empty_cache()
+
+    configs = []
+    for w in [x for x in args.configs.split(",") if x and x != args.workload]:
+        try:
+            lines = min(args.config_lines_per_gpu, args.lines_per_gpu)
+            c, _, _ = device_config_run(env, w, lines, args.config_steps, 3)
+            configs.append(c)
+        except Exception as ex:  # noqa: BLE001  (a failing extra config must not hide the headline)
+            configs.append({"key": w, "workload": WORKLOADS[w][0], "error": "%s: %s" % (type(ex).__name__, str(ex)[:300])})
+            torch.cuda.empty_cache()
 
     if rank == 0:
-        peak, peak_src = hbm_peak()
-        dom = max(kern, key=kern.get) if kern else None
-        roof = None
-        if dom:
-            ach = in_bytes / (kern[dom] / 1e3) / 1e9
-            # DRAM bytes per launch from the committed ncu --set full capture of the same kernel (profiles/
-            # r1h_ncu_summary_readme.txt: 1.370 GB read + 0.320 GB written per 1.002 GB of text), scaled to this launch
-            traffic = NCU_DRAM_BYTES_PER_TEXT_BYTE.get(dom)
-            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic * in_bytes if traffic else None,
-                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per text byte (profiles/r1h_ncu_summary_readme.txt) x bytes of this launch" if traffic else None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": in_bytes,
-                    "kernel_ms": kern[dom], "all_kernels_ms": kern,
-                    "whole_step_frac": (in_bytes / (ms_max / 1e3) / 1e9) / peak,
-                    "whole_step_frac_of_8TBps": (in_bytes / (ms_max / 1e3) / 1e9) / 8000.0}
-        # CPU baseline on rank 0: bounded sample of the same workload
-        from oracle import gorp_oracle
-        cores = os.cpu_count() or 1
-        if args.skip_cpu:
-            args.cpu_lines = BLOCK_LINES
-        creps = max(1, args.cpu_lines // BLOCK_LINES)
-        ctext = np.tile(block, creps)
-        cst = gorp_oracle.split_lines(ctext)
-        o = gorp_oracle.Gorp(definition_of(args.workload))
-        o.extract_batch(block, gorp_oracle.split_lines(block), threads=cores)
-        t0 = time.perf_counter()
-        o.extract_batch(ctext, cst, threads=cores)
-        cdt = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        o.extract_batch(block, gorp_oracle.split_lines(block), threads=1)
-        cdt1 = time.perf_counter() - t0
-        cpu = {"value": len(cst[0]) / cdt, "unit": "lines/s", "cores": cores, "kind": "port",
-               "sample": "%d lines (%.2f GB) of the same workload, all %d host threads; 1 thread: %.0f lines/s"
-                         % (len(cst[0]), ctext.nbytes / 1e9, cores, BLOCK_LINES / cdt1),
-               "note": "C restatement of the reference's Gorp.extract loop (JVM unavailable in this image)"}
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "lines/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
-            "data": "synthetic", "input_gb_per_s": in_bytes * world / (ms_max / 1e3) / 1e9,
-            "config": {"workload": WORKLOAD, "lines_per_gpu": n_lines, "units_per_gpu": n_units,
-                       "bytes_per_gpu": in_bytes, "block": "%d-line seeded block tiled %dx in HBM" % (BLOCK_LINES, reps),
-                       "l2": "input (%.1f GB) is far larger than L2, no flush needed" % (in_bytes / 1e9),
-                       "parallelism": "lines sharded per GPU as contiguous ranges, tables replicated; no data-path collective"
-                                      + (", one NCCL all-reduce of the %d-bin histogram per step" % n_bins if world > 1 else "")},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches.value),
+            "metric": METRIC, "value": head["value"], "unit": "lines/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+            "data": "synthetic", "input_gb_per_s": head["input_gb_per_s"],
+            "config": head["config"], "roofline": head["roofline"], "cpu_baseline": head.get("cpu_baseline"), "e2e": e2e, "clocks": clocks,
+            "gpu_launches": head["gpu_launches"], "parity": head["parity"],
+            "configs": configs,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -22,8 +22,9 @@ CUDA_SOURCES = [os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "kernels", "
                 os.path.join(CSRC, "kernels", "fast.cu"), os.path.join(CSRC, "kernels", "onepass.cu"),
                 os.path.join(CSRC, "kernels", "chunkwalk.cu"), os.path.join(CSRC, "kernels", "dfawalk.cu"),
                 os.path.join(CSRC, "kernels", "capwalk.cu")]
-NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC,-Wall", "-shared", "-I", os.path.join(ROOT, "include")]
+OBJ_DIR = os.path.join(HERE, "_obj")
+COMPILE_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+                 "-Xcompiler", "-fPIC,-Wall", "-I", os.path.join(ROOT, "include")]
 
 
 def _newer(target, sources):
@@ -43,12 +44,38 @@ def nvcc_path():
     return "nvcc"
 
 
+def _compile_one(args):
+    src, obj, verbose = args
+    cmd = [nvcc_path()] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    subprocess.check_call(cmd)
+    return obj
+
+
 def build(force=False, verbose=False):
+    """One object per source (compiled in parallel, only what changed), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    import fcntl
     srcs = CUDA_SOURCES + HOST_SOURCES
     if not force and not _newer(LIB, srcs):
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    lock = open(os.path.join(OBJ_DIR, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)  # several ranks may get here at once (torchrun): one builds, the others wait
+    if not force and not _newer(LIB, srcs):
+        return LIB
+    headers = []
+    for d in (os.path.join(CSRC, "host"), os.path.join(CSRC, "kernels"), os.path.join(ROOT, "include")):
+        headers += [os.path.join(d, f) for f in os.listdir(d) if f.endswith((".h", ".hpp", ".cuh"))]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    jobs, objs = [], []
+    for s in srcs:
+        obj = os.path.join(OBJ_DIR, os.path.basename(s) + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(s), newest_header):
+            jobs.append((s, obj, verbose))
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4) or 1) as ex:
+        list(ex.map(_compile_one, jobs))
+    subprocess.check_call([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
     return LIB
 
 

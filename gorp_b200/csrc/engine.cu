@@ -145,6 +145,7 @@ struct DeviceCtx {
     // the D2H of the rows of piece k-1 (s_out); the rows of all pieces accumulate in acc_*
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2]{}, ev_free[2]{}, ev_rows = nullptr;
+    cudaEvent_t ev_done = nullptr;  // end of the last call on this context: the next call's stream waits for it (shared scratch)
     DevBuf textbuf[2], offbuf[2], bytebuf[2], acc_ext, acc_off, acc_spans, acc_hist;
     // per-call scratch, serialised by `mu`
     std::mutex mu;
@@ -168,6 +169,7 @@ struct DeviceCtx {
         for (auto& e : ev_free)
             if (e) cudaEventDestroy(e);
         if (ev_rows) cudaEventDestroy(ev_rows);
+        if (ev_done) cudaEventDestroy(ev_done);
         if (stream) cudaStreamDestroy(stream);
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
@@ -216,6 +218,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     for (auto& e : c.ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c.ev_free) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.ev_rows, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
     if (const char* f = std::getenv("GORP_FORCE_GENERAL")) c.force_general = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TWOPASS")) c.force_twopass = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TILES")) c.force_tiles = f[0] == '1';
@@ -571,6 +574,20 @@ void collect_times(DeviceCtx& c) {
     c.n_ev = 0;
 }
 
+// restores the calling thread's current CUDA device when a call returns
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 struct Timer {
     DeviceCtx& c;
     cudaStream_t s;
@@ -580,6 +597,13 @@ struct Timer {
             collect_times(c);  // the previous timed call, if any
             cudaEventRecord(c.ev[0], s);
         }
+    }
+    // a retry re-measures from here: the slots recorded since `n` are dropped
+    int position() const { return c.n_ev; }
+    void rewind(int n) {
+        if (!on || n > c.n_ev) return;
+        c.n_ev = n;
+        cudaEventRecord(c.ev[n], s);
     }
     void mark(const char* name, int launches) {
         c.launches += launches;
@@ -600,7 +624,9 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
     Launch L{stream, c.sm_count};
     c.hist.reserve((c.n_ext + 2) * 8);
     bool exact = false;
+    const int tm_pos = tm.position();
     for (int attempt = 0; attempt < 2; ++attempt) {
+        tm.rewind(tm_pos);
         OnePassParams P{};
         P.text = d_text;
         P.n_units = n_units;
@@ -696,7 +722,9 @@ bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
     Launch L{stream, c.sm_count};
     c.hist.reserve((c.n_ext + 2) * 8);
     bool exact = false;
+    const int tm_pos = tm.position();
     for (int attempt = 0; attempt < 12; ++attempt) {
+        tm.rewind(tm_pos);
         uint32_t threads = 0, tile = 0;
         if (!k0_onepass_plan(c.onepass, c.lines_per_unit, c.onepass_shrink, &threads, &tile)) return false;
         OnePassParams P{};
@@ -793,7 +821,9 @@ bool run_dfawalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
     if (!k0_dfawalk_plan(c.dfawalk, &threads, &in_smem)) return false;
     Launch L{stream, c.sm_count};
     bool exact = false;
+    const int tm_pos = tm.position();
     for (int attempt = 0; attempt < 2; ++attempt) {
+        tm.rewind(tm_pos);
         DfaWalkParams P{};
         P.text = d_text;
         P.n_units = n_units;
@@ -1047,10 +1077,11 @@ struct DeviceRun {  // what one device produced for its pieces
 // Processes pieces [p0, p1) on device context c. Rows accumulate in c.acc_*; when `hr` is given (single-device call) the
 // rows of every finished piece are copied to the host arrays at once, overlapping the next pieces.
 // `text8` (ISO-8859-1 bytes, text form only) replaces `text`: the bytes are staged and widened to UTF-16 on the device.
+// The caller holds c.mu (a multi-device call keeps every participating device locked until its rows are copied out).
 void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_t* text8, const int64_t* off, const std::vector<Piece>& pieces,
                 size_t p0, size_t p1, HostResult* hr, DeviceRun& run) {
-    std::lock_guard<std::mutex> lock(c.mu);
     CK(cudaSetDevice(c.device));
+    CK(cudaStreamWaitEvent(c.stream, c.ev_done, 0));  // a device-resident call on another stream may still use the scratch
     Launch L{c.stream, c.sm_count};
     const size_t E2 = e->def.extractions.size() + 2;
     const uint32_t stride = e->match_only ? 0u : c.max_slots;
@@ -1156,6 +1187,7 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_
     } else {
         CK(cudaStreamSynchronize(c.stream));
     }
+    CK(cudaEventRecord(c.ev_done, c.stream));
     run.n_rows = rows;
     run.stride = static_cast<int32_t>(stride);
 }
@@ -1181,14 +1213,20 @@ int extract_host(gorp_engine* e, const uint16_t* text, const uint8_t* text8, int
         const size_t G = std::min(e->devs.size(), pieces.size());
         int64_t nl = 0;
         int32_t stride = 0;
+        DeviceGuard restore_device;
         if (G <= 1) {
             DeviceRun run;
+            std::lock_guard<std::mutex> lock(e->devs[0]->mu);
             run_pieces(e, *e->devs[0], text, text8, off, pieces, 0, pieces.size(), hr.get(), run);
             nl = run.n_rows;
             stride = run.stride;
         } else {
             // contiguous ranges of pieces per device (lines shard as contiguous ranges: no data crosses devices); one
             // host thread per device; the rows are copied out once every device's row base is known
+            // every participating device stays locked (in device order) from the first kernel to the last row copied out:
+            // a concurrent call on the same engine can neither overwrite the accumulators nor free them in between
+            std::vector<std::unique_lock<std::mutex>> locks;
+            for (size_t d = 0; d < G; ++d) locks.emplace_back(e->devs[d]->mu);
             std::vector<DeviceRun> runs(G);
             std::vector<size_t> first(G + 1);
             for (size_t d = 0; d <= G; ++d) first[d] = pieces.size() * d / G;
@@ -1215,7 +1253,6 @@ int extract_host(gorp_engine* e, const uint16_t* text, const uint8_t* text8, int
             std::vector<int64_t> hist(G * E2);
             for (size_t d = 0; d < G; ++d) {
                 DeviceCtx& c = *e->devs[d];
-                std::lock_guard<std::mutex> lock(c.mu);
                 CK(cudaSetDevice(c.device));
                 const int64_t n = runs[d].n_rows;
                 if (n) CK(cudaMemcpyAsync(static_cast<int32_t*>(hr->p[0]) + base[d], c.acc_ext.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c.stream));
@@ -1481,7 +1518,12 @@ int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_d
 void gorp_engine_destroy(gorp_engine* e) { delete e; }
 
 int gorp_extract_lines(gorp_engine* e, const uint16_t* text, const int64_t* off, int64_t n_lines, gorp_result* out) {
-    if (!off) return fail(GORP_E_ARG, "null offsets");
+    if (!e || !out || !off || n_lines < 0) return fail(GORP_E_ARG, "bad argument");
+    // the offsets come from the caller: anything that is not a non-decreasing sequence starting at >= 0 would send the
+    // kernels outside the staged text
+    if (off[0] < 0) return fail(GORP_E_ARG, "offsets must start at >= 0");
+    for (int64_t i = 0; i < n_lines; ++i)
+        if (off[i + 1] < off[i]) return fail(GORP_E_ARG, strfmt("offsets must be non-decreasing (line %lld)", static_cast<long long>(i)));
     return extract_host(e, text, nullptr, n_lines > 0 ? off[n_lines] : 0, off, n_lines, out);
 }
 
@@ -1510,9 +1552,12 @@ int gorp_extract_text_device(gorp_engine* e, int dev_index, const uint16_t* d_te
     return guarded([&]() -> int {
         DeviceCtx& c = *e->devs[dev_index];
         std::lock_guard<std::mutex> lock(c.mu);
+        DeviceGuard restore_device;
         CK(cudaSetDevice(c.device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
+        CK(cudaStreamWaitEvent(st, c.ev_done, 0));  // the previous call on this context (any stream) used the same scratch
         run_pipeline(c, d_text, n_units, nullptr, 0, st, (flags & GORP_FLAG_TIME_KERNELS) != 0, out);
+        CK(cudaEventRecord(c.ev_done, st));
         if (flags & GORP_FLAG_SYNC) CK(cudaStreamSynchronize(st));
         return GORP_OK;
     });
@@ -1526,9 +1571,12 @@ int gorp_extract_lines_device(gorp_engine* e, int dev_index, const uint16_t* d_t
     return guarded([&]() -> int {
         DeviceCtx& c = *e->devs[dev_index];
         std::lock_guard<std::mutex> lock(c.mu);
+        DeviceGuard restore_device;
         CK(cudaSetDevice(c.device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
+        CK(cudaStreamWaitEvent(st, c.ev_done, 0));  // the previous call on this context (any stream) used the same scratch
         run_pipeline(c, d_text, 0, d_off, n_lines, st, (flags & GORP_FLAG_TIME_KERNELS) != 0, out);
+        CK(cudaEventRecord(c.ev_done, st));
         if (flags & GORP_FLAG_SYNC) CK(cudaStreamSynchronize(st));
         return GORP_OK;
     });
@@ -1539,6 +1587,7 @@ int gorp_kernel_times(gorp_engine* e, int dev_index, const char** names, double*
     if (!e || dev_index < 0 || dev_index >= static_cast<int>(e->devs.size()) || !n) return fail(GORP_E_ARG, "bad argument");
     DeviceCtx& c = *e->devs[dev_index];
     std::lock_guard<std::mutex> lock(c.mu);
+    DeviceGuard restore_device;
     cudaSetDevice(c.device);
     collect_times(c);
     int k = std::min(cap, c.acc_n);

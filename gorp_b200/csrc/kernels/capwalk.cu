@@ -394,7 +394,7 @@ size_t capwalk_smem_bytes(const CapImgDev& img) {
 
 void k4b_capwalk(const Launch& L, const CapWalkParams& P) {
     const size_t smem = capwalk_smem_bytes(P.img);
-    if (smem > 32 * 1024) cudaFuncSetAttribute(capwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    allow_max_dynamic_smem(capwalk_kernel);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, capwalk_kernel, kCapWalkThreads, smem);
     if (per_sm < 1) per_sm = 1;

@@ -437,7 +437,7 @@ bool k0_chunkwalk_plan(const OnePassDev& a, uint32_t* threads) {
         if (static_cast<uint64_t>(a.n_slots) * kT > 0x3FFFu) continue;  // slot offsets are 14 bits of the table entry
         const size_t smem = chunkwalk_smem_bytes(a, kT);
         if (smem > 226 * 1024) continue;
-        cudaFuncSetAttribute(chunkwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        allow_max_dynamic_smem(chunkwalk_kernel);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunkwalk_kernel, static_cast<int>(kT), smem) != cudaSuccess) {
             cudaGetLastError();
@@ -453,7 +453,7 @@ bool k0_chunkwalk_plan(const OnePassDev& a, uint32_t* threads) {
 
 int k0_chunkwalk_grid(const Launch& L, const OnePassParams& P, uint32_t threads) {
     const size_t smem = chunkwalk_smem_bytes(P.a, threads);
-    cudaFuncSetAttribute(chunkwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    allow_max_dynamic_smem(chunkwalk_kernel);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunkwalk_kernel, static_cast<int>(threads), smem);
     if (per_sm < 1) per_sm = 1;

@@ -420,10 +420,10 @@ bool k0_dfawalk_plan(const DfaWalkDev& a, uint32_t* threads, bool* in_smem) {
             int per_sm = 0;
             cudaError_t e;
             if (sm) {
-                cudaFuncSetAttribute(dfawalk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                allow_max_dynamic_smem(dfawalk_kernel<true>);
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<true>, static_cast<int>(kT), smem);
             } else {
-                cudaFuncSetAttribute(dfawalk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                allow_max_dynamic_smem(dfawalk_kernel<false>);
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<false>, static_cast<int>(kT), smem);
             }
             if (e != cudaSuccess) {
@@ -446,10 +446,10 @@ int k0_dfawalk_grid(const Launch& L, const DfaWalkParams& P, uint32_t threads, b
     const size_t smem = dfawalk_smem_bytes(P.a, threads, in_smem);
     int per_sm = 1;
     if (in_smem) {
-        cudaFuncSetAttribute(dfawalk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        allow_max_dynamic_smem(dfawalk_kernel<true>);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<true>, static_cast<int>(threads), smem);
     } else {
-        cudaFuncSetAttribute(dfawalk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        allow_max_dynamic_smem(dfawalk_kernel<false>);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<false>, static_cast<int>(threads), smem);
     }
     if (per_sm < 1) per_sm = 1;
@@ -480,11 +480,11 @@ void k2b_linewalk_scan(const Launch& L, const LineWalkParams& P, uint32_t thread
     const size_t smem = linewalk_smem_bytes(P.a, in_smem);
     int per_sm = 1;
     if (in_smem) {
-        cudaFuncSetAttribute(linewalk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        allow_max_dynamic_smem(linewalk_kernel<true>);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linewalk_kernel<true>, static_cast<int>(threads), smem);
         linewalk_kernel<true><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), static_cast<int>(threads), smem, L.stream>>>(P);
     } else {
-        cudaFuncSetAttribute(linewalk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        allow_max_dynamic_smem(linewalk_kernel<false>);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linewalk_kernel<false>, static_cast<int>(threads), smem);
         linewalk_kernel<false><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), static_cast<int>(threads), smem, L.stream>>>(P);
     }

@@ -123,7 +123,7 @@ void k2_dfa_direct(const Launch& L, const DfaDirectDev& d, const uint16_t* text,
     if (n_lines <= 0) return;
     const size_t smem = static_cast<size_t>(d.n_rows) * 512;
     if (smem > 40 * 1024)
-        cudaFuncSetAttribute(dfa_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        allow_max_dynamic_smem(dfa_direct_kernel);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfa_direct_kernel, kFastThreads, smem);
     if (per_sm < 1) per_sm = 1;
@@ -141,7 +141,7 @@ void k4_tdfa_fast(const Launch& L, const TdfaFastDev& f, const CapDev& c, const 
     if (n_lines <= 0) return;
     const size_t smem = static_cast<size_t>(f.image_words) * 4 + static_cast<size_t>(f.n_regs + 2) * kCapThreads * 4;
     if (smem > 40 * 1024)
-        cudaFuncSetAttribute(tdfa_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        allow_max_dynamic_smem(tdfa_fast_kernel);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tdfa_fast_kernel, kCapThreads, smem);
     if (per_sm < 1) per_sm = 1;

@@ -488,7 +488,7 @@ template <bool kSmem, typename Entry>
 static void launch_dfa(const Launch& L, const DfaDev& d, size_t smem, const uint16_t* text, const int64_t* line_off, int sep,
                        int64_t n_lines, int32_t* ext_id) {
     auto fn = dfa_scan_kernel<kSmem, Entry>;
-    if (smem > 40 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    allow_max_dynamic_smem(fn);
     int g = persistent_grid(L, reinterpret_cast<const void*>(fn), smem, n_lines);
     fn<<<g, kThreads, smem, L.stream>>>(d, text, line_off, sep, n_lines, ext_id);
 }

@@ -94,6 +94,21 @@ struct Launch {
     int sm_count;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-function, per-device state shared by every engine of the process:
+// it is always set to the same value (everything the device allows), so launches of engines with different table
+// sizes cannot invalidate each other's setting; only the launch's own dynamic shared-memory argument varies.
+template <class Kernel>
+inline void allow_max_dynamic_smem(Kernel kernel) {
+    cudaFuncAttributes a{};
+    int dev = 0, optin = 0;
+    if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - static_cast<int>(a.sharedSizeBytes));
+}
+
 // K1: '\n' index over UTF-16 text. tile_counts/tile_base sized ceil(n_units / kNlTile).
 constexpr int kNlTile = 8192;
 void k1_count_newlines(const Launch&, const uint16_t* text, int64_t n_units, uint32_t* tile_counts);

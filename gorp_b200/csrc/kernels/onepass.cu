@@ -552,7 +552,7 @@ bool k0_onepass_plan(const OnePassDev& a, double lines_per_unit, uint32_t shrink
 int k0_onepass_grid(const Launch& L, const OnePassParams& P, uint32_t threads) {
     const size_t smem = onepass_smem_bytes(P.a, threads, P.tile_units);
     const int block = static_cast<int>(threads + 32);  // + the look-back warp
-    cudaFuncSetAttribute(onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    allow_max_dynamic_smem(onepass_kernel);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onepass_kernel, block, smem);
     if (per_sm < 1) per_sm = 1;

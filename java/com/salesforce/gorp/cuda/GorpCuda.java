@@ -114,11 +114,15 @@ public final class GorpCuda implements AutoCloseable {
         }
     }
 
-    /** Gorp.extractAll(CharBuffer): '\n'-separated text; a direct buffer is passed zero-copy. */
+    /**
+     * Gorp.extractAll(CharBuffer): '\n'-separated text. A direct buffer in NATIVE byte order is passed zero-copy; any
+     * other buffer is copied char by char (ByteBuffer.allocateDirect(..).asCharBuffer() is BIG_ENDIAN by default: the
+     * native side reads host-order UTF-16 and would see byte-swapped units).
+     */
     public List<ExtractionResult> extractAll(CharBuffer text) throws Throwable {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment seg;
-            if (text.isDirect()) {
+            if (text.isDirect() && text.order() == java.nio.ByteOrder.nativeOrder()) {
                 seg = MemorySegment.ofBuffer(text);
             } else {
                 seg = a.allocate(Math.max(2L * text.remaining(), 2), 16);
