@@ -127,6 +127,10 @@ struct DeviceCtx {
     OnePassDev onepass{};
     OnePassDev chunkwalk{};      // same automaton, table variant of kernels/chunkwalk.cu
     DfaWalkDev dfawalk{};        // class-indexed combined DFA of kernels/dfawalk.cu (text form, any definition)
+    DfaWalkDev dfawalk_cut{};    // the same with the early-exit cut of host/tails.hpp (K2b when the tail walk follows)
+    TailDev tails{};             // per-extraction tail automata of kernels/tailwalk.cu
+    uint32_t tail_flush_every = 4;
+    DevBuf long_lines;
     CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
     bool force_k4 = false;       // GORP_FORCE_K4=1: one-line-per-thread capture kernels (K4) instead of the bucketed K4b
     DevBuf perm, items, buckets, nl_masks;
@@ -207,7 +211,7 @@ struct gorp_engine {
 
 namespace {
 
-void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fused, bool match_only) {
+void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fused, const TailSet& tailset, bool match_only) {
     CK(cudaSetDevice(c.device));
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, c.device));
@@ -422,6 +426,50 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     if (x.frz_off <= budget) best = std::max<size_t>(best, x.frz_off);  // (S + 17) rows: without the FRZ rows
                 c.capimg.smem_table_bytes = static_cast<uint32_t>((best + 15) & ~size_t(15));
                 c.capimg.enabled = capwalk_smem_bytes(c.capimg) <= 200 * 1024 ? 1u : 0u;
+            }
+        }
+        // tail tier: early-exit combined DFA + one tail automaton per extraction (host/tails.hpp, kernels/tailwalk.cu)
+        if (tailset.any && c.dfawalk.enabled && c.capimg.enabled && !std::getenv("GORP_NO_TAILS")) {
+            const DfaWalkTable t = build_dfawalk_table_cut(m, tailset.cut_of_state);
+            const TailImage img = build_tail_image(tailset, c.max_slots);
+            if (t.available && img.available) {
+                static_assert(sizeof(TailImageExt) == sizeof(TailExt), "host and device descriptors of a tail table must match");
+                std::vector<TailExt> text(img.ext.size());
+                std::memcpy(text.data(), img.ext.data(), text.size() * sizeof(TailExt));
+                TailDev& d = c.tails;
+                d.image = upload(img.image, c.owned);
+                d.ext = upload(text, c.owned);
+                d.res = upload(img.res, c.owned);
+                d.oext = upload(img.oext, c.owned);
+                d.init_slots = upload(img.init_slots, c.owned);
+                d.xcol = upload(tailset.xcol, c.owned);
+                d.pair_col = upload(tailset.pair_col, c.owned);
+                d.width = img.width;
+                d.row_bytes = img.row_bytes;
+                d.span_stride = c.max_slots;
+                d.max_table_bytes = img.max_table_bytes;
+                d.max_slots = img.max_slots;
+                for (const TailImageExt& x : img.ext) {
+                    if (!x.available) {
+                        ++d.n_without;
+                        continue;
+                    }
+                    d.max_res = std::max(d.max_res, (x.n_outcomes * c.max_slots + 3u) & ~3u);
+                    d.max_outcomes = std::max(d.max_outcomes, (x.n_outcomes + 3u) & ~3u);
+                }
+                if (tailwalk_smem_bytes(d) <= 200 * 1024) {
+                    c.dfawalk_cut.table = upload(t.rows, c.owned);
+                    c.dfawalk_cut.n_rows = t.n_rows;
+                    c.dfawalk_cut.K = t.K;
+                    c.dfawalk_cut.n_states = t.n_states;
+                    c.dfawalk_cut.fin_base = t.fin_base;
+                    c.dfawalk_cut.cls128 = upload(t.cls128, c.owned);
+                    c.dfawalk_cut.xcls = upload(t.xcls, c.owned);
+                    c.dfawalk_cut.enabled = 1;
+                    d.enabled = 1;
+                    if (const char* f = std::getenv("GORP_TAIL_FLUSH")) c.tail_flush_every = std::max(1, std::atoi(f));
+                    while (c.tail_flush_every & (c.tail_flush_every - 1)) --c.tail_flush_every;  // power of two
+                }
             }
         }
         // one-pass tier: DFA x capture automata folded into one automaton (host/fused.hpp, kernels/onepass.cu)
@@ -933,15 +981,21 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
     uint32_t lw_threads = 0;
     bool lw_smem = false;
+    // the tail walk follows: the combined-DFA walk may stop at the first state that leaves one candidate extraction
+    const bool with_tails = c.tails.enabled && !c.cap.match_only && c.max_slots > 0 && sep == 1 && !c.force_general && !c.force_k4 &&
+                            !c.force_k1k2 && n_lines > 0 && n_lines < (1ll << 32) && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0;
+    const DfaWalkDev& walk_table = with_tails ? c.dfawalk_cut : c.dfawalk;
+    bool candidates = false;  // ext_id holds candidates of the cut table: only the tail walk may follow (its conditions are those of with_tails)
     if (scanned) {
     } else if (sep == 1 && !c.force_general && !c.force_k1k2 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0 &&
-               k2b_linewalk_plan(c.dfawalk, &lw_threads, &lw_smem)) {
+               k2b_linewalk_plan(walk_table, &lw_threads, &lw_smem)) {
+        candidates = with_tails;
         LineWalkParams W{};
         W.text = d_text;
         W.n_units = n_units;
         W.line_off = d_line_off;
         W.n_lines = n_lines;
-        W.a = c.dfawalk;
+        W.a = walk_table;
         W.ext_id = c.ext_id.as<int32_t>();
         W.item_ticket = reinterpret_cast<unsigned int*>(d_n_lines + 4);
         if (const char* f = std::getenv("GORP_WALK_FLAGS")) W.flags = static_cast<uint32_t>(std::atoi(f));
@@ -971,11 +1025,15 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         const size_t max_items = nl / kCapItemLines + E + 1;
         c.perm.reserve(nl * 4 + 16);
         c.items.reserve(max_items * sizeof(CapItem));
-        c.buckets.reserve((2 * static_cast<size_t>(E) + 4) * 4);
+        c.buckets.reserve((2 * static_cast<size_t>(E) + 8) * 4);
         uint32_t* bucket_base = c.buckets.as<uint32_t>();
         uint32_t* cursor = bucket_base + E + 1;
         uint32_t* n_items = cursor + E;
         uint32_t* item_ticket = n_items + 1;
+        uint32_t* tail_ticket = n_items + 2;  // [tail_ticket, n_long]
+        const bool tails = with_tails;
+        if (candidates && !tails) throw std::logic_error("early-exit candidates without the tail walk");
+        if (tails) CK(cudaMemsetAsync(tail_ticket, 0, 8, stream));
         k4b_bucket(L, c.ext_id.as<int32_t>(), n_lines, E, c.hist.as<unsigned long long>(), bucket_base, cursor, c.perm.as<uint32_t>(),
                    c.items.as<CapItem>(), n_items, item_ticket, c.spans.as<int32_t>(), stride);
         tm.mark("k4b_bucket", 2);
@@ -996,8 +1054,33 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         W.ext_id = c.ext_id.as<int32_t>();
         W.spans = c.spans.as<int32_t>();
         W.hist = c.hist.as<unsigned long long>();
-        k4b_capwalk(L, W);
-        tm.mark("k4b_capwalk", 1);
+        if (tails) {
+            TailWalkParams T{};
+            T.text = d_text;
+            T.n_units = n_units;
+            T.line_off = d_line_off;
+            T.perm = W.perm;
+            T.items = W.items;
+            T.n_items = n_items;
+            T.item_ticket = tail_ticket;
+            T.t = c.tails;
+            T.n_ext = E;
+            T.flush_every = c.tail_flush_every;
+            T.ext_id = W.ext_id;
+            T.spans = W.spans;
+            T.hist = W.hist;
+            T.long_cap = static_cast<uint32_t>(n_units / kTailMaxLen + 2);
+            c.long_lines.reserve(static_cast<size_t>(T.long_cap) * 4);
+            T.long_lines = c.long_lines.as<uint32_t>();
+            T.n_long = tail_ticket + 1;
+            k4c_tailwalk(L, T);
+            tm.mark("k4c_tailwalk", 2);
+            W.skip_tails = c.tails.ext;
+        }
+        if (!tails || c.tails.n_without > 0) {
+            k4b_capwalk(L, W);
+            tm.mark("k4b_capwalk", 1);
+        }
     } else if (!c.cap.match_only && stride > 0) {
         if (sep == 1 && c.cap_fast.enabled && !c.force_general) {
             k4_tdfa_fast(L, c.cap_fast, c.cap, d_text, n_units, d_line_off, n_fast, stride, c.ext_id.as<int32_t>(), c.spans.as<int32_t>());
@@ -1487,6 +1570,7 @@ int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_d
         eng->match_only = (flags & 1u) != 0;
         DeviceModel model;
         FusedAutomaton fused;
+        TailSet tailset;
         if (eng->match_only) {
             model.dfa = compact_tables(eng->def.dfa);
             model.n_groups.assign(eng->def.extractions.size(), 0);
@@ -1494,6 +1578,7 @@ int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_d
             model = build_device_model(eng->def);
             fused = build_fused(model);
             finalize_device_model(model, fused);
+            if (!std::getenv("GORP_NO_TAILS")) tailset = build_tails(eng->def, model);
         }
         int avail = 0;
         if (cudaGetDeviceCount(&avail) != cudaSuccess || avail == 0) {
@@ -1507,7 +1592,7 @@ int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_d
             if (d < 0 || d >= avail) return fail(GORP_E_ARG, strfmt("device %d out of range (have %d)", d, avail));
             auto ctx = std::make_unique<DeviceCtx>();
             ctx->device = d;
-            build_device(*ctx, model, fused, eng->match_only);
+            build_device(*ctx, model, fused, tailset, eng->match_only);
             eng->devs.push_back(std::move(ctx));
         }
         *out = eng.release();

@@ -63,6 +63,129 @@ DfaWalkTable build_dfawalk_table(const DeviceModel& m) {
     return t;
 }
 
+DfaWalkTable build_dfawalk_table_cut(const DeviceModel& m, const std::vector<int32_t>& cut_of_state) {
+    DfaWalkTable t;
+    const size_t S0 = m.dfa.n_states, C = m.dfa.n_classes, E = m.n_groups.size();
+    if (cut_of_state.size() != S0) return t;
+    // head states: reachable from the start without passing a cut state, renumbered in BFS order
+    std::vector<int32_t> id(S0, -1);
+    std::vector<uint32_t> order{0};
+    id[0] = 0;
+    for (size_t i = 0; i < order.size(); ++i)
+        for (size_t c = 0; c < C; ++c) {
+            const int32_t to = m.dfa.trans[static_cast<size_t>(order[i]) * C + c];
+            if (to < 0 || cut_of_state[to] >= 0 || id[to] >= 0) continue;
+            id[to] = static_cast<int32_t>(order.size());
+            order.push_back(static_cast<uint32_t>(to));
+        }
+    const size_t S = order.size();
+    const size_t NL = C, fin_base = S + 16, R = fin_base + 1 + E;
+    const size_t K = (C + 1) | 1;  // shared memory: odd column count (see build_dfawalk_table)
+    if (R > 0xFFFF || K * 2 > 0xFFFF) return t;
+    t.rows.assign(((R * K + 7) / 8) * 8, 0);
+    for (size_t r = 0; r < R; ++r)
+        for (size_t k = 0; k < K; ++k) {
+            size_t nx;
+            if (k > NL) {
+                nx = r;  // padding column, never addressed
+            } else if (r < S) {
+                const size_t q = order[r];
+                if (k == NL) {
+                    nx = fin_base + 1 + m.dfa.accept_first[q];
+                } else {
+                    const int32_t to = m.dfa.trans[q * C + k];
+                    if (to < 0) nx = fin_base;                                        // dead: MISS at once
+                    else if (cut_of_state[to] >= 0) nx = fin_base + 1 + cut_of_state[to];  // candidate: the tail decides
+                    else nx = static_cast<size_t>(id[to]);
+                }
+            } else if (r == S) {
+                nx = fin_base;  // DEADSCAN is not used by this variant
+            } else if (r < fin_base) {
+                nx = r == S + 1 ? 0 : r - 1;  // SKIP chain
+            } else {
+                nx = r;  // FIN: absorbing
+            }
+            t.rows[r * K + k] = static_cast<uint16_t>(nx);
+        }
+    t.cls128.resize(128);
+    t.xcls.resize(65536);
+    for (size_t u = 0; u < 65536; ++u) t.xcls[u] = m.dfa.classmap[u];
+    for (size_t u = 0; u < 128; ++u) t.cls128[u] = static_cast<uint16_t>(2 * (u == 0x0A ? NL : m.dfa.classmap[u]));
+    t.n_rows = static_cast<uint32_t>(R);
+    t.K = static_cast<uint32_t>(K);
+    t.n_states = static_cast<uint32_t>(S);
+    t.n_classes = static_cast<uint32_t>(C);
+    t.fin_base = static_cast<uint32_t>(fin_base);
+    t.available = true;
+    return t;
+}
+
+TailImage build_tail_image(const TailSet& T, uint32_t span_stride) {
+    TailImage I;
+    if (!T.any) return I;
+    const size_t E = T.tails.size();
+    I.width = T.width;
+    I.row_bytes = T.width * 2;
+    I.span_stride = span_stride;
+    I.ext.assign(E, TailImageExt{});
+    for (size_t e = 0; e < E; ++e) {
+        const TailAutomaton& A = T.tails[e];
+        if (!A.available) continue;
+        const uint32_t S = A.n_states, fin_base = S + 15, n_out = static_cast<uint32_t>(A.outcomes.size()), rows = fin_base + n_out;
+        if (rows > 1023 || A.n_op_slots + 1 > 63) continue;  // 10-bit row ids, 6-bit slots
+        while (I.image.size() % 8) I.image.push_back(0);
+        TailImageExt& x = I.ext[e];
+        x.tab_off = static_cast<uint32_t>(I.image.size() * 2);
+        x.n_states = S;
+        x.fin_base = fin_base;
+        x.n_outcomes = n_out;
+        x.res_off = static_cast<uint32_t>(I.res.size());
+        x.oext_off = static_cast<uint32_t>(I.oext.size());
+        x.init_off = static_cast<uint32_t>(I.init_slots.size());
+        x.n_init = static_cast<uint32_t>(A.init_slots.size());
+        x.n_slots = A.n_op_slots + 1;
+        x.available = 1;
+        const size_t base = I.image.size();
+        I.image.resize(base + static_cast<size_t>(rows) * T.width);
+        auto put = [&](uint32_t r, uint32_t k, uint32_t next_row, uint32_t slot) {
+            I.image[base + static_cast<size_t>(r) * T.width + k] = static_cast<uint16_t>((next_row << 6) | slot);
+        };
+        for (uint32_t r = 0; r < rows; ++r)
+            for (uint32_t k = 0; k < T.width; ++k) {
+                if (r < S) {
+                    if (k == 0x0A) {
+                        put(r, k, fin_base + A.outcome_of[r], 0);
+                    } else {
+                        const uint32_t ent = A.trans[static_cast<size_t>(r) * T.width + k];
+                        if ((ent & 0xFFFFu) == 0xFFFFu) put(r, k, fin_base, 0);  // dead (or a padding column): MISS
+                        else put(r, k, ent & 0xFFFFu, ent >> 16);
+                    }
+                } else if (r < fin_base) {
+                    put(r, k, r == S ? 0u : r - 1, 0);  // SKIP chain
+                } else {
+                    put(r, k, r, 0);  // outcome rows: absorbing
+                }
+            }
+        for (uint32_t o = 0; o < n_out; ++o) {
+            const FusedAutomaton::Outcome& oc = A.outcomes[o];
+            I.oext.push_back(oc.ext_code);
+            for (uint32_t k = 0; k < span_stride; ++k) {
+                uint32_t rec = 0;
+                if (oc.ext_code >= 0 && k < A.n_boundaries) rec = A.res[oc.res_off + k];  // 2 * groups recipes per MATCH outcome
+                I.res.push_back(rec);
+            }
+        }
+        for (uint32_t s : A.init_slots) I.init_slots.push_back(static_cast<uint8_t>(s));
+        I.max_table_bytes = std::max<uint32_t>(I.max_table_bytes, (rows * I.row_bytes + 15u) & ~15u);
+        I.max_slots = std::max(I.max_slots, x.n_slots);
+        I.available = true;
+    }
+    while (I.image.size() % 8) I.image.push_back(0);
+    I.image.resize(I.image.size() + 16, 0);
+    I.init_slots.push_back(0);
+    return I;
+}
+
 CapImage build_cap_image(const DeviceModel& m, size_t max_extractions) {
     CapImage img;
     const size_t E = m.n_groups.size();

@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkPara
         const uint32_t item = s_item;
         if (item >= n_items) break;
         const CapItem it = P.items[item];
+        if (P.skip_tails && P.skip_tails[it.ext].available) continue;  // the tail walk (kernels/tailwalk.cu) takes this item
         const CapImgExt fx = P.img.ext[it.ext];
         // the extraction's table goes to shared memory when it fits: a warp-wide gather through L1 is as slow as its
         // slowest lane (one L1 miss among 32 lanes costs the whole warp an L2 round trip), LDS has no such tail

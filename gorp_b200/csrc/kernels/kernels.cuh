@@ -274,6 +274,7 @@ struct CapWalkParams {
     uint32_t* item_ticket;
     CapImgDev img;
     CapDev cap;                  // general tables (slow path, final states)
+    const struct TailExt* skip_tails;  // extractions whose items the tail walk (kernels/tailwalk.cu) takes, or null
     uint32_t span_stride;
     uint32_t smem_table_bytes;   // = img.smem_table_bytes, or 0 to read every table through L1/L2 (GORP_CAP_FLAGS=2)
     uint32_t flags;              // GORP_WALK_FLAGS (diagnostics): 1 = text loads L2 evict-first
@@ -287,6 +288,49 @@ void k4b_bucket(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t 
                 int32_t* spans, uint32_t span_stride);
 size_t capwalk_smem_bytes(const CapImgDev&);
 void k4b_capwalk(const Launch&, const CapWalkParams&);
+
+// K4c: tail walk — the capture half for extractions that have a tail automaton (host/tails.hpp, host/walktables.hpp:
+// TailImage) — see kernels/tailwalk.cu. Decides MISS / MATCH / CAPTURE_FAIL of candidate lines and writes their rows.
+constexpr int kTailWalkThreads = 256;
+constexpr uint32_t kTailMaxLen = 65000;   // lines at least this long take the 32-bit one-thread-per-line kernel
+struct TailExt {                 // mirrors host/walktables.hpp: TailImageExt
+    uint32_t tab_off;            // byte offset of the table inside the image (16-byte aligned)
+    uint32_t n_states, fin_base, n_outcomes;
+    uint32_t res_off, oext_off, init_off, n_init, n_slots, available;
+};
+struct TailDev {
+    const uint16_t* image;       // all tables: rows of `width` u16 entries (next row << 6) | op slot
+    const TailExt* ext;          // [E]
+    const uint32_t* res;         // [n_outcomes * span_stride] per extraction: group boundary recipes
+    const int32_t* oext;         // outcome -> ext code (-1 | e | -2-e)
+    const uint8_t* init_slots;
+    const uint16_t* xcol;        // [65536] unit -> column
+    const uint16_t* pair_col;    // [width]
+    uint32_t width, row_bytes, span_stride;
+    uint32_t max_table_bytes, max_slots, max_res, max_outcomes;  // shared-memory sizing (the largest tail)
+    uint32_t n_without;          // extractions without a tail (their items stay with the bucketed capture walk)
+    uint32_t enabled;
+};
+struct TailWalkParams {
+    const uint16_t* text;
+    int64_t n_units;
+    const int64_t* line_off;
+    const uint32_t* perm;        // line ids grouped by (candidate) extraction
+    const CapItem* items;
+    const uint32_t* n_items;
+    uint32_t* item_ticket;       // zeroed by the caller
+    TailDev t;
+    uint32_t n_ext;
+    uint32_t flush_every;        // result rows go out every `flush_every` walk iterations (power of two)
+    int32_t* ext_id;
+    int32_t* spans;
+    unsigned long long* hist;    // [E+2]: a candidate that ends as MISS / CAPTURE_FAIL moves its count
+    uint32_t* long_lines;        // [long_cap] lines handed to the 32-bit kernel
+    uint32_t* n_long;            // zeroed by the caller
+    uint32_t long_cap;
+};
+size_t tailwalk_smem_bytes(const TailDev&);
+void k4c_tailwalk(const Launch&, const TailWalkParams&);
 
 // result assembly of a batch that is pipelined in pieces: dst[i] = src[i] + bias ; dst[i] += src[i]
 void k_bias_copy(const Launch&, int64_t* dst, const int64_t* src, int64_t n, int64_t bias);

@@ -307,3 +307,156 @@ extern "C" int64_t ht_run_walk(const void* blob, size_t len, const uint16_t* tex
         return -1;
     }
 }
+
+// Tail automata (host/tails.hpp): per extraction out[4*e..] = available, states, op slots, outcomes; summary[0..4] = width,
+// cut states, compact DFA states, any. Returns the extraction count.
+#include "../../gorp_b200/csrc/host/tails.hpp"
+
+extern "C" int ht_tail_sizes(const void* blob, size_t len, uint32_t* out, int cap, uint32_t* summary, char* err, int errlen) {
+    try {
+        CompiledDefinition def = parse_blob(blob, len);
+        DeviceModel m = build_device_model(def);
+        finalize_device_model(m, build_fused(m));
+        const TailSet T = build_tails(def, m);
+        int n = 0;
+        for (auto& t : T.tails) {
+            if (n < cap) {
+                out[4 * n] = t.available ? 1u : 0u;
+                out[4 * n + 1] = t.n_states;
+                out[4 * n + 2] = t.n_op_slots;
+                out[4 * n + 3] = static_cast<uint32_t>(t.outcomes.size());
+            }
+            if (!t.available && n < 3) std::snprintf(err, errlen, "tail %d: %s", n, t.why_not.c_str());
+            ++n;
+        }
+        summary[0] = T.width;
+        summary[1] = T.n_cut_states;
+        summary[2] = m.dfa.n_states;
+        summary[3] = T.any ? 1u : 0u;
+        return n;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
+
+// The big-definition text path with the early-exit cut (host/tails.hpp) interpreted the way kernels/dfawalk.cu (K2b over
+// the cut table) and kernels/tailwalk.cu (K4c over the tail image) run it: '\n' split; combined DFA over the cut table in
+// 16-unit blocks until a FIN row (dead => MISS at once, cut state => candidate e); tail automaton of the candidate from the
+// line start, op slots hold position + 1, outcome + recipes at the end. Lines whose candidate has no tail fall back to the
+// capture automaton of the extraction (general tables) — those extractions are never cut, so the candidate is exact.
+// Returns the line count, or -1 (err) / -2 (no tails). stats[0] = lines that left the DFA walk early, [1] = units walked by
+// the DFA, [2] = cut-table states, [3] = lines decided by a tail.
+extern "C" int64_t ht_run_tails(const void* blob, size_t len, const uint16_t* text, int64_t n_units, int64_t cap_lines, int32_t* ext,
+                                int32_t* spans, int stride, uint64_t* stats, char* err, int errlen) {
+    try {
+        CompiledDefinition def = parse_blob(blob, len);
+        DeviceModel m = build_device_model(def);
+        finalize_device_model(m, build_fused(m));
+        const TailSet T = build_tails(def, m);
+        if (!T.any) return -2;
+        const DfaWalkTable D = build_dfawalk_table_cut(m, T.cut_of_state);
+        const TailImage I = build_tail_image(T, static_cast<uint32_t>(stride));
+        if (!D.available || !I.available) return -2;
+        auto unit = [&](int64_t p) -> uint32_t { return p < n_units ? text[p] : 0x0Au; };
+        if (stats) stats[0] = stats[1] = stats[3] = 0, stats[2] = D.n_states;
+        int64_t n_lines = 0, a = 0;
+        while (a < n_units) {
+            int64_t b = a;
+            while (b < n_units && text[b] != 0x0A) ++b;
+            if (n_lines >= cap_lines) return -1;
+            // ---- combined DFA, cut
+            int64_t q = a & ~int64_t(15);
+            uint32_t st = a - q ? D.n_states + static_cast<uint32_t>(a - q) : 0u;
+            while (st < D.fin_base) {
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t u = unit(q + k);
+                    const uint32_t col = u < 128 ? D.cls128[u] / 2u : D.xcls[u];
+                    st = D.rows[static_cast<size_t>(st) * D.K + col];
+                }
+                q += 16;
+            }
+            if (stats) {
+                stats[1] += static_cast<uint64_t>(std::min<int64_t>(q, b + 1) - a);
+                if (q <= b) ++stats[0];
+            }
+            const int32_t e = static_cast<int32_t>(st - D.fin_base) - 1;
+            int32_t* out = spans + n_lines * stride;
+            for (int k = 0; k < stride; ++k) out[k] = -1;
+            ext[n_lines] = e;
+            if (e >= 0 && I.ext[e].available) {
+                if (stats) ++stats[3];
+                const TailImageExt& x = I.ext[e];
+                const uint16_t* tab = I.image.data() + x.tab_off / 2;
+                std::vector<uint32_t> slots(64, 0xDEAD);  // garbage on purpose: only the init slots are reset per line
+                for (uint32_t i = 0; i < x.n_init; ++i) slots[I.init_slots[x.init_off + i]] = 0;
+                q = a & ~int64_t(15);
+                uint32_t row = a - q ? x.n_states + static_cast<uint32_t>(a - q) - 1 : 0u;
+                while (row < x.fin_base) {
+                    for (int k = 0; k < 16; ++k) {
+                        const uint32_t u = unit(q + k);
+                        uint32_t col = u < 128 ? u : T.xcol[u];
+                        if ((u & 0xFC00u) == 0xD800u && (unit(q + k + 1) & 0xFC00u) == 0xDC00u) col = T.pair_col[col];
+                        const uint32_t ent = tab[static_cast<size_t>(row) * I.width + col];
+                        row = ent >> 6;
+                        slots[ent & 63u] = static_cast<uint32_t>(q + k - a + 1);
+                    }
+                    q += 16;
+                }
+                const uint32_t o = row - x.fin_base;
+                const int32_t code = I.oext[x.oext_off + o];
+                ext[n_lines] = code;
+                if (code >= 0)
+                    for (int k = 0; k < stride; ++k) {
+                        uint32_t rec = I.res[x.res_off + static_cast<size_t>(o) * stride + k];
+                        int32_t val = -1;
+                        if (rec == 0xFF) {
+                            val = static_cast<int32_t>(b - a);
+                        } else if (rec) {
+                            uint32_t best = 0;
+                            for (; rec; rec >>= 8) best = std::max(best, slots[rec & 0xFFu]);
+                            val = static_cast<int32_t>(best) - 1;
+                        }
+                        out[k] = val;
+                    }
+            } else if (e >= 0) {  // no tail: the general capture automaton (as ht_run)
+                const Tdfa& t = m.tdfas[e];
+                std::vector<int32_t> regs(t.n_regs + 1, -7);
+                uint32_t s = 0;
+                bool ok = true;
+                const int64_t L = b - a;
+                for (int64_t i = 0; i < L; ++i) {
+                    const uint32_t u = text[a + i];
+                    uint32_t k = m.symbols.classmap[u];
+                    if ((u & 0xFC00) == 0xD800 && i + 1 < L && (text[a + i + 1] & 0xFC00) == 0xDC00) k = m.symbols.pair_hi_class;
+                    const uint32_t ent = t.trans[static_cast<size_t>(s) * t.n_classes + k];
+                    if ((ent & 0xFFFF) == 0xFFFF) {
+                        ok = false;
+                        break;
+                    }
+                    const uint32_t ol = ent >> 16;
+                    for (uint32_t i2 = t.op_off[ol]; i2 < t.op_off[ol + 1]; ++i2) {
+                        const uint32_t op = t.ops[i2], src = op & 0xFF;
+                        regs[op >> 8] = src == 0xFF ? static_cast<int32_t>(i) : regs[src];
+                    }
+                    s = ent & 0xFFFF;
+                }
+                if (ok) ok = t.accepting[s] != 0;
+                if (!ok) {
+                    ext[n_lines] = -2 - e;
+                } else {
+                    for (uint32_t k = 0; k < t.n_slots && static_cast<int>(k) < stride; ++k) {
+                        const uint8_t f = t.fin[static_cast<size_t>(s) * t.n_slots + k];
+                        out[k] = f == 0xFF ? -1 : (f == 0xFE ? static_cast<int32_t>(L) : regs[f]);
+                    }
+                }
+            }
+            ++n_lines;
+            a = b + 1;
+        }
+        return n_lines;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}

@@ -66,3 +66,24 @@ def run_walk(blob_bytes: bytes, text: np.ndarray, stride: int, smem_variant: boo
     if n < 0:
         raise RuntimeError(err.value.decode())
     return ext[:n], spans[:n, :stride]
+
+
+def run_tails(blob_bytes: bytes, text: np.ndarray, stride: int):
+    """Interprets the early-exit DFA table + tail automata (host/tails.hpp) the way kernels/dfawalk.cu (K2b) and
+    kernels/tailwalk.cu walk them. Returns (ext, spans, stats) or None when the definition gets no tails."""
+    lib = load()
+    text = np.ascontiguousarray(text, dtype=np.uint16)
+    cap = int((text == 10).sum()) + 2
+    ext = np.empty(cap, dtype=np.int32)
+    spans = np.full((cap, max(stride, 1)), -1, dtype=np.int32)
+    stats = np.zeros(4, dtype=np.uint64)
+    err = C.create_string_buffer(1024)
+    P = C.c_void_p
+    lib.ht_run_tails.restype = C.c_int64
+    n = lib.ht_run_tails(blob_bytes, C.c_size_t(len(blob_bytes)), P(text.ctypes.data), C.c_int64(len(text)), C.c_int64(cap),
+                         P(ext.ctypes.data), P(spans.ctypes.data), C.c_int(max(stride, 1)), P(stats.ctypes.data), err, C.c_int(1024))
+    if n == -2:
+        return None
+    if n < 0:
+        raise RuntimeError(err.value.decode())
+    return ext[:n], spans[:n, :stride], stats

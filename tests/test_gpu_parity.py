@@ -115,10 +115,13 @@ def test_config_corpora(name, n, monkeypatch):
     table), #5 non-ASCII UTF-16 + divergence characters + 10 KB outliers."""
     d, gen = corpus.CONFIGS[name]
     text = gen(n)
-    if name in ("weblog", "syslog200", "utf16mix"):  # both DFA tiers of the big-definition path (K0d / K1 + K2b)
+    if name in ("weblog", "syslog200", "utf16mix"):  # both DFA tiers of the big-definition path (K0d / K1 + K2b) ...
         for tier in ("1", "2"):
             monkeypatch.setenv("GORP_DFA_TIER", tier)
             check_against_oracle(d, text=text)
+        monkeypatch.setenv("GORP_NO_TAILS", "1")  # ... and the two-walk path without the early exit / tail automata
+        check_against_oracle(d, text=text)
+        monkeypatch.delenv("GORP_NO_TAILS")
         monkeypatch.delenv("GORP_DFA_TIER")
     _, b, oe = check_against_oracle(d, text=text)
     assert b.n_lines == n and (oe >= 0).sum() > n // 3
@@ -203,13 +206,17 @@ def test_full_size_properties_big_definitions(name, n, reps):
 
 
 TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
+         "dfawalk_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1", "GORP_NO_TAILS": "1"},
+         "linewalk_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_NO_TAILS": "1"},
+         "linewalk_tailwalk_flush1": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_TAIL_FLUSH": "1"},
          "dfawalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1"},
          "linewalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2"},
          "dfawalk_k4": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1", "GORP_FORCE_K4": "1"},
          "k1k2_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1"},
          "twopass_fast": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1", "GORP_FORCE_K4": "1"},
          "general": {"GORP_FORCE_GENERAL": "1"}}
-_TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES", "GORP_FORCE_K1K2", "GORP_FORCE_K4", "GORP_DFA_TIER")
+_TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES", "GORP_FORCE_K1K2", "GORP_FORCE_K4", "GORP_DFA_TIER",
+             "GORP_NO_TAILS", "GORP_TAIL_FLUSH")
 
 
 @pytest.mark.parametrize("tier", list(TIERS))
@@ -242,6 +249,21 @@ def test_every_kernel_tier_text_form(tier, monkeypatch):
     text = np.concatenate([np.concatenate((np.asarray(jdkre.to_units(s), dtype=np.uint16), [10])) for s in lines]).astype(np.uint16)
     check_against_oracle(V.README_DEF, text=text)
     check_against_oracle(V.README_DEF, text=text[:-1])  # last line not terminated
+
+
+def test_tail_walk_very_long_lines(monkeypatch):
+    """Lines of 65 000 units and more leave the 16-bit tail walk for the one-thread-per-line kernel with 32-bit positions;
+    results stay exact (spans far beyond 65 535, non-ASCII content, a candidate that ends as MISS / CAPTURE_FAIL)."""
+    monkeypatch.setenv("GORP_FORCE_TWOPASS", "1")  # the README definition would otherwise take the one-pass kernel
+    monkeypatch.setenv("GORP_DFA_TIER", "2")
+    rng = np.random.default_rng(17)
+    lines = corpus.weblog_lines(300, seed=8)
+    body = "".join(rng.choice(list("abcdefghij0123456789/"), size=70000))
+    lines += ["[1]: GET 2ms /" + body, "[2]: PUT 31ms /" + body * 3 + "\u00e9" + body, "[3]: GET 2ms /" + body + " tail",
+              "[4]: HEAD 7ms /" + body[:64990], "[5]: GET 2ms /" + body + "\x0bq", "[6]: GET 2ms /" + "\U0001F600" * 40000]
+    _, b, oe = check_against_oracle(V.README_DEF, text=corpus.lines_to_text(lines))
+    assert int(b.spans.max()) > 65535 and (oe[-6:] >= 0).sum() >= 3
+    check_against_oracle(corpus.WEBLOG_DEF, text=corpus.lines_to_text(lines))
 
 
 def test_host_calls_pipelined_in_pieces(monkeypatch):

@@ -205,6 +205,55 @@ def test_walk_tables_on_config_definitions(name):
     compare_walk_tables(d, gen(800) + TRICKY_LINES)
 
 
+def compare_tails(definition, lines, drop_last_newline=False, need_tails=False):
+    """The early-exit DFA table and the per-extraction tail automata (host/tails.hpp) interpreted the way K2b and the tail
+    walk run them, against the oracle: same outcome (MISS / MATCH / CAPTURE_FAIL) and spans on every line."""
+    g = DefinitionReader.reader(definition).read()
+    o = gorp_oracle.Gorp(definition)
+    text, starts, ends = pack(lines)
+    if drop_last_newline:
+        text = text[:-1]
+    G = max(len(x.extractor_names) for x in o.extractions)
+    oe, osp = o.extract_batch(text, (starts, ends), threads=1)
+    r = hostlib.run_tails(g.blob().bytes(), text, 2 * G)
+    if r is None:
+        assert not need_tails
+        return None
+    ext, spans, stats = r
+    assert len(ext) == len(lines)
+    bad = [i for i in range(len(lines)) if ext[i] != oe[i] or (spans[i] != osp[i][:2 * G]).any()]
+    assert not bad, [(lines[i], int(ext[i]), int(oe[i]), spans[i].tolist(), osp[i].tolist()) for i in bad[:5]]
+    return stats
+
+
+@pytest.mark.parametrize("case", ALL_DEFS)
+def test_tail_automata_reproduce_oracle(case):
+    lines = [c[0] for c in case[1]] + TRICKY_LINES
+    compare_tails(case[0], lines)
+    compare_tails(case[0], [s for s in lines if s] + ["[1]: GET 2ms /tail"], drop_last_newline=True)
+
+
+@pytest.mark.parametrize("name", ["readme", "simple", "weblog", "syslog200", "utf16mix"])
+def test_tail_automata_on_config_definitions(name):
+    from gorp_b200 import corpus
+    d, _ = corpus.CONFIGS[name]
+    if name in ("readme", "simple"):
+        text = corpus.CONFIGS[name][1](1500)
+        lines = "".join(map(chr, text.tolist())).split("\n")[:-1]
+    else:
+        lines = {"weblog": corpus.weblog_lines, "syslog200": corpus.syslog200_lines, "utf16mix": corpus.utf16_mix_lines}[name](1500)
+    stats = compare_tails(d, lines + TRICKY_LINES, need_tails=True)
+    if name == "syslog200":  # the walk over the combined DFA stops after the app name: most lines leave it early
+        assert stats[0] > 0.9 * len(lines) and stats[2] < 64, stats.tolist()
+
+
+def test_tail_automata_fuzz_small_alphabet():
+    rng = np.random.default_rng(5)
+    for definition in FUZZ_PATTERNS:
+        lines = ["".join(rng.choice(list("abcd: "), size=rng.integers(0, 24))) for _ in range(1500)]
+        compare_tails(definition, lines)
+
+
 def test_minimised_capture_automata_reproduce_oracle():
     """minimise_tdfa (Moore minimisation of the tagged automata, used for the tables of the bucketed capture walk) on every
     definition and fuzz pattern, including the small ones the engine leaves unminimised: same outcomes and spans."""
