@@ -124,8 +124,8 @@ TailImage build_tail_image(const TailSet& T, uint32_t span_stride) {
     TailImage I;
     if (!T.any) return I;
     const size_t E = T.tails.size();
-    I.width = T.width;
-    I.row_bytes = T.width * 2;
+    I.width = T.width + 2;  // an odd number of 32-bit words per row: the rows of lanes in different states spread over the banks
+    I.row_bytes = I.width * 2;
     I.span_stride = span_stride;
     I.ext.assign(E, TailImageExt{});
     for (size_t e = 0; e < E; ++e) {
@@ -133,6 +133,11 @@ TailImage build_tail_image(const TailSet& T, uint32_t span_stride) {
         if (!A.available) continue;
         const uint32_t S = A.n_states, fin_base = S + 15, n_out = static_cast<uint32_t>(A.outcomes.size()), rows = fin_base + n_out;
         if (rows > 1023 || A.n_op_slots + 1 > 63) continue;  // 10-bit row ids, 6-bit slots
+        size_t n_multi = 0;  // group boundaries with several writers (kernels/tailwalk.cu keeps at most 64 of them per table)
+        for (const FusedAutomaton::Outcome& oc : A.outcomes)
+            if (oc.ext_code >= 0)
+                for (uint32_t k = 0; k < A.n_boundaries && k < span_stride; ++k) n_multi += A.res[oc.res_off + k] >= 256u ? 1 : 0;
+        if (n_multi > 64) continue;
         while (I.image.size() % 8) I.image.push_back(0);
         TailImageExt& x = I.ext[e];
         x.tab_off = static_cast<uint32_t>(I.image.size() * 2);
@@ -146,17 +151,17 @@ TailImage build_tail_image(const TailSet& T, uint32_t span_stride) {
         x.n_slots = A.n_op_slots + 1;
         x.available = 1;
         const size_t base = I.image.size();
-        I.image.resize(base + static_cast<size_t>(rows) * T.width);
+        I.image.resize(base + static_cast<size_t>(rows) * I.width);
         auto put = [&](uint32_t r, uint32_t k, uint32_t next_row, uint32_t slot) {
-            I.image[base + static_cast<size_t>(r) * T.width + k] = static_cast<uint16_t>((next_row << 6) | slot);
+            I.image[base + static_cast<size_t>(r) * I.width + k] = static_cast<uint16_t>((next_row << 6) | slot);
         };
         for (uint32_t r = 0; r < rows; ++r)
-            for (uint32_t k = 0; k < T.width; ++k) {
+            for (uint32_t k = 0; k < I.width; ++k) {
                 if (r < S) {
                     if (k == 0x0A) {
                         put(r, k, fin_base + A.outcome_of[r], 0);
                     } else {
-                        const uint32_t ent = A.trans[static_cast<size_t>(r) * T.width + k];
+                        const uint32_t ent = k < T.width ? A.trans[static_cast<size_t>(r) * T.width + k] : 0xFFFFu;
                         if ((ent & 0xFFFFu) == 0xFFFFu) put(r, k, fin_base, 0);  // dead (or a padding column): MISS
                         else put(r, k, ent & 0xFFFFu, ent >> 16);
                     }

@@ -34,6 +34,10 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
 }
 
 // one step on an ASCII unit held in byte kByte (0 or 2) of w. `ra` = byte offset of the current row + rows_abs.
+// bytes between the same thread's cells of two consecutive slots: an odd number of 32-bit words, so that the lanes of a warp
+// that store to different slots in the same step spread over the banks (two neighbouring lanes share a word)
+constexpr uint32_t kSlotStride = kTailWalkThreads * 2 + 4;
+
 template <int kByte>
 __device__ __forceinline__ void tw_step(uint32_t& ra, uint32_t w, uint32_t rows_abs, uint32_t row_bytes, uint32_t slot_abs, uint32_t pos1) {
     uint32_t b, a;
@@ -42,7 +46,7 @@ __device__ __forceinline__ void tw_step(uint32_t& ra, uint32_t w, uint32_t rows_
     const uint32_t ent = lds_u16(a);
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ra) : "r"(ent >> 6), "r"(row_bytes), "r"(rows_abs));
     uint32_t sa;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(ent & 63u), "n"(kTailWalkThreads * 2), "r"(slot_abs));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(ent & 63u), "n"(kSlotStride), "r"(slot_abs));
     sts_u16(sa, pos1);
 }
 
@@ -67,33 +71,40 @@ __device__ __noinline__ uint32_t tw_slow16(const TailDev& T, uint32_t ra, const 
         }
         const uint32_t ent = lds_u16(ra + col * 2);
         ra = (ent >> 6) * row_bytes + rows_abs;
-        sts_u16(slot_abs + (ent & 63u) * (kTailWalkThreads * 2), pos1 + k);
+        sts_u16(slot_abs + (ent & 63u) * kSlotStride, pos1 + k);
     }
     return ra;
 }
 
 struct TwPending {  // a finished line whose result row has not been written yet
-    uint32_t line, outcome, len, bank_abs;
+    uint32_t line, outcome, bank_abs;
 };
 
+constexpr uint32_t kTwMaxMulti = 64;  // group boundaries with several writers, per extraction (else the table is refused)
+
 __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkParams P) {
-    extern __shared__ __align__(16) unsigned char s_mem[];  // [table][recipes][outcome codes][init list][slots: 2 banks]
-    __shared__ uint32_t s_item, s_cursor, s_loaded;
+    // [table][recipes][outcome codes][several-writer list][init list][slots: 2 banks x (max_slots + 2) x kSlotStride]
+    extern __shared__ __align__(16) unsigned char s_mem[];
+    __shared__ uint32_t s_item, s_cursor, s_loaded, s_n_multi;
     const TailDev& T = P.t;
     const uint32_t stride = T.span_stride;
     const uint32_t tab_bytes = T.max_table_bytes;
     uint32_t* s_res = reinterpret_cast<uint32_t*>(s_mem + tab_bytes);
     int32_t* s_oext = reinterpret_cast<int32_t*>(s_res + T.max_res);
-    uint8_t* s_init = reinterpret_cast<uint8_t*>(s_oext + T.max_outcomes);
+    uint32_t* s_multi = reinterpret_cast<uint32_t*>(s_oext + T.max_outcomes);  // (outcome << 16 | k), packed writers
+    uint8_t* s_init = reinterpret_cast<uint8_t*>(s_multi + 2 * kTwMaxMulti);
     unsigned char* s_slots = reinterpret_cast<unsigned char*>(s_init + 64);
     const uint32_t rows_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_mem));
     const uint32_t slot_abs0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_slots)) + threadIdx.x * 2;
-    const uint32_t slot_stride = kTailWalkThreads * 2, bank_bytes = T.max_slots * slot_stride;
+    // per bank: slots 0..max_slots-1 of the table (0 = dummy), then ZERO (never written: reads as "no writer") and LEN
+    const uint32_t zero_off = T.max_slots * kSlotStride, len_off = zero_off + kSlotStride, bank_bytes = len_off + kSlotStride;
     const uint32_t row_bytes = T.row_bytes;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const uint32_t n_items = *P.n_items;
     const uint32_t flush_mask = P.flush_every - 1u;
     if (threadIdx.x == 0) s_loaded = 0xFFFFFFFFu;
+    sts_u16(slot_abs0 + zero_off, 0u);
+    sts_u16(slot_abs0 + bank_bytes + zero_off, 0u);
 
     for (;;) {
         __syncthreads();  // the previous item is finished (its table and s_item / s_cursor are free)
@@ -109,12 +120,29 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
             const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(T.image) + x.tab_off);
             uint4* dst = reinterpret_cast<uint4*>(s_mem);
             for (uint32_t i = threadIdx.x; i < n16; i += kTailWalkThreads) dst[i] = __ldg(src + i);
+            if (threadIdx.x == 0) s_n_multi = 0;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < x.n_outcomes; i += kTailWalkThreads) s_oext[i] = __ldg(T.oext + x.oext_off + i);
             for (uint32_t i = threadIdx.x; i < x.n_outcomes * stride; i += kTailWalkThreads) {
                 const uint32_t rec = __ldg(T.res + x.res_off + i);
-                // one writer: byte offset of its slot inside a bank; several: bit 31 | one slot id per byte; 0 = none; 0xFF = length
-                s_res[i] = (rec == 0u || rec == 0xFFu) ? rec << 24 : (rec < 256u ? rec * slot_stride : 0x80000000u | rec);
+                const bool match = __ldg(T.oext + x.oext_off + i / stride) >= 0;
+                // a recipe becomes the byte offset (inside a bank) of the slot that holds the boundary + 1:
+                // no writer / not a MATCH outcome -> ZERO, the line length -> LEN, one writer -> its slot,
+                // several writers -> ZERO here and an entry in the several-writer list
+                uint32_t off = zero_off;
+                if (match && rec == 0xFFu) {
+                    off = len_off;
+                } else if (match && rec && rec < 256u) {
+                    off = rec * kSlotStride;
+                } else if (match && rec) {
+                    const uint32_t at = atomicAdd(&s_n_multi, 1u);
+                    if (at < kTwMaxMulti) {
+                        s_multi[2 * at] = ((i / stride) << 16) | (i % stride);
+                        s_multi[2 * at + 1] = rec;
+                    }
+                }
+                s_res[i] = off;
             }
-            for (uint32_t i = threadIdx.x; i < x.n_outcomes; i += kTailWalkThreads) s_oext[i] = __ldg(T.oext + x.oext_off + i);
             for (uint32_t i = threadIdx.x; i < x.n_init; i += kTailWalkThreads) s_init[i] = __ldg(T.init_slots + x.init_off + i);
         }
         if (threadIdx.x == 0) s_cursor = it.begin;
@@ -124,8 +152,10 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
         const int32_t cand = static_cast<int32_t>(it.ext);
         const uint32_t fin_ra = x.fin_base * row_bytes + rows_abs;
         const uint32_t skip_ra = x.n_states * row_bytes + rows_abs;  // SKIP_1; SKIP_k = skip_ra + (k - 1) * row_bytes
+        const uint32_t n_multi = min(s_n_multi, kTwMaxMulti);
 
-        // writes the result row of a finished line (the thread's own; rows are `stride` int32)
+        // writes the result row of a finished line (the thread's own; rows are `stride` int32): every entry is
+        // "what its slot holds" - 1 (ZERO slot: -1), the several-writer boundaries are patched afterwards
         auto flush = [&](const TwPending& pd) {
             const int32_t code = s_oext[pd.outcome];
             if (code != cand) {  // the candidate did not match after all: MISS (regex_e rejects) or CAPTURE_FAIL
@@ -135,15 +165,7 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
             }
             int32_t* out = P.spans + static_cast<int64_t>(pd.line) * stride;
             const uint32_t* res = s_res + pd.outcome * stride;
-            auto value = [&](uint32_t recipe) -> int32_t {
-                if (code < 0 || recipe == 0u) return -1;
-                if (recipe == 0xFF000000u) return static_cast<int32_t>(pd.len);
-                if (!(recipe & 0x80000000u)) return static_cast<int32_t>(lds_u16(pd.bank_abs + recipe)) - 1;
-                recipe &= 0x7FFFFFFFu;
-                uint32_t best = lds_u16(pd.bank_abs + (recipe & 0xFFu) * slot_stride);
-                for (recipe >>= 8; recipe; recipe >>= 8) best = max(best, lds_u16(pd.bank_abs + (recipe & 0xFFu) * slot_stride));
-                return static_cast<int32_t>(best) - 1;
-            };
+            auto value = [&](uint32_t off) -> int32_t { return static_cast<int32_t>(lds_u16(pd.bank_abs + off)) - 1; };
             if ((stride & 3u) == 0) {
                 for (uint32_t k = 0; k < stride; k += 4) {
                     const uint4 r4 = *reinterpret_cast<const uint4*>(res + k);
@@ -157,19 +179,27 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
             } else {
                 for (uint32_t k = 0; k < stride; ++k) out[k] = value(res[k]);
             }
+            for (uint32_t i = 0; i < n_multi; ++i) {  // rare: a boundary with several writers = the latest of them
+                const uint32_t key = s_multi[2 * i];
+                if ((key >> 16) != pd.outcome) continue;
+                uint32_t rec = s_multi[2 * i + 1], best = 0;
+                for (; rec; rec >>= 8) best = max(best, lds_u16(pd.bank_abs + (rec & 0xFFu) * kSlotStride));
+                out[key & 0xFFFFu] = static_cast<int32_t>(best) - 1;
+            }
         };
 
         // per-lane state: the line being walked, and the NEXT line of the lane, claimed one line ahead so that its id
-        // (perm), start and end (line_off) are loaded long before they are needed
+        // (perm), start and end (line_off) are loaded and its text is on the way to L2 long before the walk needs them
         bool exhausted = false;  // warp-uniform: the item has no unclaimed line left
         bool active = false, pending = false;
-        TwPending pd{0, 0, 0, 0};
-        uint32_t line = 0, len = 0, it_count = 0;
-        int64_t a = 0, q = 0;
+        TwPending pd{0, 0, 0};
+        uint32_t line = 0, it_count = 0;
+        int64_t a = 0, q = 0, last_q = 0;
         uint32_t ra = fin_ra, bank_abs = slot_abs0;
-        uint32_t nstage = 0;  // 0 = no next line, 1 = id requested, 2 = start and end requested
+        uint32_t nstage = 0;  // 0 = no next line, 1 = id requested, 2 = start and end requested, 3 = text prefetch issued
         uint32_t nline = 0;
         int64_t na = 0, nb = 0;
+        Units16 nxt{};  // the block at q, loaded one iteration ahead
         for (;;) {
             if (!active && nstage) {  // start the claimed line
                 if (nstage == 1) {
@@ -184,14 +214,24 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
                 } else {
                     line = nline;
                     a = na;
-                    len = static_cast<uint32_t>(len64);
                     q = a & ~int64_t(15);
+                    last_q = (nb - 1) & ~int64_t(15);  // the block that holds the line's '\n'
+                    nxt = load_units16_l2keep(P.text, q, P.n_units);
                     const uint32_t lo = static_cast<uint32_t>(a - q);
                     ra = lo ? skip_ra + (lo - 1) * row_bytes : rows_abs;
                     if (pending) bank_abs = pd.bank_abs == slot_abs0 ? slot_abs0 + bank_bytes : slot_abs0;
-                    for (uint32_t i = 0; i < x.n_init; ++i) sts_u16(bank_abs + s_init[i] * slot_stride, 0u);
+                    for (uint32_t i = 0; i < x.n_init; ++i) sts_u16(bank_abs + s_init[i] * kSlotStride, 0u);
+                    sts_u16(bank_abs + len_off, static_cast<uint32_t>(len64) + 1u);
                     active = true;
                 }
+            } else if (nstage == 2) {  // the line's bytes, in one piece, on their way to L2 while the current line is walked
+                const int64_t p0 = na & ~int64_t(15);
+                int64_t bytes = ((nb - p0) * 2 + 15) & ~int64_t(15);
+                if (p0 + bytes / 2 > P.n_units) bytes = ((P.n_units - p0) * 2) & ~int64_t(15);
+                if (bytes > 4096) bytes = 4096;
+                if (bytes > 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.text + p0), "r"(static_cast<uint32_t>(bytes)) : "memory");
+                nstage = 3;
             } else if (nstage == 1) {
                 na = __ldg(P.line_off + nline);
                 nb = __ldg(P.line_off + nline + 1);
@@ -213,7 +253,8 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
             }
             if (!__any_sync(0xffffffffu, active || nstage != 0)) break;
             if (active) {
-                const Units16 u = load_units16_l2keep(P.text, q, P.n_units);
+                const Units16 u = nxt;
+                if (q < last_q) nxt = load_units16_l2keep(P.text, q + 16, P.n_units);  // in flight during the 16 steps below
                 const uint32_t pos1 = static_cast<uint32_t>(q - a) + 1u;  // garbage while skipping: only ever stored to the dummy slot
                 if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
                     tw_step<0>(ra, u.a.x, rows_abs, row_bytes, bank_abs, pos1);
@@ -240,7 +281,6 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
                     if (pending) flush(pd);  // rare: two line ends of one lane between two flush points
                     pd.line = line;
                     pd.outcome = (ra - fin_ra) / row_bytes;
-                    pd.len = len;
                     pd.bank_abs = bank_abs;
                     pending = true;
                     active = false;
@@ -307,8 +347,8 @@ __global__ void __launch_bounds__(32) tail_long_kernel(TailWalkParams P) {
 }  // namespace
 
 size_t tailwalk_smem_bytes(const TailDev& t) {
-    return static_cast<size_t>(t.max_table_bytes) + static_cast<size_t>(t.max_res) * 4 + static_cast<size_t>(t.max_outcomes) * 4 + 64 +
-           2 * static_cast<size_t>(t.max_slots) * kTailWalkThreads * 2;
+    return static_cast<size_t>(t.max_table_bytes) + static_cast<size_t>(t.max_res) * 4 + static_cast<size_t>(t.max_outcomes) * 4 +
+           2 * kTwMaxMulti * 4 + 64 + 2 * static_cast<size_t>(t.max_slots + 2) * kSlotStride + 16;
 }
 
 void k4c_tailwalk(const Launch& L, const TailWalkParams& P) {

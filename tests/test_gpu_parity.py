@@ -311,6 +311,41 @@ def test_latin1_text_form(monkeypatch):
     assert g.extract_batch_text_latin1(b"[1]: GET 2ms /a").ext_id.tolist() == [1]
 
 
+def test_concurrent_calls_on_one_engine(monkeypatch):
+    """include/gorp_cuda.h promises that concurrent gorp_extract_* calls on one engine are allowed (the reference's Gorp is
+    immutable and "fully thread-safe", Gorp.java:22): 4 threads x several calls each, text and lines form mixed, every
+    result identical to the sequential one."""
+    import threading
+    monkeypatch.setenv("GORP_PIECE_UNITS", "60000")  # several pieces per call: the pipelined path with its shared buffers
+    jobs = []
+    for name, n in (("readme", 30000), ("weblog", 4000)):
+        d, gen = corpus.CONFIGS[name]
+        g = DefinitionReader.reader(d).read()
+        texts = [gen(n, seed=50 + k) for k in range(4)]
+        want = [g.extract_batch_text(t) for t in texts]
+        jobs.append((g, texts, want))
+    errors = []
+
+    def worker(k):
+        try:
+            for rep in range(3):
+                for g, texts, want in jobs:
+                    t = texts[(k + rep) % 4]
+                    w = want[(k + rep) % 4]
+                    b = g.extract_batch_text(t) if (k + rep) % 2 == 0 else g.extract_batch_text_latin1(t.astype(np.uint8))
+                    assert b.n_lines == w.n_lines and (b.ext_id == w.ext_id).all() and (b.spans == w.spans).all()
+                    assert (b.line_off == w.line_off).all() and (b.histogram == w.histogram).all()
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+
+
 def test_multi_device_engine(monkeypatch):
     """One engine over several GPUs: contiguous line-aligned ranges per device, rows concatenated in device order."""
     from gorp_b200 import _ffi
@@ -330,3 +365,21 @@ def test_multi_device_engine(monkeypatch):
     g3 = DefinitionReader.reader(corpus.WEBLOG_DEF).read(devices=list(range(n)))
     check_against_oracle(corpus.WEBLOG_DEF, lines=lines, gorp=g3)
     check_against_oracle(corpus.WEBLOG_DEF, text=corpus.lines_to_text(lines), gorp=g3)
+    # two host threads x all devices on the same engine: a call keeps every participating device until its rows are out
+    import threading
+    want = g.extract_batch_text(text)
+    errors = []
+
+    def worker():
+        try:
+            for _ in range(4):
+                b = g.extract_batch_text(text)
+                assert (b.ext_id == want.ext_id).all() and (b.spans == want.spans).all() and (b.line_off == want.line_off).all()
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+    ts = [threading.Thread(target=worker) for _ in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
