@@ -17,8 +17,10 @@ contiguous ranges, tables replicated, no data-path collective ("weak" scaling: t
   cpu_baseline the oracle's C restatement of the reference loop on the host cores (JVM unavailable here)
 
 Parity inside the bench (the parity tests proper are tests/ -m gpu): per config, the order-independent 64-bit hash of
-(line index, ext_id, spans) of the first block of lines computed from the GPU result must equal the hash computed
-from the CPU oracle's result for the same lines, and the batch histogram must equal the tiled block's.
+(line index, ext_id, spans) of the first 1 M lines of every rank's shard computed from the GPU result must equal the hash
+computed from the CPU oracle's result for the same lines (regenerated on the CPU: line i of a corpus is a pure function
+of (seed, i), gorp_b200/corpusgen.py), the device-generated text must equal the host-generated text there, and the
+histogram must equal the per-line outcomes. `parity.corpus_hash` sums all shards: the same number for every GPU count.
 
 --impl reference times the CPU restatement alone (the reference is pure Java; no JVM exists in this image), same
 `config` as this arm, on a bounded sample of it per step.
@@ -48,7 +50,8 @@ WORKLOADS = {
     "syslog200": ("config#4 200-extraction definition, combined DFA outgrows shared memory", 200_000),
     "utf16mix": ("config#5 nginx/Apache definition, non-ASCII UTF-16 + divergence characters + 10 KB outlier lines", 200_000),
 }
-SEED_OF = {"simple": 1, "readme": 2, "weblog": 3, "syslog200": 4, "utf16mix": 5}
+PREFIX_LINES = 1_000_000          # per rank: lines whose GPU rows are compared with the CPU oracle's (hash + histogram)
+CONFIG5_TOTAL_LINES = 281_600_000  # config #5: 100 GB of UTF-16 (355 B per line on average), sharded over the ranks
 EXTRA_CONFIGS = ["syslog200", "utf16mix", "weblog", "simple"]  # configs[] order: the 40 %-target config first
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # written by tools_ncu_traffic.py from an ncu --set full capture
 
@@ -132,9 +135,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_block(rank, workload):
-    from gorp_b200 import corpus
-    return corpus.CONFIGS[workload][1](WORKLOADS[workload][1], seed=0x5EED0000 + SEED_OF[workload] + 16 * rank)
+def host_lines(workload, first_line, n):
+    """Lines [first_line, first_line + n) of the workload's corpus, generated on the CPU (gorp_b200/corpusgen.py: line i is
+    a pure function of (seed, i); the GPU shards hold the same units, generated on the device)."""
+    from gorp_b200 import corpusgen
+    return corpusgen.host_text(workload, first_line, n)
 
 
 def definition_of(workload):
@@ -142,14 +147,12 @@ def definition_of(workload):
     return corpus.CONFIGS[workload][0]
 
 
-def config_dict(workload, lines_per_gpu, block_units, world, n_bins):
+def config_dict(workload, lines_per_gpu, world, n_bins):
     """The `config` object of a bench line; the reference arm prints the same object."""
-    desc, block_lines = WORKLOADS[workload]
-    reps = max(1, lines_per_gpu // block_lines)
-    n_units = reps * block_units
-    return {"workload": desc, "lines_per_gpu": reps * block_lines, "units_per_gpu": n_units, "bytes_per_gpu": n_units * 2,
-            "block": "%d-line seeded block (per-rank seed) tiled %dx in HBM" % (block_lines, reps),
-            "l2": "input (%.1f GB) is far larger than L2, no flush needed" % (n_units * 2 / 1e9),
+    desc, _ = WORKLOADS[workload]
+    return {"workload": desc, "lines_per_gpu": lines_per_gpu, "lines": lines_per_gpu * world,
+            "corpus": "counter-based generator: line i = f(seed, i), no tiling; rank r holds lines [r*L, (r+1)*L), generated on the device",
+            "l2": "the input of a step (GBs per GPU) is far larger than L2, no flush needed",
             "parallelism": "lines sharded per GPU as contiguous ranges, tables replicated; no data-path collective"
                            + (", one NCCL all-reduce of the %d-bin histogram per step" % n_bins if world > 1 else "")}
 
@@ -161,20 +164,18 @@ def run_reference(args, rank, world):
         return
     from oracle import gorp_oracle
     cores = os.cpu_count() or 1
-    desc, block_lines = WORKLOADS[args.workload]
-    block = make_block(0, args.workload)
     o = gorp_oracle.Gorp(definition_of(args.workload))
-    bst = gorp_oracle.split_lines(block)
-    o.extract_batch(block, bst, threads=cores)  # build + page-in
+    probe = host_lines(args.workload, 0, 200_000)
+    pst = gorp_oracle.split_lines(probe)
+    o.extract_batch(probe, pst, threads=cores)  # build + page-in
     t0 = time.perf_counter()
-    o.extract_batch(block, bst, threads=cores)
-    rate = block_lines / max(time.perf_counter() - t0, 1e-6)
-    total_lines = (args.lines_per_gpu // block_lines) * block_lines * world
+    o.extract_batch(probe, pst, threads=cores)
+    rate = len(pst[0]) / max(time.perf_counter() - t0, 1e-6)
+    total_lines = args.lines_per_gpu * world
     budget = args.ref_budget_s / max(args.steps + args.warmup, 1)
     sample_lines = total_lines if args.ref_lines == 0 else args.ref_lines
-    sample_lines = int(min(sample_lines, max(rate * budget * 0.8, block_lines)))
-    reps = max(1, sample_lines // block_lines)
-    text = np.tile(block, reps)
+    sample_lines = int(min(sample_lines, max(rate * budget * 0.8, 200_000)))
+    text = host_lines(args.workload, 0, sample_lines)
     starts, ends = gorp_oracle.split_lines(text)
     for _ in range(args.warmup):
         o.extract_batch(text, (starts, ends), threads=cores)
@@ -185,12 +186,12 @@ def run_reference(args, rank, world):
     n = len(starts)
     val = n / dt
     n_bins = len(o.extractions) + 2
-    sample = "%d lines (%.2f GB UTF-16) of the config's %d lines per step, all %d host threads" % (n, text.nbytes / 1e9, total_lines, cores)
+    sample = "the first %d lines (%.2f GB UTF-16) of the config's %d lines per step, all %d host threads" % (n, text.nbytes / 1e9, total_lines, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "lines/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic", "input_gb_per_s": text.nbytes / dt / 1e9,
-        "config": config_dict(args.workload, args.lines_per_gpu, block.size, world, n_bins),
+        "config": config_dict(args.workload, args.lines_per_gpu, world, n_bins),
         "reference_note": "the reference is pure Java and no JVM exists in this image: C restatement of Gorp.extract "
                           "(oracle/gorp_oracle.c), one extract per line, static partition over host threads; a rate metric, "
                           "measured on a bounded sample of the config per step",
@@ -203,19 +204,19 @@ class Env:
     pass
 
 
-def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None, keep=False):
-    """One config, device-resident: returns the result dict (and, with keep=True, the engine / block for the e2e leg)."""
+def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None, keep=False, first_line=None, corpus_note=None):
+    """One config, device-resident: returns the result dict (and, with keep=True, the engine / text for the e2e leg)."""
     torch, dist, lib, _ffi, Blob, _check, cudart = env.torch, env.dist, env.lib, env.ffi, env.Blob, env.check, env.cudart
-    from gorp_b200 import parityhash, sharding
+    from gorp_b200 import corpusgen, parityhash, sharding
     from oracle import gorp_oracle
     rank, world, dev = env.rank, env.world, env.dev
-    desc, block_lines = WORKLOADS[workload]
-    block = make_block(rank, workload)
-    reps = max(1, lines_per_gpu // block_lines)
-    n_lines = reps * block_lines
-    d_block = torch.from_numpy(block.view(np.int16)).to(dev)
-    d_text = d_block.repeat(reps)
-    del d_block
+    desc, _ = WORKLOADS[workload]
+    n_lines = lines_per_gpu
+    first_line = rank * n_lines if first_line is None else first_line
+    t0 = time.perf_counter()
+    d_text = corpusgen.device_text(workload, first_line, n_lines, dev)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
     n_units = d_text.numel()
     in_bytes = n_units * 2
     blob = Blob.from_definition(definition_of(workload))
@@ -229,11 +230,14 @@ def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None,
     dres = _ffi.DeviceResult()
     d_hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
 
-    # the block through the host-buffer call: its histogram (the tiled batch must give reps x that)
-    res0 = _ffi.Result()
-    _check(lib.gorp_extract_text(eng, block.ctypes.data, block.size, C.byref(res0)))
-    block_hist = np.ctypeslib.as_array(res0.histogram, (n_bins,)).copy()
-    lib.gorp_result_release(eng, C.byref(res0))
+    # the prefix of this rank's shard on the CPU: the same generator (line i = f(seed, i)), then the oracle
+    n_prefix = min(PREFIX_LINES, n_lines)
+    prefix = host_lines(workload, first_line, n_prefix)
+    assert (d_text[:prefix.size].cpu().numpy().view(np.uint16) == prefix).all(), "device-generated text differs from the host-generated text"
+    o = gorp_oracle.Gorp(definition_of(workload))
+    cores = os.cpu_count() or 1
+    pst = gorp_oracle.split_lines(prefix)
+    oe, osp = o.extract_batch(prefix, pst, threads=cores)
 
     def step(flags=0):
         _check(lib.gorp_extract_text_device(eng, 0, d_text.data_ptr(), n_units, stream, flags, C.byref(dres)))
@@ -252,22 +256,21 @@ def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None,
         step()
     torch.cuda.synchronize()
     assert dres.n_lines == n_lines, (dres.n_lines, n_lines)
-    (err,) = cudart.cudaMemcpyAsync(d_hist.data_ptr(), dres.d_histogram, n_bins * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, stream)
-    assert int(err) == 0, err
-    assert (d_hist.cpu().numpy() == reps * block_hist).all(), (d_hist.cpu().numpy().tolist(), (reps * block_hist).tolist())
-    # parity at full size: hash of the first block's rows (GPU result of the timed path) == hash of the oracle's rows
-    ext_t, sp_t = parityhash.device_results(dres, dev)
-    first_line = rank * n_lines
-    gpu_prefix = parityhash.hash_torch(first_line, ext_t[:block_lines], sp_t[:block_lines])
-    gpu_total = parityhash.hash_torch(first_line, ext_t, sp_t)
-    o = gorp_oracle.Gorp(definition_of(workload))
-    cores = os.cpu_count() or 1
-    bst = gorp_oracle.split_lines(block)
-    oe, osp = o.extract_batch(block, bst, threads=cores)
+    # parity at full size: rows of the shard's first lines (GPU result of the timed path) vs the oracle's rows — per-line
+    # outcomes through the 64-bit hash, and the whole shard's hash for the corpus hash (identical for every GPU count)
     stride = int(dres.span_stride)
+    ext_t, sp_t = parityhash.device_results(dres, dev)
+    gpu_prefix = parityhash.hash_torch(first_line, ext_t[:n_prefix], sp_t[:n_prefix])
+    gpu_total = parityhash.hash_torch(first_line, ext_t, sp_t)
     cpu_prefix = parityhash.hash_numpy(first_line, oe, osp[:, :stride])
     assert gpu_prefix == cpu_prefix, "parity hash mismatch on %s: gpu %x cpu %x" % (workload, gpu_prefix, cpu_prefix)
-    del ext_t, sp_t
+    local_hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
+    (err,) = cudart.cudaMemcpyAsync(local_hist.data_ptr(), dres.d_histogram, n_bins * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, stream)
+    assert int(err) == 0, err
+    torch.cuda.synchronize()
+    bins = torch.where(ext_t >= 0, ext_t, torch.where(ext_t == -1, n_bins - 2, n_bins - 1)).to(torch.int64)
+    assert (torch.bincount(bins, minlength=n_bins) == local_hist).all(), "histogram differs from the per-line outcomes"
+    del ext_t, sp_t, bins
     names = (C.c_char_p * 16)()
     tot = (C.c_double * 16)()
     cnt, calls, launches = C.c_int(), C.c_int64(), C.c_int64()
@@ -305,14 +308,13 @@ def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None,
     for i in range(cnt.value):  # a kernel that is marked twice in one call (retry) adds up
         kern[names[i].decode()] = kern.get(names[i].decode(), 0.0) + tot[i] / max(calls.value, 1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    h = torch.tensor([gpu_total & 0xFFFFFFFF, gpu_total >> 32], dtype=torch.int64, device=dev)
+    h = torch.tensor([gpu_total & 0xFFFFFFFF, gpu_total >> 32, in_bytes], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # 64-bit modular sum over ranks: 32-bit halves, carried
-        dist.all_reduce(h, op=dist.ReduceOp.SUM)
+        dist.all_reduce(h, op=dist.ReduceOp.SUM)  # 64-bit modular sum over ranks: 32-bit halves, carried below
     ms_max = float(t.item())
-    lo, hi = int(h[0].item()), int(h[1].item())
-    corpus_hash = (lo + (hi << 32)) & ((1 << 64) - 1)
+    corpus_hash = (int(h[0].item()) + (int(h[1].item()) << 32)) & ((1 << 64) - 1)
+    job_bytes = int(h[2].item())
     total_lines = n_lines * world
     peak, peak_src = hbm_peak()
     dom = max(kern, key=kern.get) if kern else None
@@ -323,39 +325,46 @@ def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None,
         per_kernel = {k: v["dram_bytes_per_text_byte"] * in_bytes for k, v in tr.items() if k in kern}
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": per_kernel.get(dom),
-                "traffic_step": sum(per_kernel.values()) if per_kernel and len(per_kernel) == len(kern) else None,
+                "traffic_step": sum(per_kernel.values()) if per_kernel else None,
                 "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum per text byte (%s) x bytes of this launch"
                                    % tr[dom]["source"]) if dom in tr else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": in_bytes,
                 "kernel_ms": kern[dom], "all_kernels_ms": kern,
-                "whole_step_frac": (in_bytes / (ms_max / 1e3) / 1e9) / peak,
-                "whole_step_frac_of_8TBps": (in_bytes / (ms_max / 1e3) / 1e9) / 8000.0}
+                "whole_step_frac": (job_bytes / world / (ms_max / 1e3) / 1e9) / peak,
+                "whole_step_frac_of_8TBps": (job_bytes / world / (ms_max / 1e3) / 1e9) / 8000.0,
+                "whole_step_note": "job input bytes / (n_gpus x step time x HBM peak): the aggregate HBM-read roofline fraction"}
+    cfg = config_dict(workload, lines_per_gpu, world, n_bins)
+    if corpus_note:
+        cfg["corpus"] += "; " + corpus_note
     out = {"workload": desc, "key": workload, "lines": total_lines, "lines_per_gpu": n_lines, "bytes_per_gpu": in_bytes,
-           "ms_per_step": ms_max, "value": total_lines / (ms_max / 1e3), "unit": "lines/s",
-           "input_gb_per_s": in_bytes * world / (ms_max / 1e3) / 1e9, "steps": steps, "roofline": roof,
-           "parity": {"prefix_lines_per_rank": block_lines, "prefix_hash_gpu": "%016x" % gpu_prefix,
+           "job_bytes": job_bytes, "ms_per_step": ms_max, "value": total_lines / (ms_max / 1e3), "unit": "lines/s",
+           "input_gb_per_s": job_bytes / (ms_max / 1e3) / 1e9, "steps": steps, "roofline": roof,
+           "parity": {"prefix_lines_per_rank": n_prefix, "prefix_hash_gpu": "%016x" % gpu_prefix,
                       "prefix_hash_cpu_oracle": "%016x" % cpu_prefix, "prefix_equal": True,
-                      "corpus_hash": "%016x" % corpus_hash, "histogram_equals_tiled_block": True,
-                      "what": "order-independent 64-bit hash of (global line index, ext_id, spans) — gorp_b200/parityhash.py"},
-           "gpu_launches": int(launches.value), "engine_create_s": create_s,
-           "config": config_dict(workload, lines_per_gpu, block.size, world, n_bins)}
+                      "device_text_equals_host_text_on_prefix": True,
+                      "corpus_hash": "%016x" % corpus_hash, "corpus_lines": total_lines,
+                      "histogram_equals_per_line_outcomes": True,
+                      "what": "order-independent 64-bit hash of (global line index, ext_id, spans) — gorp_b200/parityhash.py; the "
+                              "corpus hash sums every rank's shard and is the same number for every GPU count over the same lines"},
+           "gpu_launches": int(launches.value), "engine_create_s": create_s, "corpus_generate_s": gen_s, "config": cfg}
     # CPU baseline on rank 0: bounded sample of the same workload
     if rank == 0 and not env.args.skip_cpu:
-        creps = max(1, env.args.cpu_lines // block_lines)
-        ctext = np.tile(block, creps)
-        cst = gorp_oracle.split_lines(ctext)
+        c_lines = min(env.args.cpu_lines, n_lines)
+        ctext = prefix if c_lines <= n_prefix else host_lines(workload, first_line, c_lines)
+        cst = pst if c_lines <= n_prefix else gorp_oracle.split_lines(ctext)
         t0 = time.perf_counter()
         o.extract_batch(ctext, cst, threads=cores)
         cdt = time.perf_counter() - t0
+        one = 200_000
         t0 = time.perf_counter()
-        o.extract_batch(block, bst, threads=1)
+        o.extract_batch(prefix, (pst[0][:one], pst[1][:one]), threads=1)
         cdt1 = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": len(cst[0]) / cdt, "unit": "lines/s", "cores": cores, "kind": "port",
-                               "sample": "%d lines (%.2f GB) of the same workload, all %d host threads; 1 thread: %.0f lines/s"
-                                         % (len(cst[0]), ctext.nbytes / 1e9, cores, block_lines / cdt1),
+                               "sample": "the first %d lines (%.2f GB) of the same workload, all %d host threads; 1 thread: %.0f lines/s"
+                                         % (len(cst[0]), ctext.nbytes / 1e9, cores, min(one, len(pst[0])) / cdt1),
                                "note": "C restatement of the reference's Gorp.extract loop (JVM unavailable in this image)"}
     if keep:
-        return out, clocks, (eng, block, reps, n_units, in_bytes, barrier)
+        return out, clocks, (eng, d_text, n_lines, n_units, in_bytes, barrier)
     del d_text
     lib.gorp_engine_destroy(eng)
     torch.cuda.empty_cache()
@@ -365,8 +374,7 @@ def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None,
 def e2e_run(env, kept, workload):
     """config #2 end to end through the host-buffer C ABI (H2D + kernels + D2H inside the timed region)."""
     torch, dist, lib, _ffi, _check = env.torch, env.dist, env.lib, env.ffi, env.check
-    eng, block, reps, n_units, in_bytes, barrier = kept
-    block_lines = WORKLOADS[workload][1]
+    eng, d_text, n_lines, n_units, in_bytes, barrier = kept
     world, dev, args = env.world, env.dev, env.args
     try:
         if args.skip_e2e:
@@ -376,12 +384,16 @@ def e2e_run(env, kept, workload):
             if ln.startswith("MemAvailable"):
                 avail_gb = int(ln.split()[1]) / 1e6
         per_rank_gb = in_bytes / 1e9 * 1.6
-        e2e_reps = reps if avail_gb > per_rank_gb * world * 1.5 + 16 else max(1, int(reps * (avail_gb - 16) / (per_rank_gb * world * 1.5)))
-        e2e_lines = e2e_reps * block_lines
-        h_text = torch.empty(e2e_reps * block.size, dtype=torch.int16).pin_memory()
+        frac = 1.0 if avail_gb > per_rank_gb * world * 1.5 + 16 else max(0.01, (avail_gb - 16) / (per_rank_gb * world * 1.5))
+        # the host batch = the leading part of this rank's shard (cut after a '\n'), copied out of HBM once, outside the timed region
+        e2e_units = n_units
+        if frac < 1.0:
+            cut = int(n_units * frac)
+            nl = torch.nonzero(d_text[cut:cut + 100000] == 10)
+            e2e_units = cut + int(nl[0].item()) + 1
+        h_text = torch.empty(e2e_units, dtype=torch.int16).pin_memory()
+        h_text.copy_(d_text[:e2e_units])
         h_np = h_text.numpy().view(np.uint16)
-        for r in range(e2e_reps):
-            h_np[r * block.size:(r + 1) * block.size] = block
         res = _ffi.Result()
 
         def e2e_step():
@@ -397,20 +409,21 @@ def e2e_run(env, kept, workload):
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        ll = torch.tensor([nl], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ll, op=dist.ReduceOp.SUM)
         d2h = nl * 4 + (nl + 1) * 8 + ns * 4 + 5 * 8
-        e2e = {"value": e2e_lines * world / float(tt.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h_np.size * 2),
-               "d2h_bytes_per_step": int(d2h), "lines_per_step_per_gpu": int(e2e_lines), "ms_per_step": float(tt.item()) * 1e3,
+        e2e = {"value": int(ll.item()) / float(tt.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h_np.size * 2),
+               "d2h_bytes_per_step": int(d2h), "lines_per_step_per_gpu": int(nl), "ms_per_step": float(tt.item()) * 1e3,
                "h2d_gb_per_s_per_gpu": h_np.size * 2 / float(tt.item()) / 1e9,
                "timing": "host wall clock around gorp_extract_text (it returns after the last D2H), max over ranks"}
         # the same call fed with ISO-8859-1 bytes (what a JDK 9+ String with the LATIN1 coder holds; the synthetic corpus is
         # ASCII): gorp_extract_text_latin1 widens on the device, the host-to-device copy moves half the bytes
-        if int(block.max()) < 256:
-            h8_np = h_text.numpy().view(np.uint8)[:e2e_reps * block.size]  # reuses the pinned buffer of the UTF-16 run
-            b8 = block.astype(np.uint8)
-            for r in range(e2e_reps):
-                h8_np[r * block.size:(r + 1) * block.size] = b8
+        if int(d_text.max().item()) < 256 and int(d_text.min().item()) >= 0:
+            h8 = torch.empty(e2e_units, dtype=torch.uint8).pin_memory()
+            h8.copy_(d_text[:e2e_units].to(torch.uint8))
+            h8_np = h8.numpy()
 
             def e2e8_step():
                 _check(lib.gorp_extract_text_latin1(eng, h8_np.ctypes.data, h8_np.size, C.byref(res)))
@@ -427,9 +440,10 @@ def e2e_run(env, kept, workload):
             tt8 = torch.tensor([dt8], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tt8, op=dist.ReduceOp.MAX)
-            e2e["latin1_input"] = {"value": e2e_lines * world / float(tt8.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h8_np.size),
+            e2e["latin1_input"] = {"value": int(ll.item()) / float(tt8.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h8_np.size),
                                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt8.item()) * 1e3,
                                    "call": "gorp_extract_text_latin1 (ISO-8859-1 bytes in, widened to UTF-16 on the device)"}
+            del h8
         del h_text
     except Exception as ex:  # noqa: BLE001
         e2e = {"value": None, "unit": "lines/s", "error": str(ex)[:200]}
@@ -494,7 +508,14 @@ def main():
     for w in [x for x in args.configs.split(",") if x and x != args.workload]:
         try:
             lines = min(args.config_lines_per_gpu, args.lines_per_gpu)
-            c, _, _ = device_config_run(env, w, lines, args.config_steps, 3)
+            note, steps = None, args.config_steps
+            if w == "utf16mix" and args.lines_per_gpu >= 100_000_000:
+                # config #5 as specified: a 100 GB corpus sharded over 2 / 4 / 8 GPUs; one GPU runs one shard of the 8-way split
+                lines = CONFIG5_TOTAL_LINES // max(world, 8 if world == 1 else world)
+                note = ("the 100 GB corpus (%d lines) sharded over %d GPUs" % (CONFIG5_TOTAL_LINES, world) if world > 1 else
+                        "1 GPU: the first shard of the 8-way split of the 100 GB corpus (%d of %d lines)" % (lines, CONFIG5_TOTAL_LINES))
+                steps = args.config_steps if lines <= 40_000_000 else max(3, args.config_steps * 40_000_000 // lines)
+            c, _, _ = device_config_run(env, w, lines, steps, 3, corpus_note=note)
             configs.append(c)
         except Exception as ex:  # noqa: BLE001  (a failing extra config must not hide the headline)
             configs.append({"key": w, "workload": WORKLOADS[w][0], "error": "%s: %s" % (type(ex).__name__, str(ex)[:300])})
