@@ -129,8 +129,8 @@ struct DeviceCtx {
     DfaWalkDev dfawalk{};        // class-indexed combined DFA of kernels/dfawalk.cu (text form, any definition)
     DfaWalkDev dfawalk_cut{};    // the same with the early-exit cut of host/tails.hpp (K2b when the tail walk follows)
     TailDev tails{};             // per-extraction tail automata of kernels/tailwalk.cu
-    uint32_t tail_flush_every = 4;
-    DevBuf long_lines;
+    uint32_t tail_flush_every = 4;  // walk iterations per round of the tail walk (GORP_TAIL_FLUSH)
+    DevBuf long_lines, recs;
     CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
     bool force_k4 = false;       // GORP_FORCE_K4=1: one-line-per-thread capture kernels (K4) instead of the bucketed K4b
     DevBuf perm, items, buckets, nl_masks;
@@ -467,8 +467,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     c.dfawalk_cut.xcls = upload(t.xcls, c.owned);
                     c.dfawalk_cut.enabled = 1;
                     d.enabled = 1;
-                    if (const char* f = std::getenv("GORP_TAIL_FLUSH")) c.tail_flush_every = std::max(1, std::atoi(f));
-                    while (c.tail_flush_every & (c.tail_flush_every - 1)) --c.tail_flush_every;  // power of two
+                    if (const char* f = std::getenv("GORP_TAIL_FLUSH")) c.tail_flush_every = std::min(64, std::max(1, std::atoi(f)));
                 }
             }
         }
@@ -1033,9 +1032,13 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         uint32_t* tail_ticket = n_items + 2;  // [tail_ticket, n_long]
         const bool tails = with_tails;
         if (candidates && !tails) throw std::logic_error("early-exit candidates without the tail walk");
-        if (tails) CK(cudaMemsetAsync(tail_ticket, 0, 8, stream));
+        if (tails) {
+            CK(cudaMemsetAsync(tail_ticket, 0, 8, stream));
+            c.recs.reserve(nl * sizeof(LineRec) + 16);
+        }
         k4b_bucket(L, c.ext_id.as<int32_t>(), n_lines, E, c.hist.as<unsigned long long>(), bucket_base, cursor, c.perm.as<uint32_t>(),
-                   c.items.as<CapItem>(), n_items, item_ticket, c.spans.as<int32_t>(), stride);
+                   c.items.as<CapItem>(), n_items, item_ticket, c.spans.as<int32_t>(), stride, tails ? d_line_off : nullptr,
+                   tails ? c.recs.as<LineRec>() : nullptr);
         tm.mark("k4b_bucket", 2);
         CapWalkParams W{};
         W.text = d_text;
@@ -1065,7 +1068,8 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
             T.item_ticket = tail_ticket;
             T.t = c.tails;
             T.n_ext = E;
-            T.flush_every = c.tail_flush_every;
+            T.round_iters = c.tail_flush_every;
+            T.recs = c.recs.as<LineRec>();
             T.ext_id = W.ext_id;
             T.spans = W.spans;
             T.hist = W.hist;

@@ -283,9 +283,10 @@ struct CapWalkParams {
     unsigned long long* hist;    // [E+2]: a capture failure moves one count from bin e to bin E+1
 };
 // hist (K3 layout) -> bucket_base[E+1], cursor[E], items (<= n_lines / kCapItemLines + E), perm; MISS rows := -1
+struct LineRec;
 void k4b_bucket(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, const unsigned long long* hist,
                 uint32_t* bucket_base, uint32_t* cursor, uint32_t* perm, CapItem* items, uint32_t* n_items, uint32_t* item_ticket,
-                int32_t* spans, uint32_t span_stride);
+                int32_t* spans, uint32_t span_stride, const int64_t* line_off = nullptr, LineRec* recs = nullptr);
 size_t capwalk_smem_bytes(const CapImgDev&);
 void k4b_capwalk(const Launch&, const CapWalkParams&);
 
@@ -311,17 +312,22 @@ struct TailDev {
     uint32_t n_without;          // extractions without a tail (their items stay with the bucketed capture walk)
     uint32_t enabled;
 };
+struct LineRec {                 // what the tail walk needs to start a line, in one 16-byte load (written by the bucket pass)
+    int64_t start;               // unit offset of the line
+    uint32_t line, len;          // line id; length in units (without the '\n')
+};
 struct TailWalkParams {
     const uint16_t* text;
     int64_t n_units;
     const int64_t* line_off;
+    const LineRec* recs;         // [n_lines] parallel to perm: the lines grouped by (candidate) extraction
     const uint32_t* perm;        // line ids grouped by (candidate) extraction
     const CapItem* items;
     const uint32_t* n_items;
     uint32_t* item_ticket;       // zeroed by the caller
     TailDev t;
     uint32_t n_ext;
-    uint32_t flush_every;        // result rows go out every `flush_every` walk iterations (power of two)
+    uint32_t round_iters;        // walk iterations (16 units each) between two service points
     int32_t* ext_id;
     int32_t* spans;
     unsigned long long* hist;    // [E+2]: a candidate that ends as MISS / CAPTURE_FAIL moves its count

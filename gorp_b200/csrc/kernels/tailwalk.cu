@@ -14,8 +14,13 @@
 //
 // no class lookup, no trap rows, no register copies. Positions are line-relative and held as u16 (+1, 0 = not written):
 // lines of kTailMaxLen units or more are handed to a one-thread-per-line kernel with 32-bit slots (tail_long_kernel).
-// Result rows are written by the thread that walked the line, batched every `flush_every` iterations so that the lanes
-// of a warp that have a finished line write together; two banks of slots keep the finished line's positions meanwhile.
+// A warp works in ROUNDS of `round_iters` walk iterations (16 units each). Everything that is not the walk happens at the
+// service point between two rounds, for all lanes that need it at once (so that code runs with many active lanes instead of
+// once per lane and iteration): result rows of the lines that ended in the last round (written by the thread that walked
+// the line), line starts, claims of the next lines (one record load per line: start, length, id — written by the bucket
+// pass). A lane whose line ends inside a round idles until the next service point. The first 32 bytes of a lane's next
+// line are loaded into registers and the rest is prefetched into L2 half a round after the claim, so a line start
+// never waits for memory.
 #include "device_common.cuh"
 
 namespace gorp {
@@ -52,7 +57,7 @@ __device__ __forceinline__ void tw_step(uint32_t& ra, uint32_t w, uint32_t rows_
 
 // 16 units that hold a unit >= 0x80: unit by unit through the column map (global, L1/L2 resident). A high surrogate
 // followed by a low surrogate takes the PAIR column (java.util.regex consumes the pair as one character).
-__device__ __noinline__ uint32_t tw_slow16(const TailDev& T, uint32_t ra, const Units16& u, const uint16_t* __restrict__ text, int64_t q,
+__device__ __noinline__ uint32_t tw_slow16(const TailDev& T, uint32_t ra, const Units16 u, const uint16_t* __restrict__ text, int64_t q,
                                            int64_t n_units, uint32_t rows_abs, uint32_t row_bytes, uint32_t fin_ra, uint32_t slot_abs,
                                            uint32_t pos1) {
     const uint32_t w[8] = {u.a.x, u.a.y, u.a.z, u.a.w, u.b.x, u.b.y, u.b.z, u.b.w};
@@ -76,14 +81,10 @@ __device__ __noinline__ uint32_t tw_slow16(const TailDev& T, uint32_t ra, const 
     return ra;
 }
 
-struct TwPending {  // a finished line whose result row has not been written yet
-    uint32_t line, outcome, bank_abs;
-};
-
 constexpr uint32_t kTwMaxMulti = 64;  // group boundaries with several writers, per extraction (else the table is refused)
 
 __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkParams P) {
-    // [table][recipes][outcome codes][several-writer list][init list][slots: 2 banks x (max_slots + 2) x kSlotStride]
+    // [table][recipes][outcome codes][several-writer list][init list][slots: (max_slots + 2) x kSlotStride]
     extern __shared__ __align__(16) unsigned char s_mem[];
     __shared__ uint32_t s_item, s_cursor, s_loaded, s_n_multi;
     const TailDev& T = P.t;
@@ -95,16 +96,15 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
     uint8_t* s_init = reinterpret_cast<uint8_t*>(s_multi + 2 * kTwMaxMulti);
     unsigned char* s_slots = reinterpret_cast<unsigned char*>(s_init + 64);
     const uint32_t rows_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_mem));
-    const uint32_t slot_abs0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_slots)) + threadIdx.x * 2;
-    // per bank: slots 0..max_slots-1 of the table (0 = dummy), then ZERO (never written: reads as "no writer") and LEN
-    const uint32_t zero_off = T.max_slots * kSlotStride, len_off = zero_off + kSlotStride, bank_bytes = len_off + kSlotStride;
+    const uint32_t slot_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_slots)) + threadIdx.x * 2;
+    // slots 0..max_slots-1 of the table (0 = dummy), then ZERO (never written: reads as "no writer") and LEN
+    const uint32_t zero_off = T.max_slots * kSlotStride, len_off = zero_off + kSlotStride;
     const uint32_t row_bytes = T.row_bytes;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const uint32_t n_items = *P.n_items;
-    const uint32_t flush_mask = P.flush_every - 1u;
+    const uint32_t round_iters = P.round_iters;
     if (threadIdx.x == 0) s_loaded = 0xFFFFFFFFu;
-    sts_u16(slot_abs0 + zero_off, 0u);
-    sts_u16(slot_abs0 + bank_bytes + zero_off, 0u);
+    sts_u16(slot_abs + zero_off, 0u);
 
     for (;;) {
         __syncthreads();  // the previous item is finished (its table and s_item / s_cursor are free)
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
             for (uint32_t i = threadIdx.x; i < x.n_outcomes * stride; i += kTailWalkThreads) {
                 const uint32_t rec = __ldg(T.res + x.res_off + i);
                 const bool match = __ldg(T.oext + x.oext_off + i / stride) >= 0;
-                // a recipe becomes the byte offset (inside a bank) of the slot that holds the boundary + 1:
+                // a recipe becomes the byte offset of the slot that holds the boundary + 1:
                 // no writer / not a MATCH outcome -> ZERO, the line length -> LEN, one writer -> its slot,
                 // several writers -> ZERO here and an entry in the several-writer list
                 uint32_t off = zero_off;
@@ -156,16 +156,16 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
 
         // writes the result row of a finished line (the thread's own; rows are `stride` int32): every entry is
         // "what its slot holds" - 1 (ZERO slot: -1), the several-writer boundaries are patched afterwards
-        auto flush = [&](const TwPending& pd) {
-            const int32_t code = s_oext[pd.outcome];
+        auto flush = [&](uint32_t fline, uint32_t outcome) {
+            const int32_t code = s_oext[outcome];
             if (code != cand) {  // the candidate did not match after all: MISS (regex_e rejects) or CAPTURE_FAIL
-                P.ext_id[pd.line] = code;
+                P.ext_id[fline] = code;
                 atomicAdd(P.hist + cand, ~0ull);  // -1
                 atomicAdd(P.hist + P.n_ext + (code == -1 ? 0u : 1u), 1ull);
             }
-            int32_t* out = P.spans + static_cast<int64_t>(pd.line) * stride;
-            const uint32_t* res = s_res + pd.outcome * stride;
-            auto value = [&](uint32_t off) -> int32_t { return static_cast<int32_t>(lds_u16(pd.bank_abs + off)) - 1; };
+            int32_t* out = P.spans + static_cast<int64_t>(fline) * stride;
+            const uint32_t* res = s_res + outcome * stride;
+            auto value = [&](uint32_t off) -> int32_t { return static_cast<int32_t>(lds_u16(slot_abs + off)) - 1; };
             if ((stride & 3u) == 0) {
                 for (uint32_t k = 0; k < stride; k += 4) {
                     const uint4 r4 = *reinterpret_cast<const uint4*>(res + k);
@@ -181,61 +181,41 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
             }
             for (uint32_t i = 0; i < n_multi; ++i) {  // rare: a boundary with several writers = the latest of them
                 const uint32_t key = s_multi[2 * i];
-                if ((key >> 16) != pd.outcome) continue;
+                if ((key >> 16) != outcome) continue;
                 uint32_t rec = s_multi[2 * i + 1], best = 0;
-                for (; rec; rec >>= 8) best = max(best, lds_u16(pd.bank_abs + (rec & 0xFFu) * kSlotStride));
+                for (; rec; rec >>= 8) best = max(best, lds_u16(slot_abs + (rec & 0xFFu) * kSlotStride));
                 out[key & 0xFFFFu] = static_cast<int32_t>(best) - 1;
             }
         };
 
-        // per-lane state: the line being walked, and the NEXT line of the lane, claimed one line ahead so that its id
-        // (perm), start and end (line_off) are loaded and its text is on the way to L2 long before the walk needs them
         bool exhausted = false;  // warp-uniform: the item has no unclaimed line left
-        bool active = false, pending = false;
-        TwPending pd{0, 0, 0};
-        uint32_t line = 0, it_count = 0;
+        bool active = false, has_fin = false;
+        uint32_t line = 0, fin_outcome = 0;
         int64_t a = 0, q = 0, last_q = 0;
-        uint32_t ra = fin_ra, bank_abs = slot_abs0;
-        uint32_t nstage = 0;  // 0 = no next line, 1 = id requested, 2 = start and end requested, 3 = text prefetch issued
-        uint32_t nline = 0;
-        int64_t na = 0, nb = 0;
+        uint32_t ra = fin_ra;
         Units16 nxt{};  // the block at q, loaded one iteration ahead
+        // the lane's NEXT line: 0 = none, 1 = record requested, 2 = record here, first block requested, rest on its way to L2
+        uint32_t nstage = 0;
+        uint4 nrec = make_uint4(0, 0, 0, 0);  // LineRec: start (x, y), line id (z), length (w)
+        Units16 nfirst{};
         for (;;) {
-            if (!active && nstage) {  // start the claimed line
-                if (nstage == 1) {
-                    na = __ldg(P.line_off + nline);
-                    nb = __ldg(P.line_off + nline + 1);
-                }
+            // ================= service point
+            if (has_fin) {
+                flush(line, fin_outcome);
+                has_fin = false;
+            }
+            if (!active && nstage == 2) {  // start the claimed line
+                line = nrec.z;
+                a = static_cast<int64_t>(static_cast<uint64_t>(nrec.x) | (static_cast<uint64_t>(nrec.y) << 32));
+                q = a & ~int64_t(15);
+                last_q = (a + nrec.w) & ~int64_t(15);  // the block that holds the line's '\n'
+                nxt = nfirst;
+                const uint32_t lo = static_cast<uint32_t>(a - q);
+                ra = lo ? skip_ra + (lo - 1) * row_bytes : rows_abs;
+                for (uint32_t i = 0; i < x.n_init; ++i) sts_u16(slot_abs + s_init[i] * kSlotStride, 0u);
+                sts_u16(slot_abs + len_off, nrec.w + 1u);
+                active = true;
                 nstage = 0;
-                const int64_t len64 = nb - 1 - na;
-                if (len64 >= static_cast<int64_t>(kTailMaxLen)) {  // 32-bit positions: tail_long_kernel
-                    const uint32_t slot = atomicAdd(P.n_long, 1u);
-                    if (slot < P.long_cap) P.long_lines[slot] = nline;
-                } else {
-                    line = nline;
-                    a = na;
-                    q = a & ~int64_t(15);
-                    last_q = (nb - 1) & ~int64_t(15);  // the block that holds the line's '\n'
-                    nxt = load_units16_l2keep(P.text, q, P.n_units);
-                    const uint32_t lo = static_cast<uint32_t>(a - q);
-                    ra = lo ? skip_ra + (lo - 1) * row_bytes : rows_abs;
-                    if (pending) bank_abs = pd.bank_abs == slot_abs0 ? slot_abs0 + bank_bytes : slot_abs0;
-                    for (uint32_t i = 0; i < x.n_init; ++i) sts_u16(bank_abs + s_init[i] * kSlotStride, 0u);
-                    sts_u16(bank_abs + len_off, static_cast<uint32_t>(len64) + 1u);
-                    active = true;
-                }
-            } else if (nstage == 2) {  // the line's bytes, in one piece, on their way to L2 while the current line is walked
-                const int64_t p0 = na & ~int64_t(15);
-                int64_t bytes = ((nb - p0) * 2 + 15) & ~int64_t(15);
-                if (p0 + bytes / 2 > P.n_units) bytes = ((P.n_units - p0) * 2) & ~int64_t(15);
-                if (bytes > 4096) bytes = 4096;
-                if (bytes > 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.text + p0), "r"(static_cast<uint32_t>(bytes)) : "memory");
-                nstage = 3;
-            } else if (nstage == 1) {
-                na = __ldg(P.line_off + nline);
-                nb = __ldg(P.line_off + nline + 1);
-                nstage = 2;
             }
             if (!exhausted) {  // lanes without a next line claim the next entries of the item
                 const uint32_t want = __ballot_sync(0xffffffffu, nstage == 0);
@@ -245,53 +225,66 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
                     base = __shfl_sync(0xffffffffu, base, 0);
                     const uint32_t idx = base + static_cast<uint32_t>(__popc(want & lt_mask));
                     if (nstage == 0 && idx < it.end) {
-                        nline = __ldg(P.perm + idx);
+                        nrec = __ldg(reinterpret_cast<const uint4*>(P.recs) + idx);
                         nstage = 1;
                     }
                     exhausted = base + static_cast<uint32_t>(__popc(want)) >= it.end;
                 }
             }
             if (!__any_sync(0xffffffffu, active || nstage != 0)) break;
-            if (active) {
-                const Units16 u = nxt;
-                if (q < last_q) nxt = load_units16_l2keep(P.text, q + 16, P.n_units);  // in flight during the 16 steps below
-                const uint32_t pos1 = static_cast<uint32_t>(q - a) + 1u;  // garbage while skipping: only ever stored to the dummy slot
-                if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
-                    tw_step<0>(ra, u.a.x, rows_abs, row_bytes, bank_abs, pos1);
-                    tw_step<2>(ra, u.a.x, rows_abs, row_bytes, bank_abs, pos1 + 1);
-                    tw_step<0>(ra, u.a.y, rows_abs, row_bytes, bank_abs, pos1 + 2);
-                    tw_step<2>(ra, u.a.y, rows_abs, row_bytes, bank_abs, pos1 + 3);
-                    tw_step<0>(ra, u.a.z, rows_abs, row_bytes, bank_abs, pos1 + 4);
-                    tw_step<2>(ra, u.a.z, rows_abs, row_bytes, bank_abs, pos1 + 5);
-                    tw_step<0>(ra, u.a.w, rows_abs, row_bytes, bank_abs, pos1 + 6);
-                    tw_step<2>(ra, u.a.w, rows_abs, row_bytes, bank_abs, pos1 + 7);
-                    tw_step<0>(ra, u.b.x, rows_abs, row_bytes, bank_abs, pos1 + 8);
-                    tw_step<2>(ra, u.b.x, rows_abs, row_bytes, bank_abs, pos1 + 9);
-                    tw_step<0>(ra, u.b.y, rows_abs, row_bytes, bank_abs, pos1 + 10);
-                    tw_step<2>(ra, u.b.y, rows_abs, row_bytes, bank_abs, pos1 + 11);
-                    tw_step<0>(ra, u.b.z, rows_abs, row_bytes, bank_abs, pos1 + 12);
-                    tw_step<2>(ra, u.b.z, rows_abs, row_bytes, bank_abs, pos1 + 13);
-                    tw_step<0>(ra, u.b.w, rows_abs, row_bytes, bank_abs, pos1 + 14);
-                    tw_step<2>(ra, u.b.w, rows_abs, row_bytes, bank_abs, pos1 + 15);
-                } else {
-                    ra = tw_slow16(T, ra, u, P.text, q, P.n_units, rows_abs, row_bytes, fin_ra, bank_abs, pos1);
+            // ================= one round of the walk
+            for (uint32_t k = 0; k < round_iters; ++k) {
+                if (active) {
+                    const Units16 u = nxt;
+                    if (q < last_q) nxt = load_units16_l2keep(P.text, q + 16, P.n_units);  // in flight during the 16 steps below
+                    const uint32_t pos1 = static_cast<uint32_t>(q - a) + 1u;  // garbage while skipping: only ever stored to the dummy slot
+                    if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                        tw_step<0>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1);
+                        tw_step<2>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1 + 1);
+                        tw_step<0>(ra, u.a.y, rows_abs, row_bytes, slot_abs, pos1 + 2);
+                        tw_step<2>(ra, u.a.y, rows_abs, row_bytes, slot_abs, pos1 + 3);
+                        tw_step<0>(ra, u.a.z, rows_abs, row_bytes, slot_abs, pos1 + 4);
+                        tw_step<2>(ra, u.a.z, rows_abs, row_bytes, slot_abs, pos1 + 5);
+                        tw_step<0>(ra, u.a.w, rows_abs, row_bytes, slot_abs, pos1 + 6);
+                        tw_step<2>(ra, u.a.w, rows_abs, row_bytes, slot_abs, pos1 + 7);
+                        tw_step<0>(ra, u.b.x, rows_abs, row_bytes, slot_abs, pos1 + 8);
+                        tw_step<2>(ra, u.b.x, rows_abs, row_bytes, slot_abs, pos1 + 9);
+                        tw_step<0>(ra, u.b.y, rows_abs, row_bytes, slot_abs, pos1 + 10);
+                        tw_step<2>(ra, u.b.y, rows_abs, row_bytes, slot_abs, pos1 + 11);
+                        tw_step<0>(ra, u.b.z, rows_abs, row_bytes, slot_abs, pos1 + 12);
+                        tw_step<2>(ra, u.b.z, rows_abs, row_bytes, slot_abs, pos1 + 13);
+                        tw_step<0>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 14);
+                        tw_step<2>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 15);
+                    } else {
+                        ra = tw_slow16(T, ra, u, P.text, q, P.n_units, rows_abs, row_bytes, fin_ra, slot_abs, pos1);
+                    }
+                    q += 16;
+                    if (ra >= fin_ra) {  // the line ended inside these 16 units (its '\n', a dead transition, or the end of the text)
+                        fin_outcome = (ra - fin_ra) / row_bytes;
+                        has_fin = true;
+                        active = false;
+                    }
                 }
-                q += 16;
-                if (ra >= fin_ra) {  // the line ended inside these 16 units (its '\n', a dead transition, or the end of the text)
-                    if (pending) flush(pd);  // rare: two line ends of one lane between two flush points
-                    pd.line = line;
-                    pd.outcome = (ra - fin_ra) / row_bytes;
-                    pd.bank_abs = bank_abs;
-                    pending = true;
-                    active = false;
+                if (k == 0 && nstage == 1) {  // the record claimed at the service point is here: get the line's text moving
+                    const int64_t na = static_cast<int64_t>(static_cast<uint64_t>(nrec.x) | (static_cast<uint64_t>(nrec.y) << 32));
+                    if (nrec.w >= kTailMaxLen) {  // 32-bit positions: tail_long_kernel
+                        const uint32_t slot = atomicAdd(P.n_long, 1u);
+                        if (slot < P.long_cap) P.long_lines[slot] = nrec.z;
+                        nstage = 0;
+                    } else {
+                        const int64_t p0 = na & ~int64_t(15);
+                        nfirst = load_units16_l2keep(P.text, p0, P.n_units);
+                        int64_t bytes = ((na + nrec.w + 1 - p0) * 2 + 15) & ~int64_t(15);
+                        if (p0 + bytes / 2 > P.n_units) bytes = ((P.n_units - p0) * 2) & ~int64_t(15);
+                        if (bytes > 4096) bytes = 4096;
+                        if (bytes > 32)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.text + p0 + 16), "r"(static_cast<uint32_t>(bytes - 32)) : "memory");
+                        nstage = 2;
+                    }
                 }
-            }
-            if ((++it_count & flush_mask) == 0 && pending) {
-                flush(pd);
-                pending = false;
+                if (!__any_sync(0xffffffffu, active)) break;
             }
         }
-        if (pending) flush(pd);
     }
 }
 
@@ -348,7 +341,7 @@ __global__ void __launch_bounds__(32) tail_long_kernel(TailWalkParams P) {
 
 size_t tailwalk_smem_bytes(const TailDev& t) {
     return static_cast<size_t>(t.max_table_bytes) + static_cast<size_t>(t.max_res) * 4 + static_cast<size_t>(t.max_outcomes) * 4 +
-           2 * kTwMaxMulti * 4 + 64 + 2 * static_cast<size_t>(t.max_slots + 2) * kSlotStride + 16;
+           2 * kTwMaxMulti * 4 + 64 + static_cast<size_t>(t.max_slots + 2) * kSlotStride + 16;
 }
 
 void k4c_tailwalk(const Launch& L, const TailWalkParams& P) {
