@@ -449,6 +449,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                 d.span_stride = c.max_slots;
                 d.max_table_bytes = img.max_table_bytes;
                 d.max_slots = img.max_slots;
+                d.nl_data_col = tailset.nl_data_col;
                 for (const TailImageExt& x : img.ext) {
                     if (!x.available) {
                         ++d.n_without;
@@ -980,13 +981,15 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;
     uint32_t lw_threads = 0;
     bool lw_smem = false;
-    // the tail walk follows: the combined-DFA walk may stop at the first state that leaves one candidate extraction
-    const bool with_tails = c.tails.enabled && !c.cap.match_only && c.max_slots > 0 && sep == 1 && !c.force_general && !c.force_k4 &&
-                            !c.force_k1k2 && n_lines > 0 && n_lines < (1ll << 32) && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0;
+    // the tail walk follows: the combined-DFA walk may stop at the first state that leaves one candidate extraction.
+    // Both walkers also serve the List<String> form (sep == 0: lines end where the offsets say, a '\n' is content).
+    const bool with_tails = c.tails.enabled && !c.cap.match_only && c.max_slots > 0 && !c.force_general && !c.force_k4 &&
+                            !c.force_k1k2 && n_lines > 0 && n_lines < (1ll << 32) && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0 &&
+                            (sep == 1 || n_units > 0);
     const DfaWalkDev& walk_table = with_tails ? c.dfawalk_cut : c.dfawalk;
     bool candidates = false;  // ext_id holds candidates of the cut table: only the tail walk may follow (its conditions are those of with_tails)
     if (scanned) {
-    } else if (sep == 1 && !c.force_general && !c.force_k1k2 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0 &&
+    } else if ((sep == 1 || with_tails) && !c.force_general && !c.force_k1k2 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0 &&
                k2b_linewalk_plan(walk_table, &lw_threads, &lw_smem)) {
         candidates = with_tails;
         LineWalkParams W{};
@@ -996,6 +999,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         W.n_lines = n_lines;
         W.a = walk_table;
         W.ext_id = c.ext_id.as<int32_t>();
+        W.lines_form = sep == 0 ? 1u : 0u;
         W.item_ticket = reinterpret_cast<unsigned int*>(d_n_lines + 4);
         if (const char* f = std::getenv("GORP_WALK_FLAGS")) W.flags = static_cast<uint32_t>(std::atoi(f));
         CK(cudaMemsetAsync(W.item_ticket, 0, 4, stream));
@@ -1013,7 +1017,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     const uint32_t stride = c.max_slots;
     c.spans.reserve((nl * stride + 4) * 4);
     bool hist_done = false;
-    if (!c.cap.match_only && stride > 0 && sep == 1 && c.capimg.enabled && !c.force_general && !c.force_k4 && n_lines > 0 &&
+    if (!c.cap.match_only && stride > 0 && (sep == 1 || with_tails) && c.capimg.enabled && !c.force_general && !c.force_k4 && n_lines > 0 &&
         n_lines < (1ll << 32)) {
         // K4b: histogram -> buckets by extraction -> one warp per work item (kernels/capwalk.cu)
         const uint32_t E = c.n_ext;
@@ -1038,7 +1042,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
         }
         k4b_bucket(L, c.ext_id.as<int32_t>(), n_lines, E, c.hist.as<unsigned long long>(), bucket_base, cursor, c.perm.as<uint32_t>(),
                    c.items.as<CapItem>(), n_items, item_ticket, c.spans.as<int32_t>(), stride, tails ? d_line_off : nullptr,
-                   tails ? c.recs.as<LineRec>() : nullptr);
+                   tails ? c.recs.as<LineRec>() : nullptr, sep);
         tm.mark("k4b_bucket", 2);
         CapWalkParams W{};
         W.text = d_text;
@@ -1069,6 +1073,8 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
             T.t = c.tails;
             T.n_ext = E;
             T.round_iters = c.tail_flush_every;
+            T.lines_form = sep == 0 ? 1u : 0u;
+            if (const char* f = std::getenv("GORP_TAIL_FLAGS")) T.flags = static_cast<uint32_t>(std::atoi(f));
             T.recs = c.recs.as<LineRec>();
             T.ext_id = W.ext_id;
             T.spans = W.spans;
@@ -1081,7 +1087,13 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
             tm.mark("k4c_tailwalk", 2);
             W.skip_tails = c.tails.ext;
         }
-        if (!tails || c.tails.n_without > 0) {
+        if (sep == 0) {  // List<String> form: the lines of extractions without a tail take the one-line-per-thread capture kernel
+            if (c.tails.n_without > 0) {
+                k4_tdfa_capture(L, c.cap, d_text, d_line_off, sep, n_lines, stride, c.ext_id.as<int32_t>(), c.spans.as<int32_t>(), c.tails.ext,
+                                c.hist.as<unsigned long long>());
+                tm.mark("k4_tdfa_capture", 1);
+            }
+        } else if (!tails || c.tails.n_without > 0) {
             k4b_capwalk(L, W);
             tm.mark("k4b_capwalk", 1);
         }
@@ -1231,7 +1243,7 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_
         int64_t nl;
         if (off) {
             const uint16_t* vbase = c.textbuf[b].as<uint16_t>() + kTextPad + (pc.u0 & 15) - pc.u0;  // text[i] lives at vbase + i
-            nl = run_pipeline(c, vbase, 0, c.offbuf[b].as<int64_t>(), pc.l1 - pc.l0, c.stream, false, &dr);
+            nl = run_pipeline(c, vbase, pc.u1, c.offbuf[b].as<int64_t>(), pc.l1 - pc.l0, c.stream, false, &dr);  // text[i] valid for i < u1
         } else {
             if (text8) {
                 k_widen_latin1(L, c.bytebuf[b].as<uint8_t>(), c.textbuf[b].as<uint16_t>(), units);
@@ -1664,7 +1676,12 @@ int gorp_extract_lines_device(gorp_engine* e, int dev_index, const uint16_t* d_t
         CK(cudaSetDevice(c.device));
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         CK(cudaStreamWaitEvent(st, c.ev_done, 0));  // the previous call on this context (any stream) used the same scratch
-        run_pipeline(c, d_text, 0, d_off, n_lines, st, (flags & GORP_FLAG_TIME_KERNELS) != 0, out);
+        int64_t n_units = 0;  // the extent of the text = the last offset (the block walkers must not read beyond it)
+        if (n_lines > 0 && c.tails.enabled) {
+            CK(cudaMemcpyAsync(&n_units, d_off + n_lines, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        run_pipeline(c, d_text, n_units, d_off, n_lines, st, (flags & GORP_FLAG_TIME_KERNELS) != 0, out);
         CK(cudaEventRecord(c.ev_done, st));
         if (flags & GORP_FLAG_SYNC) CK(cudaStreamSynchronize(st));
         return GORP_OK;

@@ -82,6 +82,28 @@ __device__ __forceinline__ Units16 load_units16_l2keep(const uint16_t* __restric
     return r;
 }
 
+// same as load_units16_l2keep, asking L2 to fetch the whole 128-byte (or 256-byte) neighbourhood: a walker that reads its line
+// 32 bytes at a time finds the following blocks in L2, and DRAM serves full bursts instead of one 64-byte atom per 32-byte
+// sector request
+template <int kPrefetchBytes>
+__device__ __forceinline__ Units16 load_units16_l2wide(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units) {
+    Units16 r;
+    if (pos + 16 <= n_units) {
+        if (kPrefetchBytes == 256)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+                         : "l"(text + pos));
+        else
+            asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+                         : "l"(text + pos));
+    } else {
+        r.a = load_chunk(text, pos, n_units);
+        r.b = load_chunk(text, pos + 8, n_units);
+    }
+    return r;
+}
+
 // same, with the default cache policy: for walkers that come back to the neighbouring sectors of the same 128-byte line
 __device__ __forceinline__ Units16 load_units16_keep(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units) {
     Units16 r;

@@ -108,6 +108,28 @@ __device__ __noinline__ uint32_t dw_slow8(const DfaWalkDev& A, uint32_t st, uint
     return st;
 }
 
+// Lines form (List<String>): 16 units unit by unit with explicit line bounds — a line ends at `end` (no '\n' there: the
+// NL column is applied instead of reading a unit) and a '\n' before `end` is line content (its class through the full map).
+template <bool kSmem>
+__device__ __noinline__ uint32_t dw_bounded16(const DfaWalkDev& A, uint32_t st, const Units16 u, int64_t q, int64_t a, int64_t end,
+                                              uint32_t cx_abs, uint32_t tab_abs, uint32_t row_bytes, const unsigned char* __restrict__ tab_g) {
+    const uint32_t w[8] = {u.a.x, u.a.y, u.a.z, u.a.w, u.b.x, u.b.y, u.b.z, u.b.w};
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+        if (st >= A.fin_base) break;
+        const int64_t p = q + k;
+        uint32_t cx;
+        if (p >= end) {
+            cx = lds32(cx_abs + 0x0Au * 4);  // the NL column: what a '\n'-terminated line reads at its end
+        } else {
+            const uint32_t cu = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xFFFFu);
+            cx = (cu < 0x80u && cu != 0x0Au) || p < a ? lds32(cx_abs + (cu & 0x7Fu) * 4) : (kSmem ? tab_abs : 0u) + 2u * __ldg(A.xcls + cu);
+        }
+        st = dw_next<kSmem>(st, cx, row_bytes, tab_g);
+    }
+    return st;
+}
+
 template <bool kSmem>
 __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -310,7 +332,7 @@ __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
 // at a time in 32-byte blocks and claims its next line one line ahead (ballot-ranked, no atomics), so lanes stay busy
 // whatever the line lengths are (long or ragged lines, 10 KB outliers) — the case the chunk-owner walk above handles
 // badly, because there a thread's work is fixed by where the lines happen to start.
-template <bool kSmem>
+template <bool kSmem, bool kLines>
 __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t kT = blockDim.x;
@@ -342,11 +364,13 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
         int64_t cursor = static_cast<int64_t>(item) * kLineItemLines;  // warp-uniform: next unclaimed line of the item
         const int64_t end = cursor + kLineItemLines < P.n_lines ? cursor + kLineItemLines : P.n_lines;
         bool active = false, has_next = false;
-        int64_t line = 0, nline = 0, q = 0, na = 0;
+        int64_t line = 0, nline = 0, q = 0, na = 0, a = 0, lend = 0, nlend = 0;  // lend: where the line ends (lines form)
         uint32_t st = 0;
         for (;;) {
             if (!active && has_next) {  // start the claimed line
                 line = nline;
+                a = na;
+                lend = nlend;
                 q = na & ~int64_t(15);
                 const uint32_t lo = static_cast<uint32_t>(na - q);
                 st = lo ? skip0 + lo : 0u;
@@ -360,6 +384,7 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
                     if (!has_next && idx < end) {
                         nline = idx;
                         na = __ldg(P.line_off + idx);
+                        if (kLines) nlend = __ldg(P.line_off + idx + 1);
                         has_next = true;
                     }
                     cursor += __popc(want);
@@ -368,7 +393,9 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
             if (!__any_sync(0xffffffffu, active || has_next)) break;
             if (active) {
                 const Units16 u = P.flags & 1u ? load_units16(P.text, q, P.n_units) : load_units16_l2keep(P.text, q, P.n_units);
-                if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                // lines form: the fast path needs a block that lies inside the line and holds no '\n' (there it is content)
+                const bool plain = !kLines || (q + 16 <= lend && nl_mask16(u) == 0u);
+                if (plain && ((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
                     st = dw_step<kSmem, 0>(st, u.a.x, cx_abs, row_bytes, tab_g);
                     st = dw_step<kSmem, 2>(st, u.a.x, cx_abs, row_bytes, tab_g);
                     st = dw_step<kSmem, 0>(st, u.a.y, cx_abs, row_bytes, tab_g);
@@ -385,12 +412,14 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
                     st = dw_step<kSmem, 2>(st, u.b.z, cx_abs, row_bytes, tab_g);
                     st = dw_step<kSmem, 0>(st, u.b.w, cx_abs, row_bytes, tab_g);
                     st = dw_step<kSmem, 2>(st, u.b.w, cx_abs, row_bytes, tab_g);
+                } else if (kLines) {
+                    st = dw_bounded16<kSmem>(A, st, u, q, a, lend, cx_abs, tab_abs, row_bytes, tab_g);
                 } else {
                     st = dw_slow8<kSmem>(A, st, u.a, cx_abs, tab_abs, row_bytes, tab_g);
                     st = dw_slow8<kSmem>(A, st, u.b, cx_abs, tab_abs, row_bytes, tab_g);
                 }
                 q += 16;
-                if (st >= fin_base) {  // reached the line's '\n' (or the end of the text)
+                if (st >= fin_base) {  // reached the line's '\n' (or the end of the text / of the string)
                     P.ext_id[line] = static_cast<int32_t>(st - fin_base) - 1;
                     active = false;
                 }
@@ -476,17 +505,22 @@ bool k2b_linewalk_plan(const DfaWalkDev& a, uint32_t* threads, bool* in_smem) {
     return true;
 }
 
+template <bool kSmem, bool kLines>
+static void launch_linewalk(const Launch& L, const LineWalkParams& P, uint32_t threads, size_t smem) {
+    int per_sm = 1;
+    allow_max_dynamic_smem(linewalk_kernel<kSmem, kLines>);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linewalk_kernel<kSmem, kLines>, static_cast<int>(threads), smem);
+    linewalk_kernel<kSmem, kLines><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), static_cast<int>(threads), smem, L.stream>>>(P);
+}
+
 void k2b_linewalk_scan(const Launch& L, const LineWalkParams& P, uint32_t threads, bool in_smem) {
     const size_t smem = linewalk_smem_bytes(P.a, in_smem);
-    int per_sm = 1;
     if (in_smem) {
-        allow_max_dynamic_smem(linewalk_kernel<true>);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linewalk_kernel<true>, static_cast<int>(threads), smem);
-        linewalk_kernel<true><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), static_cast<int>(threads), smem, L.stream>>>(P);
+        if (P.lines_form) launch_linewalk<true, true>(L, P, threads, smem);
+        else launch_linewalk<true, false>(L, P, threads, smem);
     } else {
-        allow_max_dynamic_smem(linewalk_kernel<false>);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linewalk_kernel<false>, static_cast<int>(threads), smem);
-        linewalk_kernel<false><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), static_cast<int>(threads), smem, L.stream>>>(P);
+        if (P.lines_form) launch_linewalk<false, true>(L, P, threads, smem);
+        else launch_linewalk<false, false>(L, P, threads, smem);
     }
 }
 

@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(kThreads) dfa_scan_kernel(DfaDev d, const uint
 __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const uint16_t* __restrict__ text,
                                                                 const int64_t* __restrict__ line_off, int sep,
                                                                 int64_t n_lines, uint32_t span_stride,
-                                                                int32_t* __restrict__ ext_id, int32_t* __restrict__ spans) {
+                                                                int32_t* __restrict__ ext_id, int32_t* __restrict__ spans,
+                                                                const TailExt* __restrict__ skip_tails, unsigned long long* __restrict__ hist) {
     __shared__ uint16_t s_cls[128];
     for (int i = threadIdx.x; i < 128; i += kThreads) s_cls[i] = c.cls[i];
     __syncthreads();
@@ -323,9 +324,11 @@ __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const 
         const int32_t e = ext_id[line];
         int32_t* out = spans + line * span_stride;
         if (e < 0) {
-            for (uint32_t s = 0; s < span_stride; ++s) out[s] = -1;
+            if (!skip_tails)  // (with skip_tails the bucket pass has filled the rows of the MISS lines)
+                for (uint32_t s = 0; s < span_stride; ++s) out[s] = -1;
             continue;
         }
+        if (skip_tails && skip_tails[e].available) continue;  // the tail walk (kernels/tailwalk.cu) owns this line
         const ExtDev x = c.ext[e];
         const int64_t a = line_off[line], b = line_off[line + 1] - sep;
         const uint32_t* __restrict__ tr = c.tdfa_trans + x.trans_off;
@@ -370,6 +373,10 @@ __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const 
         const bool ok = __ldg(c.tdfa_accepting + x.acc_off + st) != 0;  // the dead row is not accepting
         if (!ok) {
             ext_id[line] = -2 - e;
+            if (hist) {  // the histogram was taken before the capture pass: move the line's count
+                atomicAdd(hist + e, ~0ull);
+                atomicAdd(hist + c.n_ext + 1, 1ull);
+            }
             for (uint32_t s = 0; s < span_stride; ++s) out[s] = -1;
             continue;
         }
@@ -510,10 +517,10 @@ void k2_dfa_scan(const Launch& L, const DfaDev& d, const uint16_t* text, const i
 }
 
 void k4_tdfa_capture(const Launch& L, const CapDev& c, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
-                     uint32_t span_stride, int32_t* ext_id, int32_t* spans) {
+                     uint32_t span_stride, int32_t* ext_id, int32_t* spans, const TailExt* skip_tails, unsigned long long* hist) {
     if (n_lines <= 0) return;
     int g = persistent_grid(L, reinterpret_cast<const void*>(tdfa_capture_kernel), 0, n_lines);
-    tdfa_capture_kernel<<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_stride, ext_id, spans);
+    tdfa_capture_kernel<<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_stride, ext_id, spans, skip_tails, hist);
 }
 
 void k_bias_copy(const Launch& L, int64_t* dst, const int64_t* src, int64_t n, int64_t bias) {

@@ -135,8 +135,12 @@ void k2_dfa_direct(const Launch&, const DfaDirectDev&, const uint16_t* text, con
 
 // K4: capture automaton over the matched lines. Writes the result row spans[i*span_stride ..]: 2*groups entries, the
 // rest of the row (and the whole row of a MISS / capture-failed line) is -1; capture failure => ext_id = -2-e.
+// `skip_tails` (optional): only the lines whose extraction has no tail automaton are walked (the tail walk owns the others and
+// the bucket pass has filled the MISS rows); `hist` (optional): a capture failure moves the line's count (K3 ran before).
+struct TailExt;
 void k4_tdfa_capture(const Launch&, const CapDev&, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
-                     uint32_t span_stride, int32_t* ext_id, int32_t* spans);
+                     uint32_t span_stride, int32_t* ext_id, int32_t* spans, const TailExt* skip_tails = nullptr,
+                     unsigned long long* hist = nullptr);
 
 // K4 fast tier: lines [0, n_lines) are '\n'-terminated in the text.
 void k4_tdfa_fast(const Launch&, const TdfaFastDev&, const CapDev&, const uint16_t* text, int64_t n_units,
@@ -237,6 +241,7 @@ struct LineWalkParams {
     int32_t* ext_id;
     unsigned int* item_ticket;   // zeroed by the caller
     uint32_t flags;              // GORP_WALK_FLAGS (diagnostics): 1 = text loads L2 evict-first
+    uint32_t lines_form;         // 1: List<String> form — line i = [line_off[i], line_off[i+1]), a '\n' is content
 };
 bool k2b_linewalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem);
 void k2b_linewalk_scan(const Launch&, const LineWalkParams&, uint32_t threads, bool in_smem);
@@ -286,7 +291,7 @@ struct CapWalkParams {
 struct LineRec;
 void k4b_bucket(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, const unsigned long long* hist,
                 uint32_t* bucket_base, uint32_t* cursor, uint32_t* perm, CapItem* items, uint32_t* n_items, uint32_t* item_ticket,
-                int32_t* spans, uint32_t span_stride, const int64_t* line_off = nullptr, LineRec* recs = nullptr);
+                int32_t* spans, uint32_t span_stride, const int64_t* line_off = nullptr, LineRec* recs = nullptr, int sep = 1);
 size_t capwalk_smem_bytes(const CapImgDev&);
 void k4b_capwalk(const Launch&, const CapWalkParams&);
 
@@ -309,6 +314,7 @@ struct TailDev {
     const uint16_t* pair_col;    // [width]
     uint32_t width, row_bytes, span_stride;
     uint32_t max_table_bytes, max_slots, max_res, max_outcomes;  // shared-memory sizing (the largest tail)
+    uint32_t nl_data_col;        // column of a '\n' that is line content (List<String> form)
     uint32_t n_without;          // extractions without a tail (their items stay with the bucketed capture walk)
     uint32_t enabled;
 };
@@ -328,6 +334,9 @@ struct TailWalkParams {
     TailDev t;
     uint32_t n_ext;
     uint32_t round_iters;        // walk iterations (16 units each) between two service points
+    uint32_t lines_form;         // 1: List<String> form — lines end where their record says, a '\n' is content
+    uint32_t flags;              // GORP_TAIL_FLAGS (diagnostics): 1 = no L2 bulk prefetch of the next line, 2 / 4 = text loads ask
+                                 // L2 for the 128 / 256-byte neighbourhood
     int32_t* ext_id;
     int32_t* spans;
     unsigned long long* hist;    // [E+2]: a candidate that ends as MISS / CAPTURE_FAIL moves its count

@@ -81,8 +81,47 @@ __device__ __noinline__ uint32_t tw_slow16(const TailDev& T, uint32_t ra, const 
     return ra;
 }
 
+// Lines form (List<String>): 16 units with explicit line bounds — the line ends at `end` (the terminator column is applied
+// there instead of reading a unit), a '\n' before `end` is line content (its own column), a surrogate pair must lie inside
+// the line.
+__device__ __noinline__ uint32_t tw_bounded16(const TailDev& T, uint32_t ra, const Units16 u, const uint16_t* __restrict__ text, int64_t q,
+                                              int64_t end, uint32_t rows_abs, uint32_t row_bytes, uint32_t fin_ra, uint32_t slot_abs,
+                                              uint32_t pos1) {
+    const uint32_t w[8] = {u.a.x, u.a.y, u.a.z, u.a.w, u.b.x, u.b.y, u.b.z, u.b.w};
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+        if (ra >= fin_ra) break;
+        const int64_t p = q + k;
+        uint32_t col = 0x0Au;  // at the end of the line: the terminator column
+        if (p < end) {
+            const uint32_t cu = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xFFFFu);
+            col = cu;
+            if (cu == 0x0Au) {
+                col = T.nl_data_col;
+            } else if (cu >= 0x80u) {
+                col = __ldg(T.xcol + cu);
+                if ((cu & 0xFC00u) == 0xD800u && p + 1 < end) {
+                    const uint32_t nx = k == 15 ? __ldg(text + q + 16) : ((k & 1) ? (w[(k + 1) >> 1] & 0xFFFFu) : (w[k >> 1] >> 16));
+                    if ((nx & 0xFC00u) == 0xDC00u) col = __ldg(T.pair_col + col);
+                }
+            }
+        }
+        const uint32_t ent = lds_u16(ra + col * 2);
+        ra = (ent >> 6) * row_bytes + rows_abs;
+        sts_u16(slot_abs + (ent & 63u) * kSlotStride, pos1 + k);
+    }
+    return ra;
+}
+
+__device__ __forceinline__ Units16 tw_load(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units, uint32_t flags) {
+    if (flags & 2u) return load_units16_l2wide<128>(text, pos, n_units);
+    if (flags & 4u) return load_units16_l2wide<256>(text, pos, n_units);
+    return load_units16_l2keep(text, pos, n_units);
+}
+
 constexpr uint32_t kTwMaxMulti = 64;  // group boundaries with several writers, per extraction (else the table is refused)
 
+template <bool kLines>
 __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkParams P) {
     // [table][recipes][outcome codes][several-writer list][init list][slots: (max_slots + 2) x kSlotStride]
     extern __shared__ __align__(16) unsigned char s_mem[];
@@ -191,7 +230,7 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
         bool exhausted = false;  // warp-uniform: the item has no unclaimed line left
         bool active = false, has_fin = false;
         uint32_t line = 0, fin_outcome = 0;
-        int64_t a = 0, q = 0, last_q = 0;
+        int64_t a = 0, q = 0, last_q = 0, line_end = 0;
         uint32_t ra = fin_ra;
         Units16 nxt{};  // the block at q, loaded one iteration ahead
         // the lane's NEXT line: 0 = none, 1 = record requested, 2 = record here, first block requested, rest on its way to L2
@@ -208,7 +247,8 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
                 line = nrec.z;
                 a = static_cast<int64_t>(static_cast<uint64_t>(nrec.x) | (static_cast<uint64_t>(nrec.y) << 32));
                 q = a & ~int64_t(15);
-                last_q = (a + nrec.w) & ~int64_t(15);  // the block that holds the line's '\n'
+                line_end = a + nrec.w;
+                last_q = line_end & ~int64_t(15);  // the block that holds the line's '\n' (lines form: its end)
                 nxt = nfirst;
                 const uint32_t lo = static_cast<uint32_t>(a - q);
                 ra = lo ? skip_ra + (lo - 1) * row_bytes : rows_abs;
@@ -236,9 +276,11 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
             for (uint32_t k = 0; k < round_iters; ++k) {
                 if (active) {
                     const Units16 u = nxt;
-                    if (q < last_q) nxt = load_units16_l2keep(P.text, q + 16, P.n_units);  // in flight during the 16 steps below
+                    if (q < last_q) nxt = tw_load(P.text, q + 16, P.n_units, P.flags);  // in flight during the 16 steps below
                     const uint32_t pos1 = static_cast<uint32_t>(q - a) + 1u;  // garbage while skipping: only ever stored to the dummy slot
-                    if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                    // lines form: the fast path needs a block that lies inside the line and holds no '\n' (there it is content)
+                    const bool plain = !kLines || (q < last_q && (nl_bits4(u.a.x, u.a.y) | nl_bits4(u.a.z, u.a.w) | nl_bits4(u.b.x, u.b.y) | nl_bits4(u.b.z, u.b.w)) == 0u);
+                    if (plain && ((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
                         tw_step<0>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1);
                         tw_step<2>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1 + 1);
                         tw_step<0>(ra, u.a.y, rows_abs, row_bytes, slot_abs, pos1 + 2);
@@ -255,6 +297,8 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
                         tw_step<2>(ra, u.b.z, rows_abs, row_bytes, slot_abs, pos1 + 13);
                         tw_step<0>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 14);
                         tw_step<2>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 15);
+                    } else if (kLines) {
+                        ra = tw_bounded16(T, ra, u, P.text, q, line_end, rows_abs, row_bytes, fin_ra, slot_abs, pos1);
                     } else {
                         ra = tw_slow16(T, ra, u, P.text, q, P.n_units, rows_abs, row_bytes, fin_ra, slot_abs, pos1);
                     }
@@ -273,11 +317,11 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
                         nstage = 0;
                     } else {
                         const int64_t p0 = na & ~int64_t(15);
-                        nfirst = load_units16_l2keep(P.text, p0, P.n_units);
+                        nfirst = tw_load(P.text, p0, P.n_units, P.flags);
                         int64_t bytes = ((na + nrec.w + 1 - p0) * 2 + 15) & ~int64_t(15);
                         if (p0 + bytes / 2 > P.n_units) bytes = ((P.n_units - p0) * 2) & ~int64_t(15);
                         if (bytes > 4096) bytes = 4096;
-                        if (bytes > 32)
+                        if (bytes > 32 && !(P.flags & 1u))
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.text + p0 + 16), "r"(static_cast<uint32_t>(bytes - 32)) : "memory");
                         nstage = 2;
                     }
@@ -301,12 +345,14 @@ __global__ void __launch_bounds__(32) tail_long_kernel(TailWalkParams P) {
         const uint16_t* __restrict__ tab = reinterpret_cast<const uint16_t*>(reinterpret_cast<const unsigned char*>(T.image) + x.tab_off);
         uint32_t slots[64];
         for (uint32_t k = 0; k < 64; ++k) slots[k] = 0;
-        const int64_t a = P.line_off[line], b = P.line_off[line + 1] - 1;
+        const int64_t a = P.line_off[line], b = P.line_off[line + 1] - (P.lines_form ? 0 : 1);
         uint32_t row = 0;
         for (int64_t p = a; row < x.fin_base; ++p) {
-            const uint32_t cu = p < b && p < P.n_units ? P.text[p] : 0x0Au;  // position b holds the '\n' (or lies beyond the text)
+            const uint32_t cu = p < b && p < P.n_units ? P.text[p] : 0x0Au;  // position b holds the '\n' (or lies beyond the text / the string)
             uint32_t col = cu;
-            if (cu >= 0x80u) {
+            if (p < b && cu == 0x0Au) {  // lines form only: a '\n' inside the string is content
+                col = T.nl_data_col;
+            } else if (cu >= 0x80u) {
                 col = T.xcol[cu];
                 if ((cu & 0xFC00u) == 0xD800u && p + 1 < b && (P.text[p + 1] & 0xFC00u) == 0xDC00u) col = T.pair_col[col];
             }
@@ -346,11 +392,16 @@ size_t tailwalk_smem_bytes(const TailDev& t) {
 
 void k4c_tailwalk(const Launch& L, const TailWalkParams& P) {
     const size_t smem = tailwalk_smem_bytes(P.t);
-    allow_max_dynamic_smem(tailwalk_kernel);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel, kTailWalkThreads, smem);
-    if (per_sm < 1) per_sm = 1;
-    tailwalk_kernel<<<L.sm_count * per_sm, kTailWalkThreads, smem, L.stream>>>(P);
+    if (P.lines_form) {
+        allow_max_dynamic_smem(tailwalk_kernel<true>);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<true>, kTailWalkThreads, smem);
+        tailwalk_kernel<true><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kTailWalkThreads, smem, L.stream>>>(P);
+    } else {
+        allow_max_dynamic_smem(tailwalk_kernel<false>);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<false>, kTailWalkThreads, smem);
+        tailwalk_kernel<false><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kTailWalkThreads, smem, L.stream>>>(P);
+    }
     tail_long_kernel<<<L.sm_count, 32, 0, L.stream>>>(P);
 }
 
