@@ -204,6 +204,38 @@ class Env:
     pass
 
 
+def bind_numa(cudart, index):
+    """Bind this rank (CPU affinity + preferred memory node) to the NUMA node of its GPU, so that the pinned host buffers of
+    the end-to-end leg are local to the GPU's PCIe root: with 8 ranks on two sockets the H2D copies would otherwise cross the
+    socket interconnect. Returns what was done (reported in the bench line)."""
+    import ctypes
+    import platform
+    info = {"node": None, "cpus": None, "mempolicy": None}
+    try:
+        err, bdf = cudart.cudaDeviceGetPCIBusId(32, index)
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else str(bdf)).strip("\x00").lower()
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return info
+        info["node"] = node
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+            info["cpus"] = len(os.sched_getaffinity(0))
+        nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+        if nr is not None:
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // (8 * ctypes.sizeof(ctypes.c_ulong))] |= 1 << (node % (8 * ctypes.sizeof(ctypes.c_ulong)))
+            rc = ctypes.CDLL(None, use_errno=True).syscall(nr, 1, mask, 16 * 8 * ctypes.sizeof(ctypes.c_ulong) + 1)  # MPOL_PREFERRED
+            info["mempolicy"] = "preferred" if rc == 0 else "errno %d" % ctypes.get_errno()
+    except Exception as ex:  # noqa: BLE001
+        info["error"] = str(ex)[:120]
+    return info
+
+
 def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None, keep=False, first_line=None, corpus_note=None):
     """One config, device-resident: returns the result dict (and, with keep=True, the engine / text for the e2e leg)."""
     torch, dist, lib, _ffi, Blob, _check, cudart = env.torch, env.dist, env.lib, env.ffi, env.Blob, env.check, env.cudart
@@ -416,8 +448,22 @@ def e2e_run(env, kept, workload):
         d2h = nl * 4 + (nl + 1) * 8 + ns * 4 + 5 * 8
         e2e = {"value": int(ll.item()) / float(tt.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h_np.size * 2),
                "d2h_bytes_per_step": int(d2h), "lines_per_step_per_gpu": int(nl), "ms_per_step": float(tt.item()) * 1e3,
-               "h2d_gb_per_s_per_gpu": h_np.size * 2 / float(tt.item()) / 1e9,
+               "h2d_gb_per_s_per_gpu": h_np.size * 2 / float(tt.item()) / 1e9, "numa": env.numa,
                "timing": "host wall clock around gorp_extract_text (it returns after the last D2H), max over ranks"}
+        # the platform's ceiling for this leg: the same pinned buffer copied host -> device by all ranks at once, nothing else
+        d_scratch = torch.empty_like(d_text[:e2e_units])
+        d_scratch.copy_(h_text, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            d_scratch.copy_(h_text, non_blocking=True)
+        torch.cuda.synchronize()
+        tc = torch.tensor([(time.perf_counter() - t0) / 2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        e2e["h2d_ceiling_gb_per_s_per_gpu"] = h_np.size * 2 / float(tc.item()) / 1e9
+        e2e["h2d_ceiling_note"] = "plain cudaMemcpyAsync of the same pinned text by all %d ranks at once (max over ranks)" % world
+        del d_scratch
         # the same call fed with ISO-8859-1 bytes (what a JDK 9+ String with the LATIN1 coder holds; the synthetic corpus is
         # ASCII): gorp_extract_text_latin1 widens on the device, the host-to-device copy moves half the bytes
         if int(d_text.max().item()) < 256 and int(d_text.min().item()) >= 0:
@@ -489,9 +535,11 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_numa(cudart, local_rank) if not os.environ.get("GORP_BENCH_NO_NUMA") else {"node": None, "disabled": True}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     env = Env()
+    env.numa = numa
     env.torch, env.dist, env.lib, env.ffi, env.Blob, env.check, env.cudart = torch, dist, _ffi.lib, _ffi, Blob, _check, cudart
     env.rank, env.local_rank, env.world, env.dev, env.args = rank, local_rank, world, dev, args
 

@@ -310,6 +310,35 @@ class Gorp:
         finally:
             lib.gorp_result_release(self._eng(), C.byref(res))
 
+    def extract_batch_text_utf8(self, data) -> ExtractionBatch:
+        """'\n'-separated text held as UTF-8 bytes (a log file as it is on disk): decoded to UTF-16 on the device, results are
+        those of extract_batch_text on the decoded text (offsets in UTF-16 units). Malformed UTF-8 raises ValueError."""
+        b = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+        res = _ffi.Result()
+        _check(lib.gorp_extract_text_utf8(self._eng(), b.ctypes.data, len(b), C.byref(res)))
+        try:
+            units = np.frombuffer(b.tobytes().decode("utf-8").encode("utf-16-le"), dtype=np.uint16)
+            return ExtractionBatch(self, units, res, 1)
+        finally:
+            lib.gorp_result_release(self._eng(), C.byref(res))
+
+    def match_all(self, lines):
+        """PolyMatcher.match for a batch (Gorp.getMatcher().match(s) per string): list of ascending index lists."""
+        arrs = [to_units(s) for s in lines]
+        off = np.zeros(len(arrs) + 1, dtype=np.int64)
+        if arrs:
+            np.cumsum([len(a) for a in arrs], out=off[1:])
+        units = np.ascontiguousarray(np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.uint16), dtype=np.uint16)
+        res = _ffi.MatchResult()
+        _check(lib.gorp_match_all_lines(self._eng(), units.ctypes.data, off.ctypes.data, len(arrs), C.byref(res)))
+        try:
+            n = res.n_lines
+            aoff = np.ctypeslib.as_array(res.accept_off, (n + 1,)).copy()
+            acc = np.ctypeslib.as_array(res.accept, (max(int(aoff[-1]), 1),))[:int(aoff[-1])].copy()
+            return [acc[aoff[i]:aoff[i + 1]].tolist() for i in range(n)]
+        finally:
+            lib.gorp_match_result_release(self._eng(), C.byref(res))
+
     # -- per-line API of the reference, served by a batch of one
     def extract(self, input_: str):
         return self.extract_batch_lines([input_]).result(0, safe=False)

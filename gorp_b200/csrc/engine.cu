@@ -5,8 +5,11 @@
 //   otherwise  text form : K1 count -> scan -> K1 scatter -> K1 finish          => line_off[n+1], n_lines
 //              both forms: K2 dfa_scan => ext_id -> K4 tdfa_capture => result rows of spans -> K3 histogram
 #include <cuda_runtime.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +39,9 @@ int fail(int code, const std::string& msg) {
 struct CudaError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
+struct ArgError : std::runtime_error {  // bad input data (reported as GORP_E_ARG)
+    using std::runtime_error::runtime_error;
+};
 
 #define CK(expr)                                                                                                   \
     do {                                                                                                           \
@@ -56,6 +62,8 @@ int guarded(F&& f) {
         return fail(GORP_E_BLOB, e.what());
     } catch (const CudaError& e) {
         return fail(GORP_E_CUDA, e.what());
+    } catch (const ArgError& e) {
+        return fail(GORP_E_ARG, e.what());
     } catch (const std::bad_alloc&) {
         return fail(GORP_E_OOM, "out of host memory");
     } catch (const std::exception& e) {
@@ -117,6 +125,7 @@ constexpr size_t kTileStateMinBytes = 4u << 20;
 
 struct DeviceCtx {
     int device = 0;
+    int numa_node = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     std::vector<void*> owned;  // immutable tables
@@ -127,6 +136,8 @@ struct DeviceCtx {
     OnePassDev onepass{};
     OnePassDev chunkwalk{};      // same automaton, table variant of kernels/chunkwalk.cu
     DfaWalkDev dfawalk{};        // class-indexed combined DFA of kernels/dfawalk.cu (text form, any definition)
+    MatchAllDev matchall{};      // the reference's own tables (matchAll)
+    DevBuf ma_state, ma_count, ma_off, ma_out;
     DfaWalkDev dfawalk_cut{};    // the same with the early-exit cut of host/tails.hpp (K2b when the tail walk follows)
     TailDev tails{};             // per-extraction tail automata of kernels/tailwalk.cu
     uint32_t tail_flush_every = 4;  // walk iterations per round of the tail walk (GORP_TAIL_FLUSH)
@@ -180,14 +191,57 @@ struct DeviceCtx {
     }
 };
 
+// NUMA node of a CUDA device (sysfs numa_node of its PCI function), or -1 when the platform does not say
+int device_numa_node(int device) {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* p = bdf; *p; ++p) *p = static_cast<char>(std::tolower(*p));
+    const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/numa_node";
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+
+// While alive, the calling thread prefers `node` for new pages (set_mempolicy MPOL_PREFERRED): pinned result / staging
+// buffers are allocated next to the GPU that fills them, so the D2H copies of several GPUs do not all cross the socket
+// interconnect. A no-op where the node is unknown or the syscall is not permitted.
+struct NumaPrefer {
+    bool set = false;
+    explicit NumaPrefer(int node) {
+#ifdef SYS_set_mempolicy
+        if (node < 0 || node >= 1024) return;
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        set = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8 + 1) == 0;
+#else
+        (void)node;
+#endif
+    }
+    ~NumaPrefer() {
+#ifdef SYS_set_mempolicy
+        if (set) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+#endif
+    }
+};
+
 struct HostResult {  // pinned host arrays behind a gorp_result
+    int numa_node = -1;  // of the device that fills the arrays (first device of the engine)
     void* p[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t cap[4] = {0, 0, 0, 0};
     void reserve(int i, size_t bytes, size_t keep = 0) {  // keeps the first `keep` bytes when it has to grow
         if (bytes <= cap[i]) return;
         void* q = nullptr;
         size_t want = bytes + bytes / 8 + 64;
-        CK(cudaMallocHost(&q, want));
+        {
+            NumaPrefer near_the_gpu(numa_node);
+            CK(cudaMallocHost(&q, want));
+        }
         if (p[i] && keep) std::memcpy(q, p[i], keep);
         if (p[i]) cudaFreeHost(p[i]);
         p[i] = q;
@@ -211,11 +265,13 @@ struct gorp_engine {
 
 namespace {
 
-void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fused, const TailSet& tailset, bool match_only) {
+void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fused, const TailSet& tailset, const DfaTables& raw,
+                  bool match_only) {
     CK(cudaSetDevice(c.device));
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, c.device));
     c.sm_count = prop.multiProcessorCount;
+    c.numa_node = device_numa_node(c.device);
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking));
@@ -231,6 +287,12 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     if (const char* f = std::getenv("GORP_DFA_TIER")) c.dfa_tier = std::atoi(f);
     if (const char* f = std::getenv("GORP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(std::atoi(f)));  // diagnostics
     for (auto& e : c.ev) CK(cudaEventCreate(&e));
+    // the reference's tables as they are (matchAll)
+    c.matchall.classmap = upload(raw.classmap, c.owned);
+    c.matchall.trans = upload(raw.trans, c.owned);
+    c.matchall.accept_off = upload(raw.accept_off, c.owned);
+    c.matchall.accept_list = upload(raw.accept_list, c.owned);
+    c.matchall.n_classes = raw.n_classes;
     // combined DFA
     const size_t S = m.dfa.n_states, C = m.dfa.n_classes;
     c.dfa.n_states = static_cast<uint32_t>(S);
@@ -458,7 +520,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     d.max_res = std::max(d.max_res, (x.n_outcomes * c.max_slots + 3u) & ~3u);
                     d.max_outcomes = std::max(d.max_outcomes, (x.n_outcomes + 3u) & ~3u);
                 }
-                if (tailwalk_smem_bytes(d) <= 200 * 1024) {
+                if (tailwalk_smem_bytes(d, 256) <= 200 * 1024) {
                     c.dfawalk_cut.table = upload(t.rows, c.owned);
                     c.dfawalk_cut.n_rows = t.n_rows;
                     c.dfawalk_cut.K = t.K;
@@ -1177,8 +1239,8 @@ struct DeviceRun {  // what one device produced for its pieces
 // rows of every finished piece are copied to the host arrays at once, overlapping the next pieces.
 // `text8` (ISO-8859-1 bytes, text form only) replaces `text`: the bytes are staged and widened to UTF-16 on the device.
 // The caller holds c.mu (a multi-device call keeps every participating device locked until its rows are copied out).
-void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_t* text8, const int64_t* off, const std::vector<Piece>& pieces,
-                size_t p0, size_t p1, HostResult* hr, DeviceRun& run) {
+void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_t* text8, bool utf8, const int64_t* off,
+                const std::vector<Piece>& pieces, size_t p0, size_t p1, HostResult* hr, DeviceRun& run) {
     CK(cudaSetDevice(c.device));
     CK(cudaStreamWaitEvent(c.stream, c.ev_done, 0));  // a device-resident call on another stream may still use the scratch
     Launch L{c.stream, c.sm_count};
@@ -1232,6 +1294,7 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_
     };
 
     int64_t rows = 0;
+    int64_t utf8_base = 0;  // UTF-16 units decoded from the pieces before this one (UTF-8 input: offsets are in decoded units)
     stage(p0);
     for (size_t k = p0; k < p1; ++k) {
         const Piece& pc = pieces[k];
@@ -1239,17 +1302,45 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_
         if (k + 1 < p1) stage(k + 1);  // the other buffer: its previous piece was computed (this thread waited for it)
         CK(cudaStreamWaitEvent(c.stream, c.ev_in[b], 0));
         const int64_t units = pc.u1 - pc.u0;
+        int64_t piece_bias = pc.u0;  // what turns the piece's line offsets into offsets of the whole batch
         gorp_device_result dr{};
         int64_t nl;
         if (off) {
             const uint16_t* vbase = c.textbuf[b].as<uint16_t>() + kTextPad + (pc.u0 & 15) - pc.u0;  // text[i] lives at vbase + i
             nl = run_pipeline(c, vbase, pc.u1, c.offbuf[b].as<int64_t>(), pc.l1 - pc.l0, c.stream, false, &dr);  // text[i] valid for i < u1
         } else {
-            if (text8) {
+            int64_t n_units_piece = units;
+            if (text8 && utf8) {
+                // bytes -> UTF-16 on the device: units per tile, scan, (one host round trip: total + first malformed byte), decode
+                const int64_t tiles = utf8_tiles(units);
+                c.tile_counts.reserve(static_cast<size_t>(tiles + 1) * 4);
+                c.tile_base.reserve(static_cast<size_t>(tiles + 2) * 8);
+                c.scan_scratch.reserve(static_cast<size_t>(tiles / 4096 + 8) * 8);
+                c.scalars.reserve(64);
+                unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c.scalars.as<int64_t>() + 6);
+                unsigned long long bad = ~0ull;
+                int64_t total = 0;
+                CK(cudaMemsetAsync(d_bad, 0xFF, 8, c.stream));
+                k_utf8_count(L, c.bytebuf[b].as<uint8_t>(), units, c.tile_counts.as<uint32_t>(), d_bad);
+                scan_u32_to_i64(L, c.tile_counts.as<uint32_t>(), tiles, c.tile_base.as<int64_t>(), c.scan_scratch.as<int64_t>());
+                if (units > 0) CK(cudaMemcpyAsync(&total, c.tile_base.as<int64_t>() + tiles, 8, cudaMemcpyDeviceToHost, c.stream));
+                CK(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, c.stream));
+                CK(cudaStreamSynchronize(c.stream));
+                if (bad != ~0ull)
+                    throw ArgError(strfmt("malformed UTF-8 at byte %lld (the input must be well-formed UTF-8)",
+                                          static_cast<long long>(pc.u0 + static_cast<int64_t>(bad))));
+                k_utf8_write(L, c.bytebuf[b].as<uint8_t>(), units, c.tile_base.as<int64_t>(), c.textbuf[b].as<uint16_t>());
+                c.launches += 5;
+                n_units_piece = total;
+            } else if (text8) {
                 k_widen_latin1(L, c.bytebuf[b].as<uint8_t>(), c.textbuf[b].as<uint16_t>(), units);
                 c.launches += 1;
             }
-            nl = run_pipeline(c, c.textbuf[b].as<uint16_t>(), units, nullptr, 0, c.stream, false, &dr);
+            nl = run_pipeline(c, c.textbuf[b].as<uint16_t>(), n_units_piece, nullptr, 0, c.stream, false, &dr);
+            if (utf8) {
+                piece_bias = utf8_base;
+                utf8_base += n_units_piece;
+            }
         }
         if (rows + nl > cap_rows) {  // the density estimate was too low: grow, keeping the rows gathered so far
             if (hr) CK(cudaStreamSynchronize(c.s_out));
@@ -1259,7 +1350,7 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_
         }
         // gather: rows [rows, rows + nl) of the batch
         if (nl) CK(cudaMemcpyAsync(c.acc_ext.as<int32_t>() + rows, dr.d_ext_id, static_cast<size_t>(nl) * 4, cudaMemcpyDeviceToDevice, c.stream));
-        k_bias_copy(L, c.acc_off.as<int64_t>() + rows, dr.d_line_off, nl + 1, off ? 0 : pc.u0);
+        k_bias_copy(L, c.acc_off.as<int64_t>() + rows, dr.d_line_off, nl + 1, off ? 0 : piece_bias);
         if (nl && stride)
             CK(cudaMemcpyAsync(c.acc_spans.as<int32_t>() + static_cast<size_t>(rows) * stride, dr.d_spans, static_cast<size_t>(nl) * stride * 4,
                                cudaMemcpyDeviceToDevice, c.stream));
@@ -1292,7 +1383,7 @@ void run_pieces(gorp_engine* e, DeviceCtx& c, const uint16_t* text, const uint8_
 }
 
 int extract_host(gorp_engine* e, const uint16_t* text, const uint8_t* text8, int64_t n_units, const int64_t* off, int64_t n_lines,
-                 gorp_result* out) {
+                 gorp_result* out, bool utf8 = false) {
     if (!e || !out || (!text && !text8 && n_units > 0) || n_units < 0 || n_lines < 0) return fail(GORP_E_ARG, "bad argument");
     if (e->devs.empty()) return fail(GORP_E_CUDA, "engine has no CUDA device");
     return guarded([&]() -> int {
@@ -1307,16 +1398,20 @@ int extract_host(gorp_engine* e, const uint16_t* text, const uint8_t* text8, int
                 e->pool.pop_back();
             }
         }
-        if (!hr) hr = std::make_unique<HostResult>();
+        if (!hr) {
+            hr = std::make_unique<HostResult>();
+            hr->numa_node = e->devs[0]->numa_node;
+        }
         const size_t E2 = e->def.extractions.size() + 2;
-        const size_t G = std::min(e->devs.size(), pieces.size());
+        // UTF-8 input: offsets are in decoded units, known only piece after piece — one device per call
+        const size_t G = utf8 ? 1 : std::min(e->devs.size(), pieces.size());
         int64_t nl = 0;
         int32_t stride = 0;
         DeviceGuard restore_device;
         if (G <= 1) {
             DeviceRun run;
             std::lock_guard<std::mutex> lock(e->devs[0]->mu);
-            run_pieces(e, *e->devs[0], text, text8, off, pieces, 0, pieces.size(), hr.get(), run);
+            run_pieces(e, *e->devs[0], text, text8, utf8, off, pieces, 0, pieces.size(), hr.get(), run);
             nl = run.n_rows;
             stride = run.stride;
         } else {
@@ -1333,7 +1428,7 @@ int extract_host(gorp_engine* e, const uint16_t* text, const uint8_t* text8, int
             for (size_t d = 0; d < G; ++d)
                 th.emplace_back([&, d]() {
                     runs[d].status = guarded([&]() -> int {
-                        run_pieces(e, *e->devs[d], text, text8, off, pieces, first[d], first[d + 1], nullptr, runs[d]);
+                        run_pieces(e, *e->devs[d], text, text8, false, off, pieces, first[d], first[d + 1], nullptr, runs[d]);
                         return GORP_OK;
                     });
                     if (runs[d].status != GORP_OK) runs[d].error = g_error;
@@ -1608,7 +1703,7 @@ int gorp_engine_create(const void* blob, size_t len, const int* devices, int n_d
             if (d < 0 || d >= avail) return fail(GORP_E_ARG, strfmt("device %d out of range (have %d)", d, avail));
             auto ctx = std::make_unique<DeviceCtx>();
             ctx->device = d;
-            build_device(*ctx, model, fused, tailset, eng->match_only);
+            build_device(*ctx, model, fused, tailset, eng->def.dfa, eng->match_only);
             eng->devs.push_back(std::move(ctx));
         }
         *out = eng.release();
@@ -1634,6 +1729,71 @@ int gorp_extract_text(gorp_engine* e, const uint16_t* text, int64_t n_units, gor
 
 int gorp_extract_text_latin1(gorp_engine* e, const uint8_t* text, int64_t n_bytes, gorp_result* out) {
     return extract_host(e, nullptr, text, n_bytes, nullptr, 0, out);
+}
+
+int gorp_extract_text_utf8(gorp_engine* e, const uint8_t* text, int64_t n_bytes, gorp_result* out) {
+    return extract_host(e, nullptr, text, n_bytes, nullptr, 0, out, true);
+}
+
+int gorp_match_all_lines(gorp_engine* e, const uint16_t* text, const int64_t* off, int64_t n_lines, gorp_match_result* out) {
+    if (!e || !out || !off || n_lines < 0 || e->devs.empty()) return fail(GORP_E_ARG, "bad argument");
+    if (off[0] < 0) return fail(GORP_E_ARG, "offsets must start at >= 0");
+    for (int64_t i = 0; i < n_lines; ++i)
+        if (off[i + 1] < off[i]) return fail(GORP_E_ARG, strfmt("offsets must be non-decreasing (line %lld)", static_cast<long long>(i)));
+    if (!text && n_lines > 0 && off[n_lines] > off[0]) return fail(GORP_E_ARG, "null text");
+    return guarded([&]() -> int {
+        DeviceCtx& c = *e->devs[0];
+        std::lock_guard<std::mutex> lock(c.mu);
+        DeviceGuard restore_device;
+        CK(cudaSetDevice(c.device));
+        CK(cudaStreamWaitEvent(c.stream, c.ev_done, 0));
+        Launch L{c.stream, c.sm_count};
+        const size_t nl = static_cast<size_t>(n_lines);
+        const int64_t u0 = n_lines ? off[0] : 0, u1 = n_lines ? off[n_lines] : 0;
+        c.textbuf[0].reserve(static_cast<size_t>(u1 - u0 + 64) * 2);
+        c.offbuf[0].reserve((nl + 1) * 8);
+        c.ma_state.reserve((nl + 1) * 4);
+        c.ma_count.reserve((nl + 1) * 4);
+        c.ma_off.reserve((nl + 2) * 8);
+        c.scan_scratch.reserve((nl / 4096 + 8) * 8);
+        std::unique_ptr<HostResult> hr = std::make_unique<HostResult>();
+        hr->numa_node = c.numa_node;
+        hr->reserve(1, (nl + 2) * 8);
+        int64_t total = 0;
+        if (n_lines > 0) {
+            if (u1 > u0) CK(cudaMemcpyAsync(c.textbuf[0].p, text + u0, static_cast<size_t>(u1 - u0) * 2, cudaMemcpyHostToDevice, c.stream));
+            CK(cudaMemcpyAsync(c.offbuf[0].p, off, (nl + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+            // text[i] lives at textbuf + (i - u0)
+            k_matchall_walk(L, c.matchall, c.textbuf[0].as<uint16_t>() - u0, c.offbuf[0].as<int64_t>(), n_lines, c.ma_state.as<int32_t>(),
+                            c.ma_count.as<uint32_t>());
+            scan_u32_to_i64(L, c.ma_count.as<uint32_t>(), n_lines, c.ma_off.as<int64_t>(), c.scan_scratch.as<int64_t>());
+            CK(cudaMemcpyAsync(&total, c.ma_off.as<int64_t>() + n_lines, 8, cudaMemcpyDeviceToHost, c.stream));
+            CK(cudaStreamSynchronize(c.stream));
+            c.ma_out.reserve(static_cast<size_t>(total + 1) * 4);
+            k_matchall_fill(L, c.matchall, c.ma_state.as<int32_t>(), c.ma_off.as<int64_t>(), n_lines, c.ma_out.as<int32_t>());
+            c.launches += 5;
+            hr->reserve(0, static_cast<size_t>(total + 1) * 4);
+            CK(cudaMemcpyAsync(hr->p[1], c.ma_off.p, (nl + 1) * 8, cudaMemcpyDeviceToHost, c.stream));
+            if (total) CK(cudaMemcpyAsync(hr->p[0], c.ma_out.p, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, c.stream));
+            CK(cudaStreamSynchronize(c.stream));
+        } else {
+            hr->reserve(0, 4);
+            static_cast<int64_t*>(hr->p[1])[0] = 0;
+        }
+        CK(cudaEventRecord(c.ev_done, c.stream));
+        out->n_lines = n_lines;
+        out->accept_off = static_cast<const int64_t*>(hr->p[1]);
+        out->accept = static_cast<const int32_t*>(hr->p[0]);
+        out->owner = hr.release();
+        return GORP_OK;
+    });
+}
+
+void gorp_match_result_release(gorp_engine* e, gorp_match_result* r) {
+    (void)e;
+    if (!r || !r->owner) return;
+    delete static_cast<HostResult*>(r->owner);
+    r->owner = nullptr;
 }
 
 void gorp_result_release(gorp_engine* e, gorp_result* r) {

@@ -297,7 +297,6 @@ void k4b_capwalk(const Launch&, const CapWalkParams&);
 
 // K4c: tail walk — the capture half for extractions that have a tail automaton (host/tails.hpp, host/walktables.hpp:
 // TailImage) — see kernels/tailwalk.cu. Decides MISS / MATCH / CAPTURE_FAIL of candidate lines and writes their rows.
-constexpr int kTailWalkThreads = 256;
 constexpr uint32_t kTailMaxLen = 65000;   // lines at least this long take the 32-bit one-thread-per-line kernel
 struct TailExt {                 // mirrors host/walktables.hpp: TailImageExt
     uint32_t tab_off;            // byte offset of the table inside the image (16-byte aligned)
@@ -335,7 +334,7 @@ struct TailWalkParams {
     uint32_t n_ext;
     uint32_t round_iters;        // walk iterations (16 units each) between two service points
     uint32_t lines_form;         // 1: List<String> form — lines end where their record says, a '\n' is content
-    uint32_t flags;              // GORP_TAIL_FLAGS (diagnostics): 1 = no L2 bulk prefetch of the next line, 2 / 4 = text loads ask
+    uint32_t flags;              // GORP_TAIL_FLAGS (diagnostics): 1 = L2 bulk prefetch of the next line, 2 / 4 = text loads ask
                                  // L2 for the 128 / 256-byte neighbourhood
     int32_t* ext_id;
     int32_t* spans;
@@ -344,7 +343,7 @@ struct TailWalkParams {
     uint32_t* n_long;            // zeroed by the caller
     uint32_t long_cap;
 };
-size_t tailwalk_smem_bytes(const TailDev&);
+size_t tailwalk_smem_bytes(const TailDev&, int threads);
 void k4c_tailwalk(const Launch&, const TailWalkParams&);
 
 // result assembly of a batch that is pipelined in pieces: dst[i] = src[i] + bias ; dst[i] += src[i]
@@ -352,6 +351,24 @@ void k_bias_copy(const Launch&, int64_t* dst, const int64_t* src, int64_t n, int
 void k_accumulate(const Launch&, int64_t* dst, const int64_t* src, int n);
 // dst[i] = src[i] (ISO-8859-1 byte -> UTF-16 unit); both 16-byte aligned
 void k_widen_latin1(const Launch&, const uint8_t* src, uint16_t* dst, int64_t n);
+
+// UTF-8 ingest (kernels/utf8.cu): src = well-formed UTF-8 bytes (16-byte aligned), dst = the UTF-16 units they decode to.
+// count: tile_counts[utf8_tiles(n)] = UTF-16 units per 4096-byte tile, *first_bad = offset of the first malformed byte (preset
+// to ~0 by the caller); write: tile_base = exclusive scan of tile_counts.
+int64_t utf8_tiles(int64_t n_bytes);
+void k_utf8_count(const Launch&, const uint8_t* src, int64_t n, uint32_t* tile_counts, unsigned long long* first_bad);
+void k_utf8_write(const Launch&, const uint8_t* src, int64_t n, const int64_t* tile_base, uint16_t* dst);
+
+// matchAll (kernels/matchall.cu): the reference's own tables on the device
+struct MatchAllDev {
+    const uint16_t* classmap;    // [65536] Automata._alphabet
+    const int32_t* trans;        // [S * C]  Automata._transitions, -1 = dead
+    const uint32_t* accept_off;  // [S + 1]  CSR of Automata._accept
+    const int32_t* accept_list;
+    uint32_t n_classes;
+};
+void k_matchall_walk(const Launch&, const MatchAllDev&, const uint16_t* text, const int64_t* off, int64_t n_lines, int32_t* state, uint32_t* count);
+void k_matchall_fill(const Launch&, const MatchAllDev&, const int32_t* state, const int64_t* out_off, int64_t n_lines, int32_t* out);
 
 // K3: per-extraction histogram (E entries, then MISS, then capture failures).
 void k3_histogram(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist);

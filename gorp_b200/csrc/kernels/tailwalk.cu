@@ -21,6 +21,8 @@
 // pass). A lane whose line ends inside a round idles until the next service point. The first 32 bytes of a lane's next
 // line are loaded into registers and the rest is prefetched into L2 half a round after the claim, so a line start
 // never waits for memory.
+#include <cstdlib>
+
 #include "device_common.cuh"
 
 namespace gorp {
@@ -41,9 +43,12 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
 // one step on an ASCII unit held in byte kByte (0 or 2) of w. `ra` = byte offset of the current row + rows_abs.
 // bytes between the same thread's cells of two consecutive slots: an odd number of 32-bit words, so that the lanes of a warp
 // that store to different slots in the same step spread over the banks (two neighbouring lanes share a word)
-constexpr uint32_t kSlotStride = kTailWalkThreads * 2 + 4;
+template <int kT>
+struct SlotStride {
+    static constexpr uint32_t value = kT * 2 + 4;
+};
 
-template <int kByte>
+template <int kByte, int kT>
 __device__ __forceinline__ void tw_step(uint32_t& ra, uint32_t w, uint32_t rows_abs, uint32_t row_bytes, uint32_t slot_abs, uint32_t pos1) {
     uint32_t b, a;
     asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
@@ -51,7 +56,7 @@ __device__ __forceinline__ void tw_step(uint32_t& ra, uint32_t w, uint32_t rows_
     const uint32_t ent = lds_u16(a);
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ra) : "r"(ent >> 6), "r"(row_bytes), "r"(rows_abs));
     uint32_t sa;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(ent & 63u), "n"(kSlotStride), "r"(slot_abs));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(ent & 63u), "n"(SlotStride<kT>::value), "r"(slot_abs));
     sts_u16(sa, pos1);
 }
 
@@ -59,7 +64,7 @@ __device__ __forceinline__ void tw_step(uint32_t& ra, uint32_t w, uint32_t rows_
 // followed by a low surrogate takes the PAIR column (java.util.regex consumes the pair as one character).
 __device__ __noinline__ uint32_t tw_slow16(const TailDev& T, uint32_t ra, const Units16 u, const uint16_t* __restrict__ text, int64_t q,
                                            int64_t n_units, uint32_t rows_abs, uint32_t row_bytes, uint32_t fin_ra, uint32_t slot_abs,
-                                           uint32_t pos1) {
+                                           uint32_t pos1, uint32_t kSlotStride) {
     const uint32_t w[8] = {u.a.x, u.a.y, u.a.z, u.a.w, u.b.x, u.b.y, u.b.z, u.b.w};
 #pragma unroll 1
     for (int k = 0; k < 16; ++k) {
@@ -86,7 +91,7 @@ __device__ __noinline__ uint32_t tw_slow16(const TailDev& T, uint32_t ra, const 
 // the line.
 __device__ __noinline__ uint32_t tw_bounded16(const TailDev& T, uint32_t ra, const Units16 u, const uint16_t* __restrict__ text, int64_t q,
                                               int64_t end, uint32_t rows_abs, uint32_t row_bytes, uint32_t fin_ra, uint32_t slot_abs,
-                                              uint32_t pos1) {
+                                              uint32_t pos1, uint32_t kSlotStride) {
     const uint32_t w[8] = {u.a.x, u.a.y, u.a.z, u.a.w, u.b.x, u.b.y, u.b.z, u.b.w};
 #pragma unroll 1
     for (int k = 0; k < 16; ++k) {
@@ -121,8 +126,10 @@ __device__ __forceinline__ Units16 tw_load(const uint16_t* __restrict__ text, in
 
 constexpr uint32_t kTwMaxMulti = 64;  // group boundaries with several writers, per extraction (else the table is refused)
 
-template <bool kLines>
-__global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkParams P) {
+template <bool kLines, int kT>
+__global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
+    constexpr uint32_t kSlotStride = SlotStride<kT>::value;
+    constexpr int kTailWalkThreads = kT;
     // [table][recipes][outcome codes][several-writer list][init list][slots: (max_slots + 2) x kSlotStride]
     extern __shared__ __align__(16) unsigned char s_mem[];
     __shared__ uint32_t s_item, s_cursor, s_loaded, s_n_multi;
@@ -281,26 +288,26 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
                     // lines form: the fast path needs a block that lies inside the line and holds no '\n' (there it is content)
                     const bool plain = !kLines || (q < last_q && (nl_bits4(u.a.x, u.a.y) | nl_bits4(u.a.z, u.a.w) | nl_bits4(u.b.x, u.b.y) | nl_bits4(u.b.z, u.b.w)) == 0u);
                     if (plain && ((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
-                        tw_step<0>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1);
-                        tw_step<2>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1 + 1);
-                        tw_step<0>(ra, u.a.y, rows_abs, row_bytes, slot_abs, pos1 + 2);
-                        tw_step<2>(ra, u.a.y, rows_abs, row_bytes, slot_abs, pos1 + 3);
-                        tw_step<0>(ra, u.a.z, rows_abs, row_bytes, slot_abs, pos1 + 4);
-                        tw_step<2>(ra, u.a.z, rows_abs, row_bytes, slot_abs, pos1 + 5);
-                        tw_step<0>(ra, u.a.w, rows_abs, row_bytes, slot_abs, pos1 + 6);
-                        tw_step<2>(ra, u.a.w, rows_abs, row_bytes, slot_abs, pos1 + 7);
-                        tw_step<0>(ra, u.b.x, rows_abs, row_bytes, slot_abs, pos1 + 8);
-                        tw_step<2>(ra, u.b.x, rows_abs, row_bytes, slot_abs, pos1 + 9);
-                        tw_step<0>(ra, u.b.y, rows_abs, row_bytes, slot_abs, pos1 + 10);
-                        tw_step<2>(ra, u.b.y, rows_abs, row_bytes, slot_abs, pos1 + 11);
-                        tw_step<0>(ra, u.b.z, rows_abs, row_bytes, slot_abs, pos1 + 12);
-                        tw_step<2>(ra, u.b.z, rows_abs, row_bytes, slot_abs, pos1 + 13);
-                        tw_step<0>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 14);
-                        tw_step<2>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 15);
+                        tw_step<0, kT>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1);
+                        tw_step<2, kT>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1 + 1);
+                        tw_step<0, kT>(ra, u.a.y, rows_abs, row_bytes, slot_abs, pos1 + 2);
+                        tw_step<2, kT>(ra, u.a.y, rows_abs, row_bytes, slot_abs, pos1 + 3);
+                        tw_step<0, kT>(ra, u.a.z, rows_abs, row_bytes, slot_abs, pos1 + 4);
+                        tw_step<2, kT>(ra, u.a.z, rows_abs, row_bytes, slot_abs, pos1 + 5);
+                        tw_step<0, kT>(ra, u.a.w, rows_abs, row_bytes, slot_abs, pos1 + 6);
+                        tw_step<2, kT>(ra, u.a.w, rows_abs, row_bytes, slot_abs, pos1 + 7);
+                        tw_step<0, kT>(ra, u.b.x, rows_abs, row_bytes, slot_abs, pos1 + 8);
+                        tw_step<2, kT>(ra, u.b.x, rows_abs, row_bytes, slot_abs, pos1 + 9);
+                        tw_step<0, kT>(ra, u.b.y, rows_abs, row_bytes, slot_abs, pos1 + 10);
+                        tw_step<2, kT>(ra, u.b.y, rows_abs, row_bytes, slot_abs, pos1 + 11);
+                        tw_step<0, kT>(ra, u.b.z, rows_abs, row_bytes, slot_abs, pos1 + 12);
+                        tw_step<2, kT>(ra, u.b.z, rows_abs, row_bytes, slot_abs, pos1 + 13);
+                        tw_step<0, kT>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 14);
+                        tw_step<2, kT>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 15);
                     } else if (kLines) {
-                        ra = tw_bounded16(T, ra, u, P.text, q, line_end, rows_abs, row_bytes, fin_ra, slot_abs, pos1);
+                        ra = tw_bounded16(T, ra, u, P.text, q, line_end, rows_abs, row_bytes, fin_ra, slot_abs, pos1, kSlotStride);
                     } else {
-                        ra = tw_slow16(T, ra, u, P.text, q, P.n_units, rows_abs, row_bytes, fin_ra, slot_abs, pos1);
+                        ra = tw_slow16(T, ra, u, P.text, q, P.n_units, rows_abs, row_bytes, fin_ra, slot_abs, pos1, kSlotStride);
                     }
                     q += 16;
                     if (ra >= fin_ra) {  // the line ended inside these 16 units (its '\n', a dead transition, or the end of the text)
@@ -321,7 +328,7 @@ __global__ void __launch_bounds__(kTailWalkThreads, 2) tailwalk_kernel(TailWalkP
                         int64_t bytes = ((na + nrec.w + 1 - p0) * 2 + 15) & ~int64_t(15);
                         if (p0 + bytes / 2 > P.n_units) bytes = ((P.n_units - p0) * 2) & ~int64_t(15);
                         if (bytes > 4096) bytes = 4096;
-                        if (bytes > 32 && !(P.flags & 1u))
+                        if (bytes > 32 && (P.flags & 1u))  // off by default: same speed, 1.24x the DRAM reads (profiles/README.md)
                             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.text + p0 + 16), "r"(static_cast<uint32_t>(bytes - 32)) : "memory");
                         nstage = 2;
                     }
@@ -385,23 +392,52 @@ __global__ void __launch_bounds__(32) tail_long_kernel(TailWalkParams P) {
 
 }  // namespace
 
-size_t tailwalk_smem_bytes(const TailDev& t) {
+size_t tailwalk_smem_bytes(const TailDev& t, int threads) {
     return static_cast<size_t>(t.max_table_bytes) + static_cast<size_t>(t.max_res) * 4 + static_cast<size_t>(t.max_outcomes) * 4 +
-           2 * kTwMaxMulti * 4 + 64 + static_cast<size_t>(t.max_slots + 2) * kSlotStride + 16;
+           2 * kTwMaxMulti * 4 + 64 + static_cast<size_t>(t.max_slots + 2) * (static_cast<size_t>(threads) * 2 + 4) + 16;
 }
 
-void k4c_tailwalk(const Launch& L, const TailWalkParams& P) {
-    const size_t smem = tailwalk_smem_bytes(P.t);
-    int per_sm = 1;
-    if (P.lines_form) {
-        allow_max_dynamic_smem(tailwalk_kernel<true>);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<true>, kTailWalkThreads, smem);
-        tailwalk_kernel<true><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kTailWalkThreads, smem, L.stream>>>(P);
-    } else {
-        allow_max_dynamic_smem(tailwalk_kernel<false>);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<false>, kTailWalkThreads, smem);
-        tailwalk_kernel<false><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kTailWalkThreads, smem, L.stream>>>(P);
+namespace {
+
+template <bool kLines, int kT>
+int tailwalk_warps_per_sm(const TailDev& t) {
+    const size_t smem = tailwalk_smem_bytes(t, kT);
+    if (smem > 226 * 1024) return 0;
+    allow_max_dynamic_smem(tailwalk_kernel<kLines, kT>);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<kLines, kT>, kT, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
     }
+    return per_sm * kT / 32;
+}
+
+template <bool kLines, int kT>
+void tailwalk_launch(const Launch& L, const TailWalkParams& P) {
+    const size_t smem = tailwalk_smem_bytes(P.t, kT);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<kLines, kT>, kT, smem);
+    tailwalk_kernel<kLines, kT><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kT, smem, L.stream>>>(P);
+}
+
+// the CTA size that keeps the most warps resident (the dependent lookup chain of a lane is latency-bound: the more warps,
+// the better it is hidden); ties: the smaller CTA
+template <bool kLines>
+void tailwalk_dispatch(const Launch& L, const TailWalkParams& P) {
+    const int w256 = tailwalk_warps_per_sm<kLines, 256>(P.t), w384 = tailwalk_warps_per_sm<kLines, 384>(P.t),
+              w512 = tailwalk_warps_per_sm<kLines, 512>(P.t);
+    int forced = 0;
+    if (const char* f = std::getenv("GORP_TAIL_THREADS")) forced = std::atoi(f);
+    if (forced == 512 ? w512 > 0 : (forced == 0 && w512 > w384 && w512 > w256)) tailwalk_launch<kLines, 512>(L, P);
+    else if (forced == 384 ? w384 > 0 : (forced == 0 && w384 > w256)) tailwalk_launch<kLines, 384>(L, P);
+    else tailwalk_launch<kLines, 256>(L, P);
+}
+
+}  // namespace
+
+void k4c_tailwalk(const Launch& L, const TailWalkParams& P) {
+    if (P.lines_form) tailwalk_dispatch<true>(L, P);
+    else tailwalk_dispatch<false>(L, P);
     tail_long_kernel<<<L.sm_count, 32, 0, L.stream>>>(P);
 }
 

@@ -117,7 +117,28 @@ int gorp_extract_text(gorp_engine* e, const uint16_t* text, int64_t n_units, gor
  * gorp_extract_text; results are identical to gorp_extract_text on the zero-extended text (spans and line_off count
  * characters == UTF-16 units). Split on byte 0x0A. */
 int gorp_extract_text_latin1(gorp_engine* e, const uint8_t* text, int64_t n_bytes, gorp_result* out);
+/* Same call for text held as UTF-8 bytes — log files as they are on disk (the reference reads UTF-8 the same way for its
+ * definitions, io/InputLineReader.java:51; a Java caller would otherwise decode the bytes to Strings first). The bytes are
+ * decoded to UTF-16 on the device (supplementary characters become surrogate pairs), so ASCII text crosses PCIe at one byte
+ * per character. Results are those of gorp_extract_text on `new String(bytes, UTF_8)`: line_off and spans count UTF-16
+ * units of the DECODED text. Split on byte 0x0A. The input must be well-formed UTF-8 (Unicode table 3-7): a malformed
+ * sequence fails the call with GORP_E_ARG and the byte offset in gorp_last_error() — no replacement characters are
+ * invented. Runs on the engine's first device. */
+int gorp_extract_text_utf8(gorp_engine* e, const uint8_t* text, int64_t n_bytes, gorp_result* out);
 void gorp_result_release(gorp_engine* e, gorp_result* r);
+
+/* PolyMatcher.match for a batch (reference autom/PolyMatcher.java:123-133, reached through Gorp.getMatcher(), Gorp.java:135-137):
+ * for every string ALL regex / extraction indexes whose automaton accepts the whole string, ascending (Automata.accept,
+ * autom/Automata.java:137-139) — not only the first one the extract path uses. CSR: the indexes of string i are
+ * accept[accept_off[i] .. accept_off[i+1]). Works on any engine (definitions and gorp_compile_patterns blobs). */
+typedef struct gorp_match_result {
+    int64_t n_lines;
+    const int64_t* accept_off; /* [n_lines + 1] */
+    const int32_t* accept;     /* [accept_off[n_lines]] */
+    void* owner;
+} gorp_match_result;
+int gorp_match_all_lines(gorp_engine* e, const uint16_t* text, const int64_t* off, int64_t n_lines, gorp_match_result* out);
+void gorp_match_result_release(gorp_engine* e, gorp_match_result* r);
 
 /* --- device-resident variants: `d_text` (and `d_off`) already live in the HBM of the engine's device `dev_index`
  * (index into the `devices` array given at creation) and must be 16-byte aligned; results stay in device memory

@@ -77,6 +77,27 @@ def test_multipattern_first_accept():
     assert b.ext_id.tolist() == [w[0] if w else -1 for _, w in V.MULTI_CASES]
 
 
+def test_match_all_accept_lists():
+    """gorp_match_all_lines: the full accept lists of PolyMatcher.match (reference MultiPatternTest.java:12-27 incl. the
+    multi-accept cases {1,2} and {3,4}), and for a definition with overlapping extractions the oracle's lists."""
+    from gorp_b200 import Blob, Gorp
+    from oracle import brics
+    g = Gorp(Blob.from_patterns(V.MULTI_PATTERNS))
+    got = g.match_all([s for s, _ in V.MULTI_CASES])
+    assert got == [list(w) for _, w in V.MULTI_CASES]
+    assert any(len(w) > 1 for w in got)
+    d = corpus.WEBLOG_DEF
+    g3 = DefinitionReader.reader(d).read()
+    o = gorp_oracle.Gorp(d)
+    pm = brics.PolyMatcher([x.autom_source for x in o.extractions])
+    lines = corpus.weblog_lines(1500, seed=6) + ["", "x"]
+    got = g3.match_all(lines)
+    want = [pm.match(jdkre.to_units(s)) for s in lines]
+    assert got == want
+    assert sum(len(w) > 1 for w in want) > 100  # CombinedGet and CombinedOther both accept a GET line
+    assert g3.match_all([]) == []
+
+
 def test_readme_sample_line_is_a_miss_and_exception_text():
     g = DefinitionReader.reader(V.README_DEF).read()
     assert g.extract("102456879: GET 123ms 200 /rest-service/v1/endpoint?foo=bar") is None
@@ -344,6 +365,44 @@ def test_concurrent_calls_on_one_engine(monkeypatch):
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+def test_utf8_text_form(monkeypatch):
+    """gorp_extract_text_utf8: UTF-8 bytes in, decoded to UTF-16 on the device; identical to the UTF-16 call on the decoded
+    text (1- to 4-byte sequences, pieces whose seams fall anywhere, last line unterminated); malformed input is refused."""
+    lines = corpus.utf16_mix_lines(6000, seed=12)
+    lines = [s for s in lines if not any(0xD800 <= ord(ch) <= 0xDFFF for ch in s)]  # lone surrogates have no UTF-8 form
+    lines += ["", "\u00e9" * 40, "\u4e2d\u6587" * 30, "\U0001F600" * 25, "[1]: GET 2ms /\U00010400\u0416x", "x" * 5000 + "\u00e9"]
+    text = "\n".join(lines) + "\n"
+    for d in (corpus.WEBLOG_DEF, V.README_DEF):
+        g = DefinitionReader.reader(d).read()
+        for piece in (None, "3000", "70000"):
+            if piece:
+                monkeypatch.setenv("GORP_PIECE_UNITS", piece)
+            for t in (text, text[:-1]):
+                b16 = g.extract_batch_text(t)
+                b8 = g.extract_batch_text_utf8(t.encode("utf-8"))
+                assert b8.n_lines == b16.n_lines and b8.span_stride == b16.span_stride
+                assert (b8.ext_id == b16.ext_id).all() and (b8.line_off == b16.line_off).all()
+                assert (b8.spans == b16.spans).all() and (b8.histogram == b16.histogram).all()
+            monkeypatch.delenv("GORP_PIECE_UNITS", raising=False)
+        check_against_oracle(d, text=np.frombuffer(text.encode("utf-16-le"), dtype=np.uint16), gorp=g)
+    g = DefinitionReader.reader(V.README_DEF).read()
+    assert g.extract_batch_text_utf8(b"").n_lines == 0
+    assert g.extract_batch_text_utf8("[1]: GET 2ms /\u00e9".encode("utf-8")).ext_id.tolist() == [1]
+    good = "[1]: GET 2ms /abc\n".encode("utf-8") * 300
+    for bad in (b"\xc0\xaf", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\x80", b"\xe4\xb8", b"\xf0\x9f\x98", b"\xff"):
+        with pytest.raises(ValueError) as ei:
+            g._eng()  # (engine exists)
+            from gorp_b200 import _ffi
+            import ctypes as C
+            buf = np.frombuffer(good + b"/x" + bad + b"y\n" + good, dtype=np.uint8)
+            res = _ffi.Result()
+            rc = _ffi.lib.gorp_extract_text_utf8(g._eng(), buf.ctypes.data, len(buf), C.byref(res))
+            if rc != 0:
+                raise ValueError(_ffi.last_error())
+            _ffi.lib.gorp_result_release(g._eng(), C.byref(res))
+        assert "malformed UTF-8 at byte %d" % (len(good) + 2) in str(ei.value), (bad, str(ei.value))
 
 
 def test_multi_device_engine(monkeypatch):
