@@ -140,6 +140,7 @@ struct DeviceCtx {
     DevBuf ma_state, ma_count, ma_off, ma_out;
     DfaWalkDev dfawalk_cut{};    // the same with the early-exit cut of host/tails.hpp (K2b when the tail walk follows)
     TailDev tails{};             // per-extraction tail automata of kernels/tailwalk.cu
+    bool cut_effective = false;  // most states of the combined DFA are cut: the chunk-owner walk with early exit (K0d cut)
     uint32_t tail_flush_every = 4;  // walk iterations per round of the tail walk (GORP_TAIL_FLUSH)
     DevBuf long_lines, recs;
     CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
@@ -530,6 +531,8 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     c.dfawalk_cut.xcls = upload(t.xcls, c.owned);
                     c.dfawalk_cut.enabled = 1;
                     d.enabled = 1;
+                    c.cut_effective = static_cast<uint64_t>(tailset.n_cut_states) * 2 > m.dfa.n_states;
+                    if (const char* f = std::getenv("GORP_CUT_WALK")) c.cut_effective = f[0] == '1';
                     if (const char* f = std::getenv("GORP_TAIL_FLUSH")) c.tail_flush_every = std::min(64, std::max(1, std::atoi(f)));
                 }
             }
@@ -923,12 +926,13 @@ bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
 // Text form, newline index + combined DFA through the chunk-walk DFA kernel (K0d): fills c.line_off / c.ext_id.
 // Returns false when the batch has to take K1 + K2 instead.
 bool run_dfawalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
-                 int64_t& n_lines, bool& ends_with_nl) {
-    if (n_units <= 0 || c.force_general || c.force_k1k2 || !c.dfawalk.enabled) return false;
+                 int64_t& n_lines, bool& ends_with_nl, bool cut) {
+    const DfaWalkDev& table = cut ? c.dfawalk_cut : c.dfawalk;
+    if (n_units <= 0 || c.force_general || c.force_k1k2 || !table.enabled) return false;
     if (reinterpret_cast<uintptr_t>(d_text) & 31) return false;  // the walk uses 256-bit loads
     uint32_t threads = 0;
     bool in_smem = false;
-    if (!k0_dfawalk_plan(c.dfawalk, &threads, &in_smem)) return false;
+    if (!k0_dfawalk_plan(table, &threads, &in_smem, cut)) return false;
     Launch L{stream, c.sm_count};
     bool exact = false;
     const int tm_pos = tm.position();
@@ -939,7 +943,8 @@ bool run_dfawalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
         P.n_units = n_units;
         const int64_t tile_units = static_cast<int64_t>(threads) * kChunkUnits;
         P.n_tiles = (n_units + tile_units - 1) / tile_units;
-        P.a = c.dfawalk;
+        P.a = table;
+        P.cut = cut ? 1u : 0u;
         P.stage_rows = kDfaWalkStagePerThread * threads;
         const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 8 + 8 + 24;
         c.tile_state.reserve(std::max<size_t>(state_bytes, kTileStateMinBytes));
@@ -957,10 +962,10 @@ bool run_dfawalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
         CK(cudaMemsetAsync(st, 0, state_bytes, stream));
         if (std::getenv("GORP_ONEPASS_DEBUG"))
             std::fprintf(stderr, "[dfawalk debug] threads=%u grid=%d smem=%zu (table %s) tiles=%lld rows=%u K=%u cap_lines=%lld\n", threads,
-                         k0_dfawalk_grid(L, P, threads, in_smem), dfawalk_smem_bytes(P.a, threads, in_smem), in_smem ? "in smem" : "global",
+                         k0_dfawalk_grid(L, P, threads, in_smem), dfawalk_smem_bytes(P.a, threads, in_smem, cut), in_smem ? "in smem" : "global",
                          static_cast<long long>(P.n_tiles), P.a.n_rows, P.a.K, static_cast<long long>(cap_lines));
         k0_dfawalk_scan(L, P, threads, in_smem);
-        tm.mark("k0_dfawalk_scan", 1);
+        tm.mark(cut ? "k0_dfawalk_cut" : "k0_dfawalk_scan", 1);
         CK(cudaGetLastError());
         int64_t totals[3] = {0, 0, 0};
         CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
@@ -994,10 +999,16 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
     bool scanned = false;  // ext_id already holds the combined-DFA result
     // long or ragged lines: a line index (K1) + lanes that pull lines dynamically (K2b) beats the chunk-owner walk (K0d),
     // whose threads are stuck with whatever lines start in their chunk
-    const bool by_lines = c.dfa_tier == 2 || (c.dfa_tier == 0 && c.lines_per_unit < 1.0 / 100.0);
-    if (!d_off && !by_lines && run_dfawalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, ends_with_nl)) {
+    // ... unless nearly every walk leaves the combined DFA early (host/tails.hpp): then a chunk owner only walks the heads of
+    // its lines and skips from line to line through the newline masks of the pre-scan — one pass over the text
+    const bool tails_ok = c.tails.enabled && !c.cap.match_only && c.max_slots > 0 && !c.force_general && !c.force_k4 && !c.force_k1k2;
+    const bool cut_walk = !d_off && tails_ok && c.cut_effective && c.dfa_tier != 2 && c.dfa_tier != 1;
+    const bool by_lines = !cut_walk && (c.dfa_tier == 2 || (c.dfa_tier == 0 && c.lines_per_unit < 1.0 / 100.0));
+    bool cut_scanned = false;
+    if (!d_off && !by_lines && run_dfawalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, ends_with_nl, cut_walk)) {
         sep = 1;
         scanned = true;
+        cut_scanned = cut_walk;
         d_line_off = c.line_off.as<int64_t>();
     } else if (!d_off) {
         sep = 1;
@@ -1049,7 +1060,7 @@ int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cons
                             !c.force_k1k2 && n_lines > 0 && n_lines < (1ll << 32) && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0 &&
                             (sep == 1 || n_units > 0);
     const DfaWalkDev& walk_table = with_tails ? c.dfawalk_cut : c.dfawalk;
-    bool candidates = false;  // ext_id holds candidates of the cut table: only the tail walk may follow (its conditions are those of with_tails)
+    bool candidates = cut_scanned;  // ext_id holds candidates of the cut table: only the tail walk may follow (its conditions are those of with_tails)
     if (scanned) {
     } else if ((sep == 1 || with_tails) && !c.force_general && !c.force_k1k2 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0 &&
                k2b_linewalk_plan(walk_table, &lw_threads, &lw_smem)) {

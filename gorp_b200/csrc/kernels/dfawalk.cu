@@ -130,7 +130,10 @@ __device__ __noinline__ uint32_t dw_bounded16(const DfaWalkDev& A, uint32_t st, 
     return st;
 }
 
-template <bool kSmem>
+// kCut: the table is the early-exit variant (host/walktables.hpp: build_dfawalk_table_cut) — a walk may reach a FIN row long
+// before the line's '\n', so the thread finds its next line through the newline bit mask of its chunk (kept from the
+// pre-scan) instead of scanning on; nothing beyond the head of a line is read a second time.
+template <bool kSmem, bool kCut>
 __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t kT = blockDim.x;
@@ -138,10 +141,11 @@ __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
     constexpr uint32_t C = kChunkUnits;
     const uint32_t row_bytes = A.K * 2;
     const uint32_t table_bytes = kSmem ? ((A.n_rows * row_bytes + 15u) & ~15u) : 0u;
-    // ---- carve shared memory: [table][cx 128 x u32][staged ext][staged start]
+    // ---- carve shared memory: [table][cx 128 x u32][staged ext][staged start][kCut: newline masks, 32 bytes per thread]
     uint32_t* s_cx = reinterpret_cast<uint32_t*>(smem + table_bytes);
     int32_t* s_sext = reinterpret_cast<int32_t*>(s_cx + 128);
     uint32_t* s_sstart = reinterpret_cast<uint32_t*>(s_sext + P.stage_rows);
+    unsigned char* s_masks = reinterpret_cast<unsigned char*>(s_sstart + P.stage_rows);  // [thread][32]: bit k of byte j = unit 8j + k
     __shared__ uint32_t s_warp[32];
     __shared__ long long s_tile, s_base;
     __shared__ int s_skip_writes;
@@ -195,14 +199,35 @@ __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
                         const int64_t room = P.n_units - 1 - p;  // positions (relative to p) that count: [0, room)
                         m = room <= 0 ? 0u : (room < 8 ? m & ((1u << static_cast<uint32_t>(room)) - 1u) : m);
                     }
-                    const uint32_t tot = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(m)));
-                    const uint32_t has = __ballot_sync(0xffffffffu, m != 0);
-                    const uint32_t fl = has ? static_cast<uint32_t>(__ffs(has)) - 1u : 0u;
-                    const uint32_t mf = __shfl_sync(0xffffffffu, m, fl);
-                    if (lane == i) {
-                        cnt = tot;
-                        first = fl * 8 + static_cast<uint32_t>(__ffs(mf)) - 1u;
+                    if (kCut) {  // the chunk's mask goes through shared memory: lane j holds byte j of the chunk of thread (warp, i)
+                        s_masks[(warp * 32 + i) * 32 + lane] = static_cast<unsigned char>(m);
+                    } else {
+                        const uint32_t tot = __reduce_add_sync(0xffffffffu, static_cast<uint32_t>(__popc(m)));
+                        const uint32_t has = __ballot_sync(0xffffffffu, m != 0);
+                        const uint32_t fl = has ? static_cast<uint32_t>(__ffs(has)) - 1u : 0u;
+                        const uint32_t mf = __shfl_sync(0xffffffffu, m, fl);
+                        if (lane == i) {
+                            cnt = tot;
+                            first = fl * 8 + static_cast<uint32_t>(__ffs(mf)) - 1u;
+                        }
                     }
+                }
+            } else if (kCut) {
+                for (uint32_t i = 0; i < 32; ++i) s_masks[(warp * 32 + i) * 32 + lane] = 0;
+            }
+        }
+        uint32_t nlm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // kCut: bit p of the 256-bit mask = unit p of this thread's chunk starts... is a '\n' that starts a line
+        if (kCut) {
+            __syncwarp();
+            const uint4 lo4 = *reinterpret_cast<const uint4*>(s_masks + threadIdx.x * 32), hi4 = *reinterpret_cast<const uint4*>(s_masks + threadIdx.x * 32 + 16);
+            nlm[0] = lo4.x, nlm[1] = lo4.y, nlm[2] = lo4.z, nlm[3] = lo4.w, nlm[4] = hi4.x, nlm[5] = hi4.y, nlm[6] = hi4.z, nlm[7] = hi4.w;
+            bool found = false;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                cnt += static_cast<uint32_t>(__popc(nlm[w]));
+                if (!found && nlm[w]) {
+                    first = w * 32 + static_cast<uint32_t>(__ffs(nlm[w])) - 1u;
+                    found = true;
                 }
             }
         }
@@ -279,9 +304,26 @@ __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
                     st = dw_slow8<kSmem>(A, st, u.b, cx_abs, tab_abs, row_bytes, tab_g);
                 }
                 if (st >= fin_base) {  // the line ended inside these 16 units: at its first '\n' at or after `start`
-                    uint32_t m = nl_mask16(u);
-                    if (q < start) m &= ~0u << (start - q);
-                    const uint32_t nl = q + static_cast<uint32_t>(__ffs(m)) - 1u;  // tile-relative position of the '\n'
+                    uint32_t nl;  // tile-relative position of the line's '\n' (kCut: 0xFFFFFFFF when it lies beyond the chunk)
+                    if (kCut) {
+                        // the walk may have stopped anywhere in the line: the next '\n' of this thread's chunk at or after `start`
+                        const uint32_t c0 = threadIdx.x * C;
+                        nl = 0xFFFFFFFFu;
+                        if (start < c0 + C) {
+                            const uint32_t rel = start > c0 ? start - c0 : 0u;  // (the line at offset 0 of the text starts before the first '\n')
+#pragma unroll
+                            for (int w = 0; w < 8; ++w) {
+                                uint32_t mw = nlm[w];
+                                if (static_cast<uint32_t>(w) == (rel >> 5)) mw &= ~0u << (rel & 31u);
+                                else if (static_cast<uint32_t>(w) < (rel >> 5)) mw = 0;
+                                if (nl == 0xFFFFFFFFu && mw) nl = c0 + w * 32 + static_cast<uint32_t>(__ffs(mw)) - 1u;
+                            }
+                        }
+                    } else {
+                        uint32_t m = nl_mask16(u);
+                        if (q < start) m &= ~0u << (start - q);
+                        nl = q + static_cast<uint32_t>(__ffs(m)) - 1u;
+                    }
                     const int32_t ext = static_cast<int32_t>(st - fin_base) - 1;
                     if (row < P.stage_rows) {
                         s_sext[row] = ext;
@@ -430,36 +472,43 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
 
 }  // namespace
 
-size_t dfawalk_smem_bytes(const DfaWalkDev& a, uint32_t threads, bool in_smem) {
+size_t dfawalk_smem_bytes(const DfaWalkDev& a, uint32_t threads, bool in_smem, bool cut) {
     size_t b = in_smem ? ((static_cast<size_t>(a.n_rows) * a.K * 2 + 15) & ~size_t(15)) : 0;
     b += 128 * 4;
     b += static_cast<size_t>(kDfaWalkStagePerThread) * threads * 8;
+    if (cut) b += static_cast<size_t>(threads) * 32;
     return b + 128;
 }
 
+namespace {
+template <class Kernel>
+int dfawalk_blocks_per_sm(Kernel kernel, uint32_t threads, size_t smem) {
+    allow_max_dynamic_smem(kernel);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, static_cast<int>(threads), smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return per_sm;
+}
+int dfawalk_blocks(uint32_t threads, size_t smem, bool in_smem, bool cut) {
+    if (cut) return dfawalk_blocks_per_sm(dfawalk_kernel<true, true>, threads, smem);
+    return in_smem ? dfawalk_blocks_per_sm(dfawalk_kernel<true, false>, threads, smem) : dfawalk_blocks_per_sm(dfawalk_kernel<false, false>, threads, smem);
+}
+}  // namespace
+
 // picks table placement and CTA size: the table goes to shared memory when that still leaves >= 16 resident warps per SM
-bool k0_dfawalk_plan(const DfaWalkDev& a, uint32_t* threads, bool* in_smem) {
+// (the early-exit variant always has its small table in shared memory)
+bool k0_dfawalk_plan(const DfaWalkDev& a, uint32_t* threads, bool* in_smem, bool cut) {
     if (!a.enabled) return false;
     for (int pass = 0; pass < 2; ++pass) {
         const bool sm = pass == 0;
+        if (cut && !sm) break;
         uint32_t best = 0, best_warps = 0;
         for (uint32_t kT : {1024u, 512u, 256u}) {
-            const size_t smem = dfawalk_smem_bytes(a, kT, sm);
+            const size_t smem = dfawalk_smem_bytes(a, kT, sm, cut);
             if (smem > 226 * 1024) continue;
-            int per_sm = 0;
-            cudaError_t e;
-            if (sm) {
-                allow_max_dynamic_smem(dfawalk_kernel<true>);
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<true>, static_cast<int>(kT), smem);
-            } else {
-                allow_max_dynamic_smem(dfawalk_kernel<false>);
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<false>, static_cast<int>(kT), smem);
-            }
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                continue;
-            }
-            const uint32_t warps = static_cast<uint32_t>(per_sm) * kT / 32;
+            const uint32_t warps = static_cast<uint32_t>(dfawalk_blocks(kT, smem, sm, cut)) * kT / 32;
             if (warps > best_warps) best = kT, best_warps = warps;
         }
         if (best && (best_warps >= 16 || !sm)) {
@@ -472,15 +521,8 @@ bool k0_dfawalk_plan(const DfaWalkDev& a, uint32_t* threads, bool* in_smem) {
 }
 
 int k0_dfawalk_grid(const Launch& L, const DfaWalkParams& P, uint32_t threads, bool in_smem) {
-    const size_t smem = dfawalk_smem_bytes(P.a, threads, in_smem);
-    int per_sm = 1;
-    if (in_smem) {
-        allow_max_dynamic_smem(dfawalk_kernel<true>);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<true>, static_cast<int>(threads), smem);
-    } else {
-        allow_max_dynamic_smem(dfawalk_kernel<false>);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfawalk_kernel<false>, static_cast<int>(threads), smem);
-    }
+    const size_t smem = dfawalk_smem_bytes(P.a, threads, in_smem, P.cut != 0);
+    int per_sm = dfawalk_blocks(threads, smem, in_smem, P.cut != 0);
     if (per_sm < 1) per_sm = 1;
     const int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
     const int g = static_cast<int>(P.n_tiles < cap ? P.n_tiles : cap);
@@ -488,10 +530,11 @@ int k0_dfawalk_grid(const Launch& L, const DfaWalkParams& P, uint32_t threads, b
 }
 
 void k0_dfawalk_scan(const Launch& L, const DfaWalkParams& P, uint32_t threads, bool in_smem) {
-    const size_t smem = dfawalk_smem_bytes(P.a, threads, in_smem);
+    const size_t smem = dfawalk_smem_bytes(P.a, threads, in_smem, P.cut != 0);
     const int g = k0_dfawalk_grid(L, P, threads, in_smem);
-    if (in_smem) dfawalk_kernel<true><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
-    else dfawalk_kernel<false><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
+    if (P.cut) dfawalk_kernel<true, true><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
+    else if (in_smem) dfawalk_kernel<true, false><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
+    else dfawalk_kernel<false, false><<<g, static_cast<int>(threads), smem, L.stream>>>(P);
 }
 
 size_t linewalk_smem_bytes(const DfaWalkDev& a, bool in_smem) {

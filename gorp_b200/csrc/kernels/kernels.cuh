@@ -222,10 +222,11 @@ struct DfaWalkParams {
     unsigned long long* tile_status;  // [n_tiles] zeroed by the caller (decoupled look-back, as OnePassParams)
     unsigned int* ticket;        // zeroed by the caller
     int64_t* totals;             // [0] n_lines, [1] 1 = the text ends with '\n', [2] flags: 1 = capacity overflow
+    uint32_t cut;                // 1: `a` is the early-exit table (ext_id = candidates, the tail walk must follow)
 };
 constexpr uint32_t kDfaWalkStagePerThread = 6;
-size_t dfawalk_smem_bytes(const DfaWalkDev&, uint32_t threads, bool in_smem);
-bool k0_dfawalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem);
+size_t dfawalk_smem_bytes(const DfaWalkDev&, uint32_t threads, bool in_smem, bool cut = false);
+bool k0_dfawalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem, bool cut = false);
 int k0_dfawalk_grid(const Launch&, const DfaWalkParams&, uint32_t threads, bool in_smem);
 void k0_dfawalk_scan(const Launch&, const DfaWalkParams&, uint32_t threads, bool in_smem);
 

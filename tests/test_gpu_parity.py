@@ -144,6 +144,11 @@ def test_config_corpora(name, n, monkeypatch):
         check_against_oracle(d, text=text)
         monkeypatch.delenv("GORP_NO_TAILS")
         monkeypatch.delenv("GORP_DFA_TIER")
+        for cut in ("1", "0"):  # the early-exit walk as chunk owner (one pass, newline masks) / over the line index (K1 + K2b)
+            monkeypatch.setenv("GORP_CUT_WALK", cut)
+            check_against_oracle(d, text=text)
+            check_against_oracle(d, text=text[:-1])
+        monkeypatch.delenv("GORP_CUT_WALK")
     _, b, oe = check_against_oracle(d, text=text)
     assert b.n_lines == n and (oe >= 0).sum() > n // 3
     if name == "utf16mix":
@@ -230,6 +235,8 @@ TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
          "dfawalk_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1", "GORP_NO_TAILS": "1"},
          "linewalk_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_NO_TAILS": "1"},
          "linewalk_tailwalk_flush1": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_TAIL_FLUSH": "1"},
+         "cutwalk_tailwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_CUT_WALK": "1", "GORP_TAIL_THREADS": "512"},
+         "linewalk_cut_tailwalk384": {"GORP_FORCE_TWOPASS": "1", "GORP_CUT_WALK": "0", "GORP_TAIL_THREADS": "384"},
          "dfawalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1"},
          "linewalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2"},
          "dfawalk_k4": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1", "GORP_FORCE_K4": "1"},
@@ -237,7 +244,7 @@ TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
          "twopass_fast": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1", "GORP_FORCE_K4": "1"},
          "general": {"GORP_FORCE_GENERAL": "1"}}
 _TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES", "GORP_FORCE_K1K2", "GORP_FORCE_K4", "GORP_DFA_TIER",
-             "GORP_NO_TAILS", "GORP_TAIL_FLUSH")
+             "GORP_NO_TAILS", "GORP_TAIL_FLUSH", "GORP_CUT_WALK", "GORP_TAIL_THREADS")
 
 
 @pytest.mark.parametrize("tier", list(TIERS))
