@@ -54,6 +54,14 @@ public final class GorpCuda implements AutoCloseable {
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
     private static final MethodHandle EXTRACT_TEXT_LATIN1 = fn("gorp_extract_text_latin1",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+    private static final MethodHandle EXTRACT_TEXT_UTF8 = fn("gorp_extract_text_utf8",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+    // struct gorp_match_result { int64 n_lines; const int64* accept_off; const int32* accept; void* owner; }
+    private static final StructLayout MATCH_RESULT = MemoryLayout.structLayout(
+            JAVA_LONG.withName("n_lines"), ADDRESS.withName("accept_off"), ADDRESS.withName("accept"), ADDRESS.withName("owner"));
+    private static final MethodHandle MATCH_ALL_LINES = fn("gorp_match_all_lines",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+    private static final MethodHandle MATCH_RESULT_RELEASE = fn("gorp_match_result_release", FunctionDescriptor.ofVoid(ADDRESS, ADDRESS));
     private static final MethodHandle RESULT_RELEASE = fn("gorp_result_release", FunctionDescriptor.ofVoid(ADDRESS, ADDRESS));
     private static final MethodHandle LAST_ERROR = fn("gorp_last_error", FunctionDescriptor.of(ADDRESS));
 
@@ -177,6 +185,113 @@ public final class GorpCuda implements AutoCloseable {
                 RESULT_RELEASE.invokeExact(engine, res);
             }
         }
+    }
+
+    /**
+     * '\n'-separated log text as UTF-8 bytes (a log file as it is on disk, e.g. a memory-mapped file): decoded to UTF-16 on
+     * the device; the columnar batch is what {@link #extractAll(CharBuffer)} would give on {@code new String(bytes, UTF_8)}.
+     * Lines are decoded from the byte buffer only when asked for. Malformed UTF-8 fails the call.
+     */
+    public ExtractionBatch extractBatchUtf8(java.nio.ByteBuffer text) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment seg;
+            if (text.isDirect()) {
+                seg = MemorySegment.ofBuffer(text);
+            } else {
+                seg = a.allocate(Math.max(text.remaining(), 1), 16);
+                MemorySegment.copy(MemorySegment.ofBuffer(text), 0, seg, 0, text.remaining());
+            }
+            final java.nio.ByteBuffer view = text.duplicate();
+            MemorySegment res = a.allocate(RESULT);
+            check((int) EXTRACT_TEXT_UTF8.invokeExact(engine, seg, (long) text.remaining(), res));
+            try {
+                // byte offsets of the lines (the native offsets count decoded UTF-16 units): one pass over the '\n' bytes
+                final int n = (int) res.get(JAVA_LONG, 0);
+                final int[] byteOff = new int[n + 1];
+                int line = 0;
+                final int base = view.position(), end = view.limit();
+                for (int p = base; p < end && line < n; ++p) if (view.get(p) == 0x0A) byteOff[++line] = p + 1 - base;
+                if (line < n) byteOff[n] = end - base + 1;  // last line not terminated
+                return batch(res, n, i -> {
+                    byte[] b = new byte[byteOff[(int) i + 1] - 1 - byteOff[(int) i]];
+                    view.get(base + byteOff[(int) i], b);
+                    return new String(b, java.nio.charset.StandardCharsets.UTF_8);
+                });
+            } finally {
+                RESULT_RELEASE.invokeExact(engine, res);
+            }
+        }
+    }
+
+    /** Columnar batch over a List&lt;String&gt; (Gorp.extractAll without materialising every ExtractionResult). */
+    public ExtractionBatch extractBatch(List<String> lines) throws Throwable {
+        final int n = lines.size();
+        long units = 0;
+        for (String s : lines) units += s.length();
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment text = a.allocate(Math.max(2 * units, 2), 16);
+            MemorySegment off = a.allocate(8L * (n + 1), 8);
+            long pos = 0;
+            for (int i = 0; i < n; ++i) {
+                String s = lines.get(i);
+                off.setAtIndex(JAVA_LONG, i, pos);
+                MemorySegment.copy(s.toCharArray(), 0, text, JAVA_CHAR, 2 * pos, s.length());
+                pos += s.length();
+            }
+            off.setAtIndex(JAVA_LONG, n, pos);
+            MemorySegment res = a.allocate(RESULT);
+            check((int) EXTRACT_LINES.invokeExact(engine, text, off, (long) n, res));
+            try {
+                return batch(res, n, i -> lines.get((int) i));
+            } finally {
+                RESULT_RELEASE.invokeExact(engine, res);
+            }
+        }
+    }
+
+    /** PolyMatcher.match for a batch (Gorp.getMatcher().match(s) per string): all accepting indexes per string, ascending. */
+    public int[][] matchAll(List<String> lines) throws Throwable {
+        final int n = lines.size();
+        long units = 0;
+        for (String s : lines) units += s.length();
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment text = a.allocate(Math.max(2 * units, 2), 16);
+            MemorySegment off = a.allocate(8L * (n + 1), 8);
+            long pos = 0;
+            for (int i = 0; i < n; ++i) {
+                String s = lines.get(i);
+                off.setAtIndex(JAVA_LONG, i, pos);
+                MemorySegment.copy(s.toCharArray(), 0, text, JAVA_CHAR, 2 * pos, s.length());
+                pos += s.length();
+            }
+            off.setAtIndex(JAVA_LONG, n, pos);
+            MemorySegment res = a.allocate(MATCH_RESULT);
+            check((int) MATCH_ALL_LINES.invokeExact(engine, text, off, (long) n, res));
+            try {
+                MemorySegment aoff = res.get(ADDRESS, 8).reinterpret(8L * (n + 1));
+                long total = aoff.getAtIndex(JAVA_LONG, n);
+                MemorySegment acc = res.get(ADDRESS, 16).reinterpret(4 * Math.max(total, 1));
+                int[][] out = new int[n][];
+                for (int i = 0; i < n; ++i) {
+                    long a0 = aoff.getAtIndex(JAVA_LONG, i), a1 = aoff.getAtIndex(JAVA_LONG, i + 1);
+                    out[i] = new int[(int) (a1 - a0)];
+                    for (int k = 0; k < out[i].length; ++k) out[i][k] = acc.getAtIndex(JAVA_INT, a0 + k);
+                }
+                return out;
+            } finally {
+                MATCH_RESULT_RELEASE.invokeExact(engine, res);
+            }
+        }
+    }
+
+    /** Copies the native result columns into heap arrays (the native buffers go back to the engine's pool). */
+    private ExtractionBatch batch(MemorySegment res, int n, java.util.function.LongFunction<String> lines) {
+        final int stride = res.get(JAVA_INT, 12), nExt = res.get(JAVA_INT, 8);
+        int[] extId = res.get(ADDRESS, 16).reinterpret(4L * Math.max(n, 1)).asSlice(0, 4L * n).toArray(JAVA_INT);
+        long[] lineOff = res.get(ADDRESS, 24).reinterpret(8L * (n + 1)).toArray(JAVA_LONG);
+        int[] spans = res.get(ADDRESS, 32).reinterpret(4L * Math.max((long) n * stride, 1)).asSlice(0, 4L * n * stride).toArray(JAVA_INT);
+        long[] hist = res.get(ADDRESS, 40).reinterpret(8L * (nExt + 2)).toArray(JAVA_LONG);
+        return new ExtractionBatch(extId, lineOff, spans, stride, hist, extractions, groups, lines);
     }
 
     private interface LineSource { String line(long i); }
