@@ -213,7 +213,7 @@ def bind_numa(cudart, index):
     info = {"node": None, "cpus": None, "mempolicy": None}
     try:
         err, bdf = cudart.cudaDeviceGetPCIBusId(32, index)
-        bdf = (bdf.decode() if isinstance(bdf, bytes) else str(bdf)).strip("\x00").lower()
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else str(bdf)).split(chr(0))[0].strip().lower()
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
         if node < 0:
             return info

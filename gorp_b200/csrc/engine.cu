@@ -141,7 +141,7 @@ struct DeviceCtx {
     DfaWalkDev dfawalk_cut{};    // the same with the early-exit cut of host/tails.hpp (K2b when the tail walk follows)
     TailDev tails{};             // per-extraction tail automata of kernels/tailwalk.cu
     bool cut_effective = false;  // most states of the combined DFA are cut: the chunk-owner walk with early exit (K0d cut)
-    uint32_t tail_flush_every = 4;  // walk iterations per round of the tail walk (GORP_TAIL_FLUSH)
+    uint32_t tail_flush_every = 8;  // walk iterations per round of the tail walk (GORP_TAIL_FLUSH)
     DevBuf long_lines, recs;
     CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
     bool force_k4 = false;       // GORP_FORCE_K4=1: one-line-per-thread capture kernels (K4) instead of the bucketed K4b
@@ -391,8 +391,9 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
         std::vector<uint8_t> fin, acc;
         for (size_t e = 0; e < E; ++e) {
             const Tdfa& t = m.tdfas[e];
-            if (t.n_regs > static_cast<uint32_t>(kMaxTdfaRegs))
-                throw UnsupportedError(strfmt("extraction #%zu needs %u tag registers (limit %d)", e, t.n_regs, kMaxTdfaRegs));
+            if (t.n_regs > static_cast<uint32_t>(kMaxTdfaRegsBig))
+                throw UnsupportedError(strfmt("extraction #%zu needs %u tag registers (limit %d)", e, t.n_regs, kMaxTdfaRegsBig));
+            c.cap.max_regs = std::max(c.cap.max_regs, t.n_regs);
             ext[e] = {t.n_states, static_cast<uint32_t>(trans.size()), static_cast<uint32_t>(opoff.size()),
                       static_cast<uint32_t>(ops.size()), static_cast<uint32_t>(fin.size()), static_cast<uint32_t>(acc.size()),
                       t.n_slots};
@@ -531,7 +532,9 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     c.dfawalk_cut.xcls = upload(t.xcls, c.owned);
                     c.dfawalk_cut.enabled = 1;
                     d.enabled = 1;
-                    c.cut_effective = static_cast<uint64_t>(tailset.n_cut_states) * 2 > m.dfa.n_states;
+                    // the chunk-owner variant of the early-exit walk (one pass, newline masks) measured 4.87 ms against 4.53 ms for
+                    // K1 + K2b on config #4 (profiles/README.md, round 2): kept as a tier (GORP_CUT_WALK=1), off by default
+                    c.cut_effective = false;
                     if (const char* f = std::getenv("GORP_CUT_WALK")) c.cut_effective = f[0] == '1';
                     if (const char* f = std::getenv("GORP_TAIL_FLUSH")) c.tail_flush_every = std::min(64, std::max(1, std::atoi(f)));
                 }

@@ -310,6 +310,9 @@ __global__ void __launch_bounds__(kThreads) dfa_scan_kernel(DfaDev d, const uint
 
 // ------------------------------------------------------------------ K4: capture automaton (TDFA), one line per thread
 // Per extraction: rows = states + 1 (last = dead), columns = symbol classes + 1 (last = identity: same state, no ops).
+// kRegs: size of the per-line register file — 32 (registers) for ordinary extractions, kMaxTdfaRegsBig (local memory) for
+// capture automata with more tag registers than that (many groups under alternations / counted repeats)
+template <int kRegs>
 __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const uint16_t* __restrict__ text,
                                                                 const int64_t* __restrict__ line_off, int sep,
                                                                 int64_t n_lines, uint32_t span_stride,
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(kThreads) tdfa_capture_kernel(CapDev c, const 
         const uint32_t* __restrict__ tr = c.tdfa_trans + x.trans_off;
         const uint32_t* __restrict__ opo = c.tdfa_op_off + x.opoff_off;
         const uint16_t* __restrict__ ops = c.tdfa_ops + x.ops_off;
-        int32_t regs[kMaxTdfaRegs];
+        int32_t regs[kRegs];
         uint32_t st = 0;
         int64_t q = a & ~int64_t(7);
         uint32_t lo = static_cast<uint32_t>(a - q);
@@ -519,8 +522,13 @@ void k2_dfa_scan(const Launch& L, const DfaDev& d, const uint16_t* text, const i
 void k4_tdfa_capture(const Launch& L, const CapDev& c, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines,
                      uint32_t span_stride, int32_t* ext_id, int32_t* spans, const TailExt* skip_tails, unsigned long long* hist) {
     if (n_lines <= 0) return;
-    int g = persistent_grid(L, reinterpret_cast<const void*>(tdfa_capture_kernel), 0, n_lines);
-    tdfa_capture_kernel<<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_stride, ext_id, spans, skip_tails, hist);
+    if (c.max_regs <= static_cast<uint32_t>(kMaxTdfaRegs)) {
+        int g = persistent_grid(L, reinterpret_cast<const void*>(tdfa_capture_kernel<kMaxTdfaRegs>), 0, n_lines);
+        tdfa_capture_kernel<kMaxTdfaRegs><<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_stride, ext_id, spans, skip_tails, hist);
+    } else {
+        int g = persistent_grid(L, reinterpret_cast<const void*>(tdfa_capture_kernel<kMaxTdfaRegsBig>), 0, n_lines);
+        tdfa_capture_kernel<kMaxTdfaRegsBig><<<g, kThreads, 0, L.stream>>>(c, text, line_off, sep, n_lines, span_stride, ext_id, spans, skip_tails, hist);
+    }
 }
 
 void k_bias_copy(const Launch& L, int64_t* dst, const int64_t* src, int64_t n, int64_t bias) {

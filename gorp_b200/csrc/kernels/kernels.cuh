@@ -13,6 +13,7 @@
 namespace gorp {
 
 constexpr int kMaxTdfaRegs = 32;   // run-time register file per line (tag registers of the capture automaton)
+constexpr int kMaxTdfaRegsBig = 256;  // ... of the variant for capture automata with more registers (host limit: 250)
 constexpr int kCapFastThreads = 512;  // CTA size of the fast capture tier (register offsets in the capture image are
                                       // pre-multiplied by kCapFastThreads * 4)
 
@@ -46,6 +47,7 @@ struct CapDev {
     const uint8_t* tdfa_accepting;
     uint32_t n_ext;
     uint32_t match_only;
+    uint32_t max_regs;             // widest register file among the extractions
 };
 
 // K2 fast tier ("T0"): combined DFA as directly ASCII-indexed rows in shared memory, text form only.

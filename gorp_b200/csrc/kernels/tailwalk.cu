@@ -428,8 +428,10 @@ void tailwalk_dispatch(const Launch& L, const TailWalkParams& P) {
               w512 = tailwalk_warps_per_sm<kLines, 512>(P.t);
     int forced = 0;
     if (const char* f = std::getenv("GORP_TAIL_THREADS")) forced = std::atoi(f);
-    if (forced == 512 ? w512 > 0 : (forced == 0 && w512 > w384 && w512 > w256)) tailwalk_launch<kLines, 512>(L, P);
-    else if (forced == 384 ? w384 > 0 : (forced == 0 && w384 > w256)) tailwalk_launch<kLines, 384>(L, P);
+    // measured on config #4 (profiles/README.md, round 2): 16 warps 8.5 ms, 24 warps (2 x 384) 7.34 ms, 32 warps (2 x 512) 7.44 ms
+    if (forced == 384 ? w384 > 0 : (forced == 0 && w384 >= 24 && w384 > w256)) tailwalk_launch<kLines, 384>(L, P);
+    else if (forced == 512 ? w512 > 0 : (forced == 0 && w512 > w384 && w512 > w256)) tailwalk_launch<kLines, 512>(L, P);
+    else if (forced == 0 && w384 > w256) tailwalk_launch<kLines, 384>(L, P);
     else tailwalk_launch<kLines, 256>(L, P);
 }
 
