@@ -338,7 +338,7 @@ struct TailWalkParams {
     uint32_t round_iters;        // walk iterations (16 units each) between two service points
     uint32_t lines_form;         // 1: List<String> form — lines end where their record says, a '\n' is content
     uint32_t flags;              // GORP_TAIL_FLAGS (diagnostics): 1 = L2 bulk prefetch of the next line, 2 / 4 = text loads ask
-                                 // L2 for the 128 / 256-byte neighbourhood
+                                 // L2 for the 128 / 256-byte neighbourhood, 8 = no just-in-time L2 prefetch four blocks ahead
     int32_t* ext_id;
     int32_t* spans;
     unsigned long long* hist;    // [E+2]: a candidate that ends as MISS / CAPTURE_FAIL moves its count

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const uint32_t n_items = *P.n_items;
     const uint32_t round_iters = P.round_iters;
+    const bool pf_ahead = !(P.flags & 8u);
     if (threadIdx.x == 0) s_loaded = 0xFFFFFFFFu;
     sts_u16(slot_abs + zero_off, 0u);
 
@@ -284,6 +285,9 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                 if (active) {
                     const Units16 u = nxt;
                     if (q < last_q) nxt = tw_load(P.text, q + 16, P.n_units, P.flags);  // in flight during the 16 steps below
+                    // ... and the 128-byte line four blocks ahead is asked into L2 just in time: the register load above then
+                    // finds its block in L2 (a whole-line prefetch at claim time came too early and was evicted again)
+                    if (pf_ahead && q + 64 <= last_q) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + q + 64));
                     const uint32_t pos1 = static_cast<uint32_t>(q - a) + 1u;  // garbage while skipping: only ever stored to the dummy slot
                     // lines form: the fast path needs a block that lies inside the line and holds no '\n' (there it is content)
                     const bool plain = !kLines || (q < last_q && (nl_bits4(u.a.x, u.a.y) | nl_bits4(u.a.z, u.a.w) | nl_bits4(u.b.x, u.b.y) | nl_bits4(u.b.z, u.b.w)) == 0u);
@@ -325,6 +329,7 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                     } else {
                         const int64_t p0 = na & ~int64_t(15);
                         nfirst = tw_load(P.text, p0, P.n_units, P.flags);
+                        if (pf_ahead && nrec.w > 48u) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + p0 + 16));
                         int64_t bytes = ((na + nrec.w + 1 - p0) * 2 + 15) & ~int64_t(15);
                         if (p0 + bytes / 2 > P.n_units) bytes = ((P.n_units - p0) * 2) & ~int64_t(15);
                         if (bytes > 4096) bytes = 4096;
