@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
                         s_sstart[row] = start;
                     } else {  // denser tile than the staging area: this row goes out directly
                         while (*reinterpret_cast<volatile unsigned int*>(&s_flag) != static_cast<unsigned int>(tile + 1)) {
+                            __nanosleep(64);
                         }
                         __threadfence_block();
                         if (!*reinterpret_cast<volatile int*>(&s_skip_writes)) {
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(1024, 1) dfawalk_kernel(DfaWalkParams P) {
         __syncthreads();
         {
             while (*reinterpret_cast<volatile unsigned int*>(&s_flag) != static_cast<unsigned int>(tile + 1)) {
+                __nanosleep(64);
             }
             __threadfence_block();
             if (!*reinterpret_cast<volatile int*>(&s_skip_writes)) {

@@ -339,6 +339,40 @@ def test_latin1_text_form(monkeypatch):
     assert g.extract_batch_text_latin1(b"[1]: GET 2ms /a").ext_id.tolist() == [1]
 
 
+def test_chunkwalk_launch_times_are_stable(monkeypatch):
+    """Round 1 found the one-pass kernel bistable (11.5 or 17.4 ms per launch, depending on unrelated allocation sizes).
+    Every launch of a series must run in the fast mode whatever the sizes of the result allocations are: the row arrays are
+    padded by 0 / 64 K / 1 M rows (GORP_PAD_ROWS shifts every allocation that follows), 25 launches each."""
+    import ctypes as C
+    import torch
+    from gorp_b200 import _ffi, corpusgen
+    from gorp_b200.api import Blob, _check
+    dev = torch.device("cuda", 0)
+    d_text = corpusgen.device_text("readme", 0, 12_000_000, dev)
+    blob = Blob.from_definition(V.README_DEF)
+    times = {}
+    for pad in ("0", "65536", "1048576"):
+        monkeypatch.setenv("GORP_PAD_ROWS", pad)
+        eng = C.c_void_p()
+        _check(_ffi.lib.gorp_engine_create(blob._ptr, blob.length, None, 0, C.byref(eng)))
+        dres = _ffi.DeviceResult()
+        stream = torch.cuda.current_stream().cuda_stream
+        ms = []
+        for k in range(28):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _check(_ffi.lib.gorp_extract_text_device(eng, 0, d_text.data_ptr(), d_text.numel(), stream, 0, C.byref(dres)))
+            e1.record()
+            torch.cuda.synchronize()
+            if k >= 3:
+                ms.append(e0.elapsed_time(e1))
+        assert dres.n_lines == 12_000_000
+        _ffi.lib.gorp_engine_destroy(eng)
+        times[pad] = ms
+    allms = [t for v in times.values() for t in v]
+    assert max(allms) < 1.2 * min(allms), {k: (round(min(v), 3), round(max(v), 3)) for k, v in times.items()}
+
+
 def test_concurrent_calls_on_one_engine(monkeypatch):
     """include/gorp_cuda.h promises that concurrent gorp_extract_* calls on one engine are allowed (the reference's Gorp is
     immutable and "fully thread-safe", Gorp.java:22): 4 threads x several calls each, text and lines form mixed, every
