@@ -136,6 +136,8 @@ struct DeviceCtx {
     OnePassDev onepass{};
     OnePassDev chunkwalk{};      // same automaton, table variant of kernels/chunkwalk.cu
     DfaWalkDev dfawalk{};        // class-indexed combined DFA of kernels/dfawalk.cu (text form, any definition)
+    PikeDev pike{};              // simulating Pike VM for extractions without a determinised capture automaton (kernels/pike.cu)
+    DevBuf pike_scratch;
     MatchAllDev matchall{};      // the reference's own tables (matchAll)
     DevBuf ma_state, ma_count, ma_off, ma_out;
     DfaWalkDev dfawalk_cut{};    // the same with the early-exit cut of host/tails.hpp (K2b when the tail walk follows)
@@ -674,6 +676,37 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
         c.cap.tdfa_ops = upload(ops, c.owned);
         c.cap.tdfa_fin = upload(fin, c.owned);
         c.cap.tdfa_accepting = upload(acc, c.owned);
+        // extractions that fall back to the simulated Pike VM
+        bool any_pike = false;
+        for (uint8_t v : m.pike_only) any_pike = any_pike || v;
+        if (any_pike) {
+            std::vector<PikeExtDev> px(E, PikeExtDev{});
+            std::vector<uint32_t> clo_off;
+            std::vector<int32_t> clo_target;
+            std::vector<unsigned long long> clo_mask;
+            std::vector<uint8_t> accepts;
+            for (size_t e = 0; e < E; ++e) {
+                if (!m.pike_only[e]) continue;
+                const PikeTables& t = m.pike[e];
+                px[e] = {static_cast<uint32_t>(clo_off.size()), t.n_insts, t.n_slots, static_cast<uint32_t>(accepts.size()), 1u};
+                const uint32_t base = static_cast<uint32_t>(clo_target.size());
+                for (uint32_t v : t.clo_off) clo_off.push_back(base + v);
+                clo_target.insert(clo_target.end(), t.clo_target.begin(), t.clo_target.end());
+                for (uint64_t v : t.clo_mask) clo_mask.push_back(v);
+                accepts.insert(accepts.end(), t.accepts.begin(), t.accepts.end());
+                c.pike.max_insts = std::max(c.pike.max_insts, t.n_insts);
+                c.pike.max_slots = std::max(c.pike.max_slots, t.n_slots);
+            }
+            c.pike.ext = upload(px, c.owned);
+            c.pike.clo_off = upload(clo_off, c.owned);
+            c.pike.clo_target = upload(clo_target, c.owned);
+            c.pike.clo_mask = upload(clo_mask, c.owned);
+            c.pike.accepts = upload(accepts, c.owned);
+            c.pike.cls = c.cap.cls;
+            c.pike.n_classes = m.symbols.n_classes;
+            c.pike.pair_hi_class = m.symbols.pair_hi_class;
+            c.pike.enabled = 1;
+        }
     }
 }
 
@@ -988,8 +1021,35 @@ bool run_dfawalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStre
 
 // Runs the device pipeline. Text form when d_off == nullptr. Caller holds c.mu and has set the device.
 // Returns n_lines (synchronises once for the text form to size the per-line arrays).
+int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, const int64_t* d_off, int64_t n_lines,
+                            cudaStream_t stream, bool timed, gorp_device_result* out);
+
+// The table-driven pipeline, then (only for definitions that have such extractions) the simulated Pike VM over the lines
+// that came out as CAPTURE_FAIL of an extraction without a determinised capture automaton.
 int64_t run_pipeline(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, const int64_t* d_off, int64_t n_lines,
                      cudaStream_t stream, bool timed, gorp_device_result* out) {
+    gorp_device_result local{};
+    gorp_device_result* r = out ? out : &local;
+    const int64_t nl = run_pipeline_tables(c, d_text, n_units, d_off, n_lines, stream, timed, r);
+    if (c.pike.enabled && nl > 0 && !c.cap.match_only && c.max_slots > 0) {
+        Launch L{stream, c.sm_count};
+        const size_t per_thread = pike_scratch_ints_per_thread(c.pike) * 4;
+        size_t threads = static_cast<size_t>(c.sm_count) * 128;
+        const size_t budget = 256ull << 20;
+        if (threads * per_thread > budget) threads = std::max<size_t>(128, budget / per_thread / 128 * 128);
+        c.pike_scratch.reserve(threads * per_thread);
+        // (the result arrays are the engine's own buffers: const only in the caller's view)
+        k_pike_fixup(L, c.pike, d_text, r->d_line_off, d_off ? 0 : 1, nl, c.max_slots, const_cast<int32_t*>(r->d_ext_id),
+                     const_cast<int32_t*>(r->d_spans), reinterpret_cast<unsigned long long*>(const_cast<int64_t*>(r->d_histogram)), c.n_ext,
+                     c.pike_scratch.as<int32_t>(), static_cast<uint32_t>(threads));
+        c.launches += 1;
+        CK(cudaGetLastError());
+    }
+    return nl;
+}
+
+int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, const int64_t* d_off, int64_t n_lines,
+                            cudaStream_t stream, bool timed, gorp_device_result* out) {
     Launch L{stream, c.sm_count};
     Timer tm(c, stream, timed);
     c.scalars.reserve(64);

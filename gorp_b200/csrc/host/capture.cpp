@@ -720,6 +720,23 @@ class TdfaBuilder {
 
   public:
     bool uses_tmp() const { return uses_tmp_; }
+
+    PikeTables tables() {
+        PikeTables t;
+        t.n_insts = static_cast<uint32_t>(p_.insts.size());
+        t.n_slots = static_cast<uint32_t>(n_slots_);
+        t.n_classes = sc_.n_classes;
+        t.clo_off.push_back(0);
+        for (size_t pc = 0; pc < p_.insts.size(); ++pc) {
+            for (auto& ce : closure(static_cast<int>(pc))) {
+                t.clo_target.push_back(ce.target);
+                t.clo_mask.push_back(ce.mask);
+            }
+            t.clo_off.push_back(static_cast<uint32_t>(t.clo_target.size()));
+        }
+        for (auto& row : accepts_) t.accepts.insert(t.accepts.end(), row.begin(), row.end());
+        return t;
+    }
 };
 
 }  // namespace
@@ -783,6 +800,24 @@ void minimise_tdfa(Tdfa& t) {
         m.fin.insert(m.fin.end(), t.fin.begin() + static_cast<long>(s * G), t.fin.begin() + static_cast<long>((s + 1) * G));
     }
     t = std::move(m);
+}
+
+PikeTables build_pike_tables(const CaptureProgram& p, const SymbolClasses& sc) {
+    TdfaBuilder b(p, sc, 1, 1);
+    return b.tables();
+}
+
+Tdfa placeholder_tdfa(const CaptureProgram& p, const SymbolClasses& sc) {
+    Tdfa t;
+    t.n_states = 1;
+    t.n_classes = sc.n_classes;
+    t.n_regs = 0;
+    t.n_slots = static_cast<uint32_t>(2 * p.n_groups);
+    t.trans.assign(sc.n_classes, 0xFFFFu);
+    t.op_off = {0, 0};
+    t.accepting = {0};
+    t.fin.assign(t.n_slots, 0xFF);
+    return t;
 }
 
 Tdfa build_tdfa(const CaptureProgram& p, const SymbolClasses& sc, size_t max_states, size_t max_regs) {

@@ -51,6 +51,22 @@ struct Tdfa {
 // Throws UnsupportedError when the determinisation exceeds the limits.
 Tdfa build_tdfa(const CaptureProgram& p, const SymbolClasses& sc, size_t max_states = 60000, size_t max_regs = 250);
 
+// A capture automaton that accepts nothing: stands in for an extraction whose determinisation exceeded the limits. Every
+// line it is asked about ends as CAPTURE_FAIL on the table-driven paths; the simulating Pike-VM pass (PikeTables,
+// kernels/pike.cu) then decides those lines for real.
+Tdfa placeholder_tdfa(const CaptureProgram& p, const SymbolClasses& sc);
+
+// The Pike program flattened for simulation (no determinisation): per instruction its epsilon closure in priority order
+// (consuming target or MATCH, SAVE slots passed on the way) and, per symbol class, whether the instruction accepts it.
+struct PikeTables {
+    uint32_t n_insts = 0, n_slots = 0, n_classes = 0;
+    std::vector<uint32_t> clo_off;    // [n_insts + 1]
+    std::vector<int32_t> clo_target;  // consuming instruction index, -1 = MATCH
+    std::vector<uint64_t> clo_mask;   // SAVE slots set to the current position on the way
+    std::vector<uint8_t> accepts;     // [n_insts * n_classes]
+};
+PikeTables build_pike_tables(const CaptureProgram& p, const SymbolClasses& sc);
+
 // Merges the states of `t` that no input suffix can tell apart (same acceptance, final recipe, command lists and equivalent
 // successors). Used for the per-extraction tables of the bucketed capture walk; the one-pass product automaton
 // (host/fused.hpp) is minimised as a whole and is built from the unminimised automata.

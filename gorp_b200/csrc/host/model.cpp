@@ -1,5 +1,7 @@
 #include "model.hpp"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace gorp {
@@ -202,7 +204,22 @@ DeviceModel build_device_model(const CompiledDefinition& d) {
         m.programs.push_back(std::move(p));
     }
     m.symbols = build_symbol_classes(m.programs);
-    for (auto& p : m.programs) m.tdfas.push_back(build_tdfa(p, m.symbols));
+    size_t max_states = 60000;
+    if (const char* f = std::getenv("GORP_TDFA_MAX_STATES")) max_states = static_cast<size_t>(std::max(2, std::atoi(f)));  // tests
+    m.pike.resize(m.programs.size());
+    for (size_t e = 0; e < m.programs.size(); ++e) {
+        try {
+            m.tdfas.push_back(build_tdfa(m.programs[e], m.symbols, max_states));
+            m.pike_only.push_back(0);
+        } catch (const UnsupportedError&) {
+            // the determinisation outgrew the limits (states / registers / command lists): the reference accepts any regex
+            // Pattern.compile accepts (jdkre/JDKRegexpExtractionCooker.java:20-26), so the extraction falls back to a
+            // simulated Pike VM instead of being refused
+            m.tdfas.push_back(placeholder_tdfa(m.programs[e], m.symbols));
+            m.pike_only.push_back(1);
+            m.pike[e] = build_pike_tables(m.programs[e], m.symbols);
+        }
+    }
     return m;
 }
 

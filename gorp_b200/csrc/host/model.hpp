@@ -44,6 +44,10 @@ struct DeviceModel {
     std::vector<CaptureProgram> programs;
     std::vector<Tdfa> tdfas;
     std::vector<uint32_t> n_groups;
+    // extractions whose capture automaton could not be determinised within the limits: `tdfas[e]` is a placeholder that
+    // accepts nothing and `pike[e]` holds the tables of the simulating Pike-VM pass that decides their lines
+    std::vector<uint8_t> pike_only;
+    std::vector<PikeTables> pike;
 };
 DeviceModel build_device_model(const CompiledDefinition& d);
 

@@ -373,6 +373,30 @@ struct MatchAllDev {
 void k_matchall_walk(const Launch&, const MatchAllDev&, const uint16_t* text, const int64_t* off, int64_t n_lines, int32_t* state, uint32_t* count);
 void k_matchall_fill(const Launch&, const MatchAllDev&, const int32_t* state, const int64_t* out_off, int64_t n_lines, int32_t* out);
 
+// Simulating Pike VM for extractions whose capture automaton could not be determinised (kernels/pike.cu)
+struct PikeExtDev {
+    uint32_t inst_off;    // of the extraction's n_insts + 1 entries in clo_off
+    uint32_t n_insts, n_slots;
+    uint32_t acc_off;     // of its n_insts * n_classes bytes in accepts
+    uint32_t enabled;     // 0: the extraction has a real capture automaton
+};
+struct PikeDev {
+    const PikeExtDev* ext;             // [E]
+    const uint32_t* clo_off;           // closure CSR (global indexes into clo_target / clo_mask)
+    const int32_t* clo_target;
+    const unsigned long long* clo_mask;
+    const uint8_t* accepts;
+    const uint16_t* cls;               // [65536] unit -> symbol class of the capture side
+    uint32_t n_classes, pair_hi_class;
+    uint32_t max_insts, max_slots;
+    uint32_t enabled;
+};
+size_t pike_scratch_ints_per_thread(const PikeDev&);
+// decides the lines that came out as CAPTURE_FAIL(e) for an extraction e with P.ext[e].enabled: MATCH (ext_id, spans, histogram
+// are patched) or a real capture failure (left as they are). scratch: scratch_threads * pike_scratch_ints_per_thread ints.
+void k_pike_fixup(const Launch&, const PikeDev&, const uint16_t* text, const int64_t* line_off, int sep, int64_t n_lines, uint32_t span_stride,
+                  int32_t* ext_id, int32_t* spans, unsigned long long* hist, uint32_t n_ext, int32_t* scratch, uint32_t scratch_threads);
+
 // K3: per-extraction histogram (E entries, then MISS, then capture failures).
 void k3_histogram(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, unsigned long long* hist);
 

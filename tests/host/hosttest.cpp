@@ -66,6 +66,52 @@ extern "C" int ht_run(const void* blob, size_t len, const uint16_t* text, const 
             if (ok) ok = t.accepting[s] != 0;
             if (!ok) {
                 ext[l] = -2 - e;
+                if (m.pike_only[e]) {  // the simulated Pike VM decides (kernels/pike.cu, same loop)
+                    const PikeTables& P = m.pike[e];
+                    const uint32_t ent = 1 + P.n_slots;
+                    std::vector<int32_t> lists[2];
+                    lists[0].assign(static_cast<size_t>(P.n_insts) * ent, -1);
+                    lists[1] = lists[0];
+                    std::vector<uint32_t> seen(P.n_insts, 0);
+                    uint32_t gen = 0, n_cur = 1;
+                    int cur = 0;
+                    lists[0][0] = 0;
+                    for (int64_t p = 0; p < L && n_cur; ++p) {
+                        uint32_t c = m.symbols.classmap[u[p]];
+                        if ((u[p] & 0xFC00) == 0xD800 && p + 1 < L && (u[p + 1] & 0xFC00) == 0xDC00) c = m.symbols.pair_hi_class;
+                        ++gen;
+                        uint32_t n_nxt = 0;
+                        const std::vector<int32_t>& from = lists[cur];
+                        std::vector<int32_t>& to = lists[cur ^ 1];
+                        for (uint32_t i = 0; i < n_cur; ++i) {
+                            const int32_t pc = from[i * ent];
+                            for (uint32_t j = P.clo_off[pc]; j < P.clo_off[pc + 1]; ++j) {
+                                const int32_t tg = P.clo_target[j];
+                                if (tg < 0 || seen[tg] == gen) continue;
+                                seen[tg] = gen;
+                                if (!P.accepts[static_cast<size_t>(tg) * P.n_classes + c]) continue;
+                                to[n_nxt * ent] = tg + 1;
+                                for (uint32_t k = 0; k < P.n_slots; ++k)
+                                    to[n_nxt * ent + 1 + k] = (P.clo_mask[j] >> k) & 1 ? static_cast<int32_t>(p) : from[i * ent + 1 + k];
+                                ++n_nxt;
+                            }
+                        }
+                        cur ^= 1;
+                        n_cur = n_nxt;
+                    }
+                    bool matched = false;
+                    for (uint32_t i = 0; i < n_cur && !matched; ++i) {
+                        const int32_t pc = lists[cur][i * ent];
+                        for (uint32_t j = P.clo_off[pc]; j < P.clo_off[pc + 1]; ++j) {
+                            if (P.clo_target[j] >= 0) continue;
+                            for (uint32_t k = 0; k < P.n_slots && static_cast<int>(k) < stride; ++k)
+                                spans[l * stride + k] = (P.clo_mask[j] >> k) & 1 ? static_cast<int32_t>(L) : lists[cur][i * ent + 1 + k];
+                            matched = true;
+                            break;
+                        }
+                    }
+                    if (matched) ext[l] = e;
+                }
                 continue;
             }
             for (uint32_t k = 0; k < t.n_slots && static_cast<int>(k) < stride; ++k) {

@@ -279,6 +279,26 @@ def test_every_kernel_tier_text_form(tier, monkeypatch):
     check_against_oracle(V.README_DEF, text=text[:-1])  # last line not terminated
 
 
+def test_pike_vm_fallback(monkeypatch):
+    """Capture automata that cannot be determinised within the limits are not refused: a simulated Pike VM decides their
+    lines (kernels/pike.cu). The state limit is forced down so that (a) every extraction and (b) only the large ones of a
+    definition take the fallback; text and List<String> form, every outcome, against the oracle."""
+    names = "abcdefghi"
+    ambiguous = "extract e {\n template " + ":".join("$%s(%%{[ab:]*})" % n for n in names) + "\n}\n"  # 9 groups, 2 812 states
+    rng = np.random.default_rng(23)
+    amb_lines = ["".join(rng.choice(list("ab:::"), size=rng.integers(0, 40))) for _ in range(3000)]
+    for limit in ("2", "500"):
+        monkeypatch.setenv("GORP_TDFA_MAX_STATES", limit)
+        check_against_oracle(ambiguous, lines=amb_lines)
+        check_against_oracle(ambiguous, text=corpus.lines_to_text(amb_lines))
+        for d, lines in ((V.README_DEF, TRICKY_LINES + ["[1]: GET 2ms /" + "a" * 3000]), (corpus.WEBLOG_DEF, corpus.utf16_mix_lines(1500, seed=4))):
+            check_against_oracle(d, lines=lines)
+            check_against_oracle(d, text=corpus.lines_to_text(lines))
+            monkeypatch.setenv("GORP_FORCE_TWOPASS", "1")
+            check_against_oracle(d, text=corpus.lines_to_text(lines))
+            monkeypatch.delenv("GORP_FORCE_TWOPASS")
+
+
 def test_tail_walk_very_long_lines(monkeypatch):
     """Lines of 65 000 units and more leave the 16-bit tail walk for the one-thread-per-line kernel with 32-bit positions;
     results stay exact (spans far beyond 65 535, non-ASCII content, a candidate that ends as MISS / CAPTURE_FAIL)."""

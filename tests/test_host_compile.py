@@ -254,6 +254,21 @@ def test_tail_automata_fuzz_small_alphabet():
         compare_tails(definition, lines)
 
 
+def test_pike_vm_fallback_reproduces_oracle(monkeypatch):
+    """Extractions whose determinisation exceeds the limits are not refused: their lines are decided by a simulated Pike
+    VM (host/capture.hpp: PikeTables, kernels/pike.cu). With the state limit forced down to 2 EVERY extraction of every
+    definition takes that path: same outcomes and spans as the oracle."""
+    monkeypatch.setenv("GORP_TDFA_MAX_STATES", "2")
+    for case in ALL_DEFS:
+        compare_host_tables(case[0], [c[0] for c in case[1]] + TRICKY_LINES)
+    rng = np.random.default_rng(13)
+    for definition in FUZZ_PATTERNS:
+        lines = ["".join(rng.choice(list("abcd: "), size=rng.integers(0, 24))) for _ in range(1200)]
+        compare_host_tables(definition, lines)
+    from gorp_b200 import corpus
+    compare_host_tables(corpus.WEBLOG_DEF, corpus.utf16_mix_lines(600) + TRICKY_LINES)
+
+
 def test_minimised_capture_automata_reproduce_oracle():
     """minimise_tdfa (Moore minimisation of the tagged automata, used for the tables of the bucketed capture walk) on every
     definition and fuzz pattern, including the small ones the engine leaves unminimised: same outcomes and spans."""
