@@ -115,10 +115,19 @@ static int bt_match(const Job *J, const int32_t *ops, const uint16_t *u, int64_t
     }
 }
 
+/* JDKRegexpCookedExtraction._constructMatch (jdkre/JDKRegexpCookedExtraction.java:51-59) materialises every group as
+ * a String (values[i] = m.group(i+1): an allocation + a copy of the group's units). The baseline pays for the copy too:
+ * each group's units are copied into a per-thread arena (a ring, so the working set stays cache-sized like a young-generation
+ * allocation buffer). The copies do not change the reported spans. */
+#define ARENA_UNITS (1u << 18)
+
 static void *worker(void *arg) {
     Job *J = (Job *)arg;
     size_t cap = 1024;
     Ent *stk = (Ent *)malloc(cap * sizeof(Ent));
+    uint16_t *arena = (uint16_t *)malloc(ARENA_UNITS * sizeof(uint16_t));
+    size_t arena_pos = 0;
+    volatile uint16_t sink = 0;
     int32_t caps[256];
     for (int64_t l = J->lo; l < J->hi; l++) {
         const uint16_t *u = J->text + J->starts[l];
@@ -142,7 +151,19 @@ static void *worker(void *arg) {
         if (r == 0) { J->ext[l] = -2 - e; continue; }
         J->ext[l] = e;
         for (int k = 0; k < 2 * g && k < J->span_stride; k++) out[k] = caps[2 + k];  /* group(1..n) */
+        for (int k = 0; k < g; k++) {                                                 /* values[k] = m.group(k + 1) */
+            int32_t s0 = caps[2 + 2 * k], s1 = caps[3 + 2 * k];
+            if (s0 < 0 || s1 <= s0) continue;
+            size_t len = (size_t)(s1 - s0);
+            if (len > ARENA_UNITS) len = ARENA_UNITS;
+            if (arena_pos + len > ARENA_UNITS) arena_pos = 0;
+            memcpy(arena + arena_pos, u + s0, len * sizeof(uint16_t));
+            sink ^= arena[arena_pos];
+            arena_pos += len;
+        }
     }
+    (void)sink;
+    free(arena);
     free(stk);
     return NULL;
 }
