@@ -1178,7 +1178,7 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
         }
         k4b_bucket(L, c.ext_id.as<int32_t>(), n_lines, E, c.hist.as<unsigned long long>(), bucket_base, cursor, c.perm.as<uint32_t>(),
                    c.items.as<CapItem>(), n_items, item_ticket, c.spans.as<int32_t>(), stride, tails ? d_line_off : nullptr,
-                   tails ? c.recs.as<LineRec>() : nullptr, sep);
+                   tails ? c.recs.as<LineRec>() : nullptr, sep, tails ? c.tails.ext : nullptr);
         tm.mark("k4b_bucket", 2);
         CapWalkParams W{};
         W.text = d_text;

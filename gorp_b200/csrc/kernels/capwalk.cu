@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(1024) bucket_plan_kernel(const unsigned long l
 __global__ void __launch_bounds__(kBucketThreads) bucket_scatter_kernel(const int32_t* __restrict__ ext_id, int64_t n_lines, uint32_t n_ext,
                                                                         uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm,
                                                                         int32_t* __restrict__ spans, uint32_t span_stride,
-                                                                        const int64_t* __restrict__ line_off, LineRec* __restrict__ recs, int sep) {
+                                                                        const int64_t* __restrict__ line_off, LineRec* __restrict__ recs, int sep,
+                                                                        const TailExt* __restrict__ tails) {
     __shared__ uint32_t s_cnt[kCapMaxBuckets];
     __shared__ uint32_t s_pos[kCapMaxBuckets];
     for (int64_t seg0 = static_cast<int64_t>(blockIdx.x) * kBucketSeg; seg0 < n_lines; seg0 += static_cast<int64_t>(gridDim.x) * kBucketSeg) {
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_scatter_kernel(const in
             if (line >= seg1) continue;
             if (mine[k] >= 0) {
                 const uint32_t at = s_pos[mine[k]] + rank[k];
-                perm[at] = static_cast<uint32_t>(line);
+                // the tail walk reads records, the bucketed capture walk (extractions without a tail) reads `perm`
+                if (!recs || !tails[mine[k]].available) perm[at] = static_cast<uint32_t>(line);
                 if (recs) {  // start, id and length of the line in one record (kernels/tailwalk.cu)
                     const int64_t a = line_off[line], len = line_off[line + 1] - sep - a;
                     const int4 r = make_int4(static_cast<int>(static_cast<uint64_t>(a) & 0xFFFFFFFFu), static_cast<int>(static_cast<uint64_t>(a) >> 32),
@@ -389,12 +391,12 @@ __global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkPara
 
 void k4b_bucket(const Launch& L, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, const unsigned long long* hist,
                 uint32_t* bucket_base, uint32_t* cursor, uint32_t* perm, CapItem* items, uint32_t* n_items, uint32_t* item_ticket,
-                int32_t* spans, uint32_t span_stride, const int64_t* line_off, LineRec* recs, int sep) {
+                int32_t* spans, uint32_t span_stride, const int64_t* line_off, LineRec* recs, int sep, const TailExt* tails) {
     bucket_plan_kernel<<<1, 1024, 0, L.stream>>>(hist, n_ext, bucket_base, cursor, items, n_items, item_ticket);
     if (n_lines <= 0) return;
     const int64_t want = (n_lines + kBucketSeg - 1) / kBucketSeg, cap = static_cast<int64_t>(L.sm_count) * 8;
     bucket_scatter_kernel<<<static_cast<int>(want < cap ? want : cap), kBucketThreads, 0, L.stream>>>(ext_id, n_lines, n_ext, cursor, perm, spans,
-                                                                                                     span_stride, line_off, recs, sep);
+                                                                                                     span_stride, line_off, recs, sep, tails);
 }
 
 size_t capwalk_smem_bytes(const CapImgDev& img) {

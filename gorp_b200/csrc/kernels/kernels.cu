@@ -136,30 +136,37 @@ __global__ void __launch_bounds__(kThreads) nl_count_mask_kernel(const uint16_t*
     }
 }
 
+// one WARP per tile (a tile holds ~60 line starts: a block-wide scan with its barrier per tile cost more than the stores):
+// lane l takes the 8 mask words of units [256 l, 256 l + 256) of the tile, the warp scans the counts, every lane writes
+// the starts of its lines.
 __global__ void __launch_bounds__(kThreads) nl_scatter_mask_kernel(const uint32_t* __restrict__ masks, const int64_t* __restrict__ tile_base,
-                                                                   int64_t* __restrict__ line_off) {
-    constexpr int kPer = kNlTile / kThreads;
-    const int64_t mine = static_cast<int64_t>(blockIdx.x) * kNlTile + static_cast<int64_t>(threadIdx.x) * kPer;
-    uint32_t mask = masks[static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x];
-    uint32_t cnt = __popc(mask), incl = cnt;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                                                   int64_t* __restrict__ line_off, int64_t n_tiles) {
+    static_assert(kNlTile == 32 * 256, "one lane = 8 mask words");
+    const uint32_t lane = threadIdx.x & 31u;
+    const int64_t tile = static_cast<int64_t>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const uint4* src = reinterpret_cast<const uint4*>(masks + tile * 256) + lane * 2;
+    const uint4 a = __ldg(src), b = __ldg(src + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cnt += __popc(w[j]);
+    uint32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= static_cast<uint32_t>(o)) incl += t;
     }
-    __shared__ uint32_t warp_tot[kThreads / 32];
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t base = 0;
+    int64_t slot = 1 + tile_base[tile] + (incl - cnt);  // line_off[j] = start of line j (j >= 1)
+    const int64_t unit1 = tile * kNlTile + static_cast<int64_t>(lane) * 256 + 1;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w)
-        if (w < warp) base += warp_tot[w];
-    int64_t slot = 1 + tile_base[blockIdx.x] + base + (incl - cnt);  // line_off[j] = start of line j (j >= 1)
-    while (mask) {
-        int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        line_off[slot++] = mine + k + 1;
+    for (int j = 0; j < 8; ++j) {
+        uint32_t m = w[j];
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            line_off[slot++] = unit1 + j * 32 + k;
+        }
     }
 }
 
@@ -470,7 +477,8 @@ void k1_count_newlines_masks(const Launch& L, const uint16_t* text, int64_t n_un
 
 void k1_scatter_masks(const Launch& L, const uint32_t* masks, int64_t n_units, const int64_t* tile_base, int64_t* line_off) {
     if (n_units <= 0) return;
-    nl_scatter_mask_kernel<<<blocks_for(n_units, kNlTile), kThreads, 0, L.stream>>>(masks, tile_base, line_off);
+    const int64_t n_tiles = (n_units + kNlTile - 1) / kNlTile;
+    nl_scatter_mask_kernel<<<blocks_for(n_tiles, kThreads / 32), kThreads, 0, L.stream>>>(masks, tile_base, line_off, n_tiles);
 }
 
 void k1_finish(const Launch& L, const uint16_t* text, int64_t n_units, const int64_t* total_newlines, int64_t* line_off,

@@ -292,9 +292,11 @@ struct CapWalkParams {
 };
 // hist (K3 layout) -> bucket_base[E+1], cursor[E], items (<= n_lines / kCapItemLines + E), perm; MISS rows := -1
 struct LineRec;
+struct TailExt;
 void k4b_bucket(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, const unsigned long long* hist,
                 uint32_t* bucket_base, uint32_t* cursor, uint32_t* perm, CapItem* items, uint32_t* n_items, uint32_t* item_ticket,
-                int32_t* spans, uint32_t span_stride, const int64_t* line_off = nullptr, LineRec* recs = nullptr, int sep = 1);
+                int32_t* spans, uint32_t span_stride, const int64_t* line_off = nullptr, LineRec* recs = nullptr, int sep = 1,
+                const TailExt* tails = nullptr);  // tails (with recs): extractions whose lines only need a record, no `perm` entry
 size_t capwalk_smem_bytes(const CapImgDev&);
 void k4b_capwalk(const Launch&, const CapWalkParams&);
 

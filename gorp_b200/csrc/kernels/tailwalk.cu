@@ -41,11 +41,15 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
 }
 
 // one step on an ASCII unit held in byte kByte (0 or 2) of w. `ra` = byte offset of the current row + rows_abs.
-// bytes between the same thread's cells of two consecutive slots: an odd number of 32-bit words, so that the lanes of a warp
-// that store to different slots in the same step spread over the banks (two neighbouring lanes share a word)
+// bytes between the same thread's cells of two consecutive slots. The 32 lanes of a warp cover 16 words of a slot's row (two
+// neighbouring lanes share a word): with a stride of 16 words mod 32 the rows of even and odd slots use the two halves of
+// the banks, so a lane that stores to another slot than its neighbours (most lanes store to the dummy slot 0) collides at
+// most with the lane it shares a word with. The earlier stride (1 word mod 32) put slot s of lane pair k on the bank of
+// slot 0 of lane pair k + s: 0.72 extra wavefronts per store (ncu, profiles/README.md round 2).
 template <int kT>
 struct SlotStride {
-    static constexpr uint32_t value = kT * 2 + 4;
+    static constexpr uint32_t value = kT * 2 + 64;
+    static_assert((value / 4) % 32 == 16, "stride of a slot row: 16 words mod 32");
 };
 
 template <int kByte, int kT>
@@ -124,6 +128,7 @@ __device__ __forceinline__ Units16 tw_load(const uint16_t* __restrict__ text, in
     return load_units16_l2keep(text, pos, n_units);
 }
 
+constexpr uint32_t kTwBins = 1024;    // bins of the per-item sort: (group of records, 32 length classes)
 constexpr uint32_t kTwMaxMulti = 64;  // group boundaries with several writers, per extraction (else the table is refused)
 
 template <bool kLines, int kT>
@@ -141,6 +146,9 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
     uint32_t* s_multi = reinterpret_cast<uint32_t*>(s_oext + T.max_outcomes);  // (outcome << 16 | k), packed writers
     uint8_t* s_init = reinterpret_cast<uint8_t*>(s_multi + 2 * kTwMaxMulti);
     unsigned char* s_slots = reinterpret_cast<unsigned char*>(s_init + 64);
+    // [order: kCapItemLines x u16][length bins: kTwBins x u32] — the item's lines sorted by length (see below)
+    uint16_t* s_order = reinterpret_cast<uint16_t*>(s_slots + (((T.max_slots + 2) * kSlotStride + 15u) & ~15u));
+    uint32_t* s_bins = reinterpret_cast<uint32_t*>(s_order + kCapItemLines);
     const uint32_t rows_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_mem));
     const uint32_t slot_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_slots)) + threadIdx.x * 2;
     // slots 0..max_slots-1 of the table (0 = dummy), then ZERO (never written: reads as "no writer") and LEN
@@ -191,6 +199,41 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                 s_res[i] = off;
             }
             for (uint32_t i = threadIdx.x; i < x.n_init; i += kTailWalkThreads) s_init[i] = __ldg(T.init_slots + x.init_off + i);
+        }
+        // The lanes of a warp walk in lock-step, so a warp is as slow as its longest line. Optional (P.flags & 16, off by default:
+        // see profiles/README.md round 2 — the walk is bound by shared-memory wavefronts, not by idle lanes): the item's lines
+        // are handed out sorted by DECREASING length inside groups of 2^G consecutive records (counting sort by the number of
+        // 16-unit blocks a line touches, in shared memory), so that the 32 lines a warp claims together end within the same
+        // iteration or two while staying close to each other in the text. The second pass finds the records in L2.
+        const uint32_t n_it = it.end - it.begin;
+        const bool sorted = (P.flags & 16u) != 0;
+        if (sorted) {
+            const uint32_t G = max(7u, min(12u, (P.flags >> 8) & 15u ? (P.flags >> 8) & 15u : 8u));
+            for (uint32_t i = threadIdx.x; i < kTwBins; i += kTailWalkThreads) s_bins[i] = 0;
+            __syncthreads();
+            const uint4* recs4 = reinterpret_cast<const uint4*>(P.recs) + it.begin;
+            auto key_of = [G](uint32_t i, const uint4 r) { return ((i >> G) << 5) + 31u - min(((r.x & 15u) + min(r.w, 0xFFFFu)) >> 4, 31u); };
+            for (uint32_t i = threadIdx.x; i < n_it; i += kTailWalkThreads) atomicAdd(&s_bins[key_of(i, __ldg(recs4 + i))], 1u);
+            __syncthreads();
+            if (threadIdx.x < 32) {  // exclusive scan of the kTwBins counts: lane l owns bins [32 l, 32 l + 32)
+                uint32_t sum = 0;
+                for (uint32_t k = 0; k < kTwBins / 32; ++k) sum += s_bins[lane * (kTwBins / 32) + k];
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= static_cast<uint32_t>(o)) incl += t;
+                }
+                uint32_t run = incl - sum;
+                for (uint32_t k = 0; k < kTwBins / 32; ++k) {
+                    const uint32_t c = s_bins[lane * (kTwBins / 32) + k];
+                    s_bins[lane * (kTwBins / 32) + k] = run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n_it; i += kTailWalkThreads)
+                s_order[atomicAdd(&s_bins[key_of(i, __ldg(recs4 + i))], 1u)] = static_cast<uint16_t>(i);
         }
         if (threadIdx.x == 0) s_cursor = it.begin;
         __syncthreads();
@@ -273,7 +316,8 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                     base = __shfl_sync(0xffffffffu, base, 0);
                     const uint32_t idx = base + static_cast<uint32_t>(__popc(want & lt_mask));
                     if (nstage == 0 && idx < it.end) {
-                        nrec = __ldg(reinterpret_cast<const uint4*>(P.recs) + idx);
+                        const uint32_t at = sorted ? it.begin + s_order[idx - it.begin] : idx;
+                        nrec = __ldg(reinterpret_cast<const uint4*>(P.recs) + at);
                         nstage = 1;
                     }
                     exhausted = base + static_cast<uint32_t>(__popc(want)) >= it.end;
@@ -397,9 +441,17 @@ __global__ void __launch_bounds__(32) tail_long_kernel(TailWalkParams P) {
 
 }  // namespace
 
+// the per-item sort (GORP_TAIL_FLAGS & 16) needs its order / bin arrays; without it they take no shared memory
+static bool tailwalk_sort_requested() {
+    const char* f = std::getenv("GORP_TAIL_FLAGS");
+    return f && (std::atoi(f) & 16);
+}
+
 size_t tailwalk_smem_bytes(const TailDev& t, int threads) {
+    const size_t sort_bytes = tailwalk_sort_requested() ? kCapItemLines * 2 + kTwBins * 4 : 0;
     return static_cast<size_t>(t.max_table_bytes) + static_cast<size_t>(t.max_res) * 4 + static_cast<size_t>(t.max_outcomes) * 4 +
-           2 * kTwMaxMulti * 4 + 64 + static_cast<size_t>(t.max_slots + 2) * (static_cast<size_t>(threads) * 2 + 4) + 16;
+           2 * kTwMaxMulti * 4 + 64 + ((static_cast<size_t>(t.max_slots + 2) * (static_cast<size_t>(threads) * 2 + 64) + 15) & ~size_t(15)) +
+           sort_bytes + 16;
 }
 
 namespace {
