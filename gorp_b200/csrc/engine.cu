@@ -808,15 +808,15 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
         CK(cudaMemsetAsync(st, 0, state_bytes, stream));
         CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
         if (std::getenv("GORP_ONEPASS_DEBUG"))
-            std::fprintf(stderr, "[chunkwalk debug] threads=%u grid=%d smem=%zu tiles=%lld n_slots=%u rows=%u cap_lines=%lld text=%p ext=%p off=%p spans=%p state=%p\n",
+            std::fprintf(stderr, "[chunkwalk debug] threads=%u grid=%d smem=%zu tiles=%lld n_slots=%u rows=%u width=%u cap_lines=%lld text=%p ext=%p off=%p spans=%p state=%p\n",
                          threads, k0_chunkwalk_grid(L, P, threads), chunkwalk_smem_bytes(P.a, threads), static_cast<long long>(P.n_tiles),
-                         P.a.n_slots, P.a.n_rows, static_cast<long long>(cap_lines), static_cast<const void*>(d_text), static_cast<void*>(P.ext_id),
+                         P.a.n_slots, P.a.n_rows, P.a.width, static_cast<long long>(cap_lines), static_cast<const void*>(d_text), static_cast<void*>(P.ext_id),
                          static_cast<void*>(P.line_off), static_cast<void*>(P.spans), static_cast<void*>(st));
         const bool debug = std::getenv("GORP_ONEPASS_DEBUG") != nullptr;
         const int grid = k0_chunkwalk_grid(L, P, threads);
         if (debug) {
-            c.debug.reserve(static_cast<size_t>(grid) * 4 * 8);
-            CK(cudaMemsetAsync(c.debug.p, 0, static_cast<size_t>(grid) * 4 * 8, stream));
+            c.debug.reserve(static_cast<size_t>(grid) * 16 * 8);
+            CK(cudaMemsetAsync(c.debug.p, 0, static_cast<size_t>(grid) * 16 * 8, stream));
             P.debug = c.debug.as<long long>();
         }
         k0_chunkwalk_extract(L, P, threads);
@@ -826,18 +826,28 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
         CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         if (debug) {  // CTAs per SM, tiles per CTA, spread of the CTA run times
-            std::vector<long long> h(static_cast<size_t>(grid) * 4);
+            std::vector<long long> h(static_cast<size_t>(grid) * 16);
             CK(cudaMemcpy(h.data(), c.debug.p, h.size() * 8, cudaMemcpyDeviceToHost));
             std::vector<int> per_sm(1024, 0);
             long long t_min = h[2], t_max = h[3], tiles_min = h[1], tiles_max = h[1], late = 0;
+            double phase[7] = {0, 0, 0, 0, 0, 0, 0};
             for (int b = 0; b < grid; ++b) {
-                ++per_sm[h[b * 4] & 1023];
-                t_min = std::min(t_min, h[b * 4 + 2]);
-                t_max = std::max(t_max, h[b * 4 + 3]);
-                tiles_min = std::min(tiles_min, h[b * 4 + 1]);
-                tiles_max = std::max(tiles_max, h[b * 4 + 1]);
+                ++per_sm[h[b * 16] & 1023];
+                t_min = std::min(t_min, h[b * 16 + 2]);
+                t_max = std::max(t_max, h[b * 16 + 3]);
+                tiles_min = std::min(tiles_min, h[b * 16 + 1]);
+                tiles_max = std::max(tiles_max, h[b * 16 + 1]);
+                for (int i = 0; i < 7; ++i) phase[i] += static_cast<double>(h[b * 16 + 4 + i]);
             }
-            for (int b = 0; b < grid; ++b) late += (h[b * 4 + 2] - t_min) > 100000 ? 1 : 0;  // started > 100 us after the first
+            {
+                double tot = 0;
+                for (int i = 0; i < 6; ++i) tot += phase[i];
+                std::fprintf(stderr, "[chunkwalk debug] thread-cycles by phase: pre-scan %.1f%%, scan+barrier %.1f%%, walk %.1f%%, wait for first row %.1f%%, "
+                                     "result rows %.1f%%, end-of-tile wait %.1f%% (look-back of warp 0: %.1f%% of one warp's time)\n",
+                             100 * phase[0] / tot, 100 * phase[1] / tot, 100 * phase[2] / tot, 100 * phase[3] / tot, 100 * phase[4] / tot,
+                             100 * phase[5] / tot, 100 * phase[6] * (threads / 32.0) / tot);
+            }
+            for (int b = 0; b < grid; ++b) late += (h[b * 16 + 2] - t_min) > 100000 ? 1 : 0;  // started > 100 us after the first
             int sm1 = 0, sm2 = 0, sm3 = 0;
             for (int v : per_sm) sm1 += v == 1, sm2 += v == 2, sm3 += v > 2;
             std::fprintf(stderr, "[chunkwalk debug] kernel span %.3f ms; SMs with 1/2/>2 CTAs: %d/%d/%d; tiles per CTA %lld..%lld; CTAs started late: %lld\n",

@@ -22,6 +22,8 @@
 // tile-relative positions and are cleared once per tile: a value below the line's own start is "not written", so no
 // per-line initialisation is needed. Occupancy: the table + slots are the only shared memory (no text buffers), which is
 // what lets 32 warps per SM hide the lookup latency — the measured reason this beats the TMA-staged tile kernel.
+#include <cstdlib>
+
 #include "device_common.cuh"
 
 namespace gorp {
@@ -75,6 +77,12 @@ struct Pending {  // a finished line whose result row has not been written yet
     uint32_t start;  // tile-relative
 };
 
+// kDbg: GORP_ONEPASS_DEBUG build of the same kernel — thread-cycles per phase, summed per CTA into P.debug[16 b + 4..11]:
+// pre-scan, block scan + barrier, clear + walk without the two below, waiting for the tile's first row (look-back),
+// result rows, end-of-tile barrier wait, look-back (warp 0), tiles
+// (A/B, round 2: variants with 384 / 256 threads per CTA that load the next 16-unit block while the current one is walked —
+// 8 more registers — ran at 13.8 / 13.9 ms against 11.65 ms: the walk phase is not bound by the latency of its block loads.)
+template <bool kDbg>
 __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t kT = blockDim.x;
@@ -124,9 +132,19 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
     bool base_known = false;
     int64_t row0 = 0;  // first result row of this thread in the current tile
     bool skip_writes = false;
+    unsigned long long dc_pre = 0, dc_scan = 0, dc_walk = 0, dc_poll = 0, dc_flush = 0, dc_endwait = 0, dc_look = 0;
+    long long dc_t = 0;
+    auto dtick = [&](unsigned long long& acc) {
+        if (kDbg) {
+            const long long now = clock64();
+            acc += static_cast<unsigned long long>(now - dc_t);
+            dc_t = now;
+        }
+    };
 
     // writes the result row of a finished line
     auto flush = [&](const Pending& pd, int64_t tile, int64_t tile0) {
+        if (kDbg) dtick(dc_walk);
         if (!base_known) {
             // the tile's first row is not known yet (look-back of warp 0 still under way). A/B (profiles/README.md round 2):
             // sleeping in this loop instead of polling changes nothing (11.56 vs 11.48 ms) — GORP_CW_PREFETCH=4 sleeps
@@ -138,6 +156,7 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
             skip_writes = *reinterpret_cast<volatile int*>(&s_skip_writes) != 0;
             base_known = true;
         }
+        if (kDbg) dtick(dc_poll);
         const uint32_t bin = s_obin[pd.outcome];
         if (smem_hist) atomicAdd(&s_hist[bin], 1u);
         else atomicAdd(P.hist + bin, 1ull);
@@ -217,10 +236,12 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
         }
         __syncthreads();
     }
+    if (kDbg) dc_t = clock64();
     for (;;) {
         __syncthreads();  // the previous tile no longer uses s_tile / s_warp; table setup done (first iteration)
         if (threadIdx.x == 0) s_tile = ticket_ahead;
         __syncthreads();
+        if (kDbg) dtick(dc_endwait);
         const int64_t tile = s_tile;
         if (tile >= P.n_tiles) break;
         ++dbg_tiles;
@@ -261,6 +282,7 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
                 }
             }
         }
+        if (kDbg) dtick(dc_pre);
         const bool line0 = tile == 0 && threadIdx.x == 0 && P.n_units > 0;  // the line at offset 0
         const uint32_t mine = cnt + (line0 ? 1u : 0u);
 
@@ -281,6 +303,7 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
         }
         row0 = wbase + incl - mine;
         base_known = false;
+        if (kDbg) dtick(dc_scan);
         if (warp == 0) {
             unsigned long long pre = 0;
             if (tile > 0) {
@@ -336,6 +359,7 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
                 *reinterpret_cast<volatile unsigned int*>(&s_flag) = static_cast<unsigned int>(tile + 1);
             }
             __syncwarp();
+            if (kDbg) dtick(dc_look);
         }
 
         // ---- walk the owned lines one after the other; positions are tile-relative (pos = unit - tile0)
@@ -377,7 +401,7 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
                 }
                 q += 16;
                 if (ent >= fin_ent) {  // the line ended inside these 16 units
-                    if (pending) flush(pd, tile, tile0);  // rare: two line ends within 2 iterations
+                    if (pending) { flush(pd, tile, tile0); if (kDbg) dtick(dc_flush); }  // rare: two line ends within 2 iterations
                     pd.outcome = (((ent >> 18) - A.fin_base * row_q) * inv_row_q) >> 16;  // exact: a multiple of row_q below 2^14
                     pd.idx = idx++;
                     pd.bank_abs = bank_abs;
@@ -399,10 +423,23 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
                 if ((++it & 1u) == 0 && pending &&
                     (base_known || *reinterpret_cast<volatile unsigned int*>(&s_flag) == static_cast<unsigned int>(tile + 1))) {
                     flush(pd, tile, tile0);
+                    if (kDbg) dtick(dc_flush);
                     pending = false;
                 }
             }
-            if (pending) flush(pd, tile, tile0);
+            if (pending) {
+                flush(pd, tile, tile0);
+                if (kDbg) dtick(dc_flush);
+            }
+        }
+        if (kDbg) dtick(dc_walk);
+    }
+    if (kDbg) {
+        unsigned long long v[7] = {dc_pre, dc_scan, dc_walk, dc_poll, dc_flush, dc_endwait, dc_look};
+        for (int i = 0; i < 7; ++i) {
+            unsigned long long x = v[i];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.debug) + blockIdx.x * 16 + 4 + i, x);
         }
     }
     if (P.debug && threadIdx.x == 0) {  // GORP_ONEPASS_DEBUG: where and how long this CTA ran
@@ -410,10 +447,10 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
         uint32_t smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        P.debug[blockIdx.x * 4 + 0] = smid;
-        P.debug[blockIdx.x * 4 + 1] = dbg_tiles;
-        P.debug[blockIdx.x * 4 + 2] = dbg_t0;
-        P.debug[blockIdx.x * 4 + 3] = t1;
+        P.debug[blockIdx.x * 16 + 0] = smid;
+        P.debug[blockIdx.x * 16 + 1] = dbg_tiles;
+        P.debug[blockIdx.x * 16 + 2] = dbg_t0;
+        P.debug[blockIdx.x * 16 + 3] = t1;
     }
     if (smem_hist) {
         __syncthreads();
@@ -423,6 +460,9 @@ __global__ void __launch_bounds__(512, 2) chunkwalk_kernel(OnePassParams P) {
 }
 
 }  // namespace
+
+using CwKernel = void (*)(OnePassParams);
+static CwKernel cw_kernel(uint32_t, bool dbg) { return dbg ? chunkwalk_kernel<true> : chunkwalk_kernel<false>; }
 
 size_t chunkwalk_smem_bytes(const OnePassDev& a, uint32_t threads) {
     size_t b = static_cast<size_t>(a.n_rows) * a.width * 4;
@@ -436,13 +476,17 @@ bool k0_chunkwalk_plan(const OnePassDev& a, uint32_t* threads) {
     if (!a.enabled) return false;
     // the CTA size that keeps the most warps resident per SM (ties: the larger CTA, fewer table copies)
     uint32_t best = 0, best_warps = 0;
+    uint32_t forced = 0;
+    if (const char* f = std::getenv("GORP_CW_THREADS")) forced = static_cast<uint32_t>(std::atoi(f));
     for (uint32_t kT : {512u, 384u, 256u, 128u}) {
+        if (forced && kT != forced) continue;
         if (static_cast<uint64_t>(a.n_slots) * kT > 0x3FFFu) continue;  // slot offsets are 14 bits of the table entry
         const size_t smem = chunkwalk_smem_bytes(a, kT);
         if (smem > 226 * 1024) continue;
-        allow_max_dynamic_smem(chunkwalk_kernel);
+        allow_max_dynamic_smem(cw_kernel(kT, false));
+        allow_max_dynamic_smem(cw_kernel(kT, true));
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunkwalk_kernel, static_cast<int>(kT), smem) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_kernel(kT, false), static_cast<int>(kT), smem) != cudaSuccess) {
             cudaGetLastError();
             continue;
         }
@@ -456,9 +500,10 @@ bool k0_chunkwalk_plan(const OnePassDev& a, uint32_t* threads) {
 
 int k0_chunkwalk_grid(const Launch& L, const OnePassParams& P, uint32_t threads) {
     const size_t smem = chunkwalk_smem_bytes(P.a, threads);
-    allow_max_dynamic_smem(chunkwalk_kernel);
+    allow_max_dynamic_smem(cw_kernel(threads, false));
+    allow_max_dynamic_smem(cw_kernel(threads, true));
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chunkwalk_kernel, static_cast<int>(threads), smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_kernel(threads, false), static_cast<int>(threads), smem);
     if (per_sm < 1) per_sm = 1;
     const int64_t cap = static_cast<int64_t>(L.sm_count) * per_sm;
     int g = static_cast<int>(P.n_tiles < cap ? P.n_tiles : cap);
@@ -468,7 +513,7 @@ int k0_chunkwalk_grid(const Launch& L, const OnePassParams& P, uint32_t threads)
 void k0_chunkwalk_extract(const Launch& L, const OnePassParams& P, uint32_t threads) {
     const size_t smem = chunkwalk_smem_bytes(P.a, threads);
     const int g = k0_chunkwalk_grid(L, P, threads);
-    chunkwalk_kernel<<<g, static_cast<int>(threads), smem, L.stream>>>(P);
+    cw_kernel(threads, P.debug != nullptr)<<<g, static_cast<int>(threads), smem, L.stream>>>(P);
 }
 
 }  // namespace gorp

@@ -1,10 +1,8 @@
 mkdir -p gpurun_out
-run() { # tag flags workload
-  GORP_TAIL_FLAGS=$2 python bench.py --workload $3 --steps 10 --warmup 3 --skip-e2e --skip-cpu --configs "" --lines-per-gpu 40000000 > gpurun_out/r2x_bench_$3_$1.json 2>> gpurun_out/r2x_err.txt
-}
-for W in syslog200 weblog utf16mix; do
-  run new 0 $W
-  run oldstore 512 $W
+for T in 512 384 256; do
+  GORP_CW_THREADS=$T python bench.py --workload readme --steps 10 --warmup 3 --skip-e2e --skip-cpu --configs "" > gpurun_out/r2z_bench_readme_t$T.json 2>> gpurun_out/r2z_err.txt
+  GORP_CW_THREADS=$T python bench.py --workload simple --lines-per-gpu 40000000 --steps 10 --warmup 3 --skip-e2e --skip-cpu --configs "" > gpurun_out/r2z_bench_simple_t$T.json 2>> gpurun_out/r2z_err.txt
 done
-python -m pytest tests -m gpu -x -q -k "config_corpora or tricky or long or edge" > gpurun_out/r2x_pytest.log 2>&1; tail -n 3 gpurun_out/r2x_pytest.log
-tail -c 400 gpurun_out/r2x_err.txt
+GORP_CW_THREADS=384 GORP_ONEPASS_DEBUG=1 python bench.py --workload readme --steps 3 --warmup 2 --skip-e2e --skip-cpu --configs "" 2>&1 >/dev/null | grep "thread-cycles" | tail -1
+GORP_CW_THREADS=256 GORP_ONEPASS_DEBUG=1 python bench.py --workload readme --steps 3 --warmup 2 --skip-e2e --skip-cpu --configs "" 2>&1 >/dev/null | grep "thread-cycles" | tail -1
+tail -c 300 gpurun_out/r2z_err.txt
