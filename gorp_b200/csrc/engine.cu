@@ -142,6 +142,8 @@ struct DeviceCtx {
     DevBuf ma_state, ma_count, ma_off, ma_out;
     DfaWalkDev dfawalk_cut{};    // the same with the early-exit cut of host/tails.hpp (K2b when the tail walk follows)
     TailDev tails{};             // per-extraction tail automata of kernels/tailwalk.cu
+    TailDev fused_tail{};        // the one-pass automaton of host/fused.hpp as ONE tail table for every line (K1 + tail walk, "fused walk")
+    bool fusedwalk_default = false;  // small definitions: K1 + fused walk instead of the chunk-owner kernel K0c (GORP_SMALL_PATH)
     bool cut_effective = false;  // most states of the combined DFA are cut: the chunk-owner walk with early exit (K0d cut)
     uint32_t tail_flush_every = 8;  // walk iterations per round of the tail walk (GORP_TAIL_FLUSH)
     DevBuf long_lines, recs;
@@ -267,6 +269,34 @@ struct gorp_engine {
 };
 
 namespace {
+
+// Uploads a tail image (host/walktables.hpp) and fills the device descriptor of kernels/tailwalk.cu.
+void upload_tail_image(const TailImage& img, const TailSet& T, uint32_t span_stride, TailDev& d, std::vector<void*>& owned) {
+    static_assert(sizeof(TailImageExt) == sizeof(TailExt), "host and device descriptors of a tail table must match");
+    std::vector<TailExt> text(img.ext.size());
+    std::memcpy(text.data(), img.ext.data(), text.size() * sizeof(TailExt));
+    d.image = upload(img.image, owned);
+    d.ext = upload(text, owned);
+    d.res = upload(img.res, owned);
+    d.oext = upload(img.oext, owned);
+    d.init_slots = upload(img.init_slots, owned);
+    d.xcol = upload(T.xcol, owned);
+    d.pair_col = upload(T.pair_col, owned);
+    d.width = img.width;
+    d.row_bytes = img.row_bytes;
+    d.span_stride = span_stride;
+    d.max_table_bytes = img.max_table_bytes;
+    d.max_slots = img.max_slots;
+    d.nl_data_col = T.nl_data_col;
+    for (const TailImageExt& x : img.ext) {
+        if (!x.available) {
+            ++d.n_without;
+            continue;
+        }
+        d.max_res = std::max(d.max_res, (x.n_outcomes * span_stride + 3u) & ~3u);
+        d.max_outcomes = std::max(d.max_outcomes, (x.n_outcomes + 3u) & ~3u);
+    }
+}
 
 void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fused, const TailSet& tailset, const DfaTables& raw,
                   bool match_only) {
@@ -499,31 +529,8 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
             const DfaWalkTable t = build_dfawalk_table_cut(m, tailset.cut_of_state);
             const TailImage img = build_tail_image(tailset, c.max_slots);
             if (t.available && img.available) {
-                static_assert(sizeof(TailImageExt) == sizeof(TailExt), "host and device descriptors of a tail table must match");
-                std::vector<TailExt> text(img.ext.size());
-                std::memcpy(text.data(), img.ext.data(), text.size() * sizeof(TailExt));
                 TailDev& d = c.tails;
-                d.image = upload(img.image, c.owned);
-                d.ext = upload(text, c.owned);
-                d.res = upload(img.res, c.owned);
-                d.oext = upload(img.oext, c.owned);
-                d.init_slots = upload(img.init_slots, c.owned);
-                d.xcol = upload(tailset.xcol, c.owned);
-                d.pair_col = upload(tailset.pair_col, c.owned);
-                d.width = img.width;
-                d.row_bytes = img.row_bytes;
-                d.span_stride = c.max_slots;
-                d.max_table_bytes = img.max_table_bytes;
-                d.max_slots = img.max_slots;
-                d.nl_data_col = tailset.nl_data_col;
-                for (const TailImageExt& x : img.ext) {
-                    if (!x.available) {
-                        ++d.n_without;
-                        continue;
-                    }
-                    d.max_res = std::max(d.max_res, (x.n_outcomes * c.max_slots + 3u) & ~3u);
-                    d.max_outcomes = std::max(d.max_outcomes, (x.n_outcomes + 3u) & ~3u);
-                }
+                upload_tail_image(img, tailset, c.max_slots, d, c.owned);
                 if (tailwalk_smem_bytes(d, 256) <= 200 * 1024) {
                     c.dfawalk_cut.table = upload(t.rows, c.owned);
                     c.dfawalk_cut.n_rows = t.n_rows;
@@ -666,6 +673,72 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                     }
                 }
             }
+        }
+        // fused walk: the same one-pass automaton laid out as ONE tail table (host/tails.hpp format) that every line walks, behind
+        // the newline index K1 — lanes claim consecutive lines (kernels/tailwalk.cu, `all` mode): no chunk ownership, no
+        // look-back, no bucket pass
+        if (fused.available && !std::getenv("GORP_NO_FUSEDWALK")) {
+            const FusedAutomaton& A = fused;
+            const uint32_t Sx = A.n_states, J = A.n_jcls;
+            TailSet FT;
+            std::vector<int32_t> col_of_j(J, -1);
+            std::vector<uint32_t> j_of_col;
+            auto col = [&](uint32_t j) {
+                if (col_of_j[j] < 0) {
+                    col_of_j[j] = static_cast<int32_t>(128 + j_of_col.size());
+                    j_of_col.push_back(j);
+                }
+                return static_cast<uint16_t>(col_of_j[j]);
+            };
+            FT.xcol.resize(65536);
+            for (uint32_t u = 0; u < 128; ++u) FT.xcol[u] = static_cast<uint16_t>(u);
+            for (uint32_t u = 128; u < 65536; ++u) FT.xcol[u] = col(A.jcls[u]);
+            for (uint32_t u = 0xD800; u < 0xDC00; ++u) col(A.pair_of[A.jcls[u]]);
+            FT.nl_data_col = col(A.jcls[0x0A]);
+            for (size_t k = 0; k < j_of_col.size(); ++k) col(A.pair_of[j_of_col[k]]);  // (closes over pairs of pairs: identity)
+            FT.width = static_cast<uint32_t>((128 + j_of_col.size() + 3) & ~size_t(3));
+            FT.pair_col.resize(FT.width);
+            for (uint32_t k = 0; k < FT.width; ++k) FT.pair_col[k] = static_cast<uint16_t>(k);
+            for (size_t k = 0; k < j_of_col.size(); ++k) FT.pair_col[128 + k] = col(A.pair_of[j_of_col[k]]);
+            TailAutomaton TA;
+            TA.available = true;
+            TA.n_states = Sx;
+            TA.trans.assign(static_cast<size_t>(Sx) * FT.width, 0xFFFFu);
+            for (uint32_t r = 0; r < Sx; ++r)
+                for (uint32_t k = 0; k < FT.width; ++k) {
+                    if (k >= 128 && k - 128 >= j_of_col.size()) continue;  // padding column: dead
+                    const uint32_t j = k < 128 ? A.jcls[k] : j_of_col[k - 128];
+                    TA.trans[static_cast<size_t>(r) * FT.width + k] = A.trans[static_cast<size_t>(r) * J + j];
+                }
+            TA.n_op_slots = A.n_op_slots;
+            TA.n_boundaries = std::max(c.max_slots, 1u);
+            TA.outcome_of = A.outcome_of;
+            for (const FusedAutomaton::Outcome& oc : A.outcomes) {  // recipes padded to the row width: 0 = no writer
+                FusedAutomaton::Outcome o2{oc.ext_code, static_cast<uint32_t>(TA.res.size())};
+                const uint32_t n = oc.ext_code >= 0 ? 2 * m.n_groups[oc.ext_code] : 0u;
+                for (uint32_t k = 0; k < TA.n_boundaries; ++k) {
+                    const uint32_t packed = k < n ? A.res[oc.res_off + k] : 0u;
+                    TA.res.push_back(packed);
+                    if (packed >= 256u)  // several writers: their slots are read through a maximum and must be reset per line
+                        for (uint32_t sh = 0; sh < 32 && ((packed >> sh) & 0xFFu); sh += 8) {
+                            const uint32_t id = (packed >> sh) & 0xFFu;
+                            if (id != FusedAutomaton::kLenSlot && std::find(TA.init_slots.begin(), TA.init_slots.end(), id) == TA.init_slots.end())
+                                TA.init_slots.push_back(id);
+                        }
+                }
+                TA.outcomes.push_back(o2);
+            }
+            FT.any = true;
+            FT.tails.push_back(std::move(TA));
+            const TailImage img = build_tail_image(FT, c.max_slots);
+            if (img.available && img.ext[0].available && c.max_slots > 0) {
+                upload_tail_image(img, FT, c.max_slots, c.fused_tail, c.owned);
+                c.fused_tail.enabled = tailwalk_smem_bytes(c.fused_tail, 256) <= 200 * 1024 ? 1u : 0u;
+            }
+            // measured (profiles/README.md round 2): config #2 K0c 11.46 ms vs K1 + fused walk 9.98 ms per 100 M lines, config #1 3.35 vs
+            // 2.67 ms per 40 M lines -> the fused walk is the default, K0c stays as a tier (GORP_SMALL_PATH=chunkwalk)
+            c.fusedwalk_default = true;
+            if (const char* f = std::getenv("GORP_SMALL_PATH")) c.fusedwalk_default = std::string(f) != "chunkwalk";
         }
         c.cap.cls = upload(m.symbols.classmap, c.owned);
         c.cap.n_classes = m.symbols.n_classes;
@@ -1067,8 +1140,12 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
     const int64_t* d_line_off;
     int sep;
     bool ends_with_nl = true;
-    if (!d_off && run_chunkwalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
-    if (!d_off && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
+    // small definitions, text form: the chunk-owner one-pass kernel K0c, or (GORP_SMALL_PATH=fusedwalk) the newline index K1
+    // followed by the fused walk — every line through the one-pass automaton laid out as a tail table
+    const bool fusedwalk = !d_off && c.fused_tail.enabled && c.fusedwalk_default && !c.force_twopass && !c.force_general && !c.force_tiles &&
+                           !c.force_k1k2 && !c.force_k4 && !c.cap.match_only && c.max_slots > 0 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0;
+    if (!d_off && !fusedwalk && run_chunkwalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
+    if (!d_off && !fusedwalk && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     bool scanned = false;  // ext_id already holds the combined-DFA result
     // long or ragged lines: a line index (K1) + lanes that pull lines dynamically (K2b) beats the chunk-owner walk (K0d),
     // whose threads are stuck with whatever lines start in their chunk
@@ -1078,7 +1155,7 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
     const bool cut_walk = !d_off && tails_ok && c.cut_effective && c.dfa_tier != 2 && c.dfa_tier != 1;
     const bool by_lines = !cut_walk && (c.dfa_tier == 2 || (c.dfa_tier == 0 && c.lines_per_unit < 1.0 / 100.0));
     bool cut_scanned = false;
-    if (!d_off && !by_lines && run_dfawalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, ends_with_nl, cut_walk)) {
+    if (!d_off && !by_lines && !fusedwalk && run_dfawalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, ends_with_nl, cut_walk)) {
         sep = 1;
         scanned = true;
         cut_scanned = cut_walk;
@@ -1122,6 +1199,46 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
     const size_t nl = static_cast<size_t>(n_lines);
     c.ext_id.reserve((nl + 1) * 4);
     c.hist.reserve((c.n_ext + 2) * 8);
+    if (fusedwalk && n_lines > 0 && n_lines < (1ll << 32)) {
+        const uint32_t stride = c.max_slots;
+        c.spans.reserve((nl * stride + 4) * 4);
+        c.buckets.reserve(64);
+        uint32_t* ticket = c.buckets.as<uint32_t>();  // [item ticket, n_long]
+        CK(cudaMemsetAsync(ticket, 0, 8, stream));
+        CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
+        TailWalkParams T{};
+        T.text = d_text;
+        T.n_units = n_units;
+        T.line_off = d_line_off;
+        T.item_ticket = ticket;
+        T.t = c.fused_tail;
+        T.n_ext = c.n_ext;
+        T.round_iters = c.tail_flush_every;
+        T.lines_form = 0;
+        if (const char* f = std::getenv("GORP_TAIL_FLAGS")) T.flags = static_cast<uint32_t>(std::atoi(f));
+        T.ext_id = c.ext_id.as<int32_t>();
+        T.spans = c.spans.as<int32_t>();
+        T.hist = c.hist.as<unsigned long long>();
+        T.long_cap = static_cast<uint32_t>(n_units / kTailMaxLen + 2);
+        c.long_lines.reserve(static_cast<size_t>(T.long_cap) * 4);
+        T.long_lines = c.long_lines.as<uint32_t>();
+        T.n_long = ticket + 1;
+        T.all = 1;
+        T.n_lines = n_lines;
+        k4c_tailwalk(L, T);
+        tm.mark("k4c_fusedwalk", 2);
+        CK(cudaGetLastError());
+        if (out) {
+            out->n_lines = n_lines;
+            out->span_stride = static_cast<int32_t>(stride);
+            out->d_ext_id = c.ext_id.as<int32_t>();
+            out->d_line_off = d_line_off;
+            out->d_spans = c.spans.as<int32_t>();
+            out->d_histogram = c.hist.as<int64_t>();
+            out->d_n_lines = d_n_lines;
+        }
+        return n_lines;
+    }
     // every line but (possibly) the last is terminated by '\n' in the text form: fast tiers; an unterminated last line
     // goes through the general kernels
     const int64_t n_fast = ends_with_nl ? n_lines : n_lines - 1;

@@ -347,6 +347,10 @@ struct TailWalkParams {
     uint32_t* long_lines;        // [long_cap] lines handed to the 32-bit kernel
     uint32_t* n_long;            // zeroed by the caller
     uint32_t long_cap;
+    // "all" mode (fused walk): t holds ONE table (the one-pass automaton of host/fused.hpp) that every line walks; no buckets,
+    // no records — work item i = lines [i * kCapItemLines, ...) of line_off, ext_id / hist are written for every line
+    uint32_t all;
+    int64_t n_lines;
 };
 size_t tailwalk_smem_bytes(const TailDev&, int threads);
 void k4c_tailwalk(const Launch&, const TailWalkParams&);

@@ -124,22 +124,18 @@ __device__ __noinline__ uint32_t tw_bounded16(const TailDev& T, uint32_t ra, con
     return ra;
 }
 
-__device__ __forceinline__ Units16 tw_load(const uint16_t* __restrict__ text, int64_t pos, int64_t n_units, uint32_t flags) {
-    if (flags & 2u) return load_units16_l2wide<128>(text, pos, n_units);
-    if (flags & 4u) return load_units16_l2wide<256>(text, pos, n_units);
-    return load_units16_l2keep(text, pos, n_units);
-}
-
 constexpr uint32_t kTwBins = 1024;    // bins of the per-item sort: (group of records, 32 length classes)
 constexpr uint32_t kTwMaxMulti = 64;  // group boundaries with several writers, per extraction (else the table is refused)
 
-template <bool kLines, int kT>
+// kAll: the fused walk — one table for every line, consecutive lines straight from the line index (no buckets, no records)
+template <bool kLines, int kT, bool kAll>
 __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
     constexpr uint32_t kSlotStride = SlotStride<kT>::value;
     constexpr int kTailWalkThreads = kT;
     // [table][recipes][outcome codes][several-writer list][init list][slots: (max_slots + 2) x kSlotStride]
     extern __shared__ __align__(16) unsigned char s_mem[];
     __shared__ uint32_t s_item, s_cursor, s_loaded, s_n_multi;
+    __shared__ uint32_t s_hist[kAll ? 256 : 1];  // kAll: lines per outcome of the one table
     const TailDev& T = P.t;
     const uint32_t stride = T.span_stride;
     const uint32_t tab_bytes = T.max_table_bytes;
@@ -157,7 +153,10 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
     const uint32_t zero_off = T.max_slots * kSlotStride, len_off = zero_off + kSlotStride;
     const uint32_t row_bytes = T.row_bytes;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
-    const uint32_t n_items = *P.n_items;
+    const uint32_t n_all = kAll ? static_cast<uint32_t>(P.n_lines) : 0u;
+    const uint32_t n_items = kAll ? (n_all + kCapItemLines - 1) / kCapItemLines : *P.n_items;
+    if (kAll)
+        for (uint32_t i = threadIdx.x; i < 256; i += kT) s_hist[i] = 0;
     const uint32_t round_iters = P.round_iters;
     const bool pf_ahead = !(P.flags & 8u);
     if (threadIdx.x == 0) s_loaded = 0xFFFFFFFFu;
@@ -169,7 +168,14 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= n_items) break;
-        const CapItem it = P.items[item];
+        CapItem it;
+        if (kAll) {
+            it.ext = 0;
+            it.begin = item * kCapItemLines;
+            it.end = min(it.begin + kCapItemLines, n_all);
+        } else {
+            it = P.items[item];
+        }
         const TailExt x = T.ext[it.ext];
         if (!x.available) continue;  // the bucketed capture walk (kernels/capwalk.cu) takes the items of this extraction
         if (s_loaded != it.ext) {
@@ -214,8 +220,20 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
             for (uint32_t i = threadIdx.x; i < kTwBins; i += kTailWalkThreads) s_bins[i] = 0;
             __syncthreads();
             const uint4* recs4 = reinterpret_cast<const uint4*>(P.recs) + it.begin;
-            auto key_of = [G](uint32_t i, const uint4 r) { return ((i >> G) << 5) + 31u - min(((r.x & 15u) + min(r.w, 0xFFFFu)) >> 4, 31u); };
-            for (uint32_t i = threadIdx.x; i < n_it; i += kTailWalkThreads) atomicAdd(&s_bins[key_of(i, __ldg(recs4 + i))], 1u);
+            auto key_of = [&](uint32_t i) {  // (group of records, 31 - 16-unit blocks the line touches)
+                uint32_t lo, len;
+                if (kAll) {
+                    const int64_t a0 = __ldg(P.line_off + it.begin + i), a1 = __ldg(P.line_off + it.begin + i + 1);
+                    lo = static_cast<uint32_t>(a0) & 15u;
+                    len = static_cast<uint32_t>(min(a1 - a0, int64_t(0xFFFF)));
+                } else {
+                    const uint4 r = __ldg(recs4 + i);
+                    lo = r.x & 15u;
+                    len = min(r.w, 0xFFFFu);
+                }
+                return ((i >> G) << 5) + 31u - min((lo + len) >> 4, 31u);
+            };
+            for (uint32_t i = threadIdx.x; i < n_it; i += kTailWalkThreads) atomicAdd(&s_bins[key_of(i)], 1u);
             __syncthreads();
             if (threadIdx.x < 32) {  // exclusive scan of the kTwBins counts: lane l owns bins [32 l, 32 l + 32)
                 uint32_t sum = 0;
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
             }
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < n_it; i += kTailWalkThreads)
-                s_order[atomicAdd(&s_bins[key_of(i, __ldg(recs4 + i))], 1u)] = static_cast<uint16_t>(i);
+                s_order[atomicAdd(&s_bins[key_of(i)], 1u)] = static_cast<uint16_t>(i);
         }
         if (threadIdx.x == 0) s_cursor = it.begin;
         __syncthreads();
@@ -243,6 +261,7 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
 
         const int32_t cand = static_cast<int32_t>(it.ext);
         const uint32_t fin_ra = x.fin_base * row_bytes + rows_abs;
+        const uint32_t inv_row_bytes = 0xFFFFFFFFu / row_bytes + 1u;
         const uint32_t skip_ra = x.n_states * row_bytes + rows_abs;  // SKIP_1; SKIP_k = skip_ra + (k - 1) * row_bytes
         const uint32_t n_multi = min(s_n_multi, kTwMaxMulti);
 
@@ -250,7 +269,10 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
         // "what its slot holds" - 1 (ZERO slot: -1), the several-writer boundaries are patched afterwards
         auto flush = [&](uint32_t fline, uint32_t outcome) {
             const int32_t code = s_oext[outcome];
-            if (code != cand) {  // the candidate did not match after all: MISS (regex_e rejects) or CAPTURE_FAIL
+            if (kAll) {
+                P.ext_id[fline] = code;
+                atomicAdd(&s_hist[outcome], 1u);
+            } else if (code != cand) {  // the candidate did not match after all: MISS (regex_e rejects) or CAPTURE_FAIL
                 P.ext_id[fline] = code;
                 atomicAdd(P.hist + cand, ~0ull);  // -1
                 atomicAdd(P.hist + P.n_ext + (code == -1 ? 0u : 1u), 1ull);
@@ -312,13 +334,28 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
         bool exhausted = false;  // warp-uniform: the item has no unclaimed line left
         bool active = false, has_fin = false;
         uint32_t line = 0, fin_outcome = 0;
-        int64_t a = 0, q = 0, last_q = 0, line_end = 0;
+        // the lane's line: `a` first unit, `len` units; the walk keeps only a pointer to its current block, the number of
+        // blocks that follow it, and the line-relative position (+1) of the block's first unit
+        int64_t a = 0;
+        uint32_t len = 0, rem = 0, pos1 = 0;
+        const uint16_t* tp = P.text;
+        bool safe = false;  // every block of the line lies inside the text: plain 256-bit loads
         uint32_t ra = fin_ra;
-        Units16 nxt{};  // the block at q, loaded one iteration ahead
+        Units16 nxt{};  // the block at tp, loaded one iteration ahead
         // the lane's NEXT line: 0 = none, 1 = record requested, 2 = record here, first block requested, rest on its way to L2
         uint32_t nstage = 0;
         uint4 nrec = make_uint4(0, 0, 0, 0);  // LineRec: start (x, y), line id (z), length (w)
         Units16 nfirst{};
+        auto load_block = [&](const uint16_t* p, bool inside) -> Units16 {
+            if (inside) {
+                Units16 r;
+                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+                             : "l"(p));
+                return r;
+            }
+            return load_units16_l2keep(P.text, p - P.text, P.n_units);  // the last blocks of the text: unit by unit, padded with '\n'
+        };
         for (;;) {
             // ================= service point
             if (has_fin) {
@@ -328,14 +365,17 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
             if (!active && nstage == 2) {  // start the claimed line
                 line = nrec.z;
                 a = static_cast<int64_t>(static_cast<uint64_t>(nrec.x) | (static_cast<uint64_t>(nrec.y) << 32));
-                q = a & ~int64_t(15);
-                line_end = a + nrec.w;
-                last_q = line_end & ~int64_t(15);  // the block that holds the line's '\n' (lines form: its end)
+                len = nrec.w;
+                const uint32_t lo = nrec.x & 15u;
+                const int64_t q = a - lo;
+                tp = P.text + q;
+                rem = (lo + len) >> 4;  // blocks after the first, up to the one that holds the line's '\n' (lines form: its end)
+                safe = q + 16 * static_cast<int64_t>(rem) + 16 <= P.n_units;
+                pos1 = 1u - lo;  // garbage while skipping: only ever stored to the dummy slot
                 nxt = nfirst;
-                const uint32_t lo = static_cast<uint32_t>(a - q);
                 ra = lo ? skip_ra + (lo - 1) * row_bytes : rows_abs;
                 for (uint32_t i = 0; i < x.n_init; ++i) sts_u16(slot_abs + s_init[i] * kSlotStride, 0u);
-                sts_u16(slot_abs + len_off, nrec.w + 1u);
+                sts_u16(slot_abs + len_off, len + 1u);
                 active = true;
                 nstage = 0;
             }
@@ -348,7 +388,14 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                     const uint32_t idx = base + static_cast<uint32_t>(__popc(want & lt_mask));
                     if (nstage == 0 && idx < it.end) {
                         const uint32_t at = sorted ? it.begin + s_order[idx - it.begin] : idx;
-                        nrec = __ldg(reinterpret_cast<const uint4*>(P.recs) + at);
+                        if (kAll) {  // consecutive lines: the record comes straight from the line index
+                            const int64_t a0 = __ldg(P.line_off + at), a1 = __ldg(P.line_off + at + 1);
+                            const int64_t l = a1 - a0 - (kLines ? 0 : 1);
+                            nrec = make_uint4(static_cast<uint32_t>(static_cast<uint64_t>(a0) & 0xFFFFFFFFu), static_cast<uint32_t>(static_cast<uint64_t>(a0) >> 32), at,
+                                              static_cast<uint32_t>(l > 0xFFFFFFFFll ? 0xFFFFFFFFll : l));
+                        } else {
+                            nrec = __ldg(reinterpret_cast<const uint4*>(P.recs) + at);
+                        }
                         nstage = 1;
                     }
                     exhausted = base + static_cast<uint32_t>(__popc(want)) >= it.end;
@@ -359,13 +406,12 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
             for (uint32_t k = 0; k < round_iters; ++k) {
                 if (active) {
                     const Units16 u = nxt;
-                    if (q < last_q) nxt = tw_load(P.text, q + 16, P.n_units, P.flags);  // in flight during the 16 steps below
-                    // ... and the 128-byte line four blocks ahead is asked into L2 just in time: the register load above then
+                    if (rem) nxt = load_block(tp + 16, safe);  // in flight during the 16 steps below
+                    // ... and the 128-byte line after the next one is asked into L2 just in time: the register load above then
                     // finds its block in L2 (a whole-line prefetch at claim time came too early and was evicted again)
-                    if (pf_ahead && (q & 63) == 0 && q + 64 <= last_q) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + q + 64));
-                    const uint32_t pos1 = static_cast<uint32_t>(q - a) + 1u;  // garbage while skipping: only ever stored to the dummy slot
+                    if (pf_ahead && (reinterpret_cast<uintptr_t>(tp) & 127u) == 0 && rem >= 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + 64));
                     // lines form: the fast path needs a block that lies inside the line and holds no '\n' (there it is content)
-                    const bool plain = !kLines || (q < last_q && (nl_bits4(u.a.x, u.a.y) | nl_bits4(u.a.z, u.a.w) | nl_bits4(u.b.x, u.b.y) | nl_bits4(u.b.z, u.b.w)) == 0u);
+                    const bool plain = !kLines || (rem && (nl_bits4(u.a.x, u.a.y) | nl_bits4(u.a.z, u.a.w) | nl_bits4(u.b.x, u.b.y) | nl_bits4(u.b.z, u.b.w)) == 0u);
                     if (plain && ((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
                         tw_step<0, kT>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1);
                         tw_step<2, kT>(ra, u.a.x, rows_abs, row_bytes, slot_abs, pos1 + 1);
@@ -384,38 +430,44 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
                         tw_step<0, kT>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 14);
                         tw_step<2, kT>(ra, u.b.w, rows_abs, row_bytes, slot_abs, pos1 + 15);
                     } else if (kLines) {
-                        ra = tw_bounded16(T, ra, u, P.text, q, line_end, rows_abs, row_bytes, fin_ra, slot_abs, pos1, kSlotStride);
+                        ra = tw_bounded16(T, ra, u, P.text, tp - P.text, a + len, rows_abs, row_bytes, fin_ra, slot_abs, pos1, kSlotStride);
                     } else {
-                        ra = tw_slow16(T, ra, u, P.text, q, P.n_units, rows_abs, row_bytes, fin_ra, slot_abs, pos1, kSlotStride);
+                        ra = tw_slow16(T, ra, u, P.text, tp - P.text, P.n_units, rows_abs, row_bytes, fin_ra, slot_abs, pos1, kSlotStride);
                     }
-                    q += 16;
+                    tp += 16;
+                    pos1 += 16u;
+                    --rem;  // (wraps on the last block: the line ends there, `rem` is set again when the next line starts)
                     if (ra >= fin_ra) {  // the line ended inside these 16 units (its '\n', a dead transition, or the end of the text)
-                        fin_outcome = (ra - fin_ra) / row_bytes;
+                        fin_outcome = __umulhi(ra - fin_ra, inv_row_bytes);  // exact: a small multiple of row_bytes
                         has_fin = true;
                         active = false;
                     }
                 }
                 if (k == 0 && nstage == 1) {  // the record claimed at the service point is here: get the line's text moving
-                    const int64_t na = static_cast<int64_t>(static_cast<uint64_t>(nrec.x) | (static_cast<uint64_t>(nrec.y) << 32));
                     if (nrec.w >= kTailMaxLen) {  // 32-bit positions: tail_long_kernel
                         const uint32_t slot = atomicAdd(P.n_long, 1u);
                         if (slot < P.long_cap) P.long_lines[slot] = nrec.z;
                         nstage = 0;
                     } else {
+                        const int64_t na = static_cast<int64_t>(static_cast<uint64_t>(nrec.x) | (static_cast<uint64_t>(nrec.y) << 32));
                         const int64_t p0 = na & ~int64_t(15);
-                        nfirst = tw_load(P.text, p0, P.n_units, P.flags);
+                        nfirst = load_block(P.text + p0, p0 + 16 <= P.n_units);
                         if (pf_ahead && (p0 & ~int64_t(63)) + 64 <= na + nrec.w)  // the 128-byte line after the first block's
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(P.text + (p0 & ~int64_t(63)) + 64));
-                        int64_t bytes = ((na + nrec.w + 1 - p0) * 2 + 15) & ~int64_t(15);
-                        if (p0 + bytes / 2 > P.n_units) bytes = ((P.n_units - p0) * 2) & ~int64_t(15);
-                        if (bytes > 4096) bytes = 4096;
-                        if (bytes > 32 && (P.flags & 1u))  // off by default: same speed, 1.24x the DRAM reads (profiles/README.md)
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.text + p0 + 16), "r"(static_cast<uint32_t>(bytes - 32)) : "memory");
                         nstage = 2;
                     }
                 }
                 if (!__any_sync(0xffffffffu, active)) break;
             }
+        }
+    }
+    if (kAll) {  // per-outcome line counts of this CTA -> the histogram bins of their codes
+        __syncthreads();
+        const TailExt x = T.ext[0];
+        for (uint32_t o = threadIdx.x; o < x.n_outcomes && o < 256u; o += kT) {
+            const int32_t code = __ldg(T.oext + x.oext_off + o);
+            const uint32_t bin = code >= 0 ? static_cast<uint32_t>(code) : (code == -1 ? P.n_ext : P.n_ext + 1u);
+            if (s_hist[o]) atomicAdd(P.hist + bin, static_cast<unsigned long long>(s_hist[o]));
         }
     }
 }
@@ -427,7 +479,7 @@ __global__ void __launch_bounds__(32) tail_long_kernel(TailWalkParams P) {
     const uint32_t stride = T.span_stride, width = T.width;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t line = P.long_lines[i];
-        const int32_t cand = P.ext_id[line];
+        const int32_t cand = P.all ? 0 : P.ext_id[line];
         if (cand < 0) continue;
         const TailExt x = T.ext[cand];
         const uint16_t* __restrict__ tab = reinterpret_cast<const uint16_t*>(reinterpret_cast<const unsigned char*>(T.image) + x.tab_off);
@@ -450,7 +502,10 @@ __global__ void __launch_bounds__(32) tail_long_kernel(TailWalkParams P) {
         }
         const uint32_t o = row - x.fin_base;
         const int32_t code = T.oext[x.oext_off + o];
-        if (code != cand) {
+        if (P.all) {
+            P.ext_id[line] = code;
+            atomicAdd(P.hist + (code >= 0 ? static_cast<uint32_t>(code) : (code == -1 ? P.n_ext : P.n_ext + 1u)), 1ull);
+        } else if (code != cand) {
             P.ext_id[line] = code;
             atomicAdd(P.hist + cand, ~0ull);
             atomicAdd(P.hist + P.n_ext + (code == -1 ? 0u : 1u), 1ull);
@@ -488,47 +543,56 @@ size_t tailwalk_smem_bytes(const TailDev& t, int threads) {
 
 namespace {
 
-template <bool kLines, int kT>
+template <bool kLines, int kT, bool kAll>
 int tailwalk_warps_per_sm(const TailDev& t) {
     const size_t smem = tailwalk_smem_bytes(t, kT);
     if (smem > 226 * 1024) return 0;
-    allow_max_dynamic_smem(tailwalk_kernel<kLines, kT>);
+    allow_max_dynamic_smem(tailwalk_kernel<kLines, kT, kAll>);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<kLines, kT>, kT, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<kLines, kT, kAll>, kT, smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
     return per_sm * kT / 32;
 }
 
-template <bool kLines, int kT>
+template <bool kLines, int kT, bool kAll>
 void tailwalk_launch(const Launch& L, const TailWalkParams& P) {
     const size_t smem = tailwalk_smem_bytes(P.t, kT);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<kLines, kT>, kT, smem);
-    tailwalk_kernel<kLines, kT><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kT, smem, L.stream>>>(P);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<kLines, kT, kAll>, kT, smem);
+    tailwalk_kernel<kLines, kT, kAll><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kT, smem, L.stream>>>(P);
 }
 
 // the CTA size that keeps the most warps resident (the dependent lookup chain of a lane is latency-bound: the more warps,
 // the better it is hidden); ties: the smaller CTA
-template <bool kLines>
+template <bool kLines, bool kAll>
 void tailwalk_dispatch(const Launch& L, const TailWalkParams& P) {
-    const int w256 = tailwalk_warps_per_sm<kLines, 256>(P.t), w384 = tailwalk_warps_per_sm<kLines, 384>(P.t),
-              w512 = tailwalk_warps_per_sm<kLines, 512>(P.t);
+    const int w256 = tailwalk_warps_per_sm<kLines, 256, kAll>(P.t), w384 = tailwalk_warps_per_sm<kLines, 384, kAll>(P.t),
+              w512 = tailwalk_warps_per_sm<kLines, 512, kAll>(P.t);
     int forced = 0;
     if (const char* f = std::getenv("GORP_TAIL_THREADS")) forced = std::atoi(f);
     // measured on config #4 (profiles/README.md, round 2): 16 warps 8.5 ms, 24 warps (2 x 384) 7.34 ms, 32 warps (2 x 512) 7.44 ms
-    if (forced == 384 ? w384 > 0 : (forced == 0 && w384 >= 24 && w384 > w256)) tailwalk_launch<kLines, 384>(L, P);
-    else if (forced == 512 ? w512 > 0 : (forced == 0 && w512 > w384 && w512 > w256)) tailwalk_launch<kLines, 512>(L, P);
-    else if (forced == 0 && w384 > w256) tailwalk_launch<kLines, 384>(L, P);
-    else tailwalk_launch<kLines, 256>(L, P);
+    // all mode (consecutive lines, small table): measured on config #2 (profiles/README.md round 2): 3 x 256 threads 10.8 ms,
+    // 2 x 384 8.5 ms, 2 x 512 (64 registers) 7.8 ms
+    if (kAll && forced == 0 && w512 >= 32) tailwalk_launch<kLines, 512, kAll>(L, P);
+    else if (forced == 384 ? w384 > 0 : (forced == 0 && w384 >= 24 && w384 > w256)) tailwalk_launch<kLines, 384, kAll>(L, P);
+    else if (forced == 512 ? w512 > 0 : (forced == 0 && w512 > w384 && w512 > w256)) tailwalk_launch<kLines, 512, kAll>(L, P);
+    else if (forced == 0 && w384 > w256) tailwalk_launch<kLines, 384, kAll>(L, P);
+    else tailwalk_launch<kLines, 256, kAll>(L, P);
 }
 
 }  // namespace
 
 void k4c_tailwalk(const Launch& L, const TailWalkParams& P) {
-    if (P.lines_form) tailwalk_dispatch<true>(L, P);
-    else tailwalk_dispatch<false>(L, P);
+    if (P.all) {
+        if (P.lines_form) tailwalk_dispatch<true, true>(L, P);
+        else tailwalk_dispatch<false, true>(L, P);
+    } else if (P.lines_form) {
+        tailwalk_dispatch<true, false>(L, P);
+    } else {
+        tailwalk_dispatch<false, false>(L, P);
+    }
     tail_long_kernel<<<L.sm_count, 32, 0, L.stream>>>(P);
 }
 

@@ -231,7 +231,7 @@ def test_full_size_properties_big_definitions(name, n, reps):
     assert (np.diff(b.line_off).reshape(reps, -1) == np.diff(b1.line_off)[None, :]).all()
 
 
-TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
+TIERS = {"k1_fusedwalk": {}, "chunkwalk": {"GORP_SMALL_PATH": "chunkwalk"}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
          "dfawalk_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1", "GORP_NO_TAILS": "1"},
          "linewalk_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_NO_TAILS": "1"},
          "linewalk_tailwalk_flush1": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_TAIL_FLUSH": "1"},
@@ -244,7 +244,7 @@ TIERS = {"chunkwalk": {}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
          "twopass_fast": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1", "GORP_FORCE_K4": "1"},
          "general": {"GORP_FORCE_GENERAL": "1"}}
 _TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES", "GORP_FORCE_K1K2", "GORP_FORCE_K4", "GORP_DFA_TIER",
-             "GORP_NO_TAILS", "GORP_TAIL_FLUSH", "GORP_CUT_WALK", "GORP_TAIL_THREADS")
+             "GORP_NO_TAILS", "GORP_TAIL_FLUSH", "GORP_CUT_WALK", "GORP_TAIL_THREADS", "GORP_SMALL_PATH")
 
 
 @pytest.mark.parametrize("tier", list(TIERS))
@@ -359,15 +359,18 @@ def test_latin1_text_form(monkeypatch):
     assert g.extract_batch_text_latin1(b"[1]: GET 2ms /a").ext_id.tolist() == [1]
 
 
-def test_chunkwalk_launch_times_are_stable(monkeypatch):
+@pytest.mark.parametrize("small_path", ["fusedwalk", "chunkwalk"])
+def test_chunkwalk_launch_times_are_stable(small_path, monkeypatch):
     """Round 1 found the one-pass kernel bistable (11.5 or 17.4 ms per launch, depending on unrelated allocation sizes).
     Every launch of a series must run in the fast mode whatever the sizes of the result allocations are: the row arrays are
-    padded by 0 / 64 K / 1 M rows (GORP_PAD_ROWS shifts every allocation that follows), 25 launches each."""
+    padded by 0 / 64 K / 1 M rows (GORP_PAD_ROWS shifts every allocation that follows), 25 launches each. The default path
+    of small definitions (K1 + fused walk: no look-back, no phase coupling between CTAs) is held to the same bound."""
     import ctypes as C
     import torch
     from gorp_b200 import _ffi, corpusgen
     from gorp_b200.api import Blob, _check
     dev = torch.device("cuda", 0)
+    monkeypatch.setenv("GORP_SMALL_PATH", small_path)
     d_text = corpusgen.device_text("readme", 0, 12_000_000, dev)
     blob = Blob.from_definition(V.README_DEF)
     times = {}
