@@ -490,7 +490,58 @@ def e2e_run(env, kept, workload):
             e2e["latin1_input"] = {"value": int(ll.item()) / float(tt8.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h8_np.size),
                                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tt8.item()) * 1e3,
                                    "call": "gorp_extract_text_latin1 (ISO-8859-1 bytes in, widened to UTF-16 on the device)"}
+            # ... and with UTF-8 bytes (what the reference's InputLineReader reads from a log file, io/InputLineReader.java:51;
+            # the ASCII corpus is its own UTF-8): validated and decoded on the device
+            def e2eu_step():
+                _check(lib.gorp_extract_text_utf8(eng, h8_np.ctypes.data, h8_np.size, C.byref(res)))
+                nlu = res.n_lines
+                lib.gorp_result_release(eng, C.byref(res))
+                return nlu
+            assert e2eu_step() == nl
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2eu_step()
+            torch.cuda.synchronize()
+            ttu = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ttu, op=dist.ReduceOp.MAX)
+            e2e["utf8_input"] = {"value": int(ll.item()) / float(ttu.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h8_np.size),
+                                 "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ttu.item()) * 1e3,
+                                 "call": "gorp_extract_text_utf8 (UTF-8 bytes in, decoded to UTF-16 on the device)"}
             del h8
+        # the List<String> form (Gorp.extractAll(List<String>), Gorp.java:145-147): the same lines as one concatenation without
+        # separators plus n + 1 offsets, on a bounded share of the batch (the offsets are another 8 bytes per line of pinned memory)
+        ln_lines = min(int(nl), 25_000_000)
+        d_off = torch.nonzero(d_text[:e2e_units] == 10).flatten()[:ln_lines] + 1  # starts of lines 1 .. ln_lines
+        cut_units = int(d_off[-1].item())
+        keep = d_text[:cut_units] != 10
+        h_lt = torch.empty(cut_units - ln_lines, dtype=torch.int16).pin_memory()
+        h_lt.copy_(d_text[:cut_units][keep])
+        h_lo = torch.zeros(ln_lines + 1, dtype=torch.int64).pin_memory()
+        h_lo[1:].copy_(d_off - torch.arange(1, ln_lines + 1, device=dev))
+        del d_off, keep
+        lt_np, lo_np = h_lt.numpy().view(np.uint16), h_lo.numpy()
+
+        def e2el_step():
+            _check(lib.gorp_extract_lines(eng, lt_np.ctypes.data, lo_np.ctypes.data, ln_lines, C.byref(res)))
+            nll = res.n_lines
+            lib.gorp_result_release(eng, C.byref(res))
+            return nll
+        assert e2el_step() == ln_lines
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2el_step()
+        torch.cuda.synchronize()
+        ttl = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ttl, op=dist.ReduceOp.MAX)
+        e2e["lines_form"] = {"value": ln_lines * world / float(ttl.item()), "unit": "lines/s", "lines_per_step_per_gpu": ln_lines,
+                             "h2d_bytes_per_step": int(lt_np.size * 2 + lo_np.size * 8), "d2h_bytes_per_step": int(d2h * ln_lines // max(int(nl), 1)),
+                             "ms_per_step": float(ttl.item()) * 1e3,
+                             "call": "gorp_extract_lines (concatenated strings + offsets: the List<String> form)"}
+        del h_lt, h_lo
         del h_text
     except Exception as ex:  # noqa: BLE001
         e2e = {"value": None, "unit": "lines/s", "error": str(ex)[:200]}

@@ -1142,7 +1142,7 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
     bool ends_with_nl = true;
     // small definitions, text form: the chunk-owner one-pass kernel K0c, or (GORP_SMALL_PATH=fusedwalk) the newline index K1
     // followed by the fused walk — every line through the one-pass automaton laid out as a tail table
-    const bool fusedwalk = !d_off && c.fused_tail.enabled && c.fusedwalk_default && !c.force_twopass && !c.force_general && !c.force_tiles &&
+    const bool fusedwalk = c.fused_tail.enabled && c.fusedwalk_default && (!d_off || n_units > 0) && !c.force_twopass && !c.force_general && !c.force_tiles &&
                            !c.force_k1k2 && !c.force_k4 && !c.cap.match_only && c.max_slots > 0 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0;
     if (!d_off && !fusedwalk && run_chunkwalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     if (!d_off && !fusedwalk && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
@@ -1214,7 +1214,7 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
         T.t = c.fused_tail;
         T.n_ext = c.n_ext;
         T.round_iters = c.tail_flush_every;
-        T.lines_form = 0;
+        T.lines_form = sep == 0 ? 1u : 0u;  // List<String> form: the caller's offsets are the line index
         if (const char* f = std::getenv("GORP_TAIL_FLAGS")) T.flags = static_cast<uint32_t>(std::atoi(f));
         T.ext_id = c.ext_id.as<int32_t>();
         T.spans = c.spans.as<int32_t>();
@@ -1225,6 +1225,13 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
         T.n_long = ticket + 1;
         T.all = 1;
         T.n_lines = n_lines;
+        // big items amortise the barrier at the end of an item (2 % at 4096 lines), small batches (the 64 MB pieces of a
+        // host-buffer call) need enough items for every CTA
+        // (an item must also give every lane of a 512-thread CTA a couple of lines: not below 1024)
+        const int64_t ctas = 2ll * c.sm_count;
+        uint32_t il = 1024;
+        while (il < 4096 && static_cast<int64_t>(il) * 2 * ctas < n_lines) il *= 2;
+        T.item_lines = il;
         k4c_tailwalk(L, T);
         tm.mark("k4c_fusedwalk", 2);
         CK(cudaGetLastError());
@@ -1588,7 +1595,12 @@ int extract_host(gorp_engine* e, const uint16_t* text, const uint8_t* text8, int
     if (!e || !out || (!text && !text8 && n_units > 0) || n_units < 0 || n_lines < 0) return fail(GORP_E_ARG, "bad argument");
     if (e->devs.empty()) return fail(GORP_E_CUDA, "engine has no CUDA device");
     return guarded([&]() -> int {
-        int64_t piece_units = kPieceUnits;
+        // byte inputs (ISO-8859-1 / UTF-8) move half the bytes per unit: 4x the units per piece keeps the per-piece overhead
+        // (a dozen small launches and one host round trip) below the copy time — measured on config #2 (profiles/README.md
+        // round 2): 149 -> 132 ms per 100 M lines of Latin-1 input
+        int64_t piece_units = text8 ? 4 * kPieceUnits : kPieceUnits;
+        // (the lines form pays two copies and a longer kernel chain per piece: larger pieces once the batch has 16 of them)
+        if (off && n_lines > 0) piece_units = std::min<int64_t>(4 * kPieceUnits, std::max<int64_t>(kPieceUnits, n_units / 16));
         if (const char* f = std::getenv("GORP_PIECE_UNITS")) piece_units = std::max<int64_t>(std::atoll(f), 1024);
         const std::vector<Piece> pieces = text8 ? plan_pieces(text8, n_units, off, n_lines, piece_units) : plan_pieces(text, n_units, off, n_lines, piece_units);
         std::unique_ptr<HostResult> hr;

@@ -350,6 +350,7 @@ struct TailWalkParams {
     // "all" mode (fused walk): t holds ONE table (the one-pass automaton of host/fused.hpp) that every line walks; no buckets,
     // no records — work item i = lines [i * kCapItemLines, ...) of line_off, ext_id / hist are written for every line
     uint32_t all;
+    uint32_t item_lines;         // lines per work item in "all" mode (<= kCapItemLines; smaller for small batches: enough items for every CTA)
     int64_t n_lines;
 };
 size_t tailwalk_smem_bytes(const TailDev&, int threads);

@@ -61,9 +61,12 @@ __device__ __forceinline__ void tw_step(uint32_t& ra, uint32_t w, uint32_t rows_
     asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a) : "r"(b), "r"(ra));
     const uint32_t ent = lds_u16(a);
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ra) : "r"(ent >> 6), "r"(row_bytes), "r"(rows_abs));
+    // the store is predicated on a real slot: most units fire no command (slot 0, the dummy), and a warp-wide store in
+    // which a few lanes hit other rows than the dummy row cost an extra wavefront (two lanes share a word)
+    const uint32_t slot = ent & 63u;
     uint32_t sa;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(ent & 63u), "n"(SlotStride<kT>::value), "r"(slot_abs));
-    sts_u16(sa, pos1);
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(slot), "n"(SlotStride<kT>::value), "r"(slot_abs));
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u16 [%0], %1; }" ::"r"(sa), "h"(static_cast<unsigned short>(pos1)), "r"(slot) : "memory");
 }
 
 // 16 units that hold a unit >= 0x80: unit by unit through the column map (global, L1/L2 resident). A high surrogate
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
     const uint32_t row_bytes = T.row_bytes;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const uint32_t n_all = kAll ? static_cast<uint32_t>(P.n_lines) : 0u;
-    const uint32_t n_items = kAll ? (n_all + kCapItemLines - 1) / kCapItemLines : *P.n_items;
+    const uint32_t item_lines = kAll ? P.item_lines : kCapItemLines;
+    const uint32_t n_items = kAll ? (n_all + item_lines - 1) / item_lines : *P.n_items;
     if (kAll)
         for (uint32_t i = threadIdx.x; i < 256; i += kT) s_hist[i] = 0;
     const uint32_t round_iters = P.round_iters;
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
         CapItem it;
         if (kAll) {
             it.ext = 0;
-            it.begin = item * kCapItemLines;
-            it.end = min(it.begin + kCapItemLines, n_all);
+            it.begin = item * item_lines;
+            it.end = min(it.begin + item_lines, n_all);
         } else {
             it = P.items[item];
         }
@@ -557,29 +561,46 @@ int tailwalk_warps_per_sm(const TailDev& t) {
 }
 
 template <bool kLines, int kT, bool kAll>
-void tailwalk_launch(const Launch& L, const TailWalkParams& P) {
+void tailwalk_launch(const Launch& L, const TailWalkParams& P, int per_sm) {
     const size_t smem = tailwalk_smem_bytes(P.t, kT);
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tailwalk_kernel<kLines, kT, kAll>, kT, smem);
     tailwalk_kernel<kLines, kT, kAll><<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kT, smem, L.stream>>>(P);
 }
 
 // the CTA size that keeps the most warps resident (the dependent lookup chain of a lane is latency-bound: the more warps,
-// the better it is hidden); ties: the smaller CTA
+// the better it is hidden); ties: the smaller CTA. The choice (three occupancy queries and attribute calls) is made once per
+// table geometry and host thread: a host-buffer call launches this kernel once per 64 MB piece.
 template <bool kLines, bool kAll>
 void tailwalk_dispatch(const Launch& L, const TailWalkParams& P) {
-    const int w256 = tailwalk_warps_per_sm<kLines, 256, kAll>(P.t), w384 = tailwalk_warps_per_sm<kLines, 384, kAll>(P.t),
-              w512 = tailwalk_warps_per_sm<kLines, 512, kAll>(P.t);
+    struct Choice {
+        size_t key = ~size_t(0);
+        int device = -1, forced = -1, threads = 0, per_sm = 0;
+    };
+    static thread_local Choice ch;
+    const size_t key = tailwalk_smem_bytes(P.t, 256);
+    int device = 0;
+    cudaGetDevice(&device);
     int forced = 0;
     if (const char* f = std::getenv("GORP_TAIL_THREADS")) forced = std::atoi(f);
-    // measured on config #4 (profiles/README.md, round 2): 16 warps 8.5 ms, 24 warps (2 x 384) 7.34 ms, 32 warps (2 x 512) 7.44 ms
-    // all mode (consecutive lines, small table): measured on config #2 (profiles/README.md round 2): 3 x 256 threads 10.8 ms,
-    // 2 x 384 8.5 ms, 2 x 512 (64 registers) 7.8 ms
-    if (kAll && forced == 0 && w512 >= 32) tailwalk_launch<kLines, 512, kAll>(L, P);
-    else if (forced == 384 ? w384 > 0 : (forced == 0 && w384 >= 24 && w384 > w256)) tailwalk_launch<kLines, 384, kAll>(L, P);
-    else if (forced == 512 ? w512 > 0 : (forced == 0 && w512 > w384 && w512 > w256)) tailwalk_launch<kLines, 512, kAll>(L, P);
-    else if (forced == 0 && w384 > w256) tailwalk_launch<kLines, 384, kAll>(L, P);
-    else tailwalk_launch<kLines, 256, kAll>(L, P);
+    if (ch.key != key || ch.device != device || ch.forced != forced) {
+        const int w256 = tailwalk_warps_per_sm<kLines, 256, kAll>(P.t), w384 = tailwalk_warps_per_sm<kLines, 384, kAll>(P.t),
+                  w512 = tailwalk_warps_per_sm<kLines, 512, kAll>(P.t);
+        // measured on config #4 (profiles/README.md, round 2): 16 warps 8.5 ms, 24 warps (2 x 384) 7.34 ms, 32 warps (2 x 512) 7.44 ms
+        // all mode (consecutive lines, small table): measured on config #2 (profiles/README.md round 2): 3 x 256 threads 10.8 ms,
+        // 2 x 384 8.5 ms, 2 x 512 (64 registers) 7.8 ms
+        int t = 256;
+        if (kAll && forced == 0 && w512 >= 32) t = 512;
+        else if (forced == 384 ? w384 > 0 : (forced == 0 && w384 >= 24 && w384 > w256)) t = 384;
+        else if (forced == 512 ? w512 > 0 : (forced == 0 && w512 > w384 && w512 > w256)) t = 512;
+        else if (forced == 0 && w384 > w256) t = 384;
+        ch.key = key;
+        ch.device = device;
+        ch.forced = forced;
+        ch.threads = t;
+        ch.per_sm = (t == 512 ? w512 : t == 384 ? w384 : w256) * 32 / t;
+    }
+    if (ch.threads == 512) tailwalk_launch<kLines, 512, kAll>(L, P, ch.per_sm);
+    else if (ch.threads == 384) tailwalk_launch<kLines, 384, kAll>(L, P, ch.per_sm);
+    else tailwalk_launch<kLines, 256, kAll>(L, P, ch.per_sm);
 }
 
 }  // namespace

@@ -42,6 +42,8 @@ def main():
         timer = next((t for k, t in TIMER_OF if k in name), None)
         if timer == "k0_dfawalk":
             timer = "k0_dfawalk_cut" if "k0_dfawalk_cut" in timers else "k0_dfawalk_scan"
+        if timer == "k4c_tailwalk" and "k4c_fusedwalk" in timers:  # the same kernel in "all" mode (small definitions)
+            timer = "k4c_fusedwalk"
         if timer is None or timer not in timers:
             continue
         a = agg.setdefault(timer, {"dram_read": 0.0, "dram_write": 0.0, "ncu_time_ms": 0.0, "kernels": []})

@@ -4,7 +4,7 @@
 #   tools_ncu_traffic.py) and one ncu --set full capture of the hot kernels (gpurun_out/<tag>_prof_<w>.ncu-rep).
 TAG=${1:-prof}
 mkdir -p gpurun_out
-for spec in "readme 16000000 chunkwalk" "syslog200 16000000 tailwalk|dfawalk|linewalk" "weblog 16000000 tailwalk|linewalk|capwalk" "utf16mix 16000000 tailwalk|linewalk|capwalk" "simple 16000000 chunkwalk"; do
+for spec in "readme 16000000 tailwalk|nl_count" "syslog200 16000000 tailwalk|dfawalk|linewalk" "weblog 16000000 tailwalk|linewalk|capwalk" "utf16mix 16000000 tailwalk|linewalk|capwalk" "simple 16000000 tailwalk"; do
     set -- $spec
     W=$1; LINES=$2; KREGEX=$3
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_$W.csv \
