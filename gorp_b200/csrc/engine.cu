@@ -678,58 +678,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
         // the newline index K1 — lanes claim consecutive lines (kernels/tailwalk.cu, `all` mode): no chunk ownership, no
         // look-back, no bucket pass
         if (fused.available && !std::getenv("GORP_NO_FUSEDWALK")) {
-            const FusedAutomaton& A = fused;
-            const uint32_t Sx = A.n_states, J = A.n_jcls;
-            TailSet FT;
-            std::vector<int32_t> col_of_j(J, -1);
-            std::vector<uint32_t> j_of_col;
-            auto col = [&](uint32_t j) {
-                if (col_of_j[j] < 0) {
-                    col_of_j[j] = static_cast<int32_t>(128 + j_of_col.size());
-                    j_of_col.push_back(j);
-                }
-                return static_cast<uint16_t>(col_of_j[j]);
-            };
-            FT.xcol.resize(65536);
-            for (uint32_t u = 0; u < 128; ++u) FT.xcol[u] = static_cast<uint16_t>(u);
-            for (uint32_t u = 128; u < 65536; ++u) FT.xcol[u] = col(A.jcls[u]);
-            for (uint32_t u = 0xD800; u < 0xDC00; ++u) col(A.pair_of[A.jcls[u]]);
-            FT.nl_data_col = col(A.jcls[0x0A]);
-            for (size_t k = 0; k < j_of_col.size(); ++k) col(A.pair_of[j_of_col[k]]);  // (closes over pairs of pairs: identity)
-            FT.width = static_cast<uint32_t>((128 + j_of_col.size() + 3) & ~size_t(3));
-            FT.pair_col.resize(FT.width);
-            for (uint32_t k = 0; k < FT.width; ++k) FT.pair_col[k] = static_cast<uint16_t>(k);
-            for (size_t k = 0; k < j_of_col.size(); ++k) FT.pair_col[128 + k] = col(A.pair_of[j_of_col[k]]);
-            TailAutomaton TA;
-            TA.available = true;
-            TA.n_states = Sx;
-            TA.trans.assign(static_cast<size_t>(Sx) * FT.width, 0xFFFFu);
-            for (uint32_t r = 0; r < Sx; ++r)
-                for (uint32_t k = 0; k < FT.width; ++k) {
-                    if (k >= 128 && k - 128 >= j_of_col.size()) continue;  // padding column: dead
-                    const uint32_t j = k < 128 ? A.jcls[k] : j_of_col[k - 128];
-                    TA.trans[static_cast<size_t>(r) * FT.width + k] = A.trans[static_cast<size_t>(r) * J + j];
-                }
-            TA.n_op_slots = A.n_op_slots;
-            TA.n_boundaries = std::max(c.max_slots, 1u);
-            TA.outcome_of = A.outcome_of;
-            for (const FusedAutomaton::Outcome& oc : A.outcomes) {  // recipes padded to the row width: 0 = no writer
-                FusedAutomaton::Outcome o2{oc.ext_code, static_cast<uint32_t>(TA.res.size())};
-                const uint32_t n = oc.ext_code >= 0 ? 2 * m.n_groups[oc.ext_code] : 0u;
-                for (uint32_t k = 0; k < TA.n_boundaries; ++k) {
-                    const uint32_t packed = k < n ? A.res[oc.res_off + k] : 0u;
-                    TA.res.push_back(packed);
-                    if (packed >= 256u)  // several writers: their slots are read through a maximum and must be reset per line
-                        for (uint32_t sh = 0; sh < 32 && ((packed >> sh) & 0xFFu); sh += 8) {
-                            const uint32_t id = (packed >> sh) & 0xFFu;
-                            if (id != FusedAutomaton::kLenSlot && std::find(TA.init_slots.begin(), TA.init_slots.end(), id) == TA.init_slots.end())
-                                TA.init_slots.push_back(id);
-                        }
-                }
-                TA.outcomes.push_back(o2);
-            }
-            FT.any = true;
-            FT.tails.push_back(std::move(TA));
+            const TailSet FT = build_fused_tailset(fused, m, c.max_slots);
             const TailImage img = build_tail_image(FT, c.max_slots);
             if (img.available && img.ext[0].available && c.max_slots > 0) {
                 upload_tail_image(img, FT, c.max_slots, c.fused_tail, c.owned);

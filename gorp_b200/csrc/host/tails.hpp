@@ -57,4 +57,10 @@ struct TailSet {
 // and none of its states is cut).
 TailSet build_tails(const CompiledDefinition& def, const DeviceModel& m, size_t max_states = 1000, size_t max_op_slots = 62);
 
+// The one-pass automaton of host/fused.hpp laid out as ONE tail (the "fused walk" of small definitions: every line walks it,
+// behind the newline index): TailSet with a single automaton whose outcomes carry the codes of all extractions; recipes are
+// padded to `span_stride` entries per outcome. Columns >= 128 are the joint classes of units >= 0x80, their PAIR_HI variants
+// and the '\n'-as-content column.
+TailSet build_fused_tailset(const FusedAutomaton& A, const DeviceModel& m, uint32_t span_stride);
+
 }  // namespace gorp

@@ -506,3 +506,67 @@ extern "C" int64_t ht_run_tails(const void* blob, size_t len, const uint16_t* te
         return -1;
     }
 }
+
+// The fused walk (small definitions): the one-pass automaton as ONE tail table (host/tails.hpp: build_fused_tailset) walked by
+// every line [starts[i], ends[i]) the way kernels/tailwalk.cu walks it in "all" mode: state 0, one lookup per unit (a unit
+// >= 0x80 through the column map, a surrogate pair through pair_col, a '\n' inside the line — List<String> form — through
+// nl_data_col), the terminator column at the end of the line, op slots hold position + 1, outcome row -> ext code + recipes.
+// Returns 0, 1 (not available) or -1 (err).
+extern "C" int ht_run_fused_tail(const void* blob, size_t len, const uint16_t* text, const int64_t* starts, const int64_t* ends, int64_t n,
+                                 int32_t* ext, int32_t* spans, int stride, char* err, int errlen) {
+    try {
+        CompiledDefinition def = parse_blob(blob, len);
+        DeviceModel m = build_device_model(def);
+        const FusedAutomaton F = build_fused(m);
+        finalize_device_model(m, F);
+        if (!F.available) {
+            std::snprintf(err, errlen, "%s", F.why_not.c_str());
+            return 1;
+        }
+        const TailSet T = build_fused_tailset(F, m, static_cast<uint32_t>(stride));
+        const TailImage I = build_tail_image(T, static_cast<uint32_t>(stride));
+        if (!I.available || !I.ext[0].available) {
+            std::snprintf(err, errlen, "the fused automaton does not fit the tail image limits");
+            return 1;
+        }
+        const TailImageExt& x = I.ext[0];
+        const uint16_t* tab = I.image.data() + x.tab_off / 2;
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t a = starts[i], b = ends[i];
+            std::vector<uint32_t> slots(64, 0xDEAD);  // garbage on purpose: only the init slots are reset per line
+            for (uint32_t k = 0; k < x.n_init; ++k) slots[I.init_slots[x.init_off + k]] = 0;
+            uint32_t row = 0;
+            for (int64_t p = a; p <= b && row < x.fin_base; ++p) {
+                uint32_t col = 0x0Au;  // the terminator
+                if (p < b) {
+                    const uint32_t u = text[p];
+                    col = u == 0x0Au ? T.nl_data_col : (u < 128 ? u : T.xcol[u]);
+                    if ((u & 0xFC00u) == 0xD800u && p + 1 < b && (text[p + 1] & 0xFC00u) == 0xDC00u) col = T.pair_col[col];
+                }
+                const uint32_t ent = tab[static_cast<size_t>(row) * I.width + col];
+                row = ent >> 6;
+                slots[ent & 63u] = static_cast<uint32_t>(p - a + 1);
+            }
+            const uint32_t o = row - x.fin_base;
+            const int32_t code = I.oext[x.oext_off + o];
+            ext[i] = code;
+            int32_t* out = spans + i * stride;
+            for (int k = 0; k < stride; ++k) {
+                uint32_t rec = I.res[x.res_off + static_cast<size_t>(o) * stride + k];
+                int32_t val = -1;
+                if (code >= 0 && rec == 0xFF) {
+                    val = static_cast<int32_t>(b - a);
+                } else if (code >= 0 && rec) {
+                    uint32_t best = 0;
+                    for (; rec; rec >>= 8) best = std::max(best, slots[rec & 0xFFu]);
+                    val = static_cast<int32_t>(best) - 1;
+                }
+                out[k] = val;
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}

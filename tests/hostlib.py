@@ -48,6 +48,27 @@ def run(blob_bytes: bytes, text: np.ndarray, starts: np.ndarray, ends: np.ndarra
     return ext, spans[:, :stride], stats
 
 
+def run_fused_tail(blob_bytes: bytes, text: np.ndarray, starts: np.ndarray, ends: np.ndarray, stride: int):
+    """Interprets the fused walk's table (the one-pass automaton as one tail image) the way kernels/tailwalk.cu walks it in
+    "all" mode. Returns (ext, spans) or None when the definition gets no one-pass automaton / it exceeds the image limits."""
+    lib = load()
+    text = np.ascontiguousarray(text, dtype=np.uint16)
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    ends = np.ascontiguousarray(ends, dtype=np.int64)
+    n = len(starts)
+    ext = np.empty(n, dtype=np.int32)
+    spans = np.full((n, max(stride, 1)), -1, dtype=np.int32)
+    err = C.create_string_buffer(1024)
+    P = C.c_void_p
+    rc = lib.ht_run_fused_tail(blob_bytes, C.c_size_t(len(blob_bytes)), P(text.ctypes.data), P(starts.ctypes.data), P(ends.ctypes.data),
+                               C.c_int64(n), P(ext.ctypes.data), P(spans.ctypes.data), C.c_int(max(stride, 1)), err, C.c_int(1024))
+    if rc == 1:
+        return None
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return ext, spans[:, :stride]
+
+
 def run_walk(blob_bytes: bytes, text: np.ndarray, stride: int, smem_variant: bool):
     """Interprets the tables of the big-definition text path (host/walktables.hpp) the way kernels/dfawalk.cu and
     kernels/capwalk.cu walk them. Returns (ext, spans) or None when the tables are not available."""

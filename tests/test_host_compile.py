@@ -67,6 +67,37 @@ def test_one_pass_automaton_reproduces_oracle(case):
     assert stats[0] == 1
 
 
+def compare_fused_walk(definition, lines):
+    """The fused walk's table (host/tails.hpp: build_fused_tailset -> TailImage), interpreted as kernels/tailwalk.cu walks it in
+    "all" mode, against the oracle — text form ('\n'-separated) and List<String> form (a '\n' inside a string is content)."""
+    g = DefinitionReader.reader(definition).read()
+    o = gorp_oracle.Gorp(definition)
+    G = max(len(x.extractor_names) for x in o.extractions)
+    text, starts, ends = pack(lines)
+    got = hostlib.run_fused_tail(g.blob().bytes(), text, starts, ends, 2 * G)
+    if got is None:
+        return False
+    oe, osp = o.extract_batch(text, (starts, ends), threads=1)
+    bad = [i for i in range(len(lines)) if got[0][i] != oe[i] or (got[1][i] != osp[i]).any()]
+    assert not bad, [(lines[i], int(got[0][i]), int(oe[i]), got[1][i].tolist(), osp[i].tolist()) for i in bad[:5]]
+    # List<String> form: strings that hold a '\n'
+    withnl = [s for s in lines if s] + ["a\nb", "[1]: GET 2ms /a\n", "\n"]
+    units = [np.asarray(jdkre.to_units(s), dtype=np.uint16) for s in withnl]
+    off = np.zeros(len(withnl) + 1, dtype=np.int64)
+    np.cumsum([len(u) for u in units], out=off[1:])
+    flat = np.concatenate(units).astype(np.uint16)
+    got = hostlib.run_fused_tail(g.blob().bytes(), flat, off[:-1], off[1:], 2 * G)
+    oe, osp = o.extract_batch(flat, off, threads=1)
+    bad = [i for i in range(len(withnl)) if got[0][i] != oe[i] or (got[1][i] != osp[i]).any()]
+    assert not bad, [(withnl[i], int(got[0][i]), int(oe[i]), got[1][i].tolist(), osp[i].tolist()) for i in bad[:5]]
+    return True
+
+
+@pytest.mark.parametrize("case", ALL_DEFS)
+def test_fused_walk_table_reproduces_oracle(case):
+    assert compare_fused_walk(case[0], [c[0] for c in case[1]] + TRICKY_LINES)
+
+
 @pytest.mark.parametrize("case", ALL_DEFS)
 def test_exported_tables_are_the_reference_tables(case):
     """The blob holds Automata._alphabet/_transitions/_accept exactly as the oracle's restatement builds them."""
@@ -137,6 +168,13 @@ FUZZ_PATTERNS = [
     "extract a {\n template $x(%{(a|b)*})$y(%{(ab)*})$z(%{b?a?})\n}\n",
     "extract a {\n template $o($i(%{a*})$j(%{b*}))$k(%{[ab]*})\n}\n",
 ]
+
+
+@pytest.mark.parametrize("definition", FUZZ_PATTERNS)
+def test_fused_walk_table_fuzz(definition):
+    rng = np.random.default_rng(5)
+    lines = ["".join(rng.choice(list("abcd: "), size=int(rng.integers(0, 9)))) for _ in range(400)]
+    compare_fused_walk(definition, lines)
 
 
 @pytest.mark.parametrize("definition", FUZZ_PATTERNS)
