@@ -146,6 +146,8 @@ struct DeviceCtx {
     bool fusedwalk_default = false;  // small definitions: K1 + fused walk instead of the chunk-owner kernel K0c (GORP_SMALL_PATH)
     bool cut_effective = false;  // most states of the combined DFA are cut: the chunk-owner walk with early exit (K0d cut)
     uint32_t tail_flush_every = 8;  // walk iterations per round of the tail walk (GORP_TAIL_FLUSH)
+    uint32_t item_lines = kCapItemLines;  // work items of the capture walks (GORP_ITEM_LINES)
+    bool item_interleave = false;         // ... listed by relative position inside their bucket (GORP_ITEM_ORDER=1)
     DevBuf long_lines, recs;
     CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
     bool force_k4 = false;       // GORP_FORCE_K4=1: one-line-per-thread capture kernels (K4) instead of the bucketed K4b
@@ -1244,7 +1246,19 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
         k3_histogram(L, c.ext_id.as<int32_t>(), n_lines, E, c.hist.as<unsigned long long>());
         tm.mark("k3_histogram", 1);
         hist_done = true;
-        const size_t max_items = nl / kCapItemLines + E + 1;
+        // work items of the two capture walks: `item_lines` entries of one bucket, listed bucket by bucket or (GORP_ITEM_ORDER=1)
+        // by relative position inside the bucket, so that concurrent items cover the same stretch of text
+        // measured on config #4 (200 buckets, profiles/README.md round 2): bucket by bucket, 4096 lines 6.77 ms; by relative
+        // position 4096 / 2048 / 1024 / 512 lines 6.02 / 5.92 / 6.23 / 7.60 ms (DRAM read 1.99x -> 1.58x the text; below 2048 the
+        // barrier and table load per item cost more than the locality brings), with 2 x 512 threads 5.78 ms. Config #3 (18
+        // buckets): 6.88 -> 7.11 ms — the concurrent items of a few big buckets never share text, so only many-bucket
+        // definitions get the interleaved order.
+        uint32_t item_lines = E >= 64 ? 2048u : c.item_lines;
+        bool interleave = E >= 64 ? true : c.item_interleave;
+        if (const char* f = std::getenv("GORP_ITEM_LINES")) item_lines = static_cast<uint32_t>(std::atoi(f));
+        if (const char* f = std::getenv("GORP_ITEM_ORDER")) interleave = f[0] == '1';
+        if (item_lines < 32 || item_lines > kCapItemLines) item_lines = kCapItemLines;
+        const size_t max_items = nl / item_lines + E + 1;
         c.perm.reserve(nl * 4 + 16);
         c.items.reserve(max_items * sizeof(CapItem));
         c.buckets.reserve((2 * static_cast<size_t>(E) + 8) * 4);
@@ -1261,7 +1275,7 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
         }
         k4b_bucket(L, c.ext_id.as<int32_t>(), n_lines, E, c.hist.as<unsigned long long>(), bucket_base, cursor, c.perm.as<uint32_t>(),
                    c.items.as<CapItem>(), n_items, item_ticket, c.spans.as<int32_t>(), stride, tails ? d_line_off : nullptr,
-                   tails ? c.recs.as<LineRec>() : nullptr, sep, tails ? c.tails.ext : nullptr);
+                   tails ? c.recs.as<LineRec>() : nullptr, sep, tails ? c.tails.ext : nullptr, item_lines, interleave);
         tm.mark("k4b_bucket", 2);
         CapWalkParams W{};
         W.text = d_text;
@@ -1293,6 +1307,7 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
             T.n_ext = E;
             T.round_iters = c.tail_flush_every;
             T.lines_form = sep == 0 ? 1u : 0u;
+            T.prefer_threads = interleave ? 512u : 0u;
             if (const char* f = std::getenv("GORP_TAIL_FLAGS")) T.flags = static_cast<uint32_t>(std::atoi(f));
             T.recs = c.recs.as<LineRec>();
             T.ext_id = W.ext_id;

@@ -28,12 +28,22 @@ constexpr int kBucketThreads = 256;
 constexpr int kBucketSeg = 4096;  // lines per CTA of the scatter pass
 
 // ------------------------------------------------------------------ bucket plan (one CTA)
+// Work items = `item_lines` consecutive entries of one bucket. With `interleave` the items are listed in order of their
+// RELATIVE position inside their bucket ((j + 1/2) / items of the bucket, quantised to kPlanBins classes) instead of bucket
+// by bucket: the lines of an extraction are spread over the whole text, so items with the same relative position cover the
+// same stretch of text — the CTAs that work through the list at the same time then share that stretch in L2 (the 128-byte
+// lines at both ends of every text line are shared with its neighbours, which belong to other buckets).
+constexpr uint32_t kPlanBins = 2048;
+
 __global__ void __launch_bounds__(1024) bucket_plan_kernel(const unsigned long long* __restrict__ hist, uint32_t n_ext,
                                                            uint32_t* __restrict__ bucket_base /* [E+1] */,
                                                            uint32_t* __restrict__ cursor /* [E] */, CapItem* __restrict__ items,
-                                                           uint32_t* __restrict__ n_items_out, uint32_t* __restrict__ item_ticket) {
+                                                           uint32_t* __restrict__ n_items_out, uint32_t* __restrict__ item_ticket,
+                                                           uint32_t item_lines, uint32_t interleave) {
     __shared__ uint32_t s_item_base[kCapMaxBuckets + 1];
     __shared__ uint32_t s_base[kCapMaxBuckets + 1];
+    __shared__ uint32_t s_bin[kPlanBins];
+    __shared__ uint32_t s_warp[32];
     for (uint32_t e = threadIdx.x; e < n_ext; e += blockDim.x) s_base[e] = static_cast<uint32_t>(hist[e]);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -43,7 +53,7 @@ __global__ void __launch_bounds__(1024) bucket_plan_kernel(const unsigned long l
             s_base[e] = run;
             s_item_base[e] = irun;
             run += n;
-            irun += (n + kCapItemLines - 1) / kCapItemLines;
+            irun += (n + item_lines - 1) / item_lines;
         }
         s_base[n_ext] = run;
         s_item_base[n_ext] = irun;
@@ -53,15 +63,63 @@ __global__ void __launch_bounds__(1024) bucket_plan_kernel(const unsigned long l
     __syncthreads();
     for (uint32_t e = threadIdx.x; e <= n_ext; e += blockDim.x) {
         bucket_base[e] = s_base[e];
-        if (e < n_ext) {
-            cursor[e] = s_base[e];
-            const uint32_t b0 = s_base[e], b1 = s_base[e + 1];
-            uint32_t k = s_item_base[e];
-            for (uint32_t b = b0; b < b1; b += kCapItemLines, ++k) {
-                const uint32_t end = b + kCapItemLines < b1 ? b + kCapItemLines : b1;
-                items[k] = CapItem{e, b, end};
-            }
+        if (e < n_ext) cursor[e] = s_base[e];
+    }
+    const uint32_t n_items = s_item_base[n_ext];
+    // item i of the bucket-by-bucket numbering: its bucket (the last one whose first item is <= i), its index inside it
+    auto locate = [&](uint32_t i, uint32_t& e, uint32_t& j, uint32_t& key) {
+        uint32_t lo = 0, hi = n_ext;  // first bucket whose base is > i
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_item_base[mid] <= i) lo = mid + 1;
+            else hi = mid;
         }
+        e = lo - 1;
+        j = i - s_item_base[e];
+        const uint32_t n = s_item_base[e + 1] - s_item_base[e];
+        key = min(kPlanBins - 1u, ((2u * j + 1u) * (kPlanBins / 2u)) / n);
+    };
+    auto put = [&](uint32_t at, uint32_t e, uint32_t j) {
+        const uint32_t b = s_base[e] + j * item_lines, b1 = s_base[e + 1];
+        items[at] = CapItem{e, b, b + item_lines < b1 ? b + item_lines : b1};
+    };
+    if (!interleave) {
+        for (uint32_t i = threadIdx.x; i < n_items; i += blockDim.x) {
+            uint32_t e, j, key;
+            locate(i, e, j, key);
+            put(i, e, j);
+        }
+        return;
+    }
+    for (uint32_t k = threadIdx.x; k < kPlanBins; k += blockDim.x) s_bin[k] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_items; i += blockDim.x) {
+        uint32_t e, j, key;
+        locate(i, e, j, key);
+        atomicAdd(&s_bin[key], 1u);
+    }
+    __syncthreads();
+    {  // exclusive scan of the kPlanBins counts: two bins per thread (blockDim.x == 1024)
+        const uint32_t c0 = s_bin[2 * threadIdx.x], c1 = s_bin[2 * threadIdx.x + 1];
+        uint32_t incl = c0 + c1;
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= static_cast<uint32_t>(o)) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (uint32_t w = 0; w < warp; ++w) wbase += s_warp[w];
+        s_bin[2 * threadIdx.x] = wbase + incl - c0 - c1;
+        s_bin[2 * threadIdx.x + 1] = wbase + incl - c1;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_items; i += blockDim.x) {
+        uint32_t e, j, key;
+        locate(i, e, j, key);
+        put(atomicAdd(&s_bin[key], 1u), e, j);
     }
 }
 
@@ -391,8 +449,10 @@ __global__ void __launch_bounds__(kCapWalkThreads, 4) capwalk_kernel(CapWalkPara
 
 void k4b_bucket(const Launch& L, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, const unsigned long long* hist,
                 uint32_t* bucket_base, uint32_t* cursor, uint32_t* perm, CapItem* items, uint32_t* n_items, uint32_t* item_ticket,
-                int32_t* spans, uint32_t span_stride, const int64_t* line_off, LineRec* recs, int sep, const TailExt* tails) {
-    bucket_plan_kernel<<<1, 1024, 0, L.stream>>>(hist, n_ext, bucket_base, cursor, items, n_items, item_ticket);
+                int32_t* spans, uint32_t span_stride, const int64_t* line_off, LineRec* recs, int sep, const TailExt* tails,
+                uint32_t item_lines, bool interleave) {
+    if (item_lines < 32 || item_lines > kCapItemLines) item_lines = kCapItemLines;
+    bucket_plan_kernel<<<1, 1024, 0, L.stream>>>(hist, n_ext, bucket_base, cursor, items, n_items, item_ticket, item_lines, interleave ? 1u : 0u);
     if (n_lines <= 0) return;
     const int64_t want = (n_lines + kBucketSeg - 1) / kBucketSeg, cap = static_cast<int64_t>(L.sm_count) * 8;
     bucket_scatter_kernel<<<static_cast<int>(want < cap ? want : cap), kBucketThreads, 0, L.stream>>>(ext_id, n_lines, n_ext, cursor, perm, spans,

@@ -296,7 +296,8 @@ struct TailExt;
 void k4b_bucket(const Launch&, const int32_t* ext_id, int64_t n_lines, uint32_t n_ext, const unsigned long long* hist,
                 uint32_t* bucket_base, uint32_t* cursor, uint32_t* perm, CapItem* items, uint32_t* n_items, uint32_t* item_ticket,
                 int32_t* spans, uint32_t span_stride, const int64_t* line_off = nullptr, LineRec* recs = nullptr, int sep = 1,
-                const TailExt* tails = nullptr);  // tails (with recs): extractions whose lines only need a record, no `perm` entry
+                const TailExt* tails = nullptr,  // tails (with recs): extractions whose lines only need a record, no `perm` entry
+                uint32_t item_lines = kCapItemLines, bool interleave = false);  // work items: size, bucket by bucket / by relative position
 size_t capwalk_smem_bytes(const CapImgDev&);
 void k4b_capwalk(const Launch&, const CapWalkParams&);
 
@@ -349,6 +350,7 @@ struct TailWalkParams {
     uint32_t long_cap;
     // "all" mode (fused walk): t holds ONE table (the one-pass automaton of host/fused.hpp) that every line walks; no buckets,
     // no records — work item i = lines [i * kCapItemLines, ...) of line_off, ext_id / hist are written for every line
+    uint32_t prefer_threads;     // CTA size the caller measured best for this work-item order (0 = by resident warps); GORP_TAIL_THREADS wins
     uint32_t all;
     uint32_t item_lines;         // lines per work item in "all" mode (<= kCapItemLines; smaller for small batches: enough items for every CTA)
     int64_t n_lines;

@@ -579,7 +579,7 @@ void tailwalk_dispatch(const Launch& L, const TailWalkParams& P) {
     const size_t key = tailwalk_smem_bytes(P.t, 256);
     int device = 0;
     cudaGetDevice(&device);
-    int forced = 0;
+    int forced = static_cast<int>(P.prefer_threads);
     if (const char* f = std::getenv("GORP_TAIL_THREADS")) forced = std::atoi(f);
     if (ch.key != key || ch.device != device || ch.forced != forced) {
         const int w256 = tailwalk_warps_per_sm<kLines, 256, kAll>(P.t), w384 = tailwalk_warps_per_sm<kLines, 384, kAll>(P.t),
