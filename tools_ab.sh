@@ -1,9 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/r3u_pytest.log 2>&1; tail -n 4 gpurun_out/r3u_pytest.log
-python bench.py > gpurun_out/r3u_bench_n1.json 2> gpurun_out/r3u_bench_n1.err; tail -c 300 gpurun_out/r3u_bench_n1.err
-python bench.py --impl reference > gpurun_out/r3u_bench_ref.json 2> gpurun_out/r3u_bench_ref.err; tail -c 300 gpurun_out/r3u_bench_ref.err
-W=syslog200
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r3u_launches_$W.csv \
-   python bench.py --workload $W --steps 1 --warmup 3 --lines-per-gpu 16000000 --skip-e2e --skip-cpu --configs "" > gpurun_out/r3u_launches_$W.json 2> gpurun_out/r3u_launches_$W.err
-ncu --set full --clock-control none --import-source on -k regex:"tailwalk_kernel" -s 3 -c 1 -f -o gpurun_out/r3u_prof_$W \
-   python bench.py --workload $W --steps 1 --warmup 3 --lines-per-gpu 16000000 --skip-e2e --skip-cpu --configs "" > gpurun_out/r3u_prof_$W.log 2>&1
+python -m pytest tests -m gpu -x -q -k "multi_device or sharding or concurrent" > gpurun_out/r3v_pytest_2gpu.log 2>&1; tail -n 3 gpurun_out/r3v_pytest_2gpu.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/r3v_bench_n2.json 2> gpurun_out/r3v_bench_n2.err; tail -c 400 gpurun_out/r3v_bench_n2.err
