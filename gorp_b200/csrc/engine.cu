@@ -151,8 +151,9 @@ struct DeviceCtx {
     DevBuf long_lines, recs;
     CapImgDev capimg{};          // per-extraction capture tables of kernels/capwalk.cu (text form, any definition)
     bool force_k4 = false;       // GORP_FORCE_K4=1: one-line-per-thread capture kernels (K4) instead of the bucketed K4b
-    DevBuf perm, items, buckets, nl_masks;
-    int dfa_tier = 0;            // GORP_DFA_TIER: 0 = by line length, 1 = chunk-owner walk (K0d), 2 = line index + lane queue (K1 + K2b)
+    DevBuf perm, items, buckets, nl_masks, cand_tmp;
+    int dfa_tier = 0;            // GORP_DFA_TIER: 0 = by line length, 1 = chunk-owner walk (K0d), 2 = line index + lane queue (K1 + K2b),
+                                 // 3 = line index with the head walk inside its count pass (K1h)
     bool force_k1k2 = false;     // GORP_FORCE_K1K2=1: newline index + DFA scan as separate kernels (K1, K2) instead of K0d
     bool force_tiles = false;    // GORP_FORCE_TILES=1: the TMA-staged tile kernel instead of the chunk-walk kernel
     uint32_t onepass_shrink = 0;  // too-dense retries remembered across calls
@@ -1086,7 +1087,7 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
                             cudaStream_t stream, bool timed, gorp_device_result* out) {
     Launch L{stream, c.sm_count};
     Timer tm(c, stream, timed);
-    c.scalars.reserve(64);
+    c.scalars.reserve(128);
     int64_t* d_n_lines = c.scalars.as<int64_t>();
     const int64_t* d_line_off;
     int sep;
@@ -1104,7 +1105,7 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
     // its lines and skips from line to line through the newline masks of the pre-scan — one pass over the text
     const bool tails_ok = c.tails.enabled && !c.cap.match_only && c.max_slots > 0 && !c.force_general && !c.force_k4 && !c.force_k1k2;
     const bool cut_walk = !d_off && tails_ok && c.cut_effective && c.dfa_tier != 2 && c.dfa_tier != 1;
-    const bool by_lines = !cut_walk && (c.dfa_tier == 2 || (c.dfa_tier == 0 && c.lines_per_unit < 1.0 / 100.0));
+    const bool by_lines = !cut_walk && (c.dfa_tier == 2 || c.dfa_tier == 3 || (c.dfa_tier == 0 && c.lines_per_unit < 1.0 / 100.0));
     bool cut_scanned = false;
     if (!d_off && !by_lines && !fusedwalk && run_dfawalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, ends_with_nl, cut_walk)) {
         sep = 1;
@@ -1118,29 +1119,67 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
         c.tile_base.reserve(static_cast<size_t>(n_tiles + 2) * 8);
         c.scan_scratch.reserve(static_cast<size_t>(n_tiles / 4096 + 8) * 8);
         const bool with_masks = !c.force_k1k2 && !c.force_general;  // the count pass leaves the '\n' masks for the scatter pass
+        // K1h (tier GORP_DFA_TIER=3, off by default): the count pass also walks the line heads over the (early-exit) combined-DFA
+        // table — the text of a tile is walked while it is in L2, and K2b's pass over the text is gone. The candidates are
+        // parked per tile and reach ext_id in the scatter pass; K2b takes over when a tile is too dense. Measured (profiles/
+        // README.md round 2): config #4 5.39 ms against 1.92 + 1.86 ms for K1 + K2b, config #3 17.8 against 2.4 + 4.0 ms — a
+        // CTA alternates between a streaming phase and a walk phase with one line per thread, and neither overlaps the other
+        // well enough; K2b's lanes that claim lines from a queue keep 48 warps per SM walking.
+        const DfaWalkDev& head_table = tails_ok ? c.dfawalk_cut : c.dfawalk;
+        bool headwalk = with_masks && !fusedwalk && !c.cap.match_only && !c.force_k4 && c.dfa_tier == 3 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0 &&
+                        n_units < (1ll << 40) && k1h_plan(head_table);
+        uint32_t* hw_scalars = nullptr;
         if (with_masks) {
-            c.nl_masks.reserve(static_cast<size_t>(n_tiles) * 256 * 4);
-            k1_count_newlines_masks(L, d_text, n_units, c.tile_counts.as<uint32_t>(), c.nl_masks.as<uint32_t>());
+            c.nl_masks.reserve(static_cast<size_t>(n_tiles + 4) * 256 * 4);
+            if (headwalk) {
+                c.cand_tmp.reserve(static_cast<size_t>(n_tiles + 4) * kHwCap * 2);
+                hw_scalars = reinterpret_cast<uint32_t*>(d_n_lines + 8);  // 3 words of the scalar block
+                CK(cudaMemsetAsync(hw_scalars, 0, 12, stream));
+                HeadWalkParams H{};
+                H.text = d_text;
+                H.n_units = n_units;
+                H.a = head_table;
+                H.tile_counts = c.tile_counts.as<uint32_t>();
+                H.masks = c.nl_masks.as<uint32_t>();
+                H.cand = c.cand_tmp.as<uint16_t>();
+                H.scalars = hw_scalars;
+                k1h_count_headwalk(L, H);
+            } else {
+                k1_count_newlines_masks(L, d_text, n_units, c.tile_counts.as<uint32_t>(), c.nl_masks.as<uint32_t>());
+            }
         } else {
             k1_count_newlines(L, d_text, n_units, c.tile_counts.as<uint32_t>());
         }
-        tm.mark("k1_count_newlines", 1);
+        tm.mark(headwalk ? "k1h_count_headwalk" : "k1_count_newlines", 1);
         scan_u32_to_i64(L, c.tile_counts.as<uint32_t>(), n_tiles, c.tile_base.as<int64_t>(), c.scan_scratch.as<int64_t>());
         tm.mark("scan_tiles", 3);
         // the one host round trip of the text form: the newline total (and the last unit) size the per-line arrays
         int64_t total_nl = 0;
         uint16_t last_unit = 0x0A;
+        uint32_t hw_dense = 0;
         CK(cudaMemcpyAsync(&total_nl, c.tile_base.as<int64_t>() + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
         if (n_units > 0) CK(cudaMemcpyAsync(&last_unit, d_text + n_units - 1, 2, cudaMemcpyDeviceToHost, stream));
+        if (headwalk) CK(cudaMemcpyAsync(&hw_dense, hw_scalars + 1, 4, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         n_lines = total_nl + (last_unit != 0x0A ? 1 : 0);
         ends_with_nl = last_unit == 0x0A;
         if (n_units > 0) c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
         c.line_off.reserve(static_cast<size_t>(total_nl + 3) * 8);
-        if (with_masks) k1_scatter_masks(L, c.nl_masks.as<uint32_t>(), n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
+        // the candidates are those of `head_table`: usable when the stages below make the same choice (with_tails) and no tile
+        // overflowed its candidate slots
+        headwalk = headwalk && !hw_dense && n_lines > 0 && n_lines < (1ll << 32);
+        if (headwalk) c.ext_id.reserve((static_cast<size_t>(n_lines) + 1) * 4);
+        if (with_masks)
+            k1_scatter_masks(L, c.nl_masks.as<uint32_t>(), n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>(),
+                             headwalk ? c.cand_tmp.as<uint16_t>() : nullptr, headwalk ? hw_scalars + 2 : nullptr,
+                             headwalk ? c.ext_id.as<int32_t>() : nullptr);
         else k1_scatter_newlines(L, d_text, n_units, c.tile_base.as<int64_t>(), c.line_off.as<int64_t>());
         k1_finish(L, d_text, n_units, c.tile_base.as<int64_t>() + n_tiles, c.line_off.as<int64_t>(), d_n_lines);
         tm.mark("k1_scatter_newlines", 2);
+        if (headwalk) {
+            scanned = true;
+            cut_scanned = tails_ok;
+        }
         d_line_off = c.line_off.as<int64_t>();
     } else {
         sep = 0;

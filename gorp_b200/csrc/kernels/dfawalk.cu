@@ -472,6 +472,162 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
     }
 }
 
+// ------------------------------------------------------------------ K1h: newline count + head walk in one pass
+// A CTA of 256 threads takes super-tiles of 4 x kNlTile = 32768 units by ticket. Phase 1 is K1's count pass (thread t reads
+// units [128 t, 128 t + 128) with streaming 128-bit loads, leaves the 4 newline mask words and the per-tile counts); the line
+// starts of the super-tile (~230 of them) are listed in shared memory by (tile, ordinal of their '\n' inside the tile).
+// Phase 2: thread i walks the head of line i over the early-exit table in shared memory (the text is in L2 from phase 1)
+// and parks the FIN row it reaches in cand[tile * kHwCap + ordinal]. Other CTAs of the SM stream while this one walks.
+constexpr int kHwThreads = 256;
+constexpr int kHwTiles = 4;
+static_assert(kHwThreads * 128 == kHwTiles * kNlTile, "a thread of K1h covers 128 units");
+
+__device__ __forceinline__ uint4 hw_ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t hw_walk_head(const HeadWalkParams& P, int64_t start, uint32_t cx_abs, uint32_t tab_abs, uint32_t row_bytes) {
+    const DfaWalkDev& A = P.a;
+    int64_t q = start & ~int64_t(15);
+    const uint32_t lo = static_cast<uint32_t>(start - q);
+    uint32_t st = lo ? A.n_states + lo : 0u;
+    while (st < A.fin_base) {
+        const Units16 u = load_units16_l2keep(P.text, q, P.n_units);
+        if (((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+            st = dw_step<true, 0>(st, u.a.x, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 2>(st, u.a.x, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 0>(st, u.a.y, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 2>(st, u.a.y, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 0>(st, u.a.z, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 2>(st, u.a.z, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 0>(st, u.a.w, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 2>(st, u.a.w, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 0>(st, u.b.x, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 2>(st, u.b.x, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 0>(st, u.b.y, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 2>(st, u.b.y, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 0>(st, u.b.z, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 2>(st, u.b.z, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 0>(st, u.b.w, cx_abs, row_bytes, nullptr);
+            st = dw_step<true, 2>(st, u.b.w, cx_abs, row_bytes, nullptr);
+        } else {
+            st = dw_slow8<true>(A, st, u.a, cx_abs, tab_abs, row_bytes, nullptr);
+            st = dw_slow8<true>(A, st, u.b, cx_abs, tab_abs, row_bytes, nullptr);
+        }
+        q += 16;
+    }
+    return st - A.fin_base;
+}
+
+__global__ void __launch_bounds__(kHwThreads) headwalk_count_kernel(HeadWalkParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DfaWalkDev& A = P.a;
+    const uint32_t row_bytes = A.K * 2;
+    const uint32_t table_bytes = (A.n_rows * row_bytes + 15u) & ~15u;
+    uint32_t* s_cx = reinterpret_cast<uint32_t*>(smem + table_bytes);
+    uint16_t* s_start = reinterpret_cast<uint16_t*>(s_cx + 128);  // [kHwTiles][kHwCap] super-tile-relative start - 1 of a line
+    __shared__ uint32_t s_wsum[kHwThreads / 32];
+    __shared__ long long s_super;
+    const uint32_t tab_abs = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const uint32_t cx_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_cx));
+    {
+        const uint32_t n16 = (A.n_rows * row_bytes + 15u) / 16u;
+        const uint4* src = reinterpret_cast<const uint4*>(A.table);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (uint32_t i = threadIdx.x; i < n16; i += kHwThreads) dst[i] = __ldg(src + i);
+    }
+    for (uint32_t i = threadIdx.x; i < 128; i += kHwThreads) s_cx[i] = tab_abs + __ldg(A.cls128 + i);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int64_t n_tiles = (P.n_units + kNlTile - 1) / kNlTile;
+    const int64_t n_super = (n_tiles + kHwTiles - 1) / kHwTiles;
+    for (;;) {
+        __syncthreads();  // table ready (first iteration); the previous super-tile no longer uses s_start / s_wsum
+        if (threadIdx.x == 0) s_super = static_cast<long long>(atomicAdd(P.scalars, 1u));
+        __syncthreads();
+        const int64_t sup = s_super;
+        if (sup >= n_super) break;
+        const int64_t base_u = sup * (kHwTiles * static_cast<int64_t>(kNlTile));
+        // ---- phase 1: the count pass of K1
+        uint32_t m[4];
+        const int64_t mine = base_u + static_cast<int64_t>(threadIdx.x) * 128;
+        if (mine + 128 <= P.n_units) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.text + mine);
+            uint4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = hw_ld_stream(src + j);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 x = v[w * 4 + j];
+                    mask |= (nl_bits4(x.x, x.y) | (nl_bits4(x.z, x.w) << 4)) << (j * 8);
+                }
+                m[w] = mask;
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                uint32_t mask = 0;
+                for (int k = 0; k < 32; ++k) {
+                    const int64_t p = mine + w * 32 + k;
+                    if (p < P.n_units && P.text[p] == 0x0A) mask |= 1u << k;
+                }
+                m[w] = mask;
+            }
+        }
+        const int64_t tile = sup * kHwTiles + (warp >> 1);  // the kNlTile tile of this warp pair (64 threads x 128 units)
+        if (tile < n_tiles) *reinterpret_cast<uint4*>(P.masks + tile * 256 + (threadIdx.x & 63u) * 4) = make_uint4(m[0], m[1], m[2], m[3]);
+        const uint32_t cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= static_cast<uint32_t>(o)) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        const uint32_t g = warp >> 1;
+        const uint32_t c_g = s_wsum[2 * g] + s_wsum[2 * g + 1];
+        uint32_t ord = ((warp & 1u) ? s_wsum[warp - 1] : 0u) + incl - cnt;
+        if ((threadIdx.x & 63u) == 0 && tile < n_tiles) {
+            P.tile_counts[tile] = c_g;
+            if (c_g > kHwCap) atomicOr(P.scalars + 1, 1u);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t mm = m[w];
+            while (mm) {
+                const uint32_t k = static_cast<uint32_t>(__ffs(mm)) - 1u;
+                mm &= mm - 1;
+                if (ord < kHwCap) s_start[g * kHwCap + ord] = static_cast<uint16_t>(threadIdx.x * 128u + w * 32u + k);  // position of the '\n'
+                ++ord;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: the heads of the lines that follow those newlines
+        uint32_t n_g[kHwTiles], total = 0;
+#pragma unroll
+        for (int t = 0; t < kHwTiles; ++t) {
+            n_g[t] = min(s_wsum[2 * t] + s_wsum[2 * t + 1], kHwCap);
+            total += n_g[t];
+        }
+        for (uint32_t i = threadIdx.x; i < total; i += kHwThreads) {
+            uint32_t t = 0, o = i;
+#pragma unroll
+            for (int k = 0; k < kHwTiles - 1; ++k)
+                if (t == static_cast<uint32_t>(k) && o >= n_g[k]) o -= n_g[k], ++t;
+            const int64_t start = base_u + s_start[t * kHwCap + o] + 1;
+            uint32_t c = 0;
+            if (start < P.n_units) c = hw_walk_head(P, start, cx_abs, tab_abs, row_bytes);
+            P.cand[(sup * kHwTiles + t) * static_cast<int64_t>(kHwCap) + o] = static_cast<uint16_t>(c);
+        }
+        if (sup == 0 && threadIdx.x == kHwThreads - 1 && P.n_units > 0) P.scalars[2] = hw_walk_head(P, 0, cx_abs, tab_abs, row_bytes);
+    }
+}
+
 }  // namespace
 
 size_t dfawalk_smem_bytes(const DfaWalkDev& a, uint32_t threads, bool in_smem, bool cut) {
@@ -541,6 +697,21 @@ void k0_dfawalk_scan(const Launch& L, const DfaWalkParams& P, uint32_t threads, 
 
 size_t linewalk_smem_bytes(const DfaWalkDev& a, bool in_smem) {
     return (in_smem ? ((static_cast<size_t>(a.n_rows) * a.K * 2 + 15) & ~size_t(15)) : 0) + 128 * 4 + 128;
+}
+
+static size_t headwalk_smem_bytes(const DfaWalkDev& a) {
+    return ((static_cast<size_t>(a.n_rows) * a.K * 2 + 15) & ~size_t(15)) + 128 * 4 + static_cast<size_t>(kHwTiles) * kHwCap * 2 + 128;
+}
+
+bool k1h_plan(const DfaWalkDev& a) { return a.enabled && a.fin_base + 65535u > a.n_rows && headwalk_smem_bytes(a) <= 110 * 1024; }
+
+void k1h_count_headwalk(const Launch& L, const HeadWalkParams& P) {
+    if (P.n_units <= 0) return;
+    const size_t smem = headwalk_smem_bytes(P.a);
+    allow_max_dynamic_smem(headwalk_count_kernel);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, headwalk_count_kernel, kHwThreads, smem);
+    headwalk_count_kernel<<<L.sm_count * (per_sm < 1 ? 1 : per_sm), kHwThreads, smem, L.stream>>>(P);
 }
 
 bool k2b_linewalk_plan(const DfaWalkDev& a, uint32_t* threads, bool* in_smem) {

@@ -119,7 +119,9 @@ void k1_scatter_newlines(const Launch&, const uint16_t* text, int64_t n_units, c
 // same pair with the '\n' masks (one u32 per 32 units, ceil(n_units / kNlTile) * 256 words) as a side product of the
 // count pass: the scatter pass then reads the masks instead of the text (one HBM pass over the text instead of two)
 void k1_count_newlines_masks(const Launch&, const uint16_t* text, int64_t n_units, uint32_t* tile_counts, uint32_t* masks);
-void k1_scatter_masks(const Launch&, const uint32_t* masks, int64_t n_units, const int64_t* tile_base, int64_t* line_off);
+// cand / cand0 / ext_id (K1h): the candidates parked per tile go to ext_id[line] on the way (cand0: the line at offset 0)
+void k1_scatter_masks(const Launch&, const uint32_t* masks, int64_t n_units, const int64_t* tile_base, int64_t* line_off,
+                      const uint16_t* cand = nullptr, const uint32_t* cand0 = nullptr, int32_t* ext_id = nullptr);
 void k1_finish(const Launch&, const uint16_t* text, int64_t n_units, const int64_t* total_newlines, int64_t* line_off,
                int64_t* n_lines_out);
 
@@ -246,6 +248,23 @@ struct LineWalkParams {
     uint32_t flags;              // GORP_WALK_FLAGS (diagnostics): 1 = text loads L2 evict-first
     uint32_t lines_form;         // 1: List<String> form — line i = [line_off[i], line_off[i+1]), a '\n' is content
 };
+// K1h: the count pass of the newline index (K1) and the combined-DFA walk of the line HEADS (K2b over the early-exit table) in
+// one pass over the text — see kernels/dfawalk.cu. The line index of a line is not known yet (the prefix sums come later),
+// so the candidate of the line that follows the j-th '\n' of an 8192-unit tile is parked in cand[tile * kHwCap + j] (value
+// = FIN row - fin_base: 0 = MISS, e + 1) and the scatter pass of K1 copies it to ext_id. `dense` is set when a tile has
+// more line starts than kHwCap (the caller then runs K2b over the line index instead).
+constexpr uint32_t kHwCap = 512;
+struct HeadWalkParams {
+    const uint16_t* text;
+    int64_t n_units;
+    DfaWalkDev a;                // table in shared memory
+    uint32_t* tile_counts;       // [n_tiles] newlines per kNlTile units (as K1)
+    uint32_t* masks;             // [n_tiles * 256] newline masks (as K1)
+    uint16_t* cand;              // [n_tiles * kHwCap]
+    uint32_t* scalars;           // [0] ticket (zeroed by the caller), [1] dense flag (zeroed), [2] candidate of the line at offset 0
+};
+bool k1h_plan(const DfaWalkDev&);
+void k1h_count_headwalk(const Launch&, const HeadWalkParams&);
 bool k2b_linewalk_plan(const DfaWalkDev&, uint32_t* threads, bool* in_smem);
 void k2b_linewalk_scan(const Launch&, const LineWalkParams&, uint32_t threads, bool in_smem);
 

@@ -237,6 +237,8 @@ TIERS = {"k1_fusedwalk": {}, "chunkwalk": {"GORP_SMALL_PATH": "chunkwalk"}, "one
          "linewalk_tailwalk_flush1": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_TAIL_FLUSH": "1"},
          "cutwalk_tailwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_CUT_WALK": "1", "GORP_TAIL_THREADS": "512"},
          "linewalk_cut_tailwalk384": {"GORP_FORCE_TWOPASS": "1", "GORP_CUT_WALK": "0", "GORP_TAIL_THREADS": "384"},
+         "k1h_tailwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "3"},
+         "k1h_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "3", "GORP_NO_TAILS": "1"},
          "dfawalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1"},
          "linewalk_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2"},
          "dfawalk_k4": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1", "GORP_FORCE_K4": "1"},
