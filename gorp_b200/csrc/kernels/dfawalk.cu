@@ -94,6 +94,17 @@ __device__ __forceinline__ uint32_t dw_step(uint32_t st, uint32_t w, uint32_t cx
     return dw_next<kSmem>(st, lds32(a), row_bytes, tab_g);
 }
 
+// the same step through a u16 copy of the column table (256 bytes = 64 words: the 32 lanes of a warp read fewer distinct words
+// of fewer rows per bank than with the u32 table: fewer wavefronts per lookup; K2b's walk is bound by them). The entries hold
+// the shared-memory address of the unit's column in row 0, which fits 16 bits because the table starts the dynamic area.
+template <int kByte>
+__device__ __forceinline__ uint32_t dw_step16(uint32_t st, uint32_t w, uint32_t c16_abs, uint32_t row_bytes) {
+    uint32_t b, a;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(b) : "r"(w), "n"(kByte == 0 ? 0x4440 : 0x4442));
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a) : "r"(b), "r"(c16_abs));
+    return dw_next<true>(st, lds16(a), row_bytes, nullptr);
+}
+
 // 8 units that hold a unit >= 0x80: unit by unit through the full class map (global, L1/L2 resident)
 template <bool kSmem>
 __device__ __noinline__ uint32_t dw_slow8(const DfaWalkDev& A, uint32_t st, uint4 v, uint32_t cx_abs, uint32_t tab_abs, uint32_t row_bytes,
@@ -384,8 +395,10 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
     const uint32_t row_bytes = A.K * 2;
     const uint32_t table_bytes = kSmem ? ((A.n_rows * row_bytes + 15u) & ~15u) : 0u;
     uint32_t* s_cx = reinterpret_cast<uint32_t*>(smem + table_bytes);
+    uint16_t* s_c16 = reinterpret_cast<uint16_t*>(s_cx + 128);
     const uint32_t tab_abs = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
     const uint32_t cx_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_cx));
+    const uint32_t c16_abs = static_cast<uint32_t>(__cvta_generic_to_shared(s_c16));
     const unsigned char* __restrict__ tab_g = reinterpret_cast<const unsigned char*>(A.table);
     if (kSmem) {
         const uint32_t n16 = (A.n_rows * row_bytes + 15u) / 16u;
@@ -393,7 +406,12 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
         uint4* dst = reinterpret_cast<uint4*>(smem);
         for (uint32_t i = threadIdx.x; i < n16; i += kT) dst[i] = __ldg(src + i);
     }
-    for (uint32_t i = threadIdx.x; i < 128; i += kT) s_cx[i] = (kSmem ? tab_abs : 0u) + __ldg(A.cls128 + i);
+    for (uint32_t i = threadIdx.x; i < 128; i += kT) {
+        s_cx[i] = (kSmem ? tab_abs : 0u) + __ldg(A.cls128 + i);
+        s_c16[i] = static_cast<uint16_t>(tab_abs + __ldg(A.cls128 + i));
+    }
+    // the u16 column table serves the fast path when the column addresses of row 0 fit 16 bits (P.flags & 2: A/B, u32 table)
+    const bool c16_ok = kSmem && tab_abs + 2u * A.K < 65536u && !(P.flags & 2u);
     __syncthreads();
     const uint32_t fin_base = A.fin_base, skip0 = A.n_states;
     const uint32_t lane = threadIdx.x & 31u;
@@ -439,7 +457,25 @@ __global__ void __launch_bounds__(768, 2) linewalk_kernel(LineWalkParams P) {
                 const Units16 u = P.flags & 1u ? load_units16(P.text, q, P.n_units) : load_units16_l2keep(P.text, q, P.n_units);
                 // lines form: the fast path needs a block that lies inside the line and holds no '\n' (there it is content)
                 const bool plain = !kLines || (q + 16 <= lend && nl_mask16(u) == 0u);
-                if (plain && ((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u) {
+                const bool ascii = plain && ((u.a.x | u.a.y | u.a.z | u.a.w | u.b.x | u.b.y | u.b.z | u.b.w) & 0xFF80FF80u) == 0u;
+                if (ascii && c16_ok) {
+                    st = dw_step16<0>(st, u.a.x, c16_abs, row_bytes);
+                    st = dw_step16<2>(st, u.a.x, c16_abs, row_bytes);
+                    st = dw_step16<0>(st, u.a.y, c16_abs, row_bytes);
+                    st = dw_step16<2>(st, u.a.y, c16_abs, row_bytes);
+                    st = dw_step16<0>(st, u.a.z, c16_abs, row_bytes);
+                    st = dw_step16<2>(st, u.a.z, c16_abs, row_bytes);
+                    st = dw_step16<0>(st, u.a.w, c16_abs, row_bytes);
+                    st = dw_step16<2>(st, u.a.w, c16_abs, row_bytes);
+                    st = dw_step16<0>(st, u.b.x, c16_abs, row_bytes);
+                    st = dw_step16<2>(st, u.b.x, c16_abs, row_bytes);
+                    st = dw_step16<0>(st, u.b.y, c16_abs, row_bytes);
+                    st = dw_step16<2>(st, u.b.y, c16_abs, row_bytes);
+                    st = dw_step16<0>(st, u.b.z, c16_abs, row_bytes);
+                    st = dw_step16<2>(st, u.b.z, c16_abs, row_bytes);
+                    st = dw_step16<0>(st, u.b.w, c16_abs, row_bytes);
+                    st = dw_step16<2>(st, u.b.w, c16_abs, row_bytes);
+                } else if (ascii) {
                     st = dw_step<kSmem, 0>(st, u.a.x, cx_abs, row_bytes, tab_g);
                     st = dw_step<kSmem, 2>(st, u.a.x, cx_abs, row_bytes, tab_g);
                     st = dw_step<kSmem, 0>(st, u.a.y, cx_abs, row_bytes, tab_g);
@@ -696,7 +732,7 @@ void k0_dfawalk_scan(const Launch& L, const DfaWalkParams& P, uint32_t threads, 
 }
 
 size_t linewalk_smem_bytes(const DfaWalkDev& a, bool in_smem) {
-    return (in_smem ? ((static_cast<size_t>(a.n_rows) * a.K * 2 + 15) & ~size_t(15)) : 0) + 128 * 4 + 128;
+    return (in_smem ? ((static_cast<size_t>(a.n_rows) * a.K * 2 + 15) & ~size_t(15)) : 0) + 128 * 4 + 128 * 2 + 128;
 }
 
 static size_t headwalk_smem_bytes(const DfaWalkDev& a) {
