@@ -1791,6 +1791,33 @@ int export_blob(const CompiledDefinition& d, bool match_only, void** blob, size_
 
 }  // namespace
 
+// First index i with off[i + 1] < off[i], or -1: the caller's offsets must be non-decreasing. Checked up front (an O(n) scan,
+// branch-free inner loop, split over a few threads for batches of millions of lines: 25 M offsets took 20 ms of a 87 ms call
+// when scanned by one thread with an early-exit branch).
+static int64_t first_decreasing_offset(const int64_t* off, int64_t n_lines) {
+    auto scan = [off](int64_t i0, int64_t i1) -> int64_t {
+        for (int64_t b = i0; b < i1; b += 4096) {
+            const int64_t e = std::min<int64_t>(b + 4096, i1);
+            int bad = 0;
+            for (int64_t i = b; i < e; ++i) bad |= off[i + 1] < off[i];
+            if (bad)
+                for (int64_t i = b; i < e; ++i)
+                    if (off[i + 1] < off[i]) return i;
+        }
+        return -1;
+    };
+    const int n_thr = n_lines >= (1 << 20) ? static_cast<int>(std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency()))) : 1;
+    if (n_thr == 1) return scan(0, n_lines);
+    std::vector<int64_t> first(n_thr, -1);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thr; ++t)
+        pool.emplace_back([&first, &scan, n_lines, n_thr, t] { first[t] = scan(n_lines * t / n_thr, n_lines * (t + 1) / n_thr); });
+    for (auto& th : pool) th.join();
+    for (int64_t f : first)
+        if (f >= 0) return f;
+    return -1;
+}
+
 extern "C" {
 
 int gorp_abi_version(void) { return GORP_ABI_VERSION; }
@@ -1934,8 +1961,8 @@ int gorp_extract_lines(gorp_engine* e, const uint16_t* text, const int64_t* off,
     // the offsets come from the caller: anything that is not a non-decreasing sequence starting at >= 0 would send the
     // kernels outside the staged text
     if (off[0] < 0) return fail(GORP_E_ARG, "offsets must start at >= 0");
-    for (int64_t i = 0; i < n_lines; ++i)
-        if (off[i + 1] < off[i]) return fail(GORP_E_ARG, strfmt("offsets must be non-decreasing (line %lld)", static_cast<long long>(i)));
+    if (const int64_t i = first_decreasing_offset(off, n_lines); i >= 0)
+        return fail(GORP_E_ARG, strfmt("offsets must be non-decreasing (line %lld)", static_cast<long long>(i)));
     return extract_host(e, text, nullptr, n_lines > 0 ? off[n_lines] : 0, off, n_lines, out);
 }
 
@@ -1954,8 +1981,8 @@ int gorp_extract_text_utf8(gorp_engine* e, const uint8_t* text, int64_t n_bytes,
 int gorp_match_all_lines(gorp_engine* e, const uint16_t* text, const int64_t* off, int64_t n_lines, gorp_match_result* out) {
     if (!e || !out || !off || n_lines < 0 || e->devs.empty()) return fail(GORP_E_ARG, "bad argument");
     if (off[0] < 0) return fail(GORP_E_ARG, "offsets must start at >= 0");
-    for (int64_t i = 0; i < n_lines; ++i)
-        if (off[i + 1] < off[i]) return fail(GORP_E_ARG, strfmt("offsets must be non-decreasing (line %lld)", static_cast<long long>(i)));
+    if (const int64_t i = first_decreasing_offset(off, n_lines); i >= 0)
+        return fail(GORP_E_ARG, strfmt("offsets must be non-decreasing (line %lld)", static_cast<long long>(i)));
     if (!text && n_lines > 0 && off[n_lines] > off[0]) return fail(GORP_E_ARG, "null text");
     return guarded([&]() -> int {
         DeviceCtx& c = *e->devs[0];

@@ -172,6 +172,26 @@ def test_edge_cases():
     check_against_oracle(d, text=np.asarray(jdkre.to_units("\n\naa\n"), dtype=np.uint16))
 
 
+def test_lines_form_rejects_decreasing_offsets():
+    """gorp_extract_lines validates the caller's offsets on the host (GORP_E_ARG, never a CUDA fault): one-thread scan for
+    small batches, split over threads from 2^20 lines on."""
+    import ctypes as C
+    from gorp_b200 import _ffi
+    g = DefinitionReader.reader(V.README_DEF).read()
+    for n, bad_at in ((10, 4), (1 << 21, 1_500_000)):
+        text = np.full(n, ord("x"), dtype=np.uint16)
+        off = np.arange(n + 1, dtype=np.int64)
+        res = _ffi.Result()
+        assert _ffi.lib.gorp_extract_lines(g._eng(), text.ctypes.data, off.ctypes.data, n, C.byref(res)) == 0
+        assert res.n_lines == n
+        _ffi.lib.gorp_result_release(g._eng(), C.byref(res))
+        off[bad_at + 1] = off[bad_at] - 1
+        rc = _ffi.lib.gorp_extract_lines(g._eng(), text.ctypes.data, off.ctypes.data, n, C.byref(res))
+        assert rc != 0 and ("line %d" % bad_at).encode() in _ffi.lib.gorp_last_error()
+    off = np.asarray([-1, 0, 1], dtype=np.int64)
+    assert _ffi.lib.gorp_extract_lines(g._eng(), text.ctypes.data, off.ctypes.data, 2, C.byref(res)) != 0
+
+
 def test_long_and_ragged_lines():
     rng = np.random.default_rng(5)
     lines = []
