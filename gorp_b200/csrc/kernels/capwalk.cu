@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_scatter_kernel(const in
                                                                         const TailExt* __restrict__ tails) {
     __shared__ uint32_t s_cnt[kCapMaxBuckets];
     __shared__ uint32_t s_pos[kCapMaxBuckets];
+    __shared__ uint8_t s_perm_needed[kCapMaxBuckets];  // 0: the extraction's lines go to the tail walk, which reads records only
+    for (uint32_t i = threadIdx.x; i < n_ext; i += kBucketThreads) s_perm_needed[i] = (!recs || !tails[i].available) ? 1 : 0;
     for (int64_t seg0 = static_cast<int64_t>(blockIdx.x) * kBucketSeg; seg0 < n_lines; seg0 += static_cast<int64_t>(gridDim.x) * kBucketSeg) {
         for (uint32_t i = threadIdx.x; i < n_ext; i += kBucketThreads) s_cnt[i] = 0;
         __syncthreads();
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_scatter_kernel(const in
             if (mine[k] >= 0) {
                 const uint32_t at = s_pos[mine[k]] + rank[k];
                 // the tail walk reads records, the bucketed capture walk (extractions without a tail) reads `perm`
-                if (!recs || !tails[mine[k]].available) perm[at] = static_cast<uint32_t>(line);
+                if (s_perm_needed[mine[k]]) perm[at] = static_cast<uint32_t>(line);
                 if (recs) {  // start, id and length of the line in one record (kernels/tailwalk.cu)
                     const int64_t a = line_off[line], len = line_off[line + 1] - sep - a;
                     const int4 r = make_int4(static_cast<int>(static_cast<uint64_t>(a) & 0xFFFFFFFFu), static_cast<int>(static_cast<uint64_t>(a) >> 32),
