@@ -509,6 +509,7 @@ def e2e_run(env, kept, workload):
             e2e["utf8_input"] = {"value": int(ll.item()) / float(ttu.item()), "unit": "lines/s", "h2d_bytes_per_step": int(h8_np.size),
                                  "d2h_bytes_per_step": int(d2h), "ms_per_step": float(ttu.item()) * 1e3,
                                  "call": "gorp_extract_text_utf8 (UTF-8 bytes in, decoded to UTF-16 on the device)"}
+            h8_np = None  # (the numpy view keeps the pinned buffer alive)
             del h8
         # the List<String> form (Gorp.extractAll(List<String>), Gorp.java:145-147): the same lines as one concatenation without
         # separators plus n + 1 offsets, on a bounded share of the batch (the offsets are another 8 bytes per line of pinned memory)
