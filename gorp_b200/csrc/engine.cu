@@ -1,9 +1,12 @@
 // Engine + C ABI of libgorpcuda (include/gorp_cuda.h). Host orchestration only; the kernels are in kernels/.
 //
 // Device pipeline per batch (one stream, no host round trip except reading the line count of the text form):
-//   text form, small definitions: K0' one-pass kernel (kernels/onepass.cu)     => everything in one HBM pass
-//   otherwise  text form : K1 count -> scan -> K1 scatter -> K1 finish          => line_off[n+1], n_lines
-//              both forms: K2 dfa_scan => ext_id -> K4 tdfa_capture => result rows of spans -> K3 histogram
+//   text form            : K1 count -> scan -> K1 scatter -> K1 finish          => line_off[n+1], n_lines
+//   small definitions    : fused walk (kernels/tailwalk.cu, "all" mode) over the line index => ext_id, spans, histogram
+//                          (tier: the chunk-owner one-pass kernel K0c, kernels/chunkwalk.cu, without K1)
+//   big definitions      : K2b line walk over the early-exit table => candidates -> K3 histogram -> bucket pass ->
+//                          K4c tail walk (+ K4b capture walk for extractions without a tail) => ext_id, spans
+//   forced tiers         : K0d, K1h, K2 dfa_scan, K4 tdfa_capture (one line per thread)
 #include <cuda_runtime.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -155,8 +158,6 @@ struct DeviceCtx {
     int dfa_tier = 0;            // GORP_DFA_TIER: 0 = by line length, 1 = chunk-owner walk (K0d), 2 = line index + lane queue (K1 + K2b),
                                  // 3 = line index with the head walk inside its count pass (K1h)
     bool force_k1k2 = false;     // GORP_FORCE_K1K2=1: newline index + DFA scan as separate kernels (K1, K2) instead of K0d
-    bool force_tiles = false;    // GORP_FORCE_TILES=1: the TMA-staged tile kernel instead of the chunk-walk kernel
-    uint32_t onepass_shrink = 0;  // too-dense retries remembered across calls
     uint32_t* d_slots = nullptr;
     uint32_t n_ext = 0;
     uint32_t max_slots = 0;
@@ -317,7 +318,6 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
     CK(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
     if (const char* f = std::getenv("GORP_FORCE_GENERAL")) c.force_general = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_TWOPASS")) c.force_twopass = f[0] == '1';
-    if (const char* f = std::getenv("GORP_FORCE_TILES")) c.force_tiles = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_K1K2")) c.force_k1k2 = f[0] == '1';
     if (const char* f = std::getenv("GORP_FORCE_K4")) c.force_k4 = f[0] == '1';
     if (const char* f = std::getenv("GORP_DFA_TIER")) c.dfa_tier = std::atoi(f);
@@ -552,7 +552,7 @@ void build_device(DeviceCtx& c, const DeviceModel& m, const FusedAutomaton& fuse
                 }
             }
         }
-        // one-pass tier: DFA x capture automata folded into one automaton (host/fused.hpp, kernels/onepass.cu)
+        // one-pass automaton: DFA x capture automata folded into one automaton (host/fused.hpp) — table of the K0c tier
         {
             const FusedAutomaton& A = fused;
             if (A.available) {
@@ -791,7 +791,7 @@ struct Timer {
 // Text form through the chunk-walk one-pass kernel. Returns false when the batch has to take another path.
 bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
                    int64_t& n_lines, gorp_device_result* out) {
-    if (n_units <= 0 || c.force_general || c.force_twopass || c.force_tiles || !c.chunkwalk.enabled) return false;
+    if (n_units <= 0 || c.force_general || c.force_twopass || !c.chunkwalk.enabled) return false;
     if (reinterpret_cast<uintptr_t>(d_text) & 31) return false;  // the walk uses 256-bit loads
     uint32_t threads = 0;
     if (!k0_chunkwalk_plan(c.chunkwalk, &threads)) return false;
@@ -881,101 +881,6 @@ bool run_chunkwalk(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaSt
         n_lines = totals[0];
         c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
         if (totals[2] & 1) {  // capacity overflow: rerun once with the exact size
-            exact = true;
-            continue;
-        }
-        CK(cudaMemcpyAsync(d_scalars, P.totals, 8, cudaMemcpyDeviceToDevice, stream));
-        if (out) {
-            out->n_lines = n_lines;
-            out->span_stride = static_cast<int32_t>(c.max_slots);
-            out->d_ext_id = P.ext_id;
-            out->d_line_off = P.line_off;
-            out->d_spans = P.spans;
-            out->d_histogram = c.hist.as<int64_t>();
-            out->d_n_lines = d_scalars;
-        }
-        return true;
-    }
-    return false;
-}
-
-// Text form through the one-pass kernel. Returns false when the batch has to take another path.
-bool run_onepass(DeviceCtx& c, const uint16_t* d_text, int64_t n_units, cudaStream_t stream, Timer& tm, int64_t* d_scalars,
-                 int64_t& n_lines, gorp_device_result* out) {
-    if (n_units <= 0 || c.force_general || c.force_twopass || !c.onepass.enabled) return false;
-    Launch L{stream, c.sm_count};
-    c.hist.reserve((c.n_ext + 2) * 8);
-    bool exact = false;
-    const int tm_pos = tm.position();
-    for (int attempt = 0; attempt < 12; ++attempt) {
-        tm.rewind(tm_pos);
-        uint32_t threads = 0, tile = 0;
-        if (!k0_onepass_plan(c.onepass, c.lines_per_unit, c.onepass_shrink, &threads, &tile)) return false;
-        OnePassParams P{};
-        P.text = d_text;
-        P.n_units = n_units;
-        P.tile_units = tile;
-        P.per = tile / threads;
-        P.n_tiles = (n_units + tile - 1) / tile;
-        P.a = c.onepass;
-        P.slots_per_ext = c.d_slots;
-        P.n_ext = c.n_ext;
-        P.span_stride = c.max_slots;
-        // look-back state: [status n_tiles][ticket (8 B)][totals 3 x int64]
-        const size_t state_bytes = static_cast<size_t>(P.n_tiles) * 8 + 8 + 24;
-        c.tile_state.reserve(std::max<size_t>(state_bytes, kTileStateMinBytes));
-        int64_t cap_lines = static_cast<int64_t>(static_cast<double>(n_units) * c.lines_per_unit * 1.25) + 4096;
-        if (exact) cap_lines = n_lines + 16;
-        c.ext_id.reserve(static_cast<size_t>(cap_lines + 1) * 4);
-        c.line_off.reserve(static_cast<size_t>(cap_lines + 2) * 8);
-        c.spans.reserve((static_cast<size_t>(cap_lines) * c.max_slots + 4) * 4);
-        P.ext_id = c.ext_id.as<int32_t>();
-        P.line_off = c.line_off.as<int64_t>();
-        P.spans = c.spans.as<int32_t>();
-        P.hist = c.hist.as<unsigned long long>();
-        P.cap_lines = cap_lines;
-        unsigned char* st = c.tile_state.as<unsigned char>();
-        P.tile_status = reinterpret_cast<unsigned long long*>(st);
-        P.ticket = reinterpret_cast<unsigned int*>(st + static_cast<size_t>(P.n_tiles) * 8);
-        P.totals = reinterpret_cast<int64_t*>(st + static_cast<size_t>(P.n_tiles) * 8 + 8);
-        CK(cudaMemsetAsync(st, 0, state_bytes, stream));
-        CK(cudaMemsetAsync(c.hist.p, 0, (c.n_ext + 2) * 8, stream));
-        const bool debug = std::getenv("GORP_ONEPASS_DEBUG") != nullptr;
-        const int grid = k0_onepass_grid(L, P, threads);
-        if (debug) {
-            c.debug.reserve(static_cast<size_t>(grid) * 24 * 8);
-            CK(cudaMemsetAsync(c.debug.p, 0, static_cast<size_t>(grid) * 24 * 8, stream));
-            P.debug = c.debug.as<long long>();
-        }
-        k0_onepass_extract(L, P, threads);
-        tm.mark("k0_onepass_extract", 1);
-        CK(cudaGetLastError());
-        int64_t totals[3] = {0, 0, 0};
-        CK(cudaMemcpyAsync(totals, P.totals, 24, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        if (debug) {  // mean cycles per tile and phase, first and last worker warp
-            std::vector<long long> h(static_cast<size_t>(grid) * 24);
-            CK(cudaMemcpy(h.data(), c.debug.p, h.size() * 8, cudaMemcpyDeviceToHost));
-            static const char* kPhase[11] = {"top_barrier", "ticket+tail+tma_wait", "barrier", "newline_masks", "scan+starts",
-                                             "sort", "walk", "walk_barrier", "stage_rows", "base_barrier", "copy_out"};
-            for (int w = 0; w < 2; ++w) {
-                double acc[12] = {0};
-                for (int b = 0; b < grid; ++b)
-                    for (int i = 0; i < 12; ++i) acc[i] += static_cast<double>(h[(static_cast<size_t>(b) * 2 + w) * 12 + i]);
-                acc[11] = std::floor(acc[11] / 4);  // tiles (the low bits are debris of value consumption)
-                std::fprintf(stderr, "[onepass debug] %s warp, tile=%u units, %d CTAs, %.0f tiles/CTA; cycles per tile:", w ? "last" : "first",
-                             tile, grid, acc[11] / grid);
-                for (int i = 0; i < 11; ++i) std::fprintf(stderr, " %s=%.0f", kPhase[i], acc[i] / std::max(acc[11], 1.0));
-                std::fprintf(stderr, "\n");
-            }
-        }
-        if (totals[2] & 2) {  // a tile held more line starts than the CTA has worker threads: smaller tiles
-            ++c.onepass_shrink;
-            continue;
-        }
-        n_lines = totals[0];
-        c.lines_per_unit = std::max(static_cast<double>(n_lines) / static_cast<double>(n_units), 1e-6);
-        if (totals[2] & 1) {  // capacity overflow: rerun with the exact size
             exact = true;
             continue;
         }
@@ -1094,10 +999,9 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
     bool ends_with_nl = true;
     // small definitions, text form: the chunk-owner one-pass kernel K0c, or (GORP_SMALL_PATH=fusedwalk) the newline index K1
     // followed by the fused walk — every line through the one-pass automaton laid out as a tail table
-    const bool fusedwalk = c.fused_tail.enabled && c.fusedwalk_default && (!d_off || n_units > 0) && !c.force_twopass && !c.force_general && !c.force_tiles &&
+    const bool fusedwalk = c.fused_tail.enabled && c.fusedwalk_default && (!d_off || n_units > 0) && !c.force_twopass && !c.force_general &&
                            !c.force_k1k2 && !c.force_k4 && !c.cap.match_only && c.max_slots > 0 && (reinterpret_cast<uintptr_t>(d_text) & 31) == 0;
     if (!d_off && !fusedwalk && run_chunkwalk(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
-    if (!d_off && !fusedwalk && run_onepass(c, d_text, n_units, stream, tm, d_n_lines, n_lines, out)) return n_lines;
     bool scanned = false;  // ext_id already holds the combined-DFA result
     // long or ragged lines: a line index (K1) + lanes that pull lines dynamically (K2b) beats the chunk-owner walk (K0d),
     // whose threads are stuck with whatever lines start in their chunk

@@ -1,8 +1,7 @@
 // K0c — one-pass "chunk owner" extraction kernel (sm_100a): every UTF-16 unit is looked at once, no shared-memory
 // staging of the text, no barrier inside the walk.
 //
-// The automaton is the one of host/fused.hpp (combined DFA x capture automata folded into one table, see
-// kernels/onepass.cu for the per-unit step):
+// The automaton is the one of host/fused.hpp (combined DFA x capture automata folded into one table):
 //
 //   per unit :  ent = LDS[row(ent) + 4*unit]              one shared-memory lookup, the only dependent chain
 //               STS slot(ent)[thread] = position          "last position at which command list `slot` fired"

@@ -150,8 +150,8 @@ void k4_tdfa_capture(const Launch&, const CapDev&, const uint16_t* text, const i
 void k4_tdfa_fast(const Launch&, const TdfaFastDev&, const CapDev&, const uint16_t* text, int64_t n_units,
                   const int64_t* line_off, int64_t n_lines, uint32_t span_stride, int32_t* ext_id, int32_t* spans);
 
-// K0': one-pass persistent kernel (text form) over the folded automaton of host/fused.hpp — see kernels/onepass.cu.
-constexpr uint32_t kOnePassOverhang = 1024;  // units staged beyond the tile (lines that cross the tile end)
+// Table of the folded automaton of host/fused.hpp as the chunk-owner one-pass kernel K0c reads it (kernels/chunkwalk.cu; the
+// TMA-staged tile kernel that first used it lost to K0c in round 1 and was removed in round 2).
 constexpr int kOnePassHistBins = 256;
 struct OnePassDev {
     const uint32_t* rows;        // [n_rows * width] raw entries: (next row << 16) | slot id
@@ -189,11 +189,6 @@ struct OnePassParams {
     int64_t* totals;                     // [0] n_lines, [2] flags: 1 = capacity overflow, 2 = tile too dense
     long long* debug;                    // optional [grid * 2 * 10] per-phase cycle counters (GORP_ONEPASS_DEBUG=1)
 };
-int k0_onepass_grid(const Launch&, const OnePassParams&, uint32_t threads);
-size_t onepass_smem_bytes(const OnePassDev&, uint32_t threads, uint32_t tile_units);
-// picks CTA size and tile size for the expected line density; `shrink` = number of too-dense retries so far
-bool k0_onepass_plan(const OnePassDev&, double lines_per_unit, uint32_t shrink, uint32_t* threads, uint32_t* tile_units);
-void k0_onepass_extract(const Launch&, const OnePassParams&, uint32_t threads);
 
 // K0c: chunk-walk one-pass kernel (text form) — see kernels/chunkwalk.cu. Uses OnePassParams (tile_units = threads *
 // kChunkUnits, per = kChunkUnits) with the DEADSCAN variant of the table.

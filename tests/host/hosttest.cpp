@@ -126,7 +126,7 @@ extern "C" int ht_run(const void* blob, size_t len, const uint16_t* text, const 
     }
 }
 
-// The one-pass automaton (host/fused.hpp) interpreted the way kernels/onepass.cu runs it: one table lookup per unit,
+// The one-pass automaton (host/fused.hpp) interpreted the way kernels/chunkwalk.cu runs it: one table lookup per unit,
 // "last position" per op slot, group boundaries resolved from the outcome at end of line.
 // stats: [0] available, [1] states, [2] joint classes, [3] op slots, [4] outcomes. Returns 1 when not available.
 extern "C" int ht_run_fused(const void* blob, size_t len, const uint16_t* text, const int64_t* starts, const int64_t* ends,

@@ -251,7 +251,7 @@ def test_full_size_properties_big_definitions(name, n, reps):
     assert (np.diff(b.line_off).reshape(reps, -1) == np.diff(b1.line_off)[None, :]).all()
 
 
-TIERS = {"k1_fusedwalk": {}, "chunkwalk": {"GORP_SMALL_PATH": "chunkwalk"}, "onepass_tiles": {"GORP_FORCE_TILES": "1"},
+TIERS = {"k1_fusedwalk": {}, "chunkwalk": {"GORP_SMALL_PATH": "chunkwalk"},
          "dfawalk_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "1", "GORP_NO_TAILS": "1"},
          "linewalk_capwalk_notails": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_NO_TAILS": "1"},
          "linewalk_tailwalk_flush1": {"GORP_FORCE_TWOPASS": "1", "GORP_DFA_TIER": "2", "GORP_TAIL_FLUSH": "1"},
@@ -265,7 +265,7 @@ TIERS = {"k1_fusedwalk": {}, "chunkwalk": {"GORP_SMALL_PATH": "chunkwalk"}, "one
          "k1k2_capwalk": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1"},
          "twopass_fast": {"GORP_FORCE_TWOPASS": "1", "GORP_FORCE_K1K2": "1", "GORP_FORCE_K4": "1"},
          "general": {"GORP_FORCE_GENERAL": "1"}}
-_TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_TILES", "GORP_FORCE_K1K2", "GORP_FORCE_K4", "GORP_DFA_TIER",
+_TIER_ENV = ("GORP_FORCE_TWOPASS", "GORP_FORCE_GENERAL", "GORP_FORCE_K1K2", "GORP_FORCE_K4", "GORP_DFA_TIER",
              "GORP_NO_TAILS", "GORP_TAIL_FLUSH", "GORP_CUT_WALK", "GORP_TAIL_THREADS", "GORP_SMALL_PATH")
 
 

@@ -14,7 +14,7 @@ import json
 import os
 import sys
 
-TIMER_OF = [("chunkwalk", "k0_chunkwalk_extract"), ("onepass", "k0_onepass_extract"), ("dfawalk_kernel", "k0_dfawalk"), ("nl_count", "k1_count_newlines"),
+TIMER_OF = [("chunkwalk", "k0_chunkwalk_extract"), ("dfawalk_kernel", "k0_dfawalk"), ("nl_count", "k1_count_newlines"),
             ("scan_", "scan_tiles"), ("nl_scatter", "k1_scatter_newlines"), ("nl_finish", "k1_scatter_newlines"), ("k1_finish", "k1_scatter_newlines"),
             ("linewalk", "k2b_linewalk_scan"), ("histogram", "k3_histogram"), ("bucket_", "k4b_bucket"), ("tailwalk", "k4c_tailwalk"),
             ("tail_long", "k4c_tailwalk"), ("capwalk", "k4b_capwalk"), ("dfa_direct", "k2_dfa_scan"), ("dfa_scan", "k2_dfa_scan"),
