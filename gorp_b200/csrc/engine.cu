@@ -1119,12 +1119,11 @@ int64_t run_pipeline_tables(DeviceCtx& c, const uint16_t* d_text, int64_t n_unit
         T.n_long = ticket + 1;
         T.all = 1;
         T.n_lines = n_lines;
-        // big items amortise the barrier at the end of an item (2 % at 4096 lines), small batches (the 64 MB pieces of a
-        // host-buffer call) need enough items for every CTA
-        // (an item must also give every lane of a 512-thread CTA a couple of lines: not below 1024)
-        const int64_t ctas = 2ll * c.sm_count;
-        uint32_t il = 1024;
-        while (il < 4096 && static_cast<int64_t>(il) * 2 * ctas < n_lines) il *= 2;
+        // work items are taken by WARPS: big enough that the lanes idling at the end of an item do not matter (half a line out of
+        // item_lines / 32), small enough that a small batch (a 64 MB piece of a host-buffer call) has items for every warp
+        const int64_t warps = 2ll * c.sm_count * 16;
+        uint32_t il = 64;
+        while (il < 1024 && static_cast<int64_t>(il) * 4 * warps < n_lines) il *= 2;
         T.item_lines = il;
         k4c_tailwalk(L, T);
         tm.mark("k4c_fusedwalk", 2);

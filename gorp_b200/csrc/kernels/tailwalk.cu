@@ -166,11 +166,54 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
     if (threadIdx.x == 0) s_loaded = 0xFFFFFFFFu;
     sts_u16(slot_abs + zero_off, 0u);
 
-    for (;;) {
-        __syncthreads();  // the previous item is finished (its table and s_item / s_cursor are free)
-        if (threadIdx.x == 0) s_item = atomicAdd(P.item_ticket, 1u);
+    // copies the table of an extraction (and its recipes / outcome codes / init list) to shared memory — called by the whole CTA
+    auto load_table = [&](const TailExt& x) {
+        const uint32_t n16 = ((x.fin_base + x.n_outcomes) * row_bytes + 15u) / 16u;
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(T.image) + x.tab_off);
+        uint4* dst = reinterpret_cast<uint4*>(s_mem);
+        for (uint32_t i = threadIdx.x; i < n16; i += kTailWalkThreads) dst[i] = __ldg(src + i);
+        if (threadIdx.x == 0) s_n_multi = 0;
         __syncthreads();
-        const uint32_t item = s_item;
+        for (uint32_t i = threadIdx.x; i < x.n_outcomes; i += kTailWalkThreads) s_oext[i] = __ldg(T.oext + x.oext_off + i);
+        for (uint32_t i = threadIdx.x; i < x.n_outcomes * stride; i += kTailWalkThreads) {
+            const uint32_t rec = __ldg(T.res + x.res_off + i);
+            const bool match = __ldg(T.oext + x.oext_off + i / stride) >= 0;
+            // a recipe becomes the byte offset of the slot that holds the boundary + 1:
+            // no writer / not a MATCH outcome -> ZERO, the line length -> LEN, one writer -> its slot,
+            // several writers -> ZERO here and an entry in the several-writer list
+            uint32_t off = zero_off;
+            if (match && rec == 0xFFu) {
+                off = len_off;
+            } else if (match && rec && rec < 256u) {
+                off = rec * kSlotStride;
+            } else if (match && rec) {
+                const uint32_t at = atomicAdd(&s_n_multi, 1u);
+                if (at < kTwMaxMulti) {
+                    s_multi[2 * at] = ((i / stride) << 16) | (i % stride);
+                    s_multi[2 * at + 1] = rec;
+                }
+            }
+            s_res[i] = off;
+        }
+        for (uint32_t i = threadIdx.x; i < x.n_init; i += kTailWalkThreads) s_init[i] = __ldg(T.init_slots + x.init_off + i);
+    };
+    // "all" mode: one table for the whole launch — loaded once, and every WARP takes work items on its own (no barrier between
+    // items, no shared cursor: the lanes that run out of lines at the end of an item idle for half a line out of item_lines / 32)
+    if (kAll) {
+        load_table(T.ext[0]);
+        __syncthreads();
+    }
+    for (;;) {
+        uint32_t item = 0;
+        if (kAll) {
+            if (lane == 0) item = atomicAdd(P.item_ticket, 1u);
+            item = __shfl_sync(0xffffffffu, item, 0);
+        } else {
+            __syncthreads();  // the previous item is finished (its table and s_item / s_cursor are free)
+            if (threadIdx.x == 0) s_item = atomicAdd(P.item_ticket, 1u);
+            __syncthreads();
+            item = s_item;
+        }
         if (item >= n_items) break;
         CapItem it;
         if (kAll) {
@@ -182,43 +225,14 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
         }
         const TailExt x = T.ext[it.ext];
         if (!x.available) continue;  // the bucketed capture walk (kernels/capwalk.cu) takes the items of this extraction
-        if (s_loaded != it.ext) {
-            const uint32_t n16 = ((x.fin_base + x.n_outcomes) * row_bytes + 15u) / 16u;
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(T.image) + x.tab_off);
-            uint4* dst = reinterpret_cast<uint4*>(s_mem);
-            for (uint32_t i = threadIdx.x; i < n16; i += kTailWalkThreads) dst[i] = __ldg(src + i);
-            if (threadIdx.x == 0) s_n_multi = 0;
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < x.n_outcomes; i += kTailWalkThreads) s_oext[i] = __ldg(T.oext + x.oext_off + i);
-            for (uint32_t i = threadIdx.x; i < x.n_outcomes * stride; i += kTailWalkThreads) {
-                const uint32_t rec = __ldg(T.res + x.res_off + i);
-                const bool match = __ldg(T.oext + x.oext_off + i / stride) >= 0;
-                // a recipe becomes the byte offset of the slot that holds the boundary + 1:
-                // no writer / not a MATCH outcome -> ZERO, the line length -> LEN, one writer -> its slot,
-                // several writers -> ZERO here and an entry in the several-writer list
-                uint32_t off = zero_off;
-                if (match && rec == 0xFFu) {
-                    off = len_off;
-                } else if (match && rec && rec < 256u) {
-                    off = rec * kSlotStride;
-                } else if (match && rec) {
-                    const uint32_t at = atomicAdd(&s_n_multi, 1u);
-                    if (at < kTwMaxMulti) {
-                        s_multi[2 * at] = ((i / stride) << 16) | (i % stride);
-                        s_multi[2 * at + 1] = rec;
-                    }
-                }
-                s_res[i] = off;
-            }
-            for (uint32_t i = threadIdx.x; i < x.n_init; i += kTailWalkThreads) s_init[i] = __ldg(T.init_slots + x.init_off + i);
-        }
+        if (!kAll && s_loaded != it.ext) load_table(x);
         // The lanes of a warp walk in lock-step, so a warp is as slow as its longest line. Optional (P.flags & 16, off by default:
         // see profiles/README.md round 2 — the walk is bound by shared-memory wavefronts, not by idle lanes): the item's lines
         // are handed out sorted by DECREASING length inside groups of 2^G consecutive records (counting sort by the number of
         // 16-unit blocks a line touches, in shared memory), so that the 32 lines a warp claims together end within the same
         // iteration or two while staying close to each other in the text. The second pass finds the records in L2.
         const uint32_t n_it = it.end - it.begin;
-        const bool sorted = (P.flags & 16u) != 0;
+        const bool sorted = !kAll && (P.flags & 16u) != 0;
         if (sorted) {
             const uint32_t G = max(7u, min(12u, (P.flags >> 8) & 15u ? (P.flags >> 8) & 15u : 8u));
             for (uint32_t i = threadIdx.x; i < kTwBins; i += kTailWalkThreads) s_bins[i] = 0;
@@ -259,9 +273,12 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
             for (uint32_t i = threadIdx.x; i < n_it; i += kTailWalkThreads)
                 s_order[atomicAdd(&s_bins[key_of(i)], 1u)] = static_cast<uint16_t>(i);
         }
-        if (threadIdx.x == 0) s_cursor = it.begin;
-        __syncthreads();
-        if (threadIdx.x == 0) s_loaded = it.ext;
+        uint32_t wcursor = it.begin;  // kAll: the warp's own cursor (warp-uniform)
+        if (!kAll) {
+            if (threadIdx.x == 0) s_cursor = it.begin;
+            __syncthreads();
+            if (threadIdx.x == 0) s_loaded = it.ext;
+        }
 
         const int32_t cand = static_cast<int32_t>(it.ext);
         const uint32_t fin_ra = x.fin_base * row_bytes + rows_abs;
@@ -386,9 +403,13 @@ __global__ void __launch_bounds__(kT, 2) tailwalk_kernel(TailWalkParams P) {
             if (!exhausted) {  // lanes without a next line claim the next entries of the item
                 const uint32_t want = __ballot_sync(0xffffffffu, nstage == 0);
                 if (want) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&s_cursor, static_cast<uint32_t>(__popc(want)));
-                    base = __shfl_sync(0xffffffffu, base, 0);
+                    uint32_t base = wcursor;
+                    if (kAll) {
+                        wcursor += static_cast<uint32_t>(__popc(want));
+                    } else {
+                        if (lane == 0) base = atomicAdd(&s_cursor, static_cast<uint32_t>(__popc(want)));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                    }
                     const uint32_t idx = base + static_cast<uint32_t>(__popc(want & lt_mask));
                     if (nstage == 0 && idx < it.end) {
                         const uint32_t at = sorted ? it.begin + s_order[idx - it.begin] : idx;
